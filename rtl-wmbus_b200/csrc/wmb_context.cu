@@ -1,0 +1,973 @@
+/*
+ * wmb_context.cu -- host side of libwmbus_b200.so: the C ABI declared in
+ * include/wmbus_b200.h, device buffers, stream orchestration and the stream/batch
+ * bookkeeping around the kernels in wmb_kernels.cuh.
+ *
+ * Per batch of IQ bytes (stream-ordered on the context's compute stream):
+ *     H2D (copy stream, double-buffered)                       [host input only]
+ *     K1  k1_demod_kernel        cu8 -> dphi (fp32) + rssi (u8), both chains
+ *     K2  k2_lanes_kernel        speculative bit-sync lanes, per chain
+ *         k2_verify_kernel       compare lane start states with predecessors' end states
+ *         k2_lanes_kernel(mode=1) + verify, repeated until no lane is refuted
+ *     K2c scan + compact         lane-local events -> per-stream rings, access-code matches
+ *     K3  size/offsets/copy      candidate frames -> pinned host memory
+ * The host then owns 3-out-of-6 / Manchester / CRC (wmb_framer.c), exactly the split
+ * BASELINE.json's north_star asks for.
+ *
+ * With -DWMB_HOSTSIM the same file builds against tests/hostsim/hostsim_cuda.h and runs
+ * the kernels' phase functions on the CPU; that build is test infrastructure only.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#ifdef WMB_HOSTSIM
+#include "hostsim_cuda.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include "wmbus_b200.h"
+#include "wmb_framer.h"
+#include "wmb_kernels.cuh"
+
+#ifndef WMB_VERSION
+#define WMB_VERSION "wmbus-b200 0.1 (sm_100a)"
+#endif
+
+static thread_local char g_err[512];
+
+static int set_err(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return set_err(WMB_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                           __FILE__, __LINE__);                                                \
+    } while (0)
+
+/* --------------------------------------------------------------------------- */
+
+struct Stream {                     /* one (chain, algo) bit stream */
+    uint32_t *ev = nullptr;         /* lane-local events                          */
+    uint32_t *cnt = nullptr;        /* per-lane counts                            */
+    uint64_t *base = nullptr;       /* per-lane ordinal base                      */
+    uint64_t *ring = nullptr;       /* global event ring                          */
+    uint64_t ring_cap = 0;          /* power of two                               */
+    StreamDev *sd = nullptr;        /* device bookkeeping                         */
+    uint64_t *cand = nullptr;       /* device candidate ordinals                  */
+    uint64_t total = 0;             /* host mirror of sd->total                   */
+    std::vector<uint64_t> pending;  /* candidates not yet complete                */
+    /* host framer bookkeeping */
+    int64_t busy_until = -1;        /* last ordinal consumed by an accepted packet */
+};
+
+struct ChainBuf {
+    float *dphi = nullptr;          /* [W_hist | M_max]                           */
+    uint8_t *rssi = nullptr;
+    float *dphi_tmp = nullptr;      /* W_hist scratch for the history shift       */
+    uint8_t *rssi_tmp = nullptr;
+    LaneState *st_start = nullptr, *st_end = nullptr, *carry = nullptr;
+    uint32_t *rerun = nullptr;
+    Stream s[WMB_N_ALGOS];
+};
+
+struct QueuedLine {
+    uint64_t end_sample;
+    int prio;                       /* chain*2 + (algo == T2A) */
+    wmb_decoded d;
+    uint8_t algo;
+};
+
+struct wmb_ctx {
+    wmb_opts o;
+    int device = 0;
+    uint32_t d = 2;                 /* effective decimation (>= 1) */
+    uint32_t chains = 3;
+    cudaStream_t cs = nullptr, xs = nullptr;       /* compute, copy */
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k1done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool allocated = false;
+
+    /* geometry */
+    size_t max_batch_bytes = 0;
+    int64_t M_max = 0;
+    uint32_t W = 32768;             /* warm-up and retained history (decimated samples) */
+    uint32_t C_fixed = 0;
+    uint32_t lanes_max = 0;
+    uint32_t cap_words_t2 = 0, cap_words_rl = 0;
+    uint32_t cand_cap = 1u << 20;
+    uint32_t frame_words_cap = 1u << 24;
+
+    /* device buffers */
+    uint8_t *d_in[2] = {nullptr, nullptr};
+    uint8_t *d_hist = nullptr, *d_hist_tmp = nullptr;
+    float *d_lut = nullptr;
+    ChainBuf cb[WMB_N_CHAINS];
+    uint32_t *d_errors = nullptr, *d_nfail = nullptr, *d_nwords = nullptr;
+    FrameHdr *d_hdr = nullptr;
+    uint32_t *d_words = nullptr;
+
+    /* pinned host mirrors */
+    uint32_t *h_small = nullptr;    /* [0] errors [1] nfail [2] nwords */
+    StreamDev *h_sd = nullptr;      /* 4 entries */
+    uint64_t *h_cand = nullptr;
+    FrameHdr *h_hdr = nullptr;
+    uint32_t *h_words = nullptr;
+
+    /* stream position */
+    uint64_t iq_consumed = 0;       /* input IQ samples handed to the device    */
+    uint64_t m_consumed = 0;        /* decimated samples produced               */
+    int64_t hist_m = 0;             /* decimated history retained (<= W)        */
+    int64_t hist_iq = 0;            /* input history retained (samples)         */
+    std::vector<uint8_t> remainder; /* bytes not yet forming a whole batch granule */
+    int buf_idx = 0;
+    uint64_t batch_no = 0;
+    int64_t last_M = 0;
+
+    /* results */
+    std::vector<FrameHdr> out_hdr;
+    std::vector<uint32_t> out_words;
+    std::vector<wmb_frame> out_frames;
+    /* manual mode (opts.manual_frames): frames wait here for wmb_poll */
+    struct Held { wmb_frame f; std::vector<uint32_t> words; };
+    std::vector<Held> held, held_prev;
+    std::vector<wmb_frame> poll_frames;
+    bool manual = false;
+    std::vector<QueuedLine> lines;
+    wmb_stats st;
+};
+
+/* --------------------------------------------------------------------------- */
+/* launches                                                                    */
+/* --------------------------------------------------------------------------- */
+
+#ifdef WMB_HOSTSIM
+#include "hostsim_launch.inl"
+#else
+static int launch_k1(wmb_ctx *c, const K1Params &p)
+{
+    const int64_t ntiles = (p.M + K1_TILE - 1) / K1_TILE;
+    if (ntiles <= 0) return WMB_OK;
+    static int sm_count = 0, blocks_per_sm = 0;
+    const size_t smem = k1_smem_bytes(p.d);
+    if (!sm_count) {
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device);
+    }
+    CUDA_TRY(cudaFuncSetAttribute(k1_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k1_demod_kernel, K1_THREADS, smem));
+    if (blocks_per_sm < 1) return set_err(WMB_E_INVAL, "decimation %u needs %zu B shared memory per CTA", p.d, smem);
+    int64_t grid = (int64_t)sm_count * blocks_per_sm;      /* persistent: whole waves of resident CTAs */
+    if (grid > ntiles) grid = ntiles;
+    k1_demod_kernel<<<(unsigned)grid, K1_THREADS, smem, c->cs>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches++;
+    return WMB_OK;
+}
+
+static int launch_k2(wmb_ctx *c, int chain, const K2Params &p)
+{
+    const unsigned grid = (p.lanes + K2_THREADS - 1) / K2_THREADS;
+    if (chain == 0) k2_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, c->cs>>>(p);
+    else            k2_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, c->cs>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches++;
+    return WMB_OK;
+}
+
+static int launch_k2_verify(wmb_ctx *c, const K2Params &p)
+{
+    const unsigned grid = (p.lanes + 255) / 256;
+    k2_verify_kernel<<<grid, 256, 0, c->cs>>>(p, c->d_nfail);
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches++;
+    return WMB_OK;
+}
+
+static int launch_k2c(wmb_ctx *c, const K2cParams &p)
+{
+    k2c_scan_kernel<<<1, 32, 0, c->cs>>>(p);
+    k2c_compact_kernel<<<p.lanes, 128, 0, c->cs>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches += 2;
+    return WMB_OK;
+}
+
+static int launch_k3(wmb_ctx *c, const K3Params &p)
+{
+    k3_size_kernel<<<(p.n + 127) / 128, 128, 0, c->cs>>>(p);
+    k3_offsets_kernel<<<1, 32, 0, c->cs>>>(p);
+    k3_copy_kernel<<<p.n, 128, 0, c->cs>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches += 3;
+    return WMB_OK;
+}
+#endif
+
+/* --------------------------------------------------------------------------- */
+/* set-up                                                                      */
+/* --------------------------------------------------------------------------- */
+
+extern "C" void wmb_default_opts(wmb_opts *o)
+{
+    memset(o, 0, sizeof(*o));
+    o->decimation = 2;          /* rtl_wmbus.c:857 */
+    o->accurate_atan = 1;       /* :859 */
+    o->rla_enabled = 1;         /* :855 */
+    o->t2_enabled = 1;          /* :856 */
+    o->t1c1_enabled = 1;        /* :862 */
+    o->s1_enabled = 1;          /* :863 */
+}
+
+extern "C" int wmb_abi_version(void) { return WMB_ABI_VERSION; }
+extern "C" const char *wmb_last_error(void) { return g_err; }
+extern "C" const char *wmb_version_string(void) { return WMB_VERSION; }
+
+extern "C" void *wmb_host_alloc(size_t nbytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) {
+        set_err(WMB_E_NOMEM, "cannot allocate %zu bytes of pinned host memory", nbytes);
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void wmb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+static uint64_t next_pow2(uint64_t v)
+{
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static uint32_t pick_chunk(const wmb_ctx *c, int64_t M)
+{
+    if (c->C_fixed) return c->C_fixed;
+    /* aim for ~8192 lanes on big batches, never below 8192 samples per lane */
+    int64_t C = (M + 8191) / 8192;
+    C = (C + 1023) / 1024 * 1024;
+    if (C < 8192) C = 8192;
+    if (C > 65536) C = 65536;
+    return (uint32_t)C;
+}
+
+static int ctx_alloc(wmb_ctx *c)
+{
+    if (c->allocated) return WMB_OK;
+    const uint32_t d = c->d;
+    c->M_max = (int64_t)(c->max_batch_bytes / (2 * (size_t)d));
+    const uint32_t C_min = c->C_fixed ? c->C_fixed : 8192;
+    c->lanes_max = (uint32_t)(c->M_max / C_min + 2);
+    const size_t per_lane_slack_t2 = 8, per_lane_slack_rl = K2_EDGE_EMIT_CAP + 8;
+    const size_t words_t2 = (size_t)c->M_max / 4 + (size_t)c->lanes_max * per_lane_slack_t2 + 1024;
+    const size_t words_rl = (size_t)c->M_max / 4 + (size_t)c->lanes_max * per_lane_slack_rl + 1024;
+    c->cap_words_t2 = (uint32_t)std::min<size_t>(words_t2, 0xFFFFFFFFu);
+    c->cap_words_rl = (uint32_t)std::min<size_t>(words_rl, 0xFFFFFFFFu);
+
+    const size_t in_bytes = c->max_batch_bytes + 4096;
+    CUDA_TRY(cudaMalloc((void **)&c->d_in[0], in_bytes));
+    CUDA_TRY(cudaMalloc((void **)&c->d_in[1], in_bytes));
+    const size_t hb = (size_t)k1_hist_bytes(d);
+    CUDA_TRY(cudaMalloc((void **)&c->d_hist, hb));
+    CUDA_TRY(cudaMalloc((void **)&c->d_hist_tmp, hb));
+    CUDA_TRY(cudaMemset(c->d_hist, 0, hb));
+    CUDA_TRY(cudaMalloc((void **)&c->d_lut, 2 * 4096 * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void **)&c->d_errors, 64));
+    CUDA_TRY(cudaMemset(c->d_errors, 0, 64));
+    c->d_nfail = c->d_errors + 1;
+    c->d_nwords = c->d_errors + 2;
+    CUDA_TRY(cudaMalloc((void **)&c->d_hdr, (size_t)c->cand_cap * sizeof(FrameHdr)));
+    CUDA_TRY(cudaMalloc((void **)&c->d_words, (size_t)c->frame_words_cap * 4));
+    CUDA_TRY(cudaMallocHost((void **)&c->h_small, 64));
+    CUDA_TRY(cudaMallocHost((void **)&c->h_sd, 4 * sizeof(StreamDev)));
+    CUDA_TRY(cudaMallocHost((void **)&c->h_cand, (size_t)c->cand_cap * 8));
+    CUDA_TRY(cudaMallocHost((void **)&c->h_hdr, (size_t)c->cand_cap * sizeof(FrameHdr)));
+    CUDA_TRY(cudaMallocHost((void **)&c->h_words, (size_t)c->frame_words_cap * 4));
+
+    /* mixer look-up tables, built with the host libm exactly like the reference
+     * (setup_lookup_tables_for_frequency_translation, rtl_wmbus.c:974-993) */
+    if (c->o.simultaneous) {
+        const int fs_khz = (int)(c->o.decimation * 800u);
+        const size_t n_max = (size_t)fs_khz / 25;
+        if (n_max == 0 || n_max > 4096) return set_err(WMB_E_INVAL, "-s needs 1 <= decimation <= 128");
+        std::vector<float> lut(2 * 4096, 0.f);
+        for (size_t n = 0; n < n_max; n++) {
+            const double phi = (2. * M_PI * (25 * n)) / fs_khz;
+            lut[n] = cosf(phi);
+            lut[4096 + n] = -sinf(phi);
+        }
+        CUDA_TRY(cudaMemcpy(c->d_lut, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+        if (!(c->chains & (1u << ch))) continue;
+        ChainBuf &b = c->cb[ch];
+        const size_t n = (size_t)c->W + (size_t)c->M_max + 64;
+        CUDA_TRY(cudaMalloc((void **)&b.dphi, n * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void **)&b.rssi, n));
+        CUDA_TRY(cudaMalloc((void **)&b.dphi_tmp, (size_t)c->W * sizeof(float)));
+        CUDA_TRY(cudaMalloc((void **)&b.rssi_tmp, c->W));
+        CUDA_TRY(cudaMalloc((void **)&b.st_start, (size_t)c->lanes_max * sizeof(LaneState)));
+        CUDA_TRY(cudaMalloc((void **)&b.st_end, (size_t)c->lanes_max * sizeof(LaneState)));
+        CUDA_TRY(cudaMalloc((void **)&b.carry, sizeof(LaneState)));
+        CUDA_TRY(cudaMalloc((void **)&b.rerun, (size_t)c->lanes_max * 4));
+        LaneState init;
+        lane_state_init(init, ch);
+        CUDA_TRY(cudaMemcpy(b.carry, &init, sizeof(init), cudaMemcpyHostToDevice));
+        for (int a = 0; a < WMB_N_ALGOS; a++) {
+            Stream &s = b.s[a];
+            const size_t words = a == WMB_ALGO_T2A ? c->cap_words_t2 : c->cap_words_rl;
+            CUDA_TRY(cudaMalloc((void **)&s.ev, words * 4));
+            CUDA_TRY(cudaMalloc((void **)&s.cnt, (size_t)c->lanes_max * 4));
+            CUDA_TRY(cudaMemset(s.cnt, 0, (size_t)c->lanes_max * 4));
+            CUDA_TRY(cudaMalloc((void **)&s.base, (size_t)c->lanes_max * 8));
+            s.ring_cap = next_pow2(words + WMB_MAXBITS + 64);
+            CUDA_TRY(cudaMalloc((void **)&s.ring, s.ring_cap * 8));
+            CUDA_TRY(cudaMalloc((void **)&s.sd, sizeof(StreamDev)));
+            CUDA_TRY(cudaMemset(s.sd, 0, sizeof(StreamDev)));
+            CUDA_TRY(cudaMalloc((void **)&s.cand, (size_t)c->cand_cap * 8));
+        }
+    }
+    c->allocated = true;
+    return WMB_OK;
+}
+
+extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
+{
+    if (!o || !out) return set_err(WMB_E_INVAL, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return set_err(WMB_E_NODEVICE, "no CUDA device available (libwmbus_b200 has no CPU fallback)");
+    if (cuda_device < 0 || cuda_device >= ndev) return set_err(WMB_E_NODEVICE, "CUDA device %d of %d", cuda_device, ndev);
+    if (o->decimation > 64) return set_err(WMB_E_INVAL, "decimation %u not supported (max 64)", o->decimation);
+    if (o->simultaneous && o->decimation == 0) return set_err(WMB_E_INVAL, "-s with -d 0 is undefined in the reference");
+    CUDA_TRY(cudaSetDevice(cuda_device));
+
+    wmb_ctx *c = new wmb_ctx();
+    c->o = *o;
+    c->device = cuda_device;
+    c->d = o->decimation ? o->decimation : 1;               /* rtl_wmbus.c:1350-1352: d==0 keeps every sample */
+    c->chains = (o->t1c1_enabled ? 1u : 0u) | (o->s1_enabled ? 2u : 0u);
+    c->W = o->warmup_samples ? o->warmup_samples : (o->remove_dc ? 98304u : 32768u);
+    c->W = (c->W + 255) / 256 * 256;
+    c->manual = o->manual_frames != 0;
+    c->C_fixed = o->chunk_samples ? (o->chunk_samples + 255) / 256 * 256 : 0;
+    if (c->C_fixed && (c->C_fixed < 1024 || c->C_fixed > K2_MAX_CHUNK)) { delete c; return set_err(WMB_E_INVAL, "chunk_samples out of range"); }
+    size_t mb = o->max_batch_mib ? (size_t)o->max_batch_mib * 1048576u : (size_t)256 * 1048576u;
+    const size_t gran = (size_t)4096 * c->d;
+    mb = (mb + gran - 1) / gran * gran;
+    c->max_batch_bytes = mb;
+    memset(&c->st, 0, sizeof(c->st));
+    if (cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->xs, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return set_err(WMB_E_CUDA, "cannot create CUDA streams");
+    }
+    for (int i = 0; i < 2; i++) { cudaEventCreate(&c->ev_h2d[i]); cudaEventCreate(&c->ev_k1done[i]); }
+    for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev_t[i]);
+    *out = c;
+    return WMB_OK;
+}
+
+extern "C" void wmb_destroy(wmb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->cs) cudaStreamSynchronize(c->cs);
+    if (c->xs) cudaStreamSynchronize(c->xs);
+    for (int i = 0; i < 2; i++) cudaFree(c->d_in[i]);
+    cudaFree(c->d_hist); cudaFree(c->d_hist_tmp); cudaFree(c->d_lut); cudaFree(c->d_errors);
+    cudaFree(c->d_hdr); cudaFree(c->d_words);
+    cudaFreeHost(c->h_small); cudaFreeHost(c->h_sd); cudaFreeHost(c->h_cand); cudaFreeHost(c->h_hdr); cudaFreeHost(c->h_words);
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+        ChainBuf &b = c->cb[ch];
+        cudaFree(b.dphi); cudaFree(b.rssi); cudaFree(b.dphi_tmp); cudaFree(b.rssi_tmp);
+        cudaFree(b.st_start); cudaFree(b.st_end); cudaFree(b.carry); cudaFree(b.rerun);
+        for (int a = 0; a < WMB_N_ALGOS; a++) {
+            Stream &s = b.s[a];
+            cudaFree(s.ev); cudaFree(s.cnt); cudaFree(s.base); cudaFree(s.ring); cudaFree(s.sd); cudaFree(s.cand);
+        }
+    }
+    for (int i = 0; i < 2; i++) { if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]); if (c->ev_k1done[i]) cudaEventDestroy(c->ev_k1done[i]); }
+    for (int i = 0; i < 6; i++) if (c->ev_t[i]) cudaEventDestroy(c->ev_t[i]);
+    if (c->cs) cudaStreamDestroy(c->cs);
+    if (c->xs) cudaStreamDestroy(c->xs);
+    delete c;
+}
+
+/* --------------------------------------------------------------------------- */
+/* one batch on the device                                                     */
+/* --------------------------------------------------------------------------- */
+
+static void fill_k2(const wmb_ctx *c, int ch, int64_t M, uint32_t C, K2Params &p)
+{
+    const ChainBuf &b = c->cb[ch];
+    memset(&p, 0, sizeof(p));
+    p.dphi = b.dphi + c->W;
+    p.rssi = b.rssi + c->W;
+    p.M = M;
+    p.hist = c->hist_m;
+    p.C = C;
+    p.W = c->W;
+    p.lanes = (uint32_t)((M + C - 1) / C);
+    p.cap_t2 = C / 4 + 8;
+    p.cap_rl = C / 4 + K2_EDGE_EMIT_CAP + 8;
+    p.ev_t2 = b.s[WMB_ALGO_T2A].ev; p.ev_rl = b.s[WMB_ALGO_RLA].ev;
+    p.cnt_t2 = b.s[WMB_ALGO_T2A].cnt; p.cnt_rl = b.s[WMB_ALGO_RLA].cnt;
+    p.st_start = b.st_start; p.st_end = b.st_end; p.carry = b.carry;
+    p.rerun = b.rerun;
+    p.errors = c->d_errors;
+    p.dc = c->o.remove_dc; p.rla = c->o.rla_enabled; p.t2 = c->o.t2_enabled;
+}
+
+/* Enqueue K1 + K2 (+ verification rounds) for one batch whose bytes are at `src`
+ * (device memory).  On return everything up to a verified bit-sync result is done and
+ * the compaction has been enqueued. */
+static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_ctx_buffer)
+{
+    const uint32_t d = c->d;
+    const int64_t n_iq = (int64_t)(nbytes / 2);
+    const int64_t M = n_iq / d;
+    c->last_M = M;
+    if (M <= 0) return WMB_OK;
+    (void)src_is_ctx_buffer;
+
+    CUDA_TRY(cudaEventRecord(c->ev_t[0], c->cs));
+    K1Params k1;
+    memset(&k1, 0, sizeof(k1));
+    k1.in = src; k1.hist = c->d_hist; k1.in_bytes = (int64_t)nbytes;
+    k1.n_hist_iq = c->hist_iq;
+    k1.M = M; k1.d = d; k1.chains = c->chains;
+    k1.accurate = c->o.accurate_atan; k1.mix = c->o.simultaneous;
+    k1.lut_n = c->o.simultaneous ? (c->o.decimation * 800u) / 25u : 1u;
+    k1.lut_phase0 = (uint32_t)((13ull * (c->iq_consumed % k1.lut_n)) % k1.lut_n);
+    k1.lut_cos = c->d_lut; k1.lut_msin = c->d_lut + 4096;
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+        k1.dphi[ch] = c->cb[ch].dphi ? c->cb[ch].dphi + c->W : nullptr;
+        k1.rssi[ch] = c->cb[ch].rssi ? c->cb[ch].rssi + c->W : nullptr;
+    }
+    int rc = launch_k1(c, k1);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_t[1], c->cs));
+
+    /* keep the last k1_hist_bytes() of the stream for the next batch's tile 0 */
+    {
+        const size_t hb = (size_t)k1_hist_bytes(d);
+        if (nbytes >= hb) {
+            CUDA_TRY(cudaMemcpyAsync(c->d_hist, src + nbytes - hb, hb, cudaMemcpyDeviceToDevice, c->cs));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(c->d_hist_tmp, c->d_hist + nbytes, hb - nbytes, cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(c->d_hist_tmp + (hb - nbytes), src, nbytes, cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(c->d_hist, c->d_hist_tmp, hb, cudaMemcpyDeviceToDevice, c->cs));
+        }
+        c->hist_iq = std::min<int64_t>(c->hist_iq + n_iq, (int64_t)hb / 2);
+    }
+    /* the input buffer may be overwritten by the next H2D from here on */
+    CUDA_TRY(cudaEventRecord(c->ev_k1done[c->buf_idx], c->cs));
+
+    const uint32_t C = pick_chunk(c, M);
+    const uint32_t lanes = (uint32_t)((M + C - 1) / C);
+    if (lanes > c->lanes_max) return set_err(WMB_E_INVAL, "internal: %u lanes > %u", lanes, c->lanes_max);
+    const bool any_sync = c->o.rla_enabled || c->o.t2_enabled;
+
+    K2Params k2[WMB_N_CHAINS];
+    if (any_sync) {
+        CUDA_TRY(cudaMemsetAsync(c->d_nfail, 0, 4, c->cs));
+        for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+            if (!(c->chains & (1u << ch))) continue;
+            fill_k2(c, ch, M, C, k2[ch]);
+            if ((uint64_t)k2[ch].lanes * k2[ch].cap_t2 > c->cap_words_t2 ||
+                (uint64_t)k2[ch].lanes * k2[ch].cap_rl > c->cap_words_rl)
+                return set_err(WMB_E_INVAL, "internal: event buffers too small for C=%u", C);
+            k2[ch].mode = 0;
+            if ((rc = launch_k2(c, ch, k2[ch]))) return rc;
+            if ((rc = launch_k2_verify(c, k2[ch]))) return rc;
+            c->st.lanes_run += k2[ch].lanes;
+        }
+        /* re-run refuted lanes until every start state is confirmed */
+        for (int round = 0;; round++) {
+            CUDA_TRY(cudaMemcpyAsync(&c->h_small[1], c->d_nfail, 4, cudaMemcpyDeviceToHost, c->cs));
+            CUDA_TRY(cudaStreamSynchronize(c->cs));
+            const uint32_t nfail = c->h_small[1];
+            if (!nfail) break;
+            if (round > (int)lanes + 2) return set_err(WMB_E_STATE, "internal: lane verification does not converge");
+            c->st.lanes_rerun += nfail;
+            c->st.lanes_run += nfail;
+            CUDA_TRY(cudaMemsetAsync(c->d_nfail, 0, 4, c->cs));
+            for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+                if (!(c->chains & (1u << ch))) continue;
+                k2[ch].mode = 1;
+                if ((rc = launch_k2(c, ch, k2[ch]))) return rc;
+                if ((rc = launch_k2_verify(c, k2[ch]))) return rc;
+            }
+        }
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_t[2], c->cs));
+
+    /* compaction into the stream rings + candidates */
+    if (any_sync) {
+        for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+            if (!(c->chains & (1u << ch))) continue;
+            ChainBuf &b = c->cb[ch];
+            for (int a = 0; a < WMB_N_ALGOS; a++) {
+                if ((a == WMB_ALGO_RLA && !c->o.rla_enabled) || (a == WMB_ALGO_T2A && !c->o.t2_enabled)) continue;
+                Stream &s = b.s[a];
+                K2cParams q;
+                memset(&q, 0, sizeof(q));
+                q.ev = s.ev; q.cnt = s.cnt; q.base = s.base;
+                q.lanes = lanes; q.cap = a == WMB_ALGO_T2A ? k2[ch].cap_t2 : k2[ch].cap_rl; q.C = C;
+                q.m_base = (int64_t)c->m_consumed;
+                q.ring = s.ring; q.ring_mask = s.ring_cap - 1;
+                q.sd = s.sd; q.cand = s.cand; q.cand_cap = c->cand_cap;
+                if ((rc = launch_k2c(c, q))) return rc;
+            }
+            /* exact state at the end of this batch becomes the next batch's lane-0 start */
+            CUDA_TRY(cudaMemcpyAsync(b.carry, b.st_end + (lanes - 1), sizeof(LaneState), cudaMemcpyDeviceToDevice, c->cs));
+        }
+    }
+
+    /* slide the dphi / rssi history: the last W samples move in front of index 0 */
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+        if (!(c->chains & (1u << ch))) continue;
+        ChainBuf &b = c->cb[ch];
+        const int64_t W = c->W;
+        if (M >= W) {
+            CUDA_TRY(cudaMemcpyAsync(b.dphi, b.dphi + M, (size_t)W * 4, cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(b.rssi, b.rssi + M, (size_t)W, cudaMemcpyDeviceToDevice, c->cs));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(b.dphi_tmp, b.dphi + M, (size_t)W * 4, cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(b.dphi, b.dphi_tmp, (size_t)W * 4, cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(b.rssi_tmp, b.rssi + M, (size_t)W, cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(b.rssi, b.rssi_tmp, (size_t)W, cudaMemcpyDeviceToDevice, c->cs));
+        }
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_t[3], c->cs));
+
+    c->hist_m = std::min<int64_t>(c->hist_m + M, c->W);
+    c->iq_consumed += (uint64_t)n_iq;
+    c->m_consumed += (uint64_t)M;
+    c->st.input_samples += (uint64_t)n_iq;
+    c->st.decimated_samples += (uint64_t)M;
+    c->st.batches++;
+    c->batch_no++;
+    return WMB_OK;
+}
+
+/* Gather frames for all new + pending candidates.  final: end of input. */
+static int gather_frames(wmb_ctx *c, bool final)
+{
+    const bool any_sync = c->o.rla_enabled || c->o.t2_enabled;
+    if (!any_sync || !c->allocated) return WMB_OK;
+    /* fetch per-stream bookkeeping */
+    int k = 0;
+    Stream *order[4];
+    int och[4], oal[4];
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+        if (!(c->chains & (1u << ch))) continue;
+        for (int a = 0; a < WMB_N_ALGOS; a++) {
+            if ((a == WMB_ALGO_RLA && !c->o.rla_enabled) || (a == WMB_ALGO_T2A && !c->o.t2_enabled)) continue;
+            CUDA_TRY(cudaMemcpyAsync(&c->h_sd[k], c->cb[ch].s[a].sd, sizeof(StreamDev), cudaMemcpyDeviceToHost, c->cs));
+            order[k] = &c->cb[ch].s[a]; och[k] = ch; oal[k] = a;
+            k++;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(&c->h_small[0], c->d_errors, 4, cudaMemcpyDeviceToHost, c->cs));
+    CUDA_TRY(cudaStreamSynchronize(c->cs));
+    if (c->h_small[0] & 1u) return set_err(WMB_E_OVERFLOW, "bit event buffer overflow (pathological input)");
+    if (c->h_small[0] & 2u) return set_err(WMB_E_OVERFLOW, "run-length tracker left its defined range (the reference would spin here)");
+
+    std::vector<FrameHdr> hdr;
+    for (int i = 0; i < k; i++) {
+        Stream &s = *order[i];
+        const StreamDev sd = c->h_sd[i];
+        if (sd.cand_overflow) return set_err(WMB_E_OVERFLOW, "too many access-code matches in one batch");
+        if (sd.total - s.total > s.ring_cap - WMB_MAXBITS - 64) return set_err(WMB_E_OVERFLOW, "bit event ring overflow");
+        s.total = sd.total;
+        std::vector<uint64_t> cand(s.pending);
+        if (sd.n_cand) {
+            CUDA_TRY(cudaMemcpyAsync(c->h_cand, s.cand, (size_t)sd.n_cand * 8, cudaMemcpyDeviceToHost, c->cs));
+            CUDA_TRY(cudaStreamSynchronize(c->cs));
+            cand.insert(cand.end(), c->h_cand, c->h_cand + sd.n_cand);
+            c->st.candidates[och[i]][oal[i]] += sd.n_cand;
+            CUDA_TRY(cudaMemsetAsync(&s.sd->n_cand, 0, 4, c->cs));
+        }
+        std::sort(cand.begin(), cand.end());
+        for (uint64_t ord : cand) {
+            FrameHdr h;
+            memset(&h, 0, sizeof(h));
+            h.ordinal = ord; h.chain = (uint8_t)och[i]; h.algo = (uint8_t)oal[i];
+            hdr.push_back(h);
+        }
+        s.pending.clear();
+    }
+    c->out_hdr.clear(); c->out_words.clear(); c->out_frames.clear();
+    if (hdr.empty()) return WMB_OK;
+    if (hdr.size() > c->cand_cap) return set_err(WMB_E_OVERFLOW, "too many pending candidates");
+
+    K3Params p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < k; i++) {
+        p.ring[och[i]][oal[i]] = order[i]->ring;
+        p.ring_mask[och[i]][oal[i]] = order[i]->ring_cap - 1;
+        p.total[och[i]][oal[i]] = order[i]->total;
+    }
+    memcpy(c->h_hdr, hdr.data(), hdr.size() * sizeof(FrameHdr));
+    CUDA_TRY(cudaMemcpyAsync(c->d_hdr, c->h_hdr, hdr.size() * sizeof(FrameHdr), cudaMemcpyHostToDevice, c->cs));
+    p.hdr = c->d_hdr; p.n = (uint32_t)hdr.size();
+    p.words = c->d_words; p.words_cap = c->frame_words_cap; p.n_words = c->d_nwords; p.errors = c->d_errors;
+    int rc = launch_k3(c, p);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->h_hdr, c->d_hdr, hdr.size() * sizeof(FrameHdr), cudaMemcpyDeviceToHost, c->cs));
+    CUDA_TRY(cudaMemcpyAsync(&c->h_small[2], c->d_nwords, 4, cudaMemcpyDeviceToHost, c->cs));
+    CUDA_TRY(cudaMemcpyAsync(&c->h_small[0], c->d_errors, 4, cudaMemcpyDeviceToHost, c->cs));
+    CUDA_TRY(cudaStreamSynchronize(c->cs));
+    if (c->h_small[0] & 4u) return set_err(WMB_E_OVERFLOW, "frame buffer overflow");
+    const uint32_t nwords = c->h_small[2];
+    if (nwords) {
+        CUDA_TRY(cudaMemcpyAsync(c->h_words, c->d_words, (size_t)nwords * 4, cudaMemcpyDeviceToHost, c->cs));
+        CUDA_TRY(cudaStreamSynchronize(c->cs));
+    }
+    c->st.d2h_bytes += (uint64_t)nwords * 4 + hdr.size() * sizeof(FrameHdr);
+
+    c->out_hdr.assign(c->h_hdr, c->h_hdr + hdr.size());
+    c->out_words.assign(c->h_words, c->h_words + nwords);
+    for (const FrameHdr &h : c->out_hdr) {
+        if (h.overflow) return set_err(WMB_E_OVERFLOW, "bit spacing exceeds 2^23 samples inside a frame");
+        if (!h.complete && !final) c->cb[h.chain].s[h.algo].pending.push_back(h.ordinal);
+        if (h.nbits == 0) continue;
+        wmb_frame f;
+        memset(&f, 0, sizeof(f));
+        f.sync_sample = h.sync_sample; f.ordinal = h.ordinal; f.chain = h.chain; f.algo = h.algo;
+        f.truncated = (uint8_t)((h.complete && !h.cut) ? 0 : 1);
+        f.reserved = (uint8_t)((!h.complete && !final) ? 1 : 0);      /* partial: will be re-delivered */
+        f.nbits = h.nbits;
+        f.bits = c->out_words.data() + h.word_off;
+        c->out_frames.push_back(f);
+    }
+    return WMB_OK;
+}
+
+static void read_timers(wmb_ctx *c)
+{
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_t[0], c->ev_t[1]) == cudaSuccess) c->st.demod_kernel_ms = ms;
+    if (cudaEventElapsedTime(&ms, c->ev_t[1], c->ev_t[2]) == cudaSuccess) c->st.bitsync_kernel_ms = ms;
+    if (cudaEventElapsedTime(&ms, c->ev_t[0], c->ev_t[3]) == cudaSuccess) c->st.batch_device_ms = ms;
+}
+
+/* --------------------------------------------------------------------------- */
+/* push / poll                                                                 */
+/* --------------------------------------------------------------------------- */
+
+/* frames gathered after each batch are appended here until the caller polls */
+struct FrameStore {
+    std::vector<FrameHdr> hdr;
+    std::vector<uint32_t> words;
+};
+
+static int process_device_batches(wmb_ctx *c, const uint8_t *dev, size_t nbytes, bool final);
+
+static int finish_batch(wmb_ctx *c, bool final)
+{
+    int rc = gather_frames(c, final);
+    if (rc) return rc;
+    read_timers(c);
+    if (c->out_frames.empty()) return WMB_OK;
+    if (!c->manual) return wmb_decode_frames(c, c->out_frames.data(), c->out_frames.size());
+    /* manual mode: keep the frames (newest version of a re-delivered partial one wins) for wmb_poll */
+    for (const wmb_frame &f : c->out_frames) {
+        wmb_ctx::Held *slot = nullptr;
+        for (auto &h : c->held)
+            if (h.f.chain == f.chain && h.f.algo == f.algo && h.f.ordinal == f.ordinal) { slot = &h; break; }
+        if (!slot) { c->held.emplace_back(); slot = &c->held.back(); }
+        slot->f = f;
+        slot->words.assign(f.bits, f.bits + f.nbits);
+    }
+    return WMB_OK;
+}
+
+static size_t batch_granule(const wmb_ctx *c) { return (size_t)4096 * c->d; }
+
+extern "C" int wmb_push_device(wmb_ctx *c, const void *dev_cu8, size_t nbytes)
+{
+    if (!c || (!dev_cu8 && nbytes)) return set_err(WMB_E_INVAL, "null argument");
+    if (nbytes % 4096) return set_err(WMB_E_INVAL, "wmb_push_device needs a multiple of 4096 bytes");
+    if (((uintptr_t)dev_cu8) & 15u) return set_err(WMB_E_INVAL, "device buffer must be 16-byte aligned");
+    if (!c->remainder.empty()) return set_err(WMB_E_STATE, "wmb_push_device after a partial host push");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ctx_alloc(c);
+    if (rc) return rc;
+    return process_device_batches(c, (const uint8_t *)dev_cu8, nbytes, false);
+}
+
+/* dev points to device memory that stays valid during the call */
+static int process_device_batches(wmb_ctx *c, const uint8_t *dev, size_t nbytes, bool final)
+{
+    const size_t gran = batch_granule(c);
+    size_t off = 0;
+    while (off < nbytes) {
+        size_t n = std::min(nbytes - off, c->max_batch_bytes);
+        if (n < nbytes - off || !final) {
+            /* keep batch boundaries on whole decimation periods */
+            if (n % gran) n -= n % gran;
+            if (n == 0) break;
+        }
+        int rc = run_batch(c, dev + off, n, false);
+        if (rc) return rc;
+        rc = finish_batch(c, false);
+        if (rc) return rc;
+        off += n;
+    }
+    if (off < nbytes) return set_err(WMB_E_INVAL, "device push must be a multiple of %zu bytes unless flushing", gran);
+    return WMB_OK;
+}
+
+/* host bytes -> device (double-buffered) -> batches */
+static int push_host_bytes(wmb_ctx *c, const uint8_t *p, size_t nbytes, bool final)
+{
+    const size_t gran = batch_granule(c);
+    size_t off = 0;
+    /* enqueue the first H2D, then for each batch: enqueue the next H2D before computing */
+    size_t cur_n = 0;
+    auto next_size = [&](size_t at) {
+        size_t n = std::min(nbytes - at, c->max_batch_bytes);
+        if (!(final && at + n == nbytes)) n -= n % gran;
+        return n;
+    };
+    cur_n = next_size(0);
+    if (cur_n == 0) {
+        c->remainder.assign(p, p + nbytes);             /* less than one granule: keep for later */
+        return WMB_OK;
+    }
+    int idx = c->buf_idx;
+    CUDA_TRY(cudaStreamWaitEvent(c->xs, c->ev_k1done[idx], 0));
+    CUDA_TRY(cudaMemcpyAsync(c->d_in[idx], p, cur_n, cudaMemcpyHostToDevice, c->xs));
+    CUDA_TRY(cudaEventRecord(c->ev_h2d[idx], c->xs));
+    while (cur_n) {
+        const size_t nxt_off = off + cur_n;
+        const size_t nxt_n = nxt_off < nbytes ? next_size(nxt_off) : 0;
+        if (nxt_n) {
+            const int nidx = idx ^ 1;
+            CUDA_TRY(cudaStreamWaitEvent(c->xs, c->ev_k1done[nidx], 0));
+            CUDA_TRY(cudaMemcpyAsync(c->d_in[nidx], p + nxt_off, nxt_n, cudaMemcpyHostToDevice, c->xs));
+            CUDA_TRY(cudaEventRecord(c->ev_h2d[nidx], c->xs));
+        }
+        CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_h2d[idx], 0));
+        c->buf_idx = idx;
+        int rc = run_batch(c, c->d_in[idx], cur_n, true);
+        if (rc) return rc;
+        c->st.h2d_bytes += cur_n;
+        rc = finish_batch(c, false);
+        if (rc) return rc;
+        off = nxt_off; cur_n = nxt_n; idx ^= 1;
+    }
+    c->buf_idx = idx;
+    CUDA_TRY(cudaStreamSynchronize(c->xs));             /* the caller may reuse its buffer now */
+    if (off < nbytes) c->remainder.assign(p + off, p + nbytes);
+    return WMB_OK;
+}
+
+extern "C" int wmb_push(wmb_ctx *c, const uint8_t *cu8, size_t nbytes)
+{
+    if (!c || (!cu8 && nbytes)) return set_err(WMB_E_INVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ctx_alloc(c);
+    if (rc) return rc;
+    if (!c->remainder.empty()) {
+        /* complete the pending granule first (remainder is always shorter than one granule) */
+        const size_t gran = batch_granule(c);
+        const size_t take = std::min(gran - c->remainder.size(), nbytes);
+        c->remainder.insert(c->remainder.end(), cu8, cu8 + take);
+        cu8 += take; nbytes -= take;
+        if (c->remainder.size() < gran) return WMB_OK;
+        std::vector<uint8_t> tmp;
+        tmp.swap(c->remainder);
+        rc = push_host_bytes(c, tmp.data(), tmp.size(), false);
+        if (rc) return rc;
+        if (!nbytes) return WMB_OK;
+    }
+    return push_host_bytes(c, cu8, nbytes, false);
+}
+
+/* end of input: process what is left in whole 4096-byte items (rtl_wmbus.c:1301-1308) */
+static int flush_input(wmb_ctx *c)
+{
+    int rc = ctx_alloc(c);
+    if (rc) return rc;
+    if (!c->remainder.empty()) {
+        std::vector<uint8_t> tmp;
+        tmp.swap(c->remainder);
+        const size_t n = tmp.size() - tmp.size() % 4096;
+        if (n) {
+            rc = push_host_bytes(c, tmp.data(), n, true);
+            if (rc) return rc;
+            c->remainder.clear();
+        }
+    }
+    return finish_batch(c, true);
+}
+
+extern "C" int wmb_poll(wmb_ctx *c, wmb_frame *out, size_t cap, size_t *n, int flush)
+{
+    if (!c || !n) return set_err(WMB_E_INVAL, "null argument");
+    *n = 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (flush) {
+        int rc = flush_input(c);
+        if (rc) return rc;
+    }
+    if (out) {
+        c->poll_frames.clear();
+        for (auto &h : c->held) { h.f.bits = h.words.data(); c->poll_frames.push_back(h.f); }
+        const size_t k = std::min(cap, c->poll_frames.size());
+        memcpy(out, c->poll_frames.data(), k * sizeof(wmb_frame));
+        *n = k;
+        /* the words stay valid until the next push/poll; forget the frames themselves */
+        c->held_prev.swap(c->held);
+        c->held.clear();
+    }
+    return WMB_OK;
+}
+
+/* --------------------------------------------------------------------------- */
+/* host framers: stream-order bookkeeping around wmb_frame_decode()            */
+/* --------------------------------------------------------------------------- */
+
+extern "C" int wmb_decode_frames(wmb_ctx *c, const wmb_frame *frames, size_t n)
+{
+    if (!c || (!frames && n)) return set_err(WMB_E_INVAL, "null argument");
+    std::vector<const wmb_frame *> v(n);
+    for (size_t i = 0; i < n; i++) v[i] = &frames[i];
+    std::sort(v.begin(), v.end(), [](const wmb_frame *a, const wmb_frame *b) {
+        if (a->chain != b->chain) return a->chain < b->chain;
+        if (a->algo != b->algo) return a->algo < b->algo;
+        return a->ordinal < b->ordinal;
+    });
+    bool blocked[WMB_N_CHAINS][WMB_N_ALGOS] = {{false, false}, {false, false}};
+    std::vector<QueuedLine> fresh;
+    for (const wmb_frame *f : v) {
+        if (f->chain >= WMB_N_CHAINS || f->algo >= WMB_N_ALGOS) return set_err(WMB_E_INVAL, "bad frame");
+        Stream &s = c->cb[f->chain].s[f->algo];
+        /* A decoder that is receiving ignores further access-code matches
+         * (t1_c1_packet_decoder.h:272-278 honours the flag only in idle). */
+        if (blocked[f->chain][f->algo]) continue;
+        if ((int64_t)f->ordinal <= s.busy_until) continue;
+        wmb_decoded d;
+        wmb_frame_decode(f, &d);
+        if (d.status == WMB_DEC_NEED_MORE) {
+            if (f->reserved) { blocked[f->chain][f->algo] = true; continue; }   /* partial: comes again */
+            if (!f->truncated) return set_err(WMB_E_STATE, "internal: frame shorter than its header demands");
+            /* cut by a run-length reset or by the end of input: the reference's decoder is reset too */
+            s.busy_until = (int64_t)(f->ordinal + d.consumed - 1);
+            continue;
+        }
+        s.busy_until = (int64_t)(f->ordinal + d.consumed - 1);
+        if (d.status == WMB_DEC_LINE) {
+            QueuedLine q;
+            q.end_sample = d.end_sample;
+            q.prio = f->chain * 2 + (f->algo == WMB_ALGO_T2A ? 1 : 0);
+            q.d = d; q.algo = f->algo;
+            fresh.push_back(q);
+            c->st.lines[f->chain][f->algo]++;
+            if (d.crc_ok) c->st.lines_crc_ok[f->chain][f->algo]++;
+        }
+    }
+    /* the reference prints in the order the per-sample state machines finish:
+     * sample index, then T1/C1-rla, T1/C1-t2a, S1-rla, S1-t2a (rtl_wmbus.c:1354-1355) */
+    std::stable_sort(fresh.begin(), fresh.end(), [](const QueuedLine &a, const QueuedLine &b) {
+        if (a.end_sample != b.end_sample) return a.end_sample < b.end_sample;
+        return a.prio < b.prio;
+    });
+    c->lines.insert(c->lines.end(), fresh.begin(), fresh.end());
+    return WMB_OK;
+}
+
+extern "C" size_t wmb_take_lines(wmb_ctx *c, char *buf, size_t cap, size_t *n_lines, int timestamp_mode)
+{
+    size_t len = 0, taken = 0;
+    if (n_lines) *n_lines = 0;
+    if (!c || !buf) return 0;
+    char ts[64];
+    for (; taken < c->lines.size(); taken++) {
+        const QueuedLine &q = c->lines[taken];
+        if (timestamp_mode == 1) snprintf(ts, sizeof(ts), "TS");
+        else wmb_make_time_string(ts, sizeof(ts));
+        const char *prefix = c->o.show_algorithm ? (q.algo == WMB_ALGO_RLA ? "rla;" : "t2a;") : "";
+        char line[1024];
+        const size_t l = wmb_format_line(&q.d, prefix, ts, line, sizeof(line));
+        if (len + l + 1 > cap) break;
+        memcpy(buf + len, line, l);
+        len += l;
+    }
+    if (len < cap) buf[len] = 0;
+    c->lines.erase(c->lines.begin(), c->lines.begin() + (long)taken);
+    if (n_lines) *n_lines = taken;
+    return len;
+}
+
+extern "C" long wmb_process(wmb_ctx *c, const uint8_t *cu8, size_t nbytes, int flush,
+                            char *out, size_t outcap, size_t *n_lines, int timestamp_mode)
+{
+    int rc = wmb_push(c, cu8, nbytes);
+    if (rc) return rc;
+    if (flush) {
+        CUDA_TRY(cudaSetDevice(c->device));
+        rc = flush_input(c);
+        if (rc) return rc;
+    }
+    return (long)wmb_take_lines(c, out, outcap, n_lines, timestamp_mode);
+}
+
+extern "C" long wmb_process_device(wmb_ctx *c, const void *dev_cu8, size_t nbytes, int flush,
+                                   char *out, size_t outcap, size_t *n_lines, int timestamp_mode)
+{
+    if (!c) return set_err(WMB_E_INVAL, "null argument");
+    if (nbytes % 4096) return set_err(WMB_E_INVAL, "need a multiple of 4096 bytes");
+    if (((uintptr_t)dev_cu8) & 15u) return set_err(WMB_E_INVAL, "device buffer must be 16-byte aligned");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ctx_alloc(c);
+    if (rc) return rc;
+    rc = process_device_batches(c, (const uint8_t *)dev_cu8, nbytes, flush != 0);
+    if (rc) return rc;
+    if (flush) {
+        rc = flush_input(c);
+        if (rc) return rc;
+    }
+    return (long)wmb_take_lines(c, out, outcap, n_lines, timestamp_mode);
+}
+
+extern "C" int wmb_get_stats(wmb_ctx *c, wmb_stats *s)
+{
+    if (!c || !s) return set_err(WMB_E_INVAL, "null argument");
+    *s = c->st;
+    return WMB_OK;
+}
+
+extern "C" long wmb_debug_copy_stage(wmb_ctx *c, int chain, float *dphi, uint8_t *rssi, size_t cap)
+{
+    if (!c || chain < 0 || chain >= WMB_N_CHAINS || !c->allocated || !c->cb[chain].dphi)
+        return set_err(WMB_E_INVAL, "stage not available");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->cs));
+    /* the last batch's outputs still sit at [W, W + last_M) until the next batch overwrites them */
+    const size_t n = std::min<size_t>((size_t)c->last_M, cap);
+    if (dphi) CUDA_TRY(cudaMemcpy(dphi, c->cb[chain].dphi + c->W, n * 4, cudaMemcpyDeviceToHost));
+    if (rssi) CUDA_TRY(cudaMemcpy(rssi, c->cb[chain].rssi + c->W, n, cudaMemcpyDeviceToHost));
+    return (long)n;
+}

@@ -1,0 +1,717 @@
+/*
+ * wmb_kernels.cuh -- the device side of libwmbus_b200 (sm_100a).
+ *
+ *   K1  demod kernel (one launch per batch, both receiver chains): stages IQ tiles
+ *       from HBM into shared memory with bulk async copies (TMA, mbarrier), then
+ *       cu8 -> int box filter -> decimate -> polar discriminator (exact fdlibm
+ *       atan2f) -> post-demod FIR -> (unsigned)RSSI.  Everything here is exactly
+ *       parallel: the only history a sample needs is bounded (box 16 input samples,
+ *       discriminator 1, FIR 45, RSSI ~16 decimated samples), so each tile
+ *       recomputes a 64-sample halo.           rtl_wmbus.c:1310-1352, :1038-1068
+ *   K2  bit-sync lanes: the sequential recurrences (DC block, the three clock
+ *       biquads, the clock-lock stencil, the run-length deglitch/PI loop and both
+ *       access-code shift registers) run one chunk per thread, each thread first
+ *       re-running a warm-up stretch from a cold state; the state it reaches at
+ *       its chunk start is later compared with its predecessor's end state
+ *       (k2_verify) and refuted lanes are re-run from the exact state, so the
+ *       result is exact by induction from the stream start. rtl_wmbus.c:1070-1115,
+ *                                                            :617-852
+ *   K2c prefix-sum + compaction of the per-lane bit events into one ring per
+ *       (chain, algorithm) stream, collecting access-code matches.
+ *   K3  frame gather: for every access-code match, the bits that follow it.
+ *
+ * The kernels are written as phase functions over an explicit (block, thread) index
+ * so that tests/hostsim can execute the identical code on the CPU (test-only).
+ */
+#pragma once
+#include "wmb_exact.cuh"
+#include "wmb_chain.cuh"
+
+/* =========================================================================== */
+/* K1: demod                                                                   */
+/* =========================================================================== */
+
+struct K1Params {
+    const uint8_t *in;          /* first byte of this batch's IQ data (16-byte aligned)     */
+    const uint8_t *hist;        /* the k1_hist_bytes() bytes that precede `in` in the stream */
+    int64_t in_bytes;           /* bytes available at `in`                                    */
+    int64_t n_hist_iq;          /* real IQ samples before batch sample 0 (older ones are "zero") */
+    int64_t M;                  /* decimated samples to produce                              */
+    uint32_t d;                 /* decimation                                                */
+    uint32_t chains;            /* bit0: T1/C1, bit1: S1                                     */
+    uint32_t accurate;          /* 0 with -a                                                 */
+    uint32_t mix;               /* -s                                                        */
+    uint32_t lut_n;             /* mixer table length (fs_kHz/25)                            */
+    uint32_t lut_phase0;        /* table index of batch sample 0                             */
+    const float *lut_cos, *lut_msin;
+    float   *dphi[WMB_N_CHAINS];   /* out: post-FIR discriminator, index 0 = batch sample 0 */
+    uint8_t *rssi[WMB_N_CHAINS];   /* out: (unsigned)rssi                                    */
+};
+
+/* shared-memory layout of one CTA */
+struct K1Smem {
+    uint8_t *bytes[2];      /* double-buffered raw IQ tile                      */
+    int32_t *v;             /* per input sample: truncated I (low 16), Q (high 16) */
+    float   *si, *sq;       /* decimated box-filter outputs, TILE+HALO           */
+    float   *draw;          /* discriminator output, TILE+HALO                   */
+    float   *mag;           /* |s|, padded                                       */
+    uint8_t *rs;            /* (unsigned)rssi, TILE                              */
+    uint64_t *bar;          /* two mbarriers                                     */
+};
+
+static inline
+#ifndef WMB_HOSTSIM
+__host__ __device__
+#endif
+int64_t k1_tile_iq(uint32_t d) { return (int64_t)d * (K1_TILE + K1_HALO) + K1_BOX_MAX; }
+
+/* bytes of stream history that must precede a batch (left overhang of tile 0) */
+static inline
+#ifndef WMB_HOSTSIM
+__host__ __device__
+#endif
+int64_t k1_hist_bytes(uint32_t d) { return 2 * ((int64_t)d * K1_HALO + K1_BOX_MAX); }
+
+static inline
+#ifndef WMB_HOSTSIM
+__host__ __device__
+#endif
+size_t k1_smem_bytes(uint32_t d)
+{
+    const size_t nb = (size_t)2 * k1_tile_iq(d);
+    const size_t n = K1_TILE + K1_HALO;
+    return 2 * nb + 4 * (size_t)k1_tile_iq(d) + 3 * 4 * n + 4 * (n + n / 32 + 1) + K1_TILE + 64 + 16;
+}
+
+WMB_HD void k1_carve(K1Smem &sm, uint8_t *base, uint32_t d)
+{
+    const size_t nb = (size_t)2 * k1_tile_iq(d);
+    const size_t n = K1_TILE + K1_HALO;
+    size_t off = 0;
+    sm.bytes[0] = base + off; off += nb;
+    sm.bytes[1] = base + off; off += nb;
+    sm.bar = (uint64_t *)(base + off); off += 16;
+    sm.v = (int32_t *)(base + off); off += 4 * (size_t)k1_tile_iq(d);
+    sm.si = (float *)(base + off); off += 4 * n;
+    sm.sq = (float *)(base + off); off += 4 * n;
+    sm.draw = (float *)(base + off); off += 4 * n;
+    sm.mag = (float *)(base + off); off += 4 * (n + n / 32 + 1);
+    sm.rs = base + off;
+}
+
+/* first IQ sample (batch-relative, may be negative) held by tile `t` */
+WMB_HD int64_t k1_tile_k0(const K1Params &p, int64_t t)
+{
+    return (int64_t)p.d * (t * K1_TILE - K1_HALO) - K1_BOX_MAX;
+}
+
+/* phase A: cu8 -> float-127.5 -> (mix) -> truncate to int   rtl_wmbus.c:1312-1334 */
+template <int CHAIN>
+WMB_D void k1_convert(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile, int tid)
+{
+    const int64_t k0 = k1_tile_k0(p, tile);
+    const int n = (int)k1_tile_iq(p.d);
+    for (int j = tid; j < n; j += K1_THREADS) {
+        const int64_t k = k0 + j;
+        int vi = 0, vq = 0;
+        if (k >= -p.n_hist_iq) {
+            float xi = wmb_fsub((float)raw[2 * j], 127.5f);
+            float xq = wmb_fsub((float)raw[2 * j + 1], 127.5f);
+            if (p.mix) {
+                /* shift_freq_plus_minus325, rtl_wmbus.c:997-1031 */
+                int64_t idx = ((int64_t)p.lut_phase0 + 13 * (k % (int64_t)p.lut_n)) % (int64_t)p.lut_n;
+                if (idx < 0) idx += p.lut_n;
+                const float c = p.lut_cos[idx], z = p.lut_msin[idx];
+                const float ix = wmb_fmul(xi, c), qx = wmb_fmul(xq, c);
+                const float iz = wmb_fmul(xi, z), qz = wmb_fmul(xq, z);
+                if (CHAIN == 0) { xi = wmb_fsub(ix, qz); xq = wmb_fadd(qx, iz); }
+                else            { xi = wmb_fadd(ix, qz); xq = wmb_fsub(qx, iz); }
+            }
+            vi = (int)xi; vq = (int)xq;             /* float -> int parameter of mavgi() */
+        }
+        sm.v[j] = (int32_t)(((uint32_t)vi & 0xFFFFu) | ((uint32_t)vq << 16));
+    }
+}
+
+/* phase B: integer box filter + decimation   moving_average_filter.h:47-54, rtl_wmbus.c:1350 */
+template <class CH>
+WMB_D void k1_box(const K1Params &p, K1Smem &sm, int tid)
+{
+    const float inv = 1.0f / (float)CH::BOX;
+    for (int r = tid; r < K1_TILE + K1_HALO; r += K1_THREADS) {
+        const int jend = (int)p.d * r + (int)p.d - 1 + K1_BOX_MAX;
+        int si = 0, sq = 0;
+#pragma unroll
+        for (int b = 0; b < CH::BOX; b++) {
+            const int32_t w = sm.v[jend - b];
+            si += (int)(int16_t)(w & 0xFFFF);
+            sq += w >> 16;
+        }
+        sm.si[r] = wmb_fmul((float)si, inv);
+        sm.sq[r] = wmb_fmul((float)sq, inv);
+    }
+}
+
+WMB_HD int k1_pad(int r) { return r + (r >> 5); }
+
+/* phase C: discriminator and |s|   rtl_wmbus.c:1047, :1066 */
+WMB_D void k1_disc_mag(const K1Params &p, K1Smem &sm, int tid)
+{
+    for (int r = tid; r < K1_TILE + K1_HALO; r += K1_THREADS) {
+        const float i = sm.si[r], q = sm.sq[r];
+        float dr = 0.f;
+        if (r > 0) {
+            const float ip = sm.si[r - 1], qp = sm.sq[r - 1];
+            dr = p.accurate ? wmb_discriminator(i, q, ip, qp) : wmb_discriminator_fast(i, q, ip, qp);
+        }
+        sm.draw[r] = dr;
+        sm.mag[k1_pad(r)] = wmb_fsqrt(wmb_fadd(wmb_fmul(i, i), wmb_fmul(q, q)));
+    }
+}
+
+/* phase D: FIR (fir.h:56-67: newest sample first, accumulate from 0) and RSSI one-pole
+ * (rtl_wmbus.c:475-484) */
+template <class CH>
+WMB_D void k1_fir_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
+{
+    const float *b = (CH::ID == 0) ? c_fir_t1c1 : c_fir_s1;
+    const int64_t m0 = tile * K1_TILE;
+    float *out = p.dphi[CH::ID];
+    for (int o = tid; o < K1_TILE; o += K1_THREADS) {
+        const int64_t m = m0 + o;
+        if (m >= p.M) break;
+        float acc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < CH::NTAPS; t++)
+            acc = wmb_fadd(acc, wmb_fmul(b[t], sm.draw[K1_HALO + o - t]));
+        out[m] = acc;
+    }
+    if (tid < K1_TILE / K1_RSSI_SEG) {
+        /* one segment per thread, started K1_RSSI_WARM samples early from r = 0 */
+        const int o0 = tid * K1_RSSI_SEG;
+        const int r0 = K1_HALO + o0 - K1_RSSI_WARM;
+        float rr = 0.0f;
+        const float A = 0.6789f, B = 1.0f - 0.6789f;
+        for (int j = 0; j < K1_RSSI_WARM + K1_RSSI_SEG; j++) {
+            rr = wmb_fadd(wmb_fmul(A, sm.mag[k1_pad(r0 + j)]), wmb_fmul(B, rr));
+            if (j >= K1_RSSI_WARM) sm.rs[o0 + j - K1_RSSI_WARM] = (uint8_t)(unsigned)rr;
+        }
+    }
+}
+
+/* phase E: coalesced store of the rssi bytes */
+template <class CH>
+WMB_D void k1_store_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
+{
+    const int64_t m0 = tile * K1_TILE;
+    uint8_t *out = p.rssi[CH::ID];
+    for (int o = tid * 4; o < K1_TILE; o += K1_THREADS * 4) {
+        const int64_t m = m0 + o;
+        if (m + 3 < p.M) {
+            *(uint32_t *)(out + m) = *(const uint32_t *)(sm.rs + o);
+        } else {
+            for (int j = 0; j < 4; j++) if (m + j < p.M) out[m + j] = sm.rs[o + j];
+        }
+    }
+}
+
+/* Which global byte ranges make up the raw tile: [hist part][in part], clamped to what
+ * exists.  Offsets are relative to the tile start; all multiples of 16 bytes. */
+struct K1Load { const uint8_t *src0; int64_t n0; const uint8_t *src1; int64_t off1, n1; };
+
+WMB_HD K1Load k1_plan_load(const K1Params &p, int64_t tile)
+{
+    K1Load L;
+    const int64_t b0 = 2 * k1_tile_k0(p, tile);             /* byte offset relative to p.in */
+    const int64_t nb = 2 * k1_tile_iq(p.d);
+    const int64_t hb = k1_hist_bytes(p.d);
+    L.src0 = nullptr; L.n0 = 0; L.src1 = nullptr; L.off1 = 0; L.n1 = 0;
+    int64_t lo = b0, hi = b0 + nb;
+    if (lo < 0) {                                            /* only tile 0 */
+        const int64_t n = (hi < 0 ? hi : 0) - lo;            /* bytes taken from hist */
+        L.src0 = p.hist + (hb + lo); L.n0 = n;
+        lo += n;
+    }
+    if (hi > p.in_bytes) hi = p.in_bytes & ~(int64_t)15;
+    if (hi > lo) { L.src1 = p.in + lo; L.off1 = lo - b0; L.n1 = hi - lo; }
+    return L;
+}
+
+#ifndef WMB_HOSTSIM
+/* ---- TMA (1-D bulk async copy) + mbarrier plumbing ---- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void k1_issue_load(const K1Params &p, K1Smem &sm, int buf, int64_t tile)
+{
+    const K1Load L = k1_plan_load(p, tile);
+    mbar_expect_tx(&sm.bar[buf], (uint32_t)(L.n0 + L.n1));
+    if (L.n0) bulk_g2s(sm.bytes[buf], L.src0, (uint32_t)L.n0, &sm.bar[buf]);
+    if (L.n1) bulk_g2s(sm.bytes[buf] + L.off1, L.src1, (uint32_t)L.n1, &sm.bar[buf]);
+}
+
+template <class CH>
+__device__ __forceinline__ void k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile,
+                                         int tid, bool need_convert)
+{
+    if (need_convert) { k1_convert<CH::ID>(p, sm, raw, tile, tid); __syncthreads(); }
+    k1_box<CH>(p, sm, tid);
+    __syncthreads();
+    k1_disc_mag(p, sm, tid);
+    __syncthreads();
+    k1_fir_rssi<CH>(p, sm, tile, tid);
+    __syncthreads();
+    k1_store_rssi<CH>(p, sm, tile, tid);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(K1_THREADS) k1_demod_kernel(const K1Params p)
+{
+    extern __shared__ __align__(128) uint8_t k1_smem_raw[];
+    K1Smem sm;
+    k1_carve(sm, k1_smem_raw, p.d);
+    const int tid = threadIdx.x;
+    const int64_t ntiles = (p.M + K1_TILE - 1) / K1_TILE;
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int64_t tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) k1_issue_load(p, sm, 0, tile);
+    uint32_t phase[2] = {0, 0};
+    int buf = 0;
+    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const int64_t next = tile + gridDim.x;
+        if (tid == 0 && next < ntiles) k1_issue_load(p, sm, buf ^ 1, next);   /* prefetch */
+        mbar_wait(&sm.bar[buf], phase[buf]);
+        phase[buf] ^= 1;
+        const uint8_t *raw = sm.bytes[buf];
+        if (p.chains & 1u) k1_chain<ChainT1C1>(p, sm, raw, tile, tid, true);
+        if (p.chains & 2u) k1_chain<ChainS1>(p, sm, raw, tile, tid, p.mix || !(p.chains & 1u));
+    }
+}
+#endif /* !WMB_HOSTSIM */
+
+/* =========================================================================== */
+/* K2: bit-sync lanes                                                          */
+/* =========================================================================== */
+
+struct K2Params {
+    const float   *dphi;        /* index 0 = batch sample 0; [-hist, M) readable            */
+    const uint8_t *rssi;
+    int64_t  M;                 /* decimated samples in this batch                          */
+    int64_t  hist;              /* valid samples before batch sample 0                      */
+    uint32_t C, W;              /* chunk and warm-up length                                 */
+    uint32_t lanes;
+    uint32_t cap_t2, cap_rl;    /* per-lane event capacity                                  */
+    uint32_t *ev_t2, *ev_rl;    /* [lanes * cap]                                            */
+    uint32_t *cnt_t2, *cnt_rl;  /* [lanes]                                                  */
+    LaneState *st_start;        /* state each lane used at its chunk start                  */
+    LaneState *st_end;          /* state each lane reached at its chunk end                 */
+    const LaneState *carry;     /* exact state at batch sample 0                            */
+    uint32_t *rerun;            /* [lanes] set by k2_verify                                 */
+    uint32_t *errors;           /* bit0 event overflow, bit1 run-length loop guard          */
+    uint32_t mode;              /* 0: speculative pass over all lanes, 1: re-run flagged    */
+    uint32_t dc, rla, t2;       /* -o, !(-r 0), !(-t 0)                                     */
+};
+
+struct K2Out { uint32_t *ev; uint32_t cap; uint32_t n; uint32_t overflow; };
+
+WMB_D void k2_emit(K2Out &o, bool live, uint32_t off, uint32_t rssi, uint32_t rst, uint32_t sync, uint32_t bit)
+{
+    if (!live) return;
+    if (o.n < o.cap) o.ev[o.n] = EV_LOCAL(off, rssi, rst, sync, bit);
+    else o.overflow = 1;
+    o.n++;
+}
+
+/* one decimated sample through the sequential part of a chain */
+template <class CH>
+WMB_D void k2_step(const K2Params &p, LaneState &s, float x, int64_t m, uint32_t off, bool live,
+                   K2Out &o_t2, K2Out &o_rl, uint32_t &err)
+{
+    const float *cf = (CH::ID == 0) ? c_iir_t1c1 : c_iir_s1;
+    if (p.dc) {                                              /* rtl_wmbus.c:501 / :511 */
+        const float alpha = 0.999f, cdc = (1.f + 0.999f) / 2.f;
+        const float y = wmb_fadd(wmb_fmul(cdc, wmb_fsub(x, s.dc_x)), wmb_fmul(alpha, s.dc_y));
+        s.dc_x = x; s.dc_y = y; x = y;
+    }
+    const uint32_t bit = (x >= 0.0f) ? 1u : 0u;              /* rtl_wmbus.c:1059 */
+
+    if (p.rla) {
+        s.rl_raw = ((s.rl_raw << 1) | bit) & CH::RAW_MASK;
+        uint32_t st;
+        if (CH::ID == 0) st = (wmb_popc(s.rl_raw) >= 3) ? 1u : 0u;         /* deglitch_filter_t1_c1 */
+        else             st = (0xFEEAu >> s.rl_raw) & 1u;                  /* deglitch_filter_s1    */
+        const uint32_t level = s.rl_flags & 1u;
+        if (st == level) {
+            s.rl_run++;
+        } else {
+            bool reset = false;
+            int n = 0;
+            if (CH::ID == 0) {                               /* rtl_wmbus.c:742-796 */
+                if (s.rl_run < 5) reset = true;
+                else {
+                    int rl = s.rl_run * 256;
+                    const int half = s.rl_a / 2;
+                    if (rl <= half) reset = true;
+                    else if (s.rl_a <= 0) { reset = true; err |= 2u; }     /* reference would spin */
+                    else {
+                        uint32_t rssi = 0;
+                        bool have = false;
+                        while (rl > half) {
+                            rl -= s.rl_a;
+                            s.rl_sr = ((s.rl_sr << 1) | level) & CH::CODE_MASK;
+                            if (n < K2_EDGE_EMIT_CAP) {
+                                if (live && !have) { rssi = p.rssi[m]; have = true; }
+                                k2_emit(o_rl, live, off, rssi, (s.rl_flags >> 1) & 1u, s.rl_sr == CH::CODE, level);
+                                s.rl_flags &= ~2u;
+                            }
+                            n++;
+                        }
+                        s.rl_b += rl;
+                        s.rl_a += (rl + s.rl_b / 16) / (32 * n);
+                    }
+                }
+                if (reset) { s.rl_a = 8 * 256; s.rl_b = 0; }
+            } else {                                         /* rtl_wmbus.c:655-698 */
+                const int spb = (s.rl_a + s.rl_b) / 2;
+                const int half = spb / 2;
+                const int run = s.rl_run;
+                if (spb <= 12 || spb >= 36) reset = true;
+                else if (run <= half) reset = true;
+                else {
+                    int rl = run;
+                    uint32_t rssi = 0;
+                    bool have = false;
+                    while (rl > half) {
+                        rl -= spb;
+                        s.rl_sr = ((s.rl_sr << 1) | level) & CH::CODE_MASK;
+                        if (n < K2_EDGE_EMIT_CAP) {
+                            if (live && !have) { rssi = p.rssi[m]; have = true; }
+                            k2_emit(o_rl, live, off, rssi, (s.rl_flags >> 1) & 1u, s.rl_sr == CH::CODE, level);
+                            s.rl_flags &= ~2u;
+                        }
+                        n++;
+                    }
+                    if (level) s.rl_b = run / n; else s.rl_a = run / n;
+                }
+                if (reset) { s.rl_a = 24; s.rl_b = 24; }
+            }
+            if (reset) {                                     /* runlength_algorithm_reset_* */
+                s.rl_raw = 0; s.rl_sr = 0;
+                s.rl_flags = 2u;                             /* decoder reset: cut frames here */
+            }
+            s.rl_flags = (s.rl_flags & ~1u) | st;
+            s.rl_run = 1;
+        }
+    }
+
+    if (p.t2) {                                              /* rtl_wmbus.c:1089-1111, iir.h:59-74 */
+        float v = wmb_fmul(x, x);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float b1 = cf[4 * k], b2 = cf[4 * k + 1], a1 = cf[4 * k + 2], a2 = cf[4 * k + 3];
+            const float h1 = s.h[2 * k], h2 = s.h[2 * k + 1];
+            const float h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a1, h1), wmb_fmul(a2, h2)));
+            v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b1, h1)), wmb_fmul(b2, h2));
+            s.h[2 * k + 1] = h1; s.h[2 * k] = h0;
+        }
+        v = wmb_fmul(v, c_iir_gain);
+        const uint32_t clk = (v >= 0.0f) ? 1u : 0u;
+        const uint32_t win = ((s.clk3 << 1) | clk) & 0xFu;  /* clk[m-3..m] */
+        s.clk3 = win & 7u;
+        if (win == 0x7u) {                                   /* low, high, high, high: sample now */
+            s.t2_sr = ((s.t2_sr << 1) | bit) & CH::CODE_MASK;
+            if (live) k2_emit(o_t2, true, off, p.rssi[m], 0u, s.t2_sr == CH::CODE, bit);
+        }
+    }
+}
+
+template <class CH>
+WMB_D void k2_lane(const K2Params &p, uint32_t lane)
+{
+    if (lane >= p.lanes) return;
+    const int64_t s0 = (int64_t)lane * p.C;
+    const int64_t e0 = (s0 + p.C < p.M) ? s0 + p.C : p.M;
+    LaneState st;
+    int64_t m;
+    if (p.mode == 0) {
+        if (lane == 0) { st = *p.carry; m = 0; }
+        else {
+            lane_state_init(st, CH::ID);
+            m = s0 - (int64_t)p.W;
+            if (m < -p.hist) m = -p.hist;
+        }
+    } else {
+        if (lane == 0 || !p.rerun[lane]) return;
+        st = p.st_end[lane - 1];
+        m = s0;
+    }
+    K2Out o_t2 = { p.ev_t2 + (size_t)lane * p.cap_t2, p.cap_t2, 0, 0 };
+    K2Out o_rl = { p.ev_rl + (size_t)lane * p.cap_rl, p.cap_rl, 0, 0 };
+    uint32_t err = 0;
+    for (; m < s0; m++) k2_step<CH>(p, st, p.dphi[m], m, 0, false, o_t2, o_rl, err);
+    p.st_start[lane] = st;
+    for (; m < e0; m++) k2_step<CH>(p, st, p.dphi[m], m, (uint32_t)(m - s0), true, o_t2, o_rl, err);
+    p.st_end[lane] = st;
+    p.cnt_t2[lane] = o_t2.n < o_t2.cap ? o_t2.n : o_t2.cap;
+    p.cnt_rl[lane] = o_rl.n < o_rl.cap ? o_rl.n : o_rl.cap;
+    if (o_t2.overflow || o_rl.overflow) err |= 1u;
+    if (err) {
+#ifdef WMB_HOSTSIM
+        *p.errors |= err;
+#else
+        atomicOr(p.errors, err);
+#endif
+    }
+}
+
+WMB_D bool lane_state_equal(const LaneState &a, const LaneState &b, const K2Params &p)
+{
+    bool eq = true;
+    if (p.dc) eq = eq && wmb_f2u(a.dc_x) == wmb_f2u(b.dc_x) && wmb_f2u(a.dc_y) == wmb_f2u(b.dc_y);
+    if (p.t2) {
+        for (int i = 0; i < 6; i++) eq = eq && wmb_f2u(a.h[i]) == wmb_f2u(b.h[i]);
+        eq = eq && a.clk3 == b.clk3 && a.t2_sr == b.t2_sr;
+    }
+    if (p.rla)
+        eq = eq && a.rl_run == b.rl_run && a.rl_a == b.rl_a && a.rl_b == b.rl_b &&
+             a.rl_flags == b.rl_flags && a.rl_raw == b.rl_raw && a.rl_sr == b.rl_sr;
+    return eq;
+}
+
+/* flags lanes whose speculative start state differs from the predecessor's end state */
+WMB_D void k2_verify_lane(const K2Params &p, uint32_t lane, uint32_t *n_fail)
+{
+    if (lane >= p.lanes) return;
+    uint32_t bad = 0;
+    if (lane > 0 && !lane_state_equal(p.st_start[lane], p.st_end[lane - 1], p)) bad = 1;
+    p.rerun[lane] = bad;
+    if (bad) {
+#ifdef WMB_HOSTSIM
+        (*n_fail)++;
+#else
+        atomicAdd(n_fail, 1u);
+#endif
+    }
+}
+
+/* =========================================================================== */
+/* K2c: per-stream prefix sum, compaction into the stream ring, candidates     */
+/* =========================================================================== */
+
+struct StreamDev {                  /* device-resident bookkeeping of one (chain, algo) stream */
+    uint64_t total;                 /* events appended so far (== next ordinal)            */
+    uint32_t n_cand;                /* candidates collected in this batch                  */
+    uint32_t cand_overflow;
+};
+
+struct K2cParams {
+    const uint32_t *ev;             /* lane-local events [lanes * cap]                     */
+    const uint32_t *cnt;            /* [lanes]                                             */
+    uint64_t *base;                 /* [lanes] out: ordinal of each lane's first event     */
+    uint32_t lanes, cap, C;
+    int64_t  m_base;                /* global decimated index of batch sample 0            */
+    uint64_t *ring; uint64_t ring_mask;
+    StreamDev *sd;
+    uint64_t *cand; uint32_t cand_cap;      /* out: ordinals of access-code matches        */
+};
+
+/* single thread: lanes is at most a few 10^4 */
+WMB_D void k2c_scan(const K2cParams &p)
+{
+    uint64_t acc = p.sd->total;
+    for (uint32_t l = 0; l < p.lanes; l++) { p.base[l] = acc; acc += p.cnt[l]; }
+    p.sd->total = acc;
+}
+
+WMB_D void k2c_compact(const K2cParams &p, uint32_t lane, int tid, int nthr)
+{
+    if (lane >= p.lanes) return;
+    const uint32_t n = p.cnt[lane];
+    const uint64_t base = p.base[lane];
+    const uint32_t *src = p.ev + (size_t)lane * p.cap;
+    const uint64_t m_lane = (uint64_t)(p.m_base + (int64_t)lane * p.C);
+    for (uint32_t i = tid; i < n; i += nthr) {
+        const uint32_t e = src[i];
+        const uint64_t m = m_lane + (e >> 11);
+        const uint64_t g = (m << 24) | ((uint64_t)((e >> 3) & 0xFFu) << 16) | (e & 7u);
+        p.ring[(base + i) & p.ring_mask] = g;
+        if (e & 2u) {
+#ifdef WMB_HOSTSIM
+            const uint32_t slot = p.sd->n_cand++;
+#else
+            const uint32_t slot = atomicAdd(&p.sd->n_cand, 1u);
+#endif
+            if (slot < p.cand_cap) p.cand[slot] = base + i;
+            else p.sd->cand_overflow = 1;
+        }
+    }
+}
+
+/* =========================================================================== */
+/* K3: frame gather                                                            */
+/* =========================================================================== */
+
+struct FrameHdr {                   /* one per candidate, device -> host                   */
+    uint64_t ordinal;
+    uint64_t sync_sample;
+    uint32_t nbits;                 /* events shipped (>= 1)                               */
+    uint32_t word_off;              /* offset into the frame word buffer                   */
+    uint8_t  chain, algo;
+    uint8_t  complete;              /* 1: all bits the header can ask for (or cut by a reset) */
+    uint8_t  overflow;              /* sample offset did not fit 23 bits                   */
+    uint8_t  cut;                   /* 1: list ends at a run-length reset                  */
+    uint8_t  pad[3];
+};
+
+struct K3Params {
+    const uint64_t *ring[WMB_N_CHAINS][WMB_N_ALGOS];
+    uint64_t ring_mask[WMB_N_CHAINS][WMB_N_ALGOS];
+    uint64_t total[WMB_N_CHAINS][WMB_N_ALGOS];
+    FrameHdr *hdr;                  /* in: ordinal/chain/algo filled by host; out: the rest */
+    uint32_t n;
+    uint32_t *words; uint32_t words_cap;
+    uint32_t *n_words;              /* out: total words used                               */
+    uint32_t *errors;
+};
+
+/* EN 13757-4 3-out-of-6 decode (t1_c1_packet_decoder.h:50-65), 0xFF = invalid */
+WMB_HD uint32_t wmb_dec3of6(uint32_t c)
+{
+    switch (c) {
+    case 0x16: return 0; case 0x0D: return 1; case 0x0E: return 2; case 0x0B: return 3;
+    case 0x1C: return 4; case 0x19: return 5; case 0x1A: return 6; case 0x13: return 7;
+    case 0x2C: return 8; case 0x25: return 9; case 0x26: return 10; case 0x23: return 11;
+    case 0x34: return 12; case 0x31: return 13; case 0x32: return 14; case 0x29: return 15;
+    default: return 0xFF;
+    }
+}
+
+/* total telegram length for an L-field, frame format A (t1_c1_packet_decoder.h:68-96) */
+WMB_HD uint32_t wmb_tlg_len_a(uint32_t L)
+{
+    return 1 + L + 2 * (1 + (L > 9 ? (L - 9 + 15) / 16 : 0));
+}
+
+/* Upper bound on the number of events (including the flagged one) the host framer can
+ * consume for the candidate at ordinal `ord`, looking only at the header bits that are
+ * already available.  Returns 0 when not even the header is there yet. */
+WMB_D uint32_t k3_bits_needed(const uint64_t *ring, uint64_t mask, uint64_t ord, uint64_t total, int chain)
+{
+    const uint64_t avail = total - ord;
+    if (chain == 0) {
+        if (avail < 13) return 0;
+        uint32_t w = 0;
+        for (int i = 1; i <= 12; i++) w = (w << 1) | EVG_BIT(ring[(ord + i) & mask]);
+        const uint32_t hi = wmb_dec3of6(w >> 6), lo = wmb_dec3of6(w & 63u);
+        if (hi != 0xFF && lo != 0xFF) return 1 + 12 * wmb_tlg_len_a((hi << 4) | lo);
+        if (w != 0x54Cu && w != 0x543u) return 13;
+        if (avail < 25) return 0;
+        uint32_t t = 0;
+        for (int i = 13; i <= 24; i++) t = (t << 1) | EVG_BIT(ring[(ord + i) & mask]);
+        if ((t >> 8) != 0xDu) return 17;
+        const uint32_t L = t & 0xFFu;
+        uint32_t len = (w == 0x543u) ? 1 + L : wmb_tlg_len_a(L);
+        if (len < 2) len = 2;
+        return 25 + 8 * (len - 1);
+    }
+    if (avail < 17) return 0;
+    uint32_t L = 0;
+    for (int i = 0; i < 8; i++) {
+        const uint32_t a = EVG_BIT(ring[(ord + 1 + 2 * i) & mask]), b = EVG_BIT(ring[(ord + 2 + 2 * i) & mask]);
+        if (a == b) return 3 + 2 * i;                       /* Manchester violation: framer stops on that chip */
+        L = (L << 1) | b;                                    /* 01 -> 1, 10 -> 0 */
+    }
+    return 1 + 16 * wmb_tlg_len_a(L);
+}
+
+/* pass 1 (thread per candidate): how many events to ship */
+WMB_D void k3_size(const K3Params &p, uint32_t i)
+{
+    if (i >= p.n) return;
+    FrameHdr &h = p.hdr[i];
+    const uint64_t *ring = p.ring[h.chain][h.algo];
+    const uint64_t mask = p.ring_mask[h.chain][h.algo], total = p.total[h.chain][h.algo];
+    const uint64_t avail = total - h.ordinal;
+    uint32_t need = k3_bits_needed(ring, mask, h.ordinal, total, h.chain);
+    uint32_t n = (need == 0 || need > avail) ? (uint32_t)avail : need;
+    uint8_t complete = (need != 0 && need <= avail) ? 1 : 0, cut = 0;
+    /* the run-length algorithm resets its decoder when it resets itself: stop there */
+    for (uint32_t j = 1; j < n; j++) {
+        if (EVG_RESET(ring[(h.ordinal + j) & mask])) { n = j; complete = 1; cut = 1; break; }
+    }
+    h.nbits = n; h.complete = complete; h.cut = cut; h.overflow = 0;
+    h.sync_sample = EVG_M(ring[h.ordinal & mask]);
+}
+
+/* pass 2 (single thread): exclusive scan of nbits -> word offsets */
+WMB_D void k3_offsets(const K3Params &p)
+{
+    uint64_t acc = 0;
+    for (uint32_t i = 0; i < p.n; i++) {
+        if (acc + p.hdr[i].nbits > p.words_cap) { p.hdr[i].nbits = 0; p.hdr[i].complete = 0; *p.errors |= 4u; }
+        p.hdr[i].word_off = (uint32_t)acc;
+        acc += p.hdr[i].nbits;
+    }
+    *p.n_words = (uint32_t)acc;
+}
+
+/* pass 3 (block per candidate): copy events as wmb_bit words */
+WMB_D void k3_copy(const K3Params &p, uint32_t i, int tid, int nthr)
+{
+    if (i >= p.n) return;
+    FrameHdr &h = p.hdr[i];
+    const uint64_t *ring = p.ring[h.chain][h.algo];
+    const uint64_t mask = p.ring_mask[h.chain][h.algo];
+    for (uint32_t j = tid; j < h.nbits; j += nthr) {
+        const uint64_t e = ring[(h.ordinal + j) & mask];
+        uint64_t off = EVG_M(e) - h.sync_sample;
+        if (off >= (1u << 23)) { off = (1u << 23) - 1; h.overflow = 1; }
+        p.words[h.word_off + j] = ((uint32_t)off << 9) | (EVG_RSSI(e) << 1) | EVG_BIT(e);
+    }
+}
+
+#ifndef WMB_HOSTSIM
+/* ---- __global__ wrappers ---- */
+template <class CH>
+__global__ void __launch_bounds__(K2_THREADS) k2_lanes_kernel(const K2Params p)
+{
+    k2_lane<CH>(p, blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void k2_verify_kernel(const K2Params p, uint32_t *n_fail)
+{
+    k2_verify_lane(p, blockIdx.x * blockDim.x + threadIdx.x, n_fail);
+}
+__global__ void k2c_scan_kernel(const K2cParams p) { if (threadIdx.x == 0 && blockIdx.x == 0) k2c_scan(p); }
+__global__ void k2c_compact_kernel(const K2cParams p) { k2c_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
+__global__ void k3_size_kernel(const K3Params p) { k3_size(p, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void k3_offsets_kernel(const K3Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) k3_offsets(p); }
+__global__ void k3_copy_kernel(const K3Params p) { k3_copy(p, blockIdx.x, threadIdx.x, blockDim.x); }
+#endif

@@ -1,0 +1,73 @@
+/*
+ * hostsim_launch.inl -- TEST INFRASTRUCTURE ONLY (see hostsim_cuda.h).
+ * CPU "launches" of the kernels in wmb_kernels.cuh: every kernel becomes a loop over its
+ * (block, thread) indices; barrier-separated phases of the demod kernel run one after
+ * another over all threads, which is what __syncthreads() guarantees on the device.
+ */
+
+template <class CH>
+static void hostsim_k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile, bool need_convert)
+{
+    if (need_convert) for (int t = 0; t < K1_THREADS; t++) k1_convert<CH::ID>(p, sm, raw, tile, t);
+    for (int t = 0; t < K1_THREADS; t++) k1_box<CH>(p, sm, t);
+    for (int t = 0; t < K1_THREADS; t++) k1_disc_mag(p, sm, t);
+    for (int t = 0; t < K1_THREADS; t++) k1_fir_rssi<CH>(p, sm, tile, t);
+    for (int t = 0; t < K1_THREADS; t++) k1_store_rssi<CH>(p, sm, tile, t);
+}
+
+static int launch_k1(wmb_ctx *c, const K1Params &p)
+{
+    const int64_t ntiles = (p.M + K1_TILE - 1) / K1_TILE;
+    std::vector<uint8_t> smem(k1_smem_bytes(p.d) + 256, 0xA5);   /* garbage-filled like real smem */
+    K1Smem sm;
+    uint8_t *base = smem.data();
+    base += (128 - ((uintptr_t)base & 127)) & 127;
+    k1_carve(sm, base, p.d);
+    for (int64_t tile = 0; tile < ntiles; tile++) {
+        const K1Load L = k1_plan_load(p, tile);
+        if (L.n0) memcpy(sm.bytes[0], L.src0, (size_t)L.n0);
+        if (L.n1) memcpy(sm.bytes[0] + L.off1, L.src1, (size_t)L.n1);
+        if ((L.n0 | L.n1 | L.off1) & 15) return set_err(WMB_E_STATE, "hostsim: unaligned bulk copy");
+        const uint8_t *raw = sm.bytes[0];
+        if (p.chains & 1u) hostsim_k1_chain<ChainT1C1>(p, sm, raw, tile, true);
+        if (p.chains & 2u) hostsim_k1_chain<ChainS1>(p, sm, raw, tile, p.mix || !(p.chains & 1u));
+    }
+    c->st.kernel_launches++;
+    return WMB_OK;
+}
+
+static int launch_k2(wmb_ctx *c, int chain, const K2Params &p)
+{
+    for (uint32_t lane = 0; lane < p.lanes; lane++) {
+        if (chain == 0) k2_lane<ChainT1C1>(p, lane);
+        else            k2_lane<ChainS1>(p, lane);
+    }
+    c->st.kernel_launches++;
+    return WMB_OK;
+}
+
+static int launch_k2_verify(wmb_ctx *c, const K2Params &p)
+{
+    for (uint32_t lane = 0; lane < p.lanes; lane++) k2_verify_lane(p, lane, c->d_nfail);
+    c->st.kernel_launches++;
+    return WMB_OK;
+}
+
+static int launch_k2c(wmb_ctx *c, const K2cParams &p)
+{
+    k2c_scan(p);
+    for (uint32_t lane = 0; lane < p.lanes; lane++)
+        for (int t = 0; t < 4; t++) k2c_compact(p, lane, t, 4);
+    c->st.kernel_launches += 2;
+    return WMB_OK;
+}
+
+static int launch_k3(wmb_ctx *c, const K3Params &p)
+{
+    for (uint32_t i = 0; i < p.n; i++) k3_size(p, i);
+    k3_offsets(p);
+    for (uint32_t i = 0; i < p.n; i++)
+        for (int t = 0; t < 4; t++) k3_copy(p, i, t, 4);
+    c->st.kernel_launches += 3;
+    return WMB_OK;
+}

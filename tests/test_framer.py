@@ -1,0 +1,110 @@
+"""Product framers (rtl-wmbus_b200/csrc/wmb_framer.c, frame-at-once) vs the oracle's per-bit state
+machines (restating t1_c1_packet_decoder.h / s1_packet_decoder.h) on random and crafted bit lists."""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+
+
+class Decoded(C.Structure):
+    _fields_ = [("status", C.c_int), ("consumed", C.c_uint32), ("end_sample", C.c_uint64), ("mode", C.c_char * 3),
+                ("crc_ok", C.c_uint8), ("ok_3of6", C.c_uint8), ("packet_rssi", C.c_uint32),
+                ("current_rssi", C.c_uint32), ("serial", C.c_uint32), ("len", C.c_uint32),
+                ("datagram", C.c_uint8 * 292)]
+
+
+def product_decode(lib, pkg, chain, bits, rssi):
+    n = len(bits)
+    words = np.zeros(n, np.uint32)
+    words[:] = (np.arange(n, dtype=np.uint32) << 9) | (rssi.astype(np.uint32) << 1) | bits.astype(np.uint32)
+    f = pkg.WmbFrame()
+    f.sync_sample = 1000; f.ordinal = 5; f.chain = chain; f.algo = 0; f.nbits = n
+    f.bits = words.ctypes.data_as(C.POINTER(C.c_uint32))
+    d = Decoded()
+    lib.wmb_frame_decode.argtypes = [C.POINTER(pkg.WmbFrame), C.POINTER(Decoded)]
+    lib.wmb_frame_decode(C.byref(f), C.byref(d))
+    line = None
+    if d.status == 1:
+        buf = C.create_string_buffer(2048)
+        lib.wmb_format_line.argtypes = [C.POINTER(Decoded), C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        lib.wmb_format_line.restype = C.c_size_t
+        k = lib.wmb_format_line(C.byref(d), b"rla;", b"TS", buf, 2048)
+        line = buf.raw[:k].decode().rstrip("\n")
+    return d.status, d.consumed, line, d.end_sample
+
+
+def oracle_decode(orc_mod, chain, bits, rssi):
+    L = orc_mod.lib()
+    out = C.create_string_buffer(4096)
+    got = C.c_int(0)
+    fn = L.orc_frame_t1c1 if chain == 0 else L.orc_frame_s1
+    consumed = fn(np.ascontiguousarray(bits, np.uint8), np.ascontiguousarray(rssi, np.uint8), len(bits), b"rla;",
+                  out, 4096, C.byref(got))
+    line = out.value.decode().rstrip("\n") if got.value else None
+    return consumed, line
+
+
+def frames_for_tests(synth):
+    e = synth.Emitter("T1", 0x12345678, l_field=0x1E, seed=5)
+    p = e.payload(3)
+    out = []
+    a = synth.frame_a(p)
+    t1 = synth.chips_t1(a, preamble_pairs=0, post_pairs=8)[len(synth.SYNC_T1C1) - 1:]
+    c1a = synth.chips_c1(a, False, preamble_pairs=0, post_pairs=8)[len(synth.SYNC_T1C1) - 1:]
+    c1b = synth.chips_c1(synth.frame_b(p), True, preamble_pairs=0, post_pairs=8)[len(synth.SYNC_T1C1) - 1:]
+    s1 = synth.chips_s1(a, preamble_pairs=0, post_pairs=8)[len(synth.SYNC_S1) - 1:]
+    big = synth.Emitter("C1B", 0x00112233, l_field=0xF0, seed=6).payload(1)
+    c1b_big = synth.chips_c1(synth.frame_b(big), True, preamble_pairs=0, post_pairs=8)[len(synth.SYNC_T1C1) - 1:]
+    t1_max = synth.chips_t1(synth.frame_a(synth.Emitter("T1", 1, l_field=0xFF, seed=7).payload(0)), 0, 8)[len(synth.SYNC_T1C1) - 1:]
+    return [(0, t1), (0, c1a), (0, c1b), (1, s1), (0, c1b_big), (0, t1_max)]
+
+
+def test_framer_on_clean_and_corrupted_frames(hostsim_lib, pkg, orc_mod):
+    synth = importlib.import_module("rtl-wmbus_b200.synth")
+    rng = np.random.default_rng(3)
+    n_lines = 0
+    for chain, chips in frames_for_tests(synth):
+        chips = chips.astype(np.uint8)
+        for trial in range(60):
+            bits = chips.copy()
+            rssi = rng.integers(20, 200, len(bits)).astype(np.uint8)
+            if trial % 3 == 1:                      # flip a few chips
+                for i in rng.integers(1, len(bits), rng.integers(1, 4)):
+                    bits[i] ^= 1
+            if trial % 3 == 2:                      # rssi drop-outs -> PACKET_CAPTURE_THRESHOLD abort
+                rssi[rng.integers(0, len(bits))] = rng.integers(0, 5)
+            if trial % 10 == 9:                     # truncated list
+                cut = rng.integers(1, len(bits))
+                bits, rssi = bits[:cut], rssi[:cut]
+            st, consumed, line, end = product_decode(hostsim_lib, pkg, chain, bits, rssi)
+            oc, oline = oracle_decode(orc_mod, chain, bits, rssi)
+            if st == 2:                             # NEED_MORE: the oracle ran through the whole list
+                assert oline is None and oc == len(bits)
+            else:
+                assert consumed == oc, (chain, trial, consumed, oc)
+                assert line == oline, (chain, trial)
+                if line:
+                    n_lines += 1
+                    assert end == 1000 + consumed - 1
+    assert n_lines > 100
+
+
+def test_framer_on_random_bits(hostsim_lib, pkg, orc_mod):
+    rng = np.random.default_rng(11)
+    for trial in range(3000):
+        chain = trial & 1
+        n = int(rng.integers(1, 400))
+        bits = rng.integers(0, 2, n).astype(np.uint8)
+        if trial % 4 == 0 and chain == 0 and n > 30:     # force the C1 mode word path
+            word = "010101001100" if trial % 8 == 0 else "010101000011"
+            bits[1:13] = np.frombuffer(word.encode(), np.uint8) - 48
+            bits[13:17] = [1, 1, 0, 1]
+            bits[17:25] = [0, 0, 0, 0, 0, 0, int(rng.integers(0, 2)), int(rng.integers(0, 2))]
+        rssi = rng.integers(3, 60, n).astype(np.uint8)
+        st, consumed, line, _ = product_decode(hostsim_lib, pkg, chain, bits, rssi)
+        oc, oline = oracle_decode(orc_mod, chain, bits, rssi)
+        if st == 2:
+            assert oline is None and oc == n
+        else:
+            assert (consumed, line) == (oc, oline), (trial, chain)

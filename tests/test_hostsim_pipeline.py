@@ -1,0 +1,51 @@
+"""`not gpu`: the library's host logic (batching, history carry-over, lane verification/re-run,
+candidate hand-over, framers, ordering) and the kernels' phase functions, executed through the C ABI
+of the CPU simulation build (tests/hostsim -- test infrastructure, not a product path)."""
+import numpy as np
+import pytest
+
+import pipeline_checks as pc
+from conftest import load_fixture
+
+
+def test_golden_lines_all_flags(pkg, hostsim_lib, golden_lines):
+    assert pc.check_golden(pkg, hostsim_lib, golden_lines) > 200
+
+
+def test_stage_outputs_bit_exact(pkg, hostsim_lib):
+    pc.check_stages(pkg, hostsim_lib, load_fixture("excerpt_samples2_a.cu8"), "")
+    pc.check_stages(pkg, hostsim_lib, load_fixture("excerpt_issue48_2m4.cu8"), "-d 3 -s -o")
+    pc.check_stages(pkg, hostsim_lib, load_fixture("synth_mixed_1m6.cu8")[:1 << 19], "-a -d 1")
+
+
+def test_geometry_and_push_invariance(pkg, hostsim_lib):
+    cu8 = load_fixture("synth_mixed_1m6.cu8")
+    variants = [dict(chunk_samples=1024, warmup_samples=32768, max_batch_mib=1),
+                dict(chunk_samples=4096, warmup_samples=256, max_batch_mib=1),      # forces lane re-runs
+                dict(chunk_samples=2048, warmup_samples=1024),
+                dict(pushes=[4096] * 7 + [12288, 4096 * 33, 1, 5000, 8191]),
+                dict(pushes=[100000, 300000], max_batch_mib=1, chunk_samples=8192, warmup_samples=512)]
+    reruns = pc.check_invariance(pkg, hostsim_lib, cu8, "-v", variants)
+    assert reruns > 0, "the short warm-up variants must exercise the re-run path"
+    pc.check_invariance(pkg, hostsim_lib, cu8, "-v -o", [dict(chunk_samples=2048, warmup_samples=2048, max_batch_mib=1)])
+    cu8s = load_fixture("synth_mixed_2m4_shift.cu8")
+    pc.check_invariance(pkg, hostsim_lib, cu8s, "-v -d 3 -s",
+                        [dict(chunk_samples=1024, warmup_samples=512, max_batch_mib=1, pushes=[4096 * 3] * 9 + [7, 4096 * 50])])
+
+
+def test_manual_frame_api(pkg, hostsim_lib):
+    pc.check_manual_frames(pkg, hostsim_lib, load_fixture("synth_mixed_1m6.cu8"), "-v")
+
+
+def test_degenerate_inputs(pkg, hostsim_lib):
+    pc.check_degenerate(pkg, hostsim_lib)
+
+
+def test_error_paths(pkg, hostsim_lib):
+    import ctypes as C
+    o = pkg.opts_from_flags(hostsim_lib, "-d 200")
+    ctx = C.c_void_p()
+    assert hostsim_lib.wmb_create(C.byref(o), 0, C.byref(ctx)) == -1        # WMB_E_INVAL
+    assert b"decimation" in hostsim_lib.wmb_last_error()
+    o = pkg.opts_from_flags(hostsim_lib, "")
+    assert hostsim_lib.wmb_create(C.byref(o), 7, C.byref(ctx)) == -2        # WMB_E_NODEVICE
