@@ -107,6 +107,8 @@ const char *wmb_version_string(void);
  * structs reset, chain/discriminator selection, mixer look-up tables). */
 int  wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out);
 void wmb_destroy(wmb_ctx *c);
+/* Start over with a new capture (same as destroy + create, without re-allocating). */
+int  wmb_reset(wmb_ctx *c);
 
 /* Page-locked host memory for input buffers (the reference reads stdin into a 4096-byte
  * stack array, rtl_wmbus.c:1249; a GPU pipeline wants to DMA straight out of the read

@@ -49,6 +49,10 @@ def _bind(lib):
     lib.wmb_version_string.restype = C.c_char_p
     lib.wmb_create.argtypes = [C.POINTER(WmbOpts), C.c_int, C.POINTER(C.c_void_p)]
     lib.wmb_destroy.argtypes = [C.c_void_p]
+    lib.wmb_reset.argtypes = [C.c_void_p]
+    lib.wmb_host_alloc.argtypes = [C.c_size_t]
+    lib.wmb_host_alloc.restype = C.c_void_p
+    lib.wmb_host_free.argtypes = [C.c_void_p]
     lib.wmb_push.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.wmb_push_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.wmb_poll.argtypes = [C.c_void_p, C.POINTER(WmbFrame), C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
@@ -66,7 +70,7 @@ def _bind(lib):
     return lib
 
 
-EXPORTS = ["wmb_default_opts", "wmb_abi_version", "wmb_last_error", "wmb_version_string", "wmb_create",
+EXPORTS = ["wmb_reset", "wmb_host_alloc", "wmb_host_free", "wmb_default_opts", "wmb_abi_version", "wmb_last_error", "wmb_version_string", "wmb_create",
            "wmb_destroy", "wmb_push", "wmb_push_device", "wmb_poll", "wmb_decode_frames", "wmb_take_lines",
            "wmb_process", "wmb_process_device", "wmb_get_stats", "wmb_debug_copy_stage"]
 
@@ -183,6 +187,9 @@ class WmbusB200:
                 break
             out += self._lines(n)
         return out
+
+    def reset(self):
+        self._check(self.lib.wmb_reset(self._ctx))
 
     def stats(self) -> WmbStats:
         s = WmbStats()

@@ -952,6 +952,36 @@ extern "C" long wmb_process_device(wmb_ctx *c, const void *dev_cu8, size_t nbyte
     return (long)wmb_take_lines(c, out, outcap, n_lines, timestamp_mode);
 }
 
+/* Back to the state right after wmb_create (a new capture starts): filter memories, stream
+ * position, pending candidates, queued lines.  Buffers stay allocated. */
+extern "C" int wmb_reset(wmb_ctx *c)
+{
+    if (!c) return set_err(WMB_E_INVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->cs) CUDA_TRY(cudaStreamSynchronize(c->cs));
+    if (c->xs) CUDA_TRY(cudaStreamSynchronize(c->xs));
+    c->iq_consumed = 0; c->m_consumed = 0; c->hist_m = 0; c->hist_iq = 0;
+    c->remainder.clear(); c->lines.clear(); c->held.clear(); c->held_prev.clear();
+    c->out_frames.clear(); c->batch_no = 0; c->last_M = 0;
+    if (c->allocated) {
+        CUDA_TRY(cudaMemsetAsync(c->d_errors, 0, 64, c->cs));
+        for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+            if (!(c->chains & (1u << ch))) continue;
+            ChainBuf &b = c->cb[ch];
+            LaneState init;
+            lane_state_init(init, ch);
+            CUDA_TRY(cudaMemcpy(b.carry, &init, sizeof(init), cudaMemcpyHostToDevice));
+            for (int a = 0; a < WMB_N_ALGOS; a++) {
+                Stream &s = b.s[a];
+                CUDA_TRY(cudaMemsetAsync(s.sd, 0, sizeof(StreamDev), c->cs));
+                s.total = 0; s.pending.clear(); s.busy_until = -1;
+            }
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->cs));
+    }
+    return WMB_OK;
+}
+
 extern "C" int wmb_get_stats(wmb_ctx *c, wmb_stats *s)
 {
     if (!c || !s) return set_err(WMB_E_INVAL, "null argument");
