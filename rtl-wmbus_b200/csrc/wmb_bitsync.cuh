@@ -1,0 +1,460 @@
+/*
+ * wmb_bitsync.cuh -- K2: the sequential recurrences of a receiver chain, restructured
+ * for the GPU.  (Round-1 profile: a single "everything per lane" kernel spent 88 % of the
+ * device time at IPC 0.19 with half the threads masked off, because a float recurrence, a
+ * branchy integer state machine and event output shared one divergent loop.)
+ *
+ *   K2a  k2a_lane      float-only lanes: [DC block] -> slicer bit, x^2 -> 3 biquads ->
+ *                      clock sign -> lock stencil.  Writes two bit-packed streams per
+ *                      decimated sample: dbits (data bit) and sbits (time2 strobe).
+ *                      Speculative warm-up + state verification (rtl_wmbus.c:497-515,
+ *                      :1059, :1089-1111; iir.h:59-74).
+ *   K2t  k2t_*         time2 bit stream: strobed data bits -> shift register -> access
+ *                      code.  Exact without speculation: each lane reports its strobe
+ *                      count and its last 24 strobed bits, a scan folds them into every
+ *                      lane's start register (rtl_wmbus.c:806-852).
+ *   K2m  k2m_lane      run-length bit sync, integer-only lanes reading dbits
+ *                      (rtl_wmbus.c:617-803).  Speculative warm-up + verification.
+ */
+#pragma once
+#include "wmb_exact.cuh"
+#include "wmb_chain.cuh"
+
+/* ------------------------------------------------------------------------------------- */
+/* K2a: clock-recovery lanes                                                             */
+/* ------------------------------------------------------------------------------------- */
+
+struct K2aParams {
+    const float *dphi;          /* index 0 = batch sample 0; [-hist, M) readable              */
+    int64_t  M, hist;
+    uint32_t C, W, lanes;       /* all multiples of 32                                        */
+    uint32_t *dbits, *sbits;    /* word w covers samples 32w..32w+31 (bit i = sample 32w+i)   */
+    IirState *st_start, *st_end;
+    const IirState *carry;
+    uint32_t *rerun;
+    uint32_t mode;              /* 0 speculative pass, 1 re-run flagged lanes                 */
+    uint32_t dc, t2;            /* -o ; time2 enabled (else only the data bits are produced)  */
+};
+
+template <class CH>
+WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
+{
+    if (lane >= p.lanes) return;
+    const float *cf = (CH::ID == 0) ? c_iir_t1c1 : c_iir_s1;
+    const int64_t s0 = (int64_t)lane * p.C;
+    const int64_t e0 = (s0 + p.C < p.M) ? s0 + p.C : p.M;
+    IirState st;
+    int64_t m;
+    if (p.mode == 0) {
+        if (lane == 0) { st = *p.carry; m = 0; }
+        else {
+            iir_state_init(st);
+            m = s0 - (int64_t)p.W;
+            if (m < -p.hist) m = -p.hist;
+        }
+    } else {
+        if (lane == 0 || !p.rerun[lane]) return;
+        st = p.st_end[lane - 1];
+        m = s0;
+    }
+    /* registers */
+    float dcx = st.dc_x, dcy = st.dc_y;
+    float h10 = st.h[0], h20 = st.h[1], h11 = st.h[2], h21 = st.h[3], h12 = st.h[4], h22 = st.h[5];
+    uint32_t clk3 = st.clk3;
+    const float b10 = cf[0], b20 = cf[1], a10 = cf[2], a20 = cf[3];
+    const float b11 = cf[4], b21 = cf[5], a11 = cf[6], a21 = cf[7];
+    const float b12 = cf[8], b22 = cf[9], a12 = cf[10], a22 = cf[11];
+    const float gain = c_iir_gain;
+    const float alpha = 0.999f, cdc = (1.f + 0.999f) / 2.f;       /* rtl_wmbus.c:501 / :511 */
+    bool saved_start = false;
+
+    while (m < e0) {
+        if (m == s0 && !saved_start) {
+            st.dc_x = dcx; st.dc_y = dcy;
+            st.h[0] = h10; st.h[1] = h20; st.h[2] = h11; st.h[3] = h21; st.h[4] = h12; st.h[5] = h22;
+            st.clk3 = clk3;
+            p.st_start[lane] = st;
+            saved_start = true;
+        }
+        const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
+        uint32_t dword = 0, cword = 0;
+        const float *x4 = p.dphi + m;
+#pragma unroll 4
+        for (int i = 0; i < n; i++) {
+            float x = x4[i];
+            if (p.dc) {
+                const float y = wmb_fadd(wmb_fmul(cdc, wmb_fsub(x, dcx)), wmb_fmul(alpha, dcy));
+                dcx = x; dcy = y; x = y;
+            }
+            dword |= (x >= 0.0f ? 1u : 0u) << i;                  /* rtl_wmbus.c:1059 */
+            if (p.t2) {
+                float v = wmb_fmul(x, x);                         /* rtl_wmbus.c:1089 */
+                float h0;
+                h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a10, h10), wmb_fmul(a20, h20)));
+                v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b10, h10)), wmb_fmul(b20, h20));
+                h20 = h10; h10 = h0;
+                h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a11, h11), wmb_fmul(a21, h21)));
+                v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b11, h11)), wmb_fmul(b21, h21));
+                h21 = h11; h11 = h0;
+                h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a12, h12), wmb_fmul(a22, h22)));
+                v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b12, h12)), wmb_fmul(b22, h22));
+                h22 = h12; h12 = h0;
+                v = wmb_fmul(v, gain);
+                cword |= (v >= 0.0f ? 1u : 0u) << i;
+            }
+        }
+        /* lock stencil on the whole word: sample the data bit where the clock reads
+         * low, high, high, high at m-3..m (rtl_wmbus.c:1092-1111) */
+        const uint64_t hist3 = ((clk3 & 1u) << 2) | (clk3 & 2u) | ((clk3 >> 2) & 1u);   /* bit2 = m-1 */
+        const uint64_t H = ((uint64_t)cword << 3) | hist3;
+        const uint32_t sword = (uint32_t)((H >> 3) & (H >> 2) & (H >> 1) & ~H);
+        if (n == 32) clk3 = ((cword >> 31) & 1u) | (((cword >> 30) & 1u) << 1) | (((cword >> 29) & 1u) << 2);
+        else {
+            for (int i = 0; i < n; i++) clk3 = ((clk3 << 1) | ((cword >> i) & 1u)) & 7u;
+        }
+        if (m >= s0) {
+            const uint32_t keep = (n == 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+            p.dbits[m >> 5] = dword & keep;
+            p.sbits[m >> 5] = sword & keep;
+        }
+        m += n;
+    }
+    st.dc_x = dcx; st.dc_y = dcy;
+    st.h[0] = h10; st.h[1] = h20; st.h[2] = h11; st.h[3] = h21; st.h[4] = h12; st.h[5] = h22;
+    st.clk3 = clk3;
+    if (!saved_start) p.st_start[lane] = st;                      /* empty lane */
+    p.st_end[lane] = st;
+}
+
+WMB_D bool iir_state_equal(const IirState &a, const IirState &b, uint32_t dc, uint32_t t2)
+{
+    bool eq = true;
+    if (dc) eq = eq && wmb_f2u(a.dc_x) == wmb_f2u(b.dc_x) && wmb_f2u(a.dc_y) == wmb_f2u(b.dc_y);
+    if (t2) {
+        for (int i = 0; i < 6; i++) eq = eq && wmb_f2u(a.h[i]) == wmb_f2u(b.h[i]);
+        eq = eq && a.clk3 == b.clk3;
+    }
+    return eq;
+}
+
+WMB_D void k2a_verify_lane(const K2aParams &p, uint32_t lane, uint32_t *n_fail)
+{
+    if (lane >= p.lanes) return;
+    uint32_t bad = 0;
+    if (lane > 0 && !iir_state_equal(p.st_start[lane], p.st_end[lane - 1], p.dc, p.t2)) bad = 1;
+    p.rerun[lane] = bad;
+    if (bad) {
+#ifdef WMB_HOSTSIM
+        (*n_fail)++;
+#else
+        atomicAdd(n_fail, 1u);
+#endif
+    }
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* K2t: time2 bit stream                                                                 */
+/* ------------------------------------------------------------------------------------- */
+
+struct StreamDev {                  /* device-resident bookkeeping of one (chain, algo) stream */
+    uint64_t total;                 /* events appended so far (== next ordinal)            */
+    uint32_t n_cand;                /* candidates collected in this batch                  */
+    uint32_t cand_overflow;
+    uint32_t t2_sr;                 /* time2: shift register carried to the next batch     */
+    uint32_t pad;
+};
+
+struct K2tParams {
+    const uint32_t *dbits, *sbits;
+    const uint8_t *rssi;            /* index 0 = batch sample 0                             */
+    int64_t  M;
+    uint32_t Cw;                    /* words per lane                                       */
+    uint32_t lanes;
+    uint32_t *cnt;                  /* [lanes] strobes per lane                             */
+    uint32_t *tail;                 /* [lanes] last <=24 strobed bits, chronological        */
+    uint32_t *tail_len;             /* [lanes]                                              */
+    uint64_t *base;                 /* [lanes] ordinal of each lane's first event           */
+    uint32_t *sr_start;             /* [lanes] shift register at the lane's first sample    */
+    uint64_t *agg_cnt; uint32_t *agg_tail, *agg_len;   /* [SCAN_THREADS] scan scratch          */
+    int64_t  m_base;
+    uint64_t *ring; uint64_t ring_mask;
+    StreamDev *sd;
+    uint64_t *cand; uint32_t cand_cap;
+};
+
+WMB_HD uint32_t k2t_words(const K2tParams &p) { return (uint32_t)((p.M + 31) >> 5); }
+
+/* pass 1: per lane, strobe count and the last strobed bits */
+template <class CH>
+WMB_D void k2t_count(const K2tParams &p, uint32_t lane)
+{
+    if (lane >= p.lanes) return;
+    const uint32_t nw = k2t_words(p);
+    const uint32_t w0 = lane * p.Cw, w1 = (w0 + p.Cw < nw) ? w0 + p.Cw : nw;
+    const int NB = (CH::ID == 0) ? 16 : 24;
+    uint32_t cnt = 0;
+    for (uint32_t w = w0; w < w1; w++) cnt += (uint32_t)wmb_popc(p.sbits[w]);
+    uint32_t tail = 0; int len = 0;
+    for (uint32_t w = w1; w > w0 && len < NB;) {
+        w--;
+        uint32_t s = p.sbits[w];
+        const uint32_t d = p.dbits[w];
+        while (s && len < NB) {
+            const int i = 31 - wmb_clz(s);
+            s &= ~(1u << i);
+            tail |= ((d >> i) & 1u) << len;
+            len++;
+        }
+    }
+    p.cnt[lane] = cnt; p.tail[lane] = tail; p.tail_len[lane] = (uint32_t)len;
+}
+
+/* scan over lanes, three phases of one SCAN_THREADS-wide block: (A) every thread folds a
+ * contiguous range of lanes, (B) one thread scans the per-thread aggregates, (C) every thread
+ * writes its lanes' event ordinals and start registers.  The fold of (register, tail) pairs is
+ * associative: appending `len` newer bits shifts the older ones up. */
+#define SCAN_THREADS 1024
+
+WMB_HD uint32_t scan_per_thread(uint32_t n) { return (n + SCAN_THREADS - 1) / SCAN_THREADS; }
+
+template <class CH>
+WMB_D void k2t_scan_a(const K2tParams &p, uint32_t t)
+{
+    const uint32_t per = scan_per_thread(p.lanes);
+    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
+    uint64_t cnt = 0, tail = 0;
+    uint32_t len = 0;
+    const uint32_t NB = (CH::ID == 0) ? 16 : 24;
+    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) {
+        cnt += p.cnt[l];
+        const uint32_t ll = p.tail_len[l];
+        tail = ((tail << ll) | p.tail[l]) & CH::CODE_MASK;
+        len = (len + ll > NB) ? NB : len + ll;
+    }
+    p.agg_cnt[t] = cnt; p.agg_tail[t] = (uint32_t)tail; p.agg_len[t] = len;
+}
+
+template <class CH>
+WMB_D void k2t_scan_b(const K2tParams &p)
+{
+    uint64_t acc = p.sd->total;
+    uint64_t sr = p.sd->t2_sr;
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) {
+        const uint64_t c = p.agg_cnt[t];
+        const uint32_t tl = p.agg_tail[t], ll = p.agg_len[t];
+        p.agg_cnt[t] = acc; p.agg_tail[t] = (uint32_t)sr;       /* exclusive prefixes */
+        acc += c;
+        sr = ((sr << ll) | tl) & CH::CODE_MASK;
+    }
+    p.sd->total = acc;
+    p.sd->t2_sr = (uint32_t)sr;
+}
+
+template <class CH>
+WMB_D void k2t_scan_c(const K2tParams &p, uint32_t t)
+{
+    const uint32_t per = scan_per_thread(p.lanes);
+    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
+    uint64_t acc = p.agg_cnt[t];
+    uint64_t sr = p.agg_tail[t];
+    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) {
+        p.base[l] = acc; p.sr_start[l] = (uint32_t)sr;
+        acc += p.cnt[l];
+        sr = ((sr << p.tail_len[l]) | p.tail[l]) & CH::CODE_MASK;
+    }
+}
+
+/* pass 2: write the events straight into the stream ring */
+template <class CH>
+WMB_D void k2t_write(const K2tParams &p, uint32_t lane)
+{
+    if (lane >= p.lanes) return;
+    const uint32_t nw = k2t_words(p);
+    const uint32_t w0 = lane * p.Cw, w1 = (w0 + p.Cw < nw) ? w0 + p.Cw : nw;
+    uint32_t sr = p.sr_start[lane];
+    uint64_t ord = p.base[lane];
+    for (uint32_t w = w0; w < w1; w++) {
+        uint32_t s = p.sbits[w];
+        const uint32_t d = p.dbits[w];
+        while (s) {
+            const int i = wmb_ffs(s) - 1;
+            s &= s - 1;
+            const uint32_t bit = (d >> i) & 1u;
+            sr = ((sr << 1) | bit) & CH::CODE_MASK;              /* rtl_wmbus.c:820 */
+            const uint32_t sync = (sr == CH::CODE) ? 1u : 0u;    /* rtl_wmbus.c:822 */
+            const int64_t m = (int64_t)w * 32 + i;
+            const uint64_t g = ((uint64_t)(p.m_base + m) << 24) | ((uint64_t)p.rssi[m] << 16) | (sync << 1) | bit;
+            p.ring[ord & p.ring_mask] = g;
+            if (sync) {
+#ifdef WMB_HOSTSIM
+                const uint32_t slot = p.sd->n_cand++;
+#else
+                const uint32_t slot = atomicAdd(&p.sd->n_cand, 1u);
+#endif
+                if (slot < p.cand_cap) p.cand[slot] = ord;
+                else p.sd->cand_overflow = 1;
+            }
+            ord++;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------- */
+/* K2m: run-length lanes                                                                 */
+/* ------------------------------------------------------------------------------------- */
+
+struct K2mParams {
+    const uint32_t *dbits;      /* word index 0 = batch sample 0; history at negative indices */
+    const uint8_t *rssi;
+    int64_t  M, hist;
+    uint32_t C, W, lanes;
+    uint32_t cap;               /* per-lane event capacity                                    */
+    uint32_t *ev;               /* [lanes * cap] lane-local events                            */
+    uint32_t *cnt;              /* [lanes]                                                    */
+    RlState *st_start, *st_end;
+    const RlState *carry;
+    uint32_t *rerun;
+    uint32_t *errors;           /* bit0 event overflow, bit1 run-length tracker out of range  */
+    uint32_t mode;
+};
+
+struct K2Out { uint32_t *ev; uint32_t cap; uint32_t n; uint32_t overflow; };
+
+WMB_D void k2_emit(K2Out &o, bool live, uint32_t off, uint32_t rssi, uint32_t rst, uint32_t sync, uint32_t bit)
+{
+    if (!live) return;
+    if (o.n < o.cap) o.ev[o.n] = EV_LOCAL(off, rssi, rst, sync, bit);
+    else o.overflow = 1;
+    o.n++;
+}
+
+/* an edge of the deglitched stream: decide between reset and bit emission */
+template <class CH>
+WMB_D void k2m_edge(const K2mParams &p, RlState &s, uint32_t st, int64_t m, uint32_t off, bool live,
+                    K2Out &o, uint32_t &err)
+{
+    const uint32_t level = s.flags & 1u;
+    bool reset = false;
+    int n = 0;
+    if (CH::ID == 0) {                                       /* rtl_wmbus.c:742-796 */
+        if (s.run < 5) reset = true;
+        else {
+            int rl = s.run * 256;
+            const int half = s.a / 2;
+            if (rl <= half) reset = true;
+            else if (s.a <= 0) { reset = true; err |= 2u; }  /* the reference would spin here */
+            else {
+                const uint32_t rssi = live ? p.rssi[m] : 0u;
+                while (rl > half) {
+                    rl -= s.a;
+                    s.sr = ((s.sr << 1) | level) & CH::CODE_MASK;
+                    if (n < K2_EDGE_EMIT_CAP) {
+                        k2_emit(o, live, off, rssi, (s.flags >> 1) & 1u, s.sr == CH::CODE, level);
+                        s.flags &= ~2u;
+                    }
+                    n++;
+                }
+                s.b += rl;
+                s.a += (rl + s.b / 16) / (32 * n);
+            }
+        }
+        if (reset) { s.a = 8 * 256; s.b = 0; }
+    } else {                                                 /* rtl_wmbus.c:655-698 */
+        const int spb = (s.a + s.b) / 2;
+        const int half = spb / 2;
+        const int run = s.run;
+        if (spb <= 12 || spb >= 36) reset = true;
+        else if (run <= half) reset = true;
+        else {
+            int rl = run;
+            const uint32_t rssi = live ? p.rssi[m] : 0u;
+            while (rl > half) {
+                rl -= spb;
+                s.sr = ((s.sr << 1) | level) & CH::CODE_MASK;
+                if (n < K2_EDGE_EMIT_CAP) {
+                    k2_emit(o, live, off, rssi, (s.flags >> 1) & 1u, s.sr == CH::CODE, level);
+                    s.flags &= ~2u;
+                }
+                n++;
+            }
+            if (level) s.b = run / n; else s.a = run / n;
+        }
+        if (reset) { s.a = 24; s.b = 24; }
+    }
+    if (reset) {                                             /* runlength_algorithm_reset_* */
+        s.raw = 0; s.sr = 0;
+        s.flags = 2u;                                        /* decoder reset: frames are cut here */
+    }
+    s.flags = (s.flags & ~1u) | st;
+    s.run = 1;
+}
+
+template <class CH>
+WMB_D void k2m_lane(const K2mParams &p, uint32_t lane)
+{
+    if (lane >= p.lanes) return;
+    const int64_t s0 = (int64_t)lane * p.C;
+    const int64_t e0 = (s0 + p.C < p.M) ? s0 + p.C : p.M;
+    RlState s;
+    int64_t m;
+    if (p.mode == 0) {
+        if (lane == 0) { s = *p.carry; m = 0; }
+        else {
+            rl_state_init(s, CH::ID);
+            m = s0 - (int64_t)p.W;
+            if (m < -p.hist) m = -p.hist;
+        }
+    } else {
+        if (lane == 0 || !p.rerun[lane]) return;
+        s = p.st_end[lane - 1];
+        m = s0;
+    }
+    K2Out o = { p.ev + (size_t)lane * p.cap, p.cap, 0, 0 };
+    uint32_t err = 0;
+    bool saved_start = false;
+    while (m < e0) {
+        if (m == s0 && !saved_start) { p.st_start[lane] = s; saved_start = true; }
+        const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
+        const uint32_t word = p.dbits[m >> 5];
+        const bool live = m >= s0;
+        for (int i = 0; i < n; i++) {
+            const uint32_t bit = (word >> i) & 1u;
+            s.raw = ((s.raw << 1) | bit) & CH::RAW_MASK;
+            uint32_t st;
+            if (CH::ID == 0) st = (wmb_popc(s.raw) >= 3) ? 1u : 0u;     /* deglitch_filter_t1_c1 */
+            else             st = (0xFEEAu >> s.raw) & 1u;              /* deglitch_filter_s1    */
+            if (st == (s.flags & 1u)) s.run++;
+            else k2m_edge<CH>(p, s, st, m + i, (uint32_t)(m + i - s0), live, o, err);
+        }
+        m += n;
+    }
+    if (!saved_start) p.st_start[lane] = s;
+    p.st_end[lane] = s;
+    p.cnt[lane] = o.n < o.cap ? o.n : o.cap;
+    if (o.overflow) err |= 1u;
+    if (err) {
+#ifdef WMB_HOSTSIM
+        *p.errors |= err;
+#else
+        atomicOr(p.errors, err);
+#endif
+    }
+}
+
+WMB_D void k2m_verify_lane(const K2mParams &p, uint32_t lane, uint32_t *n_fail)
+{
+    if (lane >= p.lanes) return;
+    uint32_t bad = 0;
+    if (lane > 0) {
+        const RlState &a = p.st_start[lane], &b = p.st_end[lane - 1];
+        if (!(a.run == b.run && a.a == b.a && a.b == b.b && a.flags == b.flags && a.raw == b.raw && a.sr == b.sr)) bad = 1;
+    }
+    p.rerun[lane] = bad;
+    if (bad) {
+#ifdef WMB_HOSTSIM
+        (*n_fail)++;
+#else
+        atomicAdd(n_fail, 1u);
+#endif
+    }
+}

@@ -93,32 +93,42 @@ WMB_CONSTANT float c_iir_s1[12] = {
     -1.605750097e-07, -1.000011787, -1.937432099, 0.9927241336 };
 WMB_CONSTANT float c_iir_gain = 1.874981046e-06;
 
-/* Sequential state of one bit-sync lane.  Two lanes agree on everything that follows a
- * sample iff these agree, which is what the speculative-start verification compares. */
-struct LaneState {
+/* Sequential state of a clock-recovery lane (K2a).  Two lanes agree on everything that
+ * follows a sample iff these agree, which is what the speculative-start verification compares. */
+struct IirState {
     float    dc_x, dc_y;        /* DC block (-o)           rtl_wmbus.c:497-515            */
     float    h[6];              /* biquad memories h1,h2 x 3 sections   iir.h:67-71       */
     uint32_t clk3;              /* last three clock signs (bit0 newest) rtl_wmbus.c:1092  */
-    uint32_t t2_sr;             /* time2 shift register, masked         rtl_wmbus.c:820   */
-    int32_t  rl_run;            /* run_length                           rtl_wmbus.c:707   */
-    int32_t  rl_a;              /* T1/C1: bit_length   S1: samples_per_bit[0]             */
-    int32_t  rl_b;              /* T1/C1: cum error    S1: samples_per_bit[1]             */
-    uint32_t rl_flags;          /* bit0 deglitched level, bit1 reset pending for next event */
-    uint32_t rl_raw;            /* raw bit history, masked                                */
-    uint32_t rl_sr;             /* run-length shift register, masked                      */
+    uint32_t pad;
 };
 
-static inline
-#ifndef WMB_HOSTSIM
-__host__ __device__
+/* Sequential state of a run-length lane (K2m / K2p) */
+struct RlState {
+    int32_t  run;               /* run_length                           rtl_wmbus.c:707   */
+    int32_t  a;                 /* T1/C1: bit_length   S1: samples_per_bit[0]             */
+    int32_t  b;                 /* T1/C1: cum error    S1: samples_per_bit[1]             */
+    uint32_t flags;             /* bit0 deglitched level, bit1 reset pending for next event */
+    uint32_t raw;               /* raw bit history, masked                                */
+    uint32_t sr;                /* run-length shift register, masked                      */
+};
+
+#ifdef WMB_HOSTSIM
+#define WMB_HDI static inline
+#else
+#define WMB_HDI static inline __host__ __device__
 #endif
-void lane_state_init(LaneState &s, int chain)
+
+WMB_HDI void iir_state_init(IirState &s)
 {
     s.dc_x = s.dc_y = 0.f;
     for (int i = 0; i < 6; i++) s.h[i] = 0.f;
-    s.clk3 = 0; s.t2_sr = 0;
-    s.rl_run = 0;
-    s.rl_a = chain == 0 ? 8 * 256 : 24;       /* rtl_wmbus.c:720, :634 */
-    s.rl_b = chain == 0 ? 0 : 24;             /* rtl_wmbus.c:721, :635 */
-    s.rl_flags = 0; s.rl_raw = 0; s.rl_sr = 0;
+    s.clk3 = 0; s.pad = 0;
+}
+
+WMB_HDI void rl_state_init(RlState &s, int chain)
+{
+    s.run = 0;
+    s.a = chain == 0 ? 8 * 256 : 24;          /* rtl_wmbus.c:720, :634 */
+    s.b = chain == 0 ? 0 : 24;                /* rtl_wmbus.c:721, :635 */
+    s.flags = 0; s.raw = 0; s.sr = 0;
 }

@@ -6,10 +6,12 @@
  * Per batch of IQ bytes (stream-ordered on the context's compute stream):
  *     H2D (copy stream, double-buffered)                       [host input only]
  *     K1  k1_demod_kernel        cu8 -> dphi (fp32) + rssi (u8), both chains
- *     K2  k2_lanes_kernel        speculative bit-sync lanes, per chain
- *         k2_verify_kernel       compare lane start states with predecessors' end states
- *         k2_lanes_kernel(mode=1) + verify, repeated until no lane is refuted
- *     K2c scan + compact         lane-local events -> per-stream rings, access-code matches
+ *     K2a k2a_lanes_kernel       clock recovery lanes -> packed data bits + time2 strobes
+ *         k2a_verify_kernel      compare lane start states with predecessors' end states;
+ *                                refuted lanes are re-run until none is left
+ *     K2t count / scan / write   time2 bit stream -> stream ring, access-code matches
+ *     K2m k2m_lanes_kernel       run-length lanes (+ verify / re-run)
+ *     K2c scan + compact         run-length events -> stream ring, access-code matches
  *     K3  size/offsets/copy      candidate frames -> pinned host memory
  * The host then owns 3-out-of-6 / Manchester / CRC (wmb_framer.c), exactly the split
  * BASELINE.json's north_star asks for.
@@ -62,13 +64,14 @@ static int set_err(int code, const char *fmt, ...)
 /* --------------------------------------------------------------------------- */
 
 struct Stream {                     /* one (chain, algo) bit stream */
-    uint32_t *ev = nullptr;         /* lane-local events                          */
+    uint32_t *ev = nullptr;         /* run-length: lane-local events              */
     uint32_t *cnt = nullptr;        /* per-lane counts                            */
     uint64_t *base = nullptr;       /* per-lane ordinal base                      */
     uint64_t *ring = nullptr;       /* global event ring                          */
     uint64_t ring_cap = 0;          /* power of two                               */
     StreamDev *sd = nullptr;        /* device bookkeeping                         */
     uint64_t *cand = nullptr;       /* device candidate ordinals                  */
+    uint64_t *agg = nullptr;        /* scan scratch [SCAN_THREADS]                */
     uint64_t total = 0;             /* host mirror of sd->total                   */
     std::vector<uint64_t> pending;  /* candidates not yet complete                */
     /* host framer bookkeeping */
@@ -76,12 +79,15 @@ struct Stream {                     /* one (chain, algo) bit stream */
 };
 
 struct ChainBuf {
-    float *dphi = nullptr;          /* [W_hist | M_max]                           */
-    uint8_t *rssi = nullptr;
-    float *dphi_tmp = nullptr;      /* W_hist scratch for the history shift       */
-    uint8_t *rssi_tmp = nullptr;
-    LaneState *st_start = nullptr, *st_end = nullptr, *carry = nullptr;
+    float *dphi = nullptr;          /* [W | M_max]  post-FIR discriminator output  */
+    uint8_t *rssi = nullptr;        /* [W | M_max]                                 */
+    uint32_t *dbits = nullptr;      /* [W/32 | M_max/32] data bits                 */
+    uint32_t *sbits = nullptr;      /* [W/32 | M_max/32] time2 strobes             */
+    IirState *ia_start = nullptr, *ia_end = nullptr, *ia_carry = nullptr;
+    RlState *rl_start = nullptr, *rl_end = nullptr, *rl_carry = nullptr;
     uint32_t *rerun = nullptr;
+    /* time2 lanes */
+    uint32_t *t2_tail = nullptr, *t2_len = nullptr, *t2_sr = nullptr, *t2_agg_tail = nullptr, *t2_agg_len = nullptr;
     Stream s[WMB_N_ALGOS];
 };
 
@@ -105,16 +111,22 @@ struct wmb_ctx {
     /* geometry */
     size_t max_batch_bytes = 0;
     int64_t M_max = 0;
-    uint32_t W = 32768;             /* warm-up and retained history (decimated samples) */
+    uint32_t W = 32768;             /* retained history (decimated samples) = max warm-up */
+    uint32_t W_a = 32768;           /* warm-up of the clock-recovery lanes               */
+    uint32_t W_m[WMB_N_CHAINS] = {32768, 131072};   /* warm-up of the run-length lanes  */
     uint32_t C_fixed = 0;
     uint32_t lanes_max = 0;
-    uint32_t cap_words_t2 = 0, cap_words_rl = 0;
+    uint32_t t2_lanes_max = 0;
+    uint32_t cap_words_rl = 0;
+    size_t ring_events = 0;
+    std::vector<void *> dev_allocs, host_allocs;
+    uint8_t *d_tmp = nullptr;       /* scratch for the history slides                    */
     uint32_t cand_cap = 1u << 20;
     uint32_t frame_words_cap = 1u << 24;
 
     /* device buffers */
     uint8_t *d_in[2] = {nullptr, nullptr};
-    uint8_t *d_hist = nullptr, *d_hist_tmp = nullptr;
+    uint8_t *d_hist = nullptr;
     float *d_lut = nullptr;
     ChainBuf cb[WMB_N_CHAINS];
     uint32_t *d_errors = nullptr, *d_nfail = nullptr, *d_nwords = nullptr;
@@ -178,28 +190,48 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     return WMB_OK;
 }
 
-static int launch_k2(wmb_ctx *c, int chain, const K2Params &p)
+static int launch_k2a(wmb_ctx *c, int chain, const K2aParams &p)
 {
     const unsigned grid = (p.lanes + K2_THREADS - 1) / K2_THREADS;
-    if (chain == 0) k2_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, c->cs>>>(p);
-    else            k2_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, c->cs>>>(p);
+    if (chain == 0) k2a_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, c->cs>>>(p);
+    else            k2a_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, c->cs>>>(p);
+    k2a_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, c->cs>>>(p, c->d_nfail);
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches++;
+    c->st.kernel_launches += 2;
     return WMB_OK;
 }
 
-static int launch_k2_verify(wmb_ctx *c, const K2Params &p)
+static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p)
 {
-    const unsigned grid = (p.lanes + 255) / 256;
-    k2_verify_kernel<<<grid, 256, 0, c->cs>>>(p, c->d_nfail);
+    const unsigned grid = (p.lanes + K2_THREADS - 1) / K2_THREADS;
+    if (chain == 0) k2m_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, c->cs>>>(p);
+    else            k2m_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, c->cs>>>(p);
+    k2m_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, c->cs>>>(p, c->d_nfail);
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches++;
+    c->st.kernel_launches += 2;
+    return WMB_OK;
+}
+
+static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
+{
+    const unsigned grid = (p.lanes + 127) / 128;
+    if (chain == 0) {
+        k2t_count_kernel<ChainT1C1><<<grid, 128, 0, c->cs>>>(p);
+        k2t_scan_kernel<ChainT1C1><<<1, SCAN_THREADS, 0, c->cs>>>(p);
+        k2t_write_kernel<ChainT1C1><<<grid, 128, 0, c->cs>>>(p);
+    } else {
+        k2t_count_kernel<ChainS1><<<grid, 128, 0, c->cs>>>(p);
+        k2t_scan_kernel<ChainS1><<<1, SCAN_THREADS, 0, c->cs>>>(p);
+        k2t_write_kernel<ChainS1><<<grid, 128, 0, c->cs>>>(p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches += 3;
     return WMB_OK;
 }
 
 static int launch_k2c(wmb_ctx *c, const K2cParams &p)
 {
-    k2c_scan_kernel<<<1, 32, 0, c->cs>>>(p);
+    k2c_scan_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(p);
     k2c_compact_kernel<<<p.lanes, 128, 0, c->cs>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches += 2;
@@ -266,6 +298,33 @@ static uint32_t pick_chunk(const wmb_ctx *c, int64_t M)
     return (uint32_t)C;
 }
 
+template <typename T>
+static int dev_alloc(wmb_ctx *c, T **p, size_t count, bool zero = false)
+{
+    void *q = nullptr;
+    const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    if (cudaMalloc(&q, bytes) != cudaSuccess) return set_err(WMB_E_NOMEM, "cudaMalloc of %zu bytes failed", bytes);
+    if (zero && cudaMemset(q, 0, bytes) != cudaSuccess) return set_err(WMB_E_CUDA, "cudaMemset failed");
+    c->dev_allocs.push_back(q);
+    *p = (T *)q;
+    return WMB_OK;
+}
+
+template <typename T>
+static int host_alloc(wmb_ctx *c, T **p, size_t count)
+{
+    void *q = nullptr;
+    if (cudaMallocHost(&q, std::max<size_t>(count * sizeof(T), 16)) != cudaSuccess)
+        return set_err(WMB_E_NOMEM, "cudaMallocHost failed");
+    c->host_allocs.push_back(q);
+    *p = (T *)q;
+    return WMB_OK;
+}
+
+#define TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+#define K2T_WORDS_PER_LANE 128u      /* 4096 decimated samples per time2 lane */
+
 static int ctx_alloc(wmb_ctx *c)
 {
     if (c->allocated) return WMB_OK;
@@ -273,31 +332,26 @@ static int ctx_alloc(wmb_ctx *c)
     c->M_max = (int64_t)(c->max_batch_bytes / (2 * (size_t)d));
     const uint32_t C_min = c->C_fixed ? c->C_fixed : 8192;
     c->lanes_max = (uint32_t)(c->M_max / C_min + 2);
-    const size_t per_lane_slack_t2 = 8, per_lane_slack_rl = K2_EDGE_EMIT_CAP + 8;
-    const size_t words_t2 = (size_t)c->M_max / 4 + (size_t)c->lanes_max * per_lane_slack_t2 + 1024;
-    const size_t words_rl = (size_t)c->M_max / 4 + (size_t)c->lanes_max * per_lane_slack_rl + 1024;
-    c->cap_words_t2 = (uint32_t)std::min<size_t>(words_t2, 0xFFFFFFFFu);
+    c->t2_lanes_max = (uint32_t)(c->M_max / (32 * K2T_WORDS_PER_LANE) + 2);
+    const size_t words_rl = (size_t)c->M_max / 4 + (size_t)c->lanes_max * (K2_EDGE_EMIT_CAP + 8) + 1024;
     c->cap_words_rl = (uint32_t)std::min<size_t>(words_rl, 0xFFFFFFFFu);
+    c->ring_events = next_pow2((size_t)c->M_max / 4 + 65536 + WMB_MAXBITS);
 
-    const size_t in_bytes = c->max_batch_bytes + 4096;
-    CUDA_TRY(cudaMalloc((void **)&c->d_in[0], in_bytes));
-    CUDA_TRY(cudaMalloc((void **)&c->d_in[1], in_bytes));
-    const size_t hb = (size_t)k1_hist_bytes(d);
-    CUDA_TRY(cudaMalloc((void **)&c->d_hist, hb));
-    CUDA_TRY(cudaMalloc((void **)&c->d_hist_tmp, hb));
-    CUDA_TRY(cudaMemset(c->d_hist, 0, hb));
-    CUDA_TRY(cudaMalloc((void **)&c->d_lut, 2 * 4096 * sizeof(float)));
-    CUDA_TRY(cudaMalloc((void **)&c->d_errors, 64));
-    CUDA_TRY(cudaMemset(c->d_errors, 0, 64));
+    TRY(dev_alloc(c, &c->d_in[0], c->max_batch_bytes + 4096));
+    TRY(dev_alloc(c, &c->d_in[1], c->max_batch_bytes + 4096));
+    TRY(dev_alloc(c, &c->d_hist, (size_t)k1_hist_bytes(d), true));
+    TRY(dev_alloc(c, &c->d_tmp, std::max<size_t>((size_t)c->W * 4, (size_t)k1_hist_bytes(d))));
+    TRY(dev_alloc(c, &c->d_lut, 2 * 4096));
+    TRY(dev_alloc(c, &c->d_errors, 16, true));
     c->d_nfail = c->d_errors + 1;
     c->d_nwords = c->d_errors + 2;
-    CUDA_TRY(cudaMalloc((void **)&c->d_hdr, (size_t)c->cand_cap * sizeof(FrameHdr)));
-    CUDA_TRY(cudaMalloc((void **)&c->d_words, (size_t)c->frame_words_cap * 4));
-    CUDA_TRY(cudaMallocHost((void **)&c->h_small, 64));
-    CUDA_TRY(cudaMallocHost((void **)&c->h_sd, 4 * sizeof(StreamDev)));
-    CUDA_TRY(cudaMallocHost((void **)&c->h_cand, (size_t)c->cand_cap * 8));
-    CUDA_TRY(cudaMallocHost((void **)&c->h_hdr, (size_t)c->cand_cap * sizeof(FrameHdr)));
-    CUDA_TRY(cudaMallocHost((void **)&c->h_words, (size_t)c->frame_words_cap * 4));
+    TRY(dev_alloc(c, &c->d_hdr, c->cand_cap));
+    TRY(dev_alloc(c, &c->d_words, c->frame_words_cap));
+    TRY(host_alloc(c, &c->h_small, 16));
+    TRY(host_alloc(c, &c->h_sd, 4));
+    TRY(host_alloc(c, &c->h_cand, c->cand_cap));
+    TRY(host_alloc(c, &c->h_hdr, c->cand_cap));
+    TRY(host_alloc(c, &c->h_words, c->frame_words_cap));
 
     /* mixer look-up tables, built with the host libm exactly like the reference
      * (setup_lookup_tables_for_frequency_translation, rtl_wmbus.c:974-993) */
@@ -318,29 +372,39 @@ static int ctx_alloc(wmb_ctx *c)
         if (!(c->chains & (1u << ch))) continue;
         ChainBuf &b = c->cb[ch];
         const size_t n = (size_t)c->W + (size_t)c->M_max + 64;
-        CUDA_TRY(cudaMalloc((void **)&b.dphi, n * sizeof(float)));
-        CUDA_TRY(cudaMalloc((void **)&b.rssi, n));
-        CUDA_TRY(cudaMalloc((void **)&b.dphi_tmp, (size_t)c->W * sizeof(float)));
-        CUDA_TRY(cudaMalloc((void **)&b.rssi_tmp, c->W));
-        CUDA_TRY(cudaMalloc((void **)&b.st_start, (size_t)c->lanes_max * sizeof(LaneState)));
-        CUDA_TRY(cudaMalloc((void **)&b.st_end, (size_t)c->lanes_max * sizeof(LaneState)));
-        CUDA_TRY(cudaMalloc((void **)&b.carry, sizeof(LaneState)));
-        CUDA_TRY(cudaMalloc((void **)&b.rerun, (size_t)c->lanes_max * 4));
-        LaneState init;
-        lane_state_init(init, ch);
-        CUDA_TRY(cudaMemcpy(b.carry, &init, sizeof(init), cudaMemcpyHostToDevice));
+        TRY(dev_alloc(c, &b.dphi, n));
+        TRY(dev_alloc(c, &b.rssi, n));
+        TRY(dev_alloc(c, &b.dbits, n / 32 + 4, true));
+        TRY(dev_alloc(c, &b.sbits, n / 32 + 4, true));
+        TRY(dev_alloc(c, &b.ia_start, c->lanes_max));
+        TRY(dev_alloc(c, &b.ia_end, c->lanes_max));
+        TRY(dev_alloc(c, &b.ia_carry, 1));
+        TRY(dev_alloc(c, &b.rl_start, c->lanes_max));
+        TRY(dev_alloc(c, &b.rl_end, c->lanes_max));
+        TRY(dev_alloc(c, &b.rl_carry, 1));
+        TRY(dev_alloc(c, &b.rerun, c->lanes_max, true));
+        TRY(dev_alloc(c, &b.t2_tail, c->t2_lanes_max));
+        TRY(dev_alloc(c, &b.t2_len, c->t2_lanes_max));
+        TRY(dev_alloc(c, &b.t2_sr, c->t2_lanes_max));
+        TRY(dev_alloc(c, &b.t2_agg_tail, SCAN_THREADS));
+        TRY(dev_alloc(c, &b.t2_agg_len, SCAN_THREADS));
+        IirState ia;
+        iir_state_init(ia);
+        CUDA_TRY(cudaMemcpy(b.ia_carry, &ia, sizeof(ia), cudaMemcpyHostToDevice));
+        RlState rl;
+        rl_state_init(rl, ch);
+        CUDA_TRY(cudaMemcpy(b.rl_carry, &rl, sizeof(rl), cudaMemcpyHostToDevice));
         for (int a = 0; a < WMB_N_ALGOS; a++) {
             Stream &s = b.s[a];
-            const size_t words = a == WMB_ALGO_T2A ? c->cap_words_t2 : c->cap_words_rl;
-            CUDA_TRY(cudaMalloc((void **)&s.ev, words * 4));
-            CUDA_TRY(cudaMalloc((void **)&s.cnt, (size_t)c->lanes_max * 4));
-            CUDA_TRY(cudaMemset(s.cnt, 0, (size_t)c->lanes_max * 4));
-            CUDA_TRY(cudaMalloc((void **)&s.base, (size_t)c->lanes_max * 8));
-            s.ring_cap = next_pow2(words + WMB_MAXBITS + 64);
-            CUDA_TRY(cudaMalloc((void **)&s.ring, s.ring_cap * 8));
-            CUDA_TRY(cudaMalloc((void **)&s.sd, sizeof(StreamDev)));
-            CUDA_TRY(cudaMemset(s.sd, 0, sizeof(StreamDev)));
-            CUDA_TRY(cudaMalloc((void **)&s.cand, (size_t)c->cand_cap * 8));
+            const uint32_t nl = a == WMB_ALGO_T2A ? c->t2_lanes_max : c->lanes_max;
+            if (a == WMB_ALGO_RLA) TRY(dev_alloc(c, &s.ev, c->cap_words_rl));
+            TRY(dev_alloc(c, &s.cnt, nl, true));
+            TRY(dev_alloc(c, &s.base, nl));
+            s.ring_cap = c->ring_events;
+            TRY(dev_alloc(c, &s.ring, s.ring_cap));
+            TRY(dev_alloc(c, &s.sd, 1, true));
+            TRY(dev_alloc(c, &s.cand, c->cand_cap));
+            TRY(dev_alloc(c, &s.agg, SCAN_THREADS));
         }
     }
     c->allocated = true;
@@ -364,8 +428,19 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
     c->device = cuda_device;
     c->d = o->decimation ? o->decimation : 1;               /* rtl_wmbus.c:1350-1352: d==0 keeps every sample */
     c->chains = (o->t1c1_enabled ? 1u : 0u) | (o->s1_enabled ? 2u : 0u);
-    c->W = o->warmup_samples ? o->warmup_samples : (o->remove_dc ? 98304u : 32768u);
-    c->W = (c->W + 255) / 256 * 256;
+    /* warm-up (decimated samples) of the speculative lanes: the clock biquads need ~20 k
+     * samples to re-join the true trajectory bit for bit, the DC block
+     * another ~18 k in front of them (A.6); a run-length lane must reach back past the
+     * start of the telegram it may begin in (A.8: <= 28 k samples T1, <= 113 k S1). */
+    if (o->warmup_samples) {
+        c->W_a = c->W_m[0] = c->W_m[1] = (o->warmup_samples + 255) / 256 * 256;
+    } else {
+        c->W_a = o->remove_dc ? 98304u : 32768u;
+        c->W_m[0] = 32768u; c->W_m[1] = 131072u;
+    }
+    c->W = c->W_a;
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++)
+        if ((c->chains & (1u << ch)) && o->rla_enabled) c->W = std::max(c->W, c->W_m[ch]);
     c->manual = o->manual_frames != 0;
     c->C_fixed = o->chunk_samples ? (o->chunk_samples + 255) / 256 * 256 : 0;
     if (c->C_fixed && (c->C_fixed < 1024 || c->C_fixed > K2_MAX_CHUNK)) { delete c; return set_err(WMB_E_INVAL, "chunk_samples out of range"); }
@@ -391,19 +466,8 @@ extern "C" void wmb_destroy(wmb_ctx *c)
     cudaSetDevice(c->device);
     if (c->cs) cudaStreamSynchronize(c->cs);
     if (c->xs) cudaStreamSynchronize(c->xs);
-    for (int i = 0; i < 2; i++) cudaFree(c->d_in[i]);
-    cudaFree(c->d_hist); cudaFree(c->d_hist_tmp); cudaFree(c->d_lut); cudaFree(c->d_errors);
-    cudaFree(c->d_hdr); cudaFree(c->d_words);
-    cudaFreeHost(c->h_small); cudaFreeHost(c->h_sd); cudaFreeHost(c->h_cand); cudaFreeHost(c->h_hdr); cudaFreeHost(c->h_words);
-    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-        ChainBuf &b = c->cb[ch];
-        cudaFree(b.dphi); cudaFree(b.rssi); cudaFree(b.dphi_tmp); cudaFree(b.rssi_tmp);
-        cudaFree(b.st_start); cudaFree(b.st_end); cudaFree(b.carry); cudaFree(b.rerun);
-        for (int a = 0; a < WMB_N_ALGOS; a++) {
-            Stream &s = b.s[a];
-            cudaFree(s.ev); cudaFree(s.cnt); cudaFree(s.base); cudaFree(s.ring); cudaFree(s.sd); cudaFree(s.cand);
-        }
-    }
+    for (void *p : c->dev_allocs) cudaFree(p);
+    for (void *p : c->host_allocs) cudaFreeHost(p);
     for (int i = 0; i < 2; i++) { if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]); if (c->ev_k1done[i]) cudaEventDestroy(c->ev_k1done[i]); }
     for (int i = 0; i < 6; i++) if (c->ev_t[i]) cudaEventDestroy(c->ev_t[i]);
     if (c->cs) cudaStreamDestroy(c->cs);
@@ -415,30 +479,41 @@ extern "C" void wmb_destroy(wmb_ctx *c)
 /* one batch on the device                                                     */
 /* --------------------------------------------------------------------------- */
 
-static void fill_k2(const wmb_ctx *c, int ch, int64_t M, uint32_t C, K2Params &p)
+/* device-to-device slide of a [hist | batch] buffer: the last `hist` elements move in front
+ * of index 0 (element size es); goes through scratch when source and destination overlap */
+static int slide_history(wmb_ctx *c, void *buf, size_t es, int64_t hist, int64_t M)
 {
-    const ChainBuf &b = c->cb[ch];
-    memset(&p, 0, sizeof(p));
-    p.dphi = b.dphi + c->W;
-    p.rssi = b.rssi + c->W;
-    p.M = M;
-    p.hist = c->hist_m;
-    p.C = C;
-    p.W = c->W;
-    p.lanes = (uint32_t)((M + C - 1) / C);
-    p.cap_t2 = C / 4 + 8;
-    p.cap_rl = C / 4 + K2_EDGE_EMIT_CAP + 8;
-    p.ev_t2 = b.s[WMB_ALGO_T2A].ev; p.ev_rl = b.s[WMB_ALGO_RLA].ev;
-    p.cnt_t2 = b.s[WMB_ALGO_T2A].cnt; p.cnt_rl = b.s[WMB_ALGO_RLA].cnt;
-    p.st_start = b.st_start; p.st_end = b.st_end; p.carry = b.carry;
-    p.rerun = b.rerun;
-    p.errors = c->d_errors;
-    p.dc = c->o.remove_dc; p.rla = c->o.rla_enabled; p.t2 = c->o.t2_enabled;
+    uint8_t *p = (uint8_t *)buf;
+    if (M >= hist) {
+        CUDA_TRY(cudaMemcpyAsync(p, p + (size_t)M * es, (size_t)hist * es, cudaMemcpyDeviceToDevice, c->cs));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(c->d_tmp, p + (size_t)M * es, (size_t)hist * es, cudaMemcpyDeviceToDevice, c->cs));
+        CUDA_TRY(cudaMemcpyAsync(p, c->d_tmp, (size_t)hist * es, cudaMemcpyDeviceToDevice, c->cs));
+    }
+    return WMB_OK;
 }
 
-/* Enqueue K1 + K2 (+ verification rounds) for one batch whose bytes are at `src`
- * (device memory).  On return everything up to a verified bit-sync result is done and
- * the compaction has been enqueued. */
+/* run `launch(mode)` for all chains, then re-run refuted lanes until every lane's start state
+ * equals its predecessor's end state */
+template <typename F>
+static int verified_pass(wmb_ctx *c, uint32_t lanes, F launch)
+{
+    CUDA_TRY(cudaMemsetAsync(c->d_nfail, 0, 4, c->cs));
+    TRY(launch(0u));
+    for (int round = 0;; round++) {
+        CUDA_TRY(cudaMemcpyAsync(&c->h_small[1], c->d_nfail, 4, cudaMemcpyDeviceToHost, c->cs));
+        CUDA_TRY(cudaStreamSynchronize(c->cs));
+        const uint32_t nfail = c->h_small[1];
+        if (!nfail) return WMB_OK;
+        if (round > (int)lanes + 2) return set_err(WMB_E_STATE, "internal: lane verification does not converge");
+        c->st.lanes_rerun += nfail;
+        c->st.lanes_run += nfail;
+        CUDA_TRY(cudaMemsetAsync(c->d_nfail, 0, 4, c->cs));
+        TRY(launch(1u));
+    }
+}
+
+/* Enqueue the whole device pass for one batch whose bytes are at `src` (device memory). */
 static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_ctx_buffer)
 {
     const uint32_t d = c->d;
@@ -448,6 +523,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
     if (M <= 0) return WMB_OK;
     (void)src_is_ctx_buffer;
 
+    /* ---- K1: demod ---- */
     CUDA_TRY(cudaEventRecord(c->ev_t[0], c->cs));
     K1Params k1;
     memset(&k1, 0, sizeof(k1));
@@ -462,8 +538,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
         k1.dphi[ch] = c->cb[ch].dphi ? c->cb[ch].dphi + c->W : nullptr;
         k1.rssi[ch] = c->cb[ch].rssi ? c->cb[ch].rssi + c->W : nullptr;
     }
-    int rc = launch_k1(c, k1);
-    if (rc) return rc;
+    TRY(launch_k1(c, k1));
     CUDA_TRY(cudaEventRecord(c->ev_t[1], c->cs));
 
     /* keep the last k1_hist_bytes() of the stream for the next batch's tile 0 */
@@ -472,9 +547,9 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
         if (nbytes >= hb) {
             CUDA_TRY(cudaMemcpyAsync(c->d_hist, src + nbytes - hb, hb, cudaMemcpyDeviceToDevice, c->cs));
         } else {
-            CUDA_TRY(cudaMemcpyAsync(c->d_hist_tmp, c->d_hist + nbytes, hb - nbytes, cudaMemcpyDeviceToDevice, c->cs));
-            CUDA_TRY(cudaMemcpyAsync(c->d_hist_tmp + (hb - nbytes), src, nbytes, cudaMemcpyDeviceToDevice, c->cs));
-            CUDA_TRY(cudaMemcpyAsync(c->d_hist, c->d_hist_tmp, hb, cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(c->d_tmp, c->d_hist + nbytes, hb - nbytes, cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(c->d_tmp + (hb - nbytes), src, nbytes, cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(c->d_hist, c->d_tmp, hb, cudaMemcpyDeviceToDevice, c->cs));
         }
         c->hist_iq = std::min<int64_t>(c->hist_iq + n_iq, (int64_t)hb / 2);
     }
@@ -485,76 +560,107 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
     const uint32_t lanes = (uint32_t)((M + C - 1) / C);
     if (lanes > c->lanes_max) return set_err(WMB_E_INVAL, "internal: %u lanes > %u", lanes, c->lanes_max);
     const bool any_sync = c->o.rla_enabled || c->o.t2_enabled;
+    const int64_t wofs = c->W / 32;                       /* word offset of batch sample 0 */
 
-    K2Params k2[WMB_N_CHAINS];
     if (any_sync) {
-        CUDA_TRY(cudaMemsetAsync(c->d_nfail, 0, 4, c->cs));
+        /* ---- K2a: clock-recovery lanes (both chains), verified ---- */
+        K2aParams ka[WMB_N_CHAINS];
         for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
             if (!(c->chains & (1u << ch))) continue;
-            fill_k2(c, ch, M, C, k2[ch]);
-            if ((uint64_t)k2[ch].lanes * k2[ch].cap_t2 > c->cap_words_t2 ||
-                (uint64_t)k2[ch].lanes * k2[ch].cap_rl > c->cap_words_rl)
-                return set_err(WMB_E_INVAL, "internal: event buffers too small for C=%u", C);
-            k2[ch].mode = 0;
-            if ((rc = launch_k2(c, ch, k2[ch]))) return rc;
-            if ((rc = launch_k2_verify(c, k2[ch]))) return rc;
-            c->st.lanes_run += k2[ch].lanes;
+            ChainBuf &b = c->cb[ch];
+            K2aParams &p = ka[ch];
+            memset(&p, 0, sizeof(p));
+            p.dphi = b.dphi + c->W; p.M = M; p.hist = c->hist_m; p.C = C; p.W = c->W_a; p.lanes = lanes;
+            p.dbits = b.dbits + wofs; p.sbits = b.sbits + wofs;
+            p.st_start = b.ia_start; p.st_end = b.ia_end; p.carry = b.ia_carry; p.rerun = b.rerun;
+            p.dc = c->o.remove_dc; p.t2 = c->o.t2_enabled;
+            c->st.lanes_run += lanes;
         }
-        /* re-run refuted lanes until every start state is confirmed */
-        for (int round = 0;; round++) {
-            CUDA_TRY(cudaMemcpyAsync(&c->h_small[1], c->d_nfail, 4, cudaMemcpyDeviceToHost, c->cs));
-            CUDA_TRY(cudaStreamSynchronize(c->cs));
-            const uint32_t nfail = c->h_small[1];
-            if (!nfail) break;
-            if (round > (int)lanes + 2) return set_err(WMB_E_STATE, "internal: lane verification does not converge");
-            c->st.lanes_rerun += nfail;
-            c->st.lanes_run += nfail;
-            CUDA_TRY(cudaMemsetAsync(c->d_nfail, 0, 4, c->cs));
+        TRY(verified_pass(c, lanes, [&](uint32_t mode) {
             for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
                 if (!(c->chains & (1u << ch))) continue;
-                k2[ch].mode = 1;
-                if ((rc = launch_k2(c, ch, k2[ch]))) return rc;
-                if ((rc = launch_k2_verify(c, k2[ch]))) return rc;
+                ka[ch].mode = mode;
+                TRY(launch_k2a(c, ch, ka[ch]));
+            }
+            return (int)WMB_OK;
+        }));
+        for (int ch = 0; ch < WMB_N_CHAINS; ch++)
+            if (c->chains & (1u << ch))
+                CUDA_TRY(cudaMemcpyAsync(c->cb[ch].ia_carry, c->cb[ch].ia_end + (lanes - 1), sizeof(IirState),
+                                         cudaMemcpyDeviceToDevice, c->cs));
+
+        /* ---- K2t: time2 bit streams straight into the rings ---- */
+        if (c->o.t2_enabled) {
+            for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+                if (!(c->chains & (1u << ch))) continue;
+                ChainBuf &b = c->cb[ch];
+                Stream &s = b.s[WMB_ALGO_T2A];
+                K2tParams p;
+                memset(&p, 0, sizeof(p));
+                p.dbits = b.dbits + wofs; p.sbits = b.sbits + wofs; p.rssi = b.rssi + c->W;
+                p.M = M; p.Cw = K2T_WORDS_PER_LANE;
+                const uint32_t nw = (uint32_t)((M + 31) / 32);
+                p.lanes = (nw + p.Cw - 1) / p.Cw;
+                if (p.lanes > c->t2_lanes_max) return set_err(WMB_E_INVAL, "internal: time2 lanes");
+                p.cnt = s.cnt; p.tail = b.t2_tail; p.tail_len = b.t2_len; p.base = s.base; p.sr_start = b.t2_sr;
+                p.agg_cnt = s.agg; p.agg_tail = b.t2_agg_tail; p.agg_len = b.t2_agg_len;
+                p.m_base = (int64_t)c->m_consumed;
+                p.ring = s.ring; p.ring_mask = s.ring_cap - 1; p.sd = s.sd; p.cand = s.cand; p.cand_cap = c->cand_cap;
+                TRY(launch_k2t(c, ch, p));
+            }
+        }
+
+        /* ---- K2m: run-length lanes, verified; then compaction into the rings ---- */
+        if (c->o.rla_enabled) {
+            K2mParams km[WMB_N_CHAINS];
+            for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+                if (!(c->chains & (1u << ch))) continue;
+                ChainBuf &b = c->cb[ch];
+                K2mParams &p = km[ch];
+                memset(&p, 0, sizeof(p));
+                p.dbits = b.dbits + wofs; p.rssi = b.rssi + c->W; p.M = M; p.hist = c->hist_m;
+                p.C = C; p.W = c->W_m[ch]; p.lanes = lanes;
+                p.cap = C / 4 + K2_EDGE_EMIT_CAP + 8;
+                if ((uint64_t)lanes * p.cap > c->cap_words_rl) return set_err(WMB_E_INVAL, "internal: event buffers too small for C=%u", C);
+                p.ev = b.s[WMB_ALGO_RLA].ev; p.cnt = b.s[WMB_ALGO_RLA].cnt;
+                p.st_start = b.rl_start; p.st_end = b.rl_end; p.carry = b.rl_carry; p.rerun = b.rerun;
+                p.errors = c->d_errors;
+                c->st.lanes_run += lanes;
+            }
+            TRY(verified_pass(c, lanes, [&](uint32_t mode) {
+                for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+                    if (!(c->chains & (1u << ch))) continue;
+                    km[ch].mode = mode;
+                    TRY(launch_k2m(c, ch, km[ch]));
+                }
+                return (int)WMB_OK;
+            }));
+            for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+                if (!(c->chains & (1u << ch))) continue;
+                ChainBuf &b = c->cb[ch];
+                Stream &s = b.s[WMB_ALGO_RLA];
+                CUDA_TRY(cudaMemcpyAsync(b.rl_carry, b.rl_end + (lanes - 1), sizeof(RlState), cudaMemcpyDeviceToDevice, c->cs));
+                K2cParams q;
+                memset(&q, 0, sizeof(q));
+                q.ev = s.ev; q.cnt = s.cnt; q.base = s.base; q.lanes = lanes; q.cap = km[ch].cap; q.C = C;
+                q.m_base = (int64_t)c->m_consumed;
+                q.ring = s.ring; q.ring_mask = s.ring_cap - 1; q.sd = s.sd; q.cand = s.cand; q.cand_cap = c->cand_cap;
+                q.agg = s.agg;
+                TRY(launch_k2c(c, q));
             }
         }
     }
     CUDA_TRY(cudaEventRecord(c->ev_t[2], c->cs));
 
-    /* compaction into the stream rings + candidates */
-    if (any_sync) {
-        for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-            if (!(c->chains & (1u << ch))) continue;
-            ChainBuf &b = c->cb[ch];
-            for (int a = 0; a < WMB_N_ALGOS; a++) {
-                if ((a == WMB_ALGO_RLA && !c->o.rla_enabled) || (a == WMB_ALGO_T2A && !c->o.t2_enabled)) continue;
-                Stream &s = b.s[a];
-                K2cParams q;
-                memset(&q, 0, sizeof(q));
-                q.ev = s.ev; q.cnt = s.cnt; q.base = s.base;
-                q.lanes = lanes; q.cap = a == WMB_ALGO_T2A ? k2[ch].cap_t2 : k2[ch].cap_rl; q.C = C;
-                q.m_base = (int64_t)c->m_consumed;
-                q.ring = s.ring; q.ring_mask = s.ring_cap - 1;
-                q.sd = s.sd; q.cand = s.cand; q.cand_cap = c->cand_cap;
-                if ((rc = launch_k2c(c, q))) return rc;
-            }
-            /* exact state at the end of this batch becomes the next batch's lane-0 start */
-            CUDA_TRY(cudaMemcpyAsync(b.carry, b.st_end + (lanes - 1), sizeof(LaneState), cudaMemcpyDeviceToDevice, c->cs));
-        }
-    }
-
-    /* slide the dphi / rssi history: the last W samples move in front of index 0 */
+    /* slide the histories: the last W samples move in front of index 0 */
     for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
         if (!(c->chains & (1u << ch))) continue;
         ChainBuf &b = c->cb[ch];
-        const int64_t W = c->W;
-        if (M >= W) {
-            CUDA_TRY(cudaMemcpyAsync(b.dphi, b.dphi + M, (size_t)W * 4, cudaMemcpyDeviceToDevice, c->cs));
-            CUDA_TRY(cudaMemcpyAsync(b.rssi, b.rssi + M, (size_t)W, cudaMemcpyDeviceToDevice, c->cs));
-        } else {
-            CUDA_TRY(cudaMemcpyAsync(b.dphi_tmp, b.dphi + M, (size_t)W * 4, cudaMemcpyDeviceToDevice, c->cs));
-            CUDA_TRY(cudaMemcpyAsync(b.dphi, b.dphi_tmp, (size_t)W * 4, cudaMemcpyDeviceToDevice, c->cs));
-            CUDA_TRY(cudaMemcpyAsync(b.rssi_tmp, b.rssi + M, (size_t)W, cudaMemcpyDeviceToDevice, c->cs));
-            CUDA_TRY(cudaMemcpyAsync(b.rssi, b.rssi_tmp, (size_t)W, cudaMemcpyDeviceToDevice, c->cs));
+        TRY(slide_history(c, b.dphi, 4, c->W, M));
+        TRY(slide_history(c, b.rssi, 1, c->W, M));
+        if (any_sync && M % 32 == 0) {                  /* only a final (flush) batch can be ragged */
+            TRY(slide_history(c, b.dbits, 4, c->W / 32, M / 32));
+            TRY(slide_history(c, b.sbits, 4, c->W / 32, M / 32));
         }
     }
     CUDA_TRY(cudaEventRecord(c->ev_t[3], c->cs));
@@ -968,9 +1074,12 @@ extern "C" int wmb_reset(wmb_ctx *c)
         for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
             if (!(c->chains & (1u << ch))) continue;
             ChainBuf &b = c->cb[ch];
-            LaneState init;
-            lane_state_init(init, ch);
-            CUDA_TRY(cudaMemcpy(b.carry, &init, sizeof(init), cudaMemcpyHostToDevice));
+            IirState ia;
+            iir_state_init(ia);
+            CUDA_TRY(cudaMemcpy(b.ia_carry, &ia, sizeof(ia), cudaMemcpyHostToDevice));
+            RlState rl;
+            rl_state_init(rl, ch);
+            CUDA_TRY(cudaMemcpy(b.rl_carry, &rl, sizeof(rl), cudaMemcpyHostToDevice));
             for (int a = 0; a < WMB_N_ALGOS; a++) {
                 Stream &s = b.s[a];
                 CUDA_TRY(cudaMemsetAsync(s.sd, 0, sizeof(StreamDev), c->cs));

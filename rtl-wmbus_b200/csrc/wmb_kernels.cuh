@@ -8,16 +8,14 @@
  *       parallel: the only history a sample needs is bounded (box 16 input samples,
  *       discriminator 1, FIR 45, RSSI ~16 decimated samples), so each tile
  *       recomputes a 64-sample halo.           rtl_wmbus.c:1310-1352, :1038-1068
- *   K2  bit-sync lanes: the sequential recurrences (DC block, the three clock
- *       biquads, the clock-lock stencil, the run-length deglitch/PI loop and both
- *       access-code shift registers) run one chunk per thread, each thread first
- *       re-running a warm-up stretch from a cold state; the state it reaches at
- *       its chunk start is later compared with its predecessor's end state
- *       (k2_verify) and refuted lanes are re-run from the exact state, so the
- *       result is exact by induction from the stream start. rtl_wmbus.c:1070-1115,
- *                                                            :617-852
- *   K2c prefix-sum + compaction of the per-lane bit events into one ring per
- *       (chain, algorithm) stream, collecting access-code matches.
+ *   K2  bit sync (wmb_bitsync.cuh): the sequential recurrences run one chunk per
+ *       thread ("lane"), each lane first re-running a warm-up stretch from a cold
+ *       state; the state it reaches at its chunk start is compared with its
+ *       predecessor's end state and refuted lanes are re-run from the exact state, so
+ *       the result is exact by induction from the stream start.
+ *                                            rtl_wmbus.c:1070-1115, :617-852
+ *   K2c prefix-sum + compaction of the per-lane run-length bit events into the
+ *       stream ring, collecting access-code matches.
  *   K3  frame gather: for every access-code match, the bits that follow it.
  *
  * The kernels are written as phase functions over an explicit (block, thread) index
@@ -317,220 +315,12 @@ __global__ void __launch_bounds__(K1_THREADS) k1_demod_kernel(const K1Params p)
 }
 #endif /* !WMB_HOSTSIM */
 
-/* =========================================================================== */
-/* K2: bit-sync lanes                                                          */
-/* =========================================================================== */
-
-struct K2Params {
-    const float   *dphi;        /* index 0 = batch sample 0; [-hist, M) readable            */
-    const uint8_t *rssi;
-    int64_t  M;                 /* decimated samples in this batch                          */
-    int64_t  hist;              /* valid samples before batch sample 0                      */
-    uint32_t C, W;              /* chunk and warm-up length                                 */
-    uint32_t lanes;
-    uint32_t cap_t2, cap_rl;    /* per-lane event capacity                                  */
-    uint32_t *ev_t2, *ev_rl;    /* [lanes * cap]                                            */
-    uint32_t *cnt_t2, *cnt_rl;  /* [lanes]                                                  */
-    LaneState *st_start;        /* state each lane used at its chunk start                  */
-    LaneState *st_end;          /* state each lane reached at its chunk end                 */
-    const LaneState *carry;     /* exact state at batch sample 0                            */
-    uint32_t *rerun;            /* [lanes] set by k2_verify                                 */
-    uint32_t *errors;           /* bit0 event overflow, bit1 run-length loop guard          */
-    uint32_t mode;              /* 0: speculative pass over all lanes, 1: re-run flagged    */
-    uint32_t dc, rla, t2;       /* -o, !(-r 0), !(-t 0)                                     */
-};
-
-struct K2Out { uint32_t *ev; uint32_t cap; uint32_t n; uint32_t overflow; };
-
-WMB_D void k2_emit(K2Out &o, bool live, uint32_t off, uint32_t rssi, uint32_t rst, uint32_t sync, uint32_t bit)
-{
-    if (!live) return;
-    if (o.n < o.cap) o.ev[o.n] = EV_LOCAL(off, rssi, rst, sync, bit);
-    else o.overflow = 1;
-    o.n++;
-}
-
-/* one decimated sample through the sequential part of a chain */
-template <class CH>
-WMB_D void k2_step(const K2Params &p, LaneState &s, float x, int64_t m, uint32_t off, bool live,
-                   K2Out &o_t2, K2Out &o_rl, uint32_t &err)
-{
-    const float *cf = (CH::ID == 0) ? c_iir_t1c1 : c_iir_s1;
-    if (p.dc) {                                              /* rtl_wmbus.c:501 / :511 */
-        const float alpha = 0.999f, cdc = (1.f + 0.999f) / 2.f;
-        const float y = wmb_fadd(wmb_fmul(cdc, wmb_fsub(x, s.dc_x)), wmb_fmul(alpha, s.dc_y));
-        s.dc_x = x; s.dc_y = y; x = y;
-    }
-    const uint32_t bit = (x >= 0.0f) ? 1u : 0u;              /* rtl_wmbus.c:1059 */
-
-    if (p.rla) {
-        s.rl_raw = ((s.rl_raw << 1) | bit) & CH::RAW_MASK;
-        uint32_t st;
-        if (CH::ID == 0) st = (wmb_popc(s.rl_raw) >= 3) ? 1u : 0u;         /* deglitch_filter_t1_c1 */
-        else             st = (0xFEEAu >> s.rl_raw) & 1u;                  /* deglitch_filter_s1    */
-        const uint32_t level = s.rl_flags & 1u;
-        if (st == level) {
-            s.rl_run++;
-        } else {
-            bool reset = false;
-            int n = 0;
-            if (CH::ID == 0) {                               /* rtl_wmbus.c:742-796 */
-                if (s.rl_run < 5) reset = true;
-                else {
-                    int rl = s.rl_run * 256;
-                    const int half = s.rl_a / 2;
-                    if (rl <= half) reset = true;
-                    else if (s.rl_a <= 0) { reset = true; err |= 2u; }     /* reference would spin */
-                    else {
-                        uint32_t rssi = 0;
-                        bool have = false;
-                        while (rl > half) {
-                            rl -= s.rl_a;
-                            s.rl_sr = ((s.rl_sr << 1) | level) & CH::CODE_MASK;
-                            if (n < K2_EDGE_EMIT_CAP) {
-                                if (live && !have) { rssi = p.rssi[m]; have = true; }
-                                k2_emit(o_rl, live, off, rssi, (s.rl_flags >> 1) & 1u, s.rl_sr == CH::CODE, level);
-                                s.rl_flags &= ~2u;
-                            }
-                            n++;
-                        }
-                        s.rl_b += rl;
-                        s.rl_a += (rl + s.rl_b / 16) / (32 * n);
-                    }
-                }
-                if (reset) { s.rl_a = 8 * 256; s.rl_b = 0; }
-            } else {                                         /* rtl_wmbus.c:655-698 */
-                const int spb = (s.rl_a + s.rl_b) / 2;
-                const int half = spb / 2;
-                const int run = s.rl_run;
-                if (spb <= 12 || spb >= 36) reset = true;
-                else if (run <= half) reset = true;
-                else {
-                    int rl = run;
-                    uint32_t rssi = 0;
-                    bool have = false;
-                    while (rl > half) {
-                        rl -= spb;
-                        s.rl_sr = ((s.rl_sr << 1) | level) & CH::CODE_MASK;
-                        if (n < K2_EDGE_EMIT_CAP) {
-                            if (live && !have) { rssi = p.rssi[m]; have = true; }
-                            k2_emit(o_rl, live, off, rssi, (s.rl_flags >> 1) & 1u, s.rl_sr == CH::CODE, level);
-                            s.rl_flags &= ~2u;
-                        }
-                        n++;
-                    }
-                    if (level) s.rl_b = run / n; else s.rl_a = run / n;
-                }
-                if (reset) { s.rl_a = 24; s.rl_b = 24; }
-            }
-            if (reset) {                                     /* runlength_algorithm_reset_* */
-                s.rl_raw = 0; s.rl_sr = 0;
-                s.rl_flags = 2u;                             /* decoder reset: cut frames here */
-            }
-            s.rl_flags = (s.rl_flags & ~1u) | st;
-            s.rl_run = 1;
-        }
-    }
-
-    if (p.t2) {                                              /* rtl_wmbus.c:1089-1111, iir.h:59-74 */
-        float v = wmb_fmul(x, x);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const float b1 = cf[4 * k], b2 = cf[4 * k + 1], a1 = cf[4 * k + 2], a2 = cf[4 * k + 3];
-            const float h1 = s.h[2 * k], h2 = s.h[2 * k + 1];
-            const float h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a1, h1), wmb_fmul(a2, h2)));
-            v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b1, h1)), wmb_fmul(b2, h2));
-            s.h[2 * k + 1] = h1; s.h[2 * k] = h0;
-        }
-        v = wmb_fmul(v, c_iir_gain);
-        const uint32_t clk = (v >= 0.0f) ? 1u : 0u;
-        const uint32_t win = ((s.clk3 << 1) | clk) & 0xFu;  /* clk[m-3..m] */
-        s.clk3 = win & 7u;
-        if (win == 0x7u) {                                   /* low, high, high, high: sample now */
-            s.t2_sr = ((s.t2_sr << 1) | bit) & CH::CODE_MASK;
-            if (live) k2_emit(o_t2, true, off, p.rssi[m], 0u, s.t2_sr == CH::CODE, bit);
-        }
-    }
-}
-
-template <class CH>
-WMB_D void k2_lane(const K2Params &p, uint32_t lane)
-{
-    if (lane >= p.lanes) return;
-    const int64_t s0 = (int64_t)lane * p.C;
-    const int64_t e0 = (s0 + p.C < p.M) ? s0 + p.C : p.M;
-    LaneState st;
-    int64_t m;
-    if (p.mode == 0) {
-        if (lane == 0) { st = *p.carry; m = 0; }
-        else {
-            lane_state_init(st, CH::ID);
-            m = s0 - (int64_t)p.W;
-            if (m < -p.hist) m = -p.hist;
-        }
-    } else {
-        if (lane == 0 || !p.rerun[lane]) return;
-        st = p.st_end[lane - 1];
-        m = s0;
-    }
-    K2Out o_t2 = { p.ev_t2 + (size_t)lane * p.cap_t2, p.cap_t2, 0, 0 };
-    K2Out o_rl = { p.ev_rl + (size_t)lane * p.cap_rl, p.cap_rl, 0, 0 };
-    uint32_t err = 0;
-    for (; m < s0; m++) k2_step<CH>(p, st, p.dphi[m], m, 0, false, o_t2, o_rl, err);
-    p.st_start[lane] = st;
-    for (; m < e0; m++) k2_step<CH>(p, st, p.dphi[m], m, (uint32_t)(m - s0), true, o_t2, o_rl, err);
-    p.st_end[lane] = st;
-    p.cnt_t2[lane] = o_t2.n < o_t2.cap ? o_t2.n : o_t2.cap;
-    p.cnt_rl[lane] = o_rl.n < o_rl.cap ? o_rl.n : o_rl.cap;
-    if (o_t2.overflow || o_rl.overflow) err |= 1u;
-    if (err) {
-#ifdef WMB_HOSTSIM
-        *p.errors |= err;
-#else
-        atomicOr(p.errors, err);
-#endif
-    }
-}
-
-WMB_D bool lane_state_equal(const LaneState &a, const LaneState &b, const K2Params &p)
-{
-    bool eq = true;
-    if (p.dc) eq = eq && wmb_f2u(a.dc_x) == wmb_f2u(b.dc_x) && wmb_f2u(a.dc_y) == wmb_f2u(b.dc_y);
-    if (p.t2) {
-        for (int i = 0; i < 6; i++) eq = eq && wmb_f2u(a.h[i]) == wmb_f2u(b.h[i]);
-        eq = eq && a.clk3 == b.clk3 && a.t2_sr == b.t2_sr;
-    }
-    if (p.rla)
-        eq = eq && a.rl_run == b.rl_run && a.rl_a == b.rl_a && a.rl_b == b.rl_b &&
-             a.rl_flags == b.rl_flags && a.rl_raw == b.rl_raw && a.rl_sr == b.rl_sr;
-    return eq;
-}
-
-/* flags lanes whose speculative start state differs from the predecessor's end state */
-WMB_D void k2_verify_lane(const K2Params &p, uint32_t lane, uint32_t *n_fail)
-{
-    if (lane >= p.lanes) return;
-    uint32_t bad = 0;
-    if (lane > 0 && !lane_state_equal(p.st_start[lane], p.st_end[lane - 1], p)) bad = 1;
-    p.rerun[lane] = bad;
-    if (bad) {
-#ifdef WMB_HOSTSIM
-        (*n_fail)++;
-#else
-        atomicAdd(n_fail, 1u);
-#endif
-    }
-}
+#include "wmb_bitsync.cuh"
 
 /* =========================================================================== */
 /* K2c: per-stream prefix sum, compaction into the stream ring, candidates     */
 /* =========================================================================== */
 
-struct StreamDev {                  /* device-resident bookkeeping of one (chain, algo) stream */
-    uint64_t total;                 /* events appended so far (== next ordinal)            */
-    uint32_t n_cand;                /* candidates collected in this batch                  */
-    uint32_t cand_overflow;
-};
 
 struct K2cParams {
     const uint32_t *ev;             /* lane-local events [lanes * cap]                     */
@@ -541,14 +331,30 @@ struct K2cParams {
     uint64_t *ring; uint64_t ring_mask;
     StreamDev *sd;
     uint64_t *cand; uint32_t cand_cap;      /* out: ordinals of access-code matches        */
+    uint64_t *agg;                  /* [SCAN_THREADS] scan scratch                         */
 };
 
-/* single thread: lanes is at most a few 10^4 */
-WMB_D void k2c_scan(const K2cParams &p)
+/* exclusive scan of the lane counts, same three-phase scheme as k2t_scan_* */
+WMB_D void k2c_scan_a(const K2cParams &p, uint32_t t)
+{
+    const uint32_t per = scan_per_thread(p.lanes);
+    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
+    uint64_t cnt = 0;
+    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) cnt += p.cnt[l];
+    p.agg[t] = cnt;
+}
+WMB_D void k2c_scan_b(const K2cParams &p)
 {
     uint64_t acc = p.sd->total;
-    for (uint32_t l = 0; l < p.lanes; l++) { p.base[l] = acc; acc += p.cnt[l]; }
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) { const uint64_t c = p.agg[t]; p.agg[t] = acc; acc += c; }
     p.sd->total = acc;
+}
+WMB_D void k2c_scan_c(const K2cParams &p, uint32_t t)
+{
+    const uint32_t per = scan_per_thread(p.lanes);
+    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
+    uint64_t acc = p.agg[t];
+    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) { p.base[l] = acc; acc += p.cnt[l]; }
 }
 
 WMB_D void k2c_compact(const K2cParams &p, uint32_t lane, int tid, int nthr)
@@ -701,15 +507,44 @@ WMB_D void k3_copy(const K3Params &p, uint32_t i, int tid, int nthr)
 #ifndef WMB_HOSTSIM
 /* ---- __global__ wrappers ---- */
 template <class CH>
-__global__ void __launch_bounds__(K2_THREADS) k2_lanes_kernel(const K2Params p)
+__global__ void __launch_bounds__(K2_THREADS) k2a_lanes_kernel(const K2aParams p)
 {
-    k2_lane<CH>(p, blockIdx.x * blockDim.x + threadIdx.x);
+    k2a_lane<CH>(p, blockIdx.x * blockDim.x + threadIdx.x);
 }
-__global__ void k2_verify_kernel(const K2Params p, uint32_t *n_fail)
+__global__ void k2a_verify_kernel(const K2aParams p, uint32_t *n_fail)
 {
-    k2_verify_lane(p, blockIdx.x * blockDim.x + threadIdx.x, n_fail);
+    k2a_verify_lane(p, blockIdx.x * blockDim.x + threadIdx.x, n_fail);
 }
-__global__ void k2c_scan_kernel(const K2cParams p) { if (threadIdx.x == 0 && blockIdx.x == 0) k2c_scan(p); }
+template <class CH>
+__global__ void k2t_count_kernel(const K2tParams p) { k2t_count<CH>(p, blockIdx.x * blockDim.x + threadIdx.x); }
+template <class CH>
+__global__ void __launch_bounds__(SCAN_THREADS) k2t_scan_kernel(const K2tParams p)
+{
+    k2t_scan_a<CH>(p, threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) k2t_scan_b<CH>(p);
+    __syncthreads();
+    k2t_scan_c<CH>(p, threadIdx.x);
+}
+template <class CH>
+__global__ void k2t_write_kernel(const K2tParams p) { k2t_write<CH>(p, blockIdx.x * blockDim.x + threadIdx.x); }
+template <class CH>
+__global__ void __launch_bounds__(K2_THREADS) k2m_lanes_kernel(const K2mParams p)
+{
+    k2m_lane<CH>(p, blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void k2m_verify_kernel(const K2mParams p, uint32_t *n_fail)
+{
+    k2m_verify_lane(p, blockIdx.x * blockDim.x + threadIdx.x, n_fail);
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k2c_scan_kernel(const K2cParams p)
+{
+    k2c_scan_a(p, threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) k2c_scan_b(p);
+    __syncthreads();
+    k2c_scan_c(p, threadIdx.x);
+}
 __global__ void k2c_compact_kernel(const K2cParams p) { k2c_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
 __global__ void k3_size_kernel(const K3Params p) { k3_size(p, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void k3_offsets_kernel(const K3Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) k3_offsets(p); }

@@ -36,26 +36,50 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     return WMB_OK;
 }
 
-static int launch_k2(wmb_ctx *c, int chain, const K2Params &p)
+static int launch_k2a(wmb_ctx *c, int chain, const K2aParams &p)
 {
     for (uint32_t lane = 0; lane < p.lanes; lane++) {
-        if (chain == 0) k2_lane<ChainT1C1>(p, lane);
-        else            k2_lane<ChainS1>(p, lane);
+        if (chain == 0) k2a_lane<ChainT1C1>(p, lane);
+        else            k2a_lane<ChainS1>(p, lane);
     }
-    c->st.kernel_launches++;
+    for (uint32_t lane = 0; lane < p.lanes; lane++) k2a_verify_lane(p, lane, c->d_nfail);
+    c->st.kernel_launches += 2;
     return WMB_OK;
 }
 
-static int launch_k2_verify(wmb_ctx *c, const K2Params &p)
+static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p)
 {
-    for (uint32_t lane = 0; lane < p.lanes; lane++) k2_verify_lane(p, lane, c->d_nfail);
-    c->st.kernel_launches++;
+    for (uint32_t lane = 0; lane < p.lanes; lane++) {
+        if (chain == 0) k2m_lane<ChainT1C1>(p, lane);
+        else            k2m_lane<ChainS1>(p, lane);
+    }
+    for (uint32_t lane = 0; lane < p.lanes; lane++) k2m_verify_lane(p, lane, c->d_nfail);
+    c->st.kernel_launches += 2;
+    return WMB_OK;
+}
+
+template <class CH>
+static void hostsim_k2t(const K2tParams &p)
+{
+    for (uint32_t lane = 0; lane < p.lanes; lane++) k2t_count<CH>(p, lane);
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2t_scan_a<CH>(p, t);
+    k2t_scan_b<CH>(p);
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2t_scan_c<CH>(p, t);
+    for (uint32_t lane = 0; lane < p.lanes; lane++) k2t_write<CH>(p, lane);
+}
+
+static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
+{
+    if (chain == 0) hostsim_k2t<ChainT1C1>(p); else hostsim_k2t<ChainS1>(p);
+    c->st.kernel_launches += 3;
     return WMB_OK;
 }
 
 static int launch_k2c(wmb_ctx *c, const K2cParams &p)
 {
-    k2c_scan(p);
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2c_scan_a(p, t);
+    k2c_scan_b(p);
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2c_scan_c(p, t);
     for (uint32_t lane = 0; lane < p.lanes; lane++)
         for (int t = 0; t < 4; t++) k2c_compact(p, lane, t, 4);
     c->st.kernel_launches += 2;
