@@ -36,11 +36,72 @@ struct K2aParams {
     uint32_t dc, t2;            /* -o ; time2 enabled (else only the data bits are produced)  */
 };
 
+/* registers of one clock-recovery lane */
+struct K2aRegs {
+    float dcx, dcy;
+    float h10, h20, h11, h21, h12, h22;
+    uint32_t clk3;
+};
+
+/* 32 decimated samples (one 128-byte line of dphi, already in registers) through the DC block,
+ * the slicer and the three biquads; returns the data-bit and clock-sign words */
+template <class CH>
+WMB_D void k2a_block(const float4 (&blk)[8], int n, uint32_t dc, uint32_t t2, K2aRegs &r,
+                     uint32_t &dword, uint32_t &cword)
+{
+    const float *cf = (CH::ID == 0) ? c_iir_t1c1 : c_iir_s1;
+    const float b10 = cf[0], b20 = cf[1], a10 = cf[2], a20 = cf[3];
+    const float b11 = cf[4], b21 = cf[5], a11 = cf[6], a21 = cf[7];
+    const float b12 = cf[8], b22 = cf[9], a12 = cf[10], a22 = cf[11];
+    const float gain = c_iir_gain;
+    const float alpha = 0.999f, cdc = (1.f + 0.999f) / 2.f;       /* rtl_wmbus.c:501 / :511 */
+    dword = 0; cword = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        if (i >= n) break;
+        const float4 q = blk[i >> 2];
+        float x = (i & 3) == 0 ? q.x : (i & 3) == 1 ? q.y : (i & 3) == 2 ? q.z : q.w;
+        if (dc) {
+            const float y = wmb_fadd(wmb_fmul(cdc, wmb_fsub(x, r.dcx)), wmb_fmul(alpha, r.dcy));
+            r.dcx = x; r.dcy = y; x = y;
+        }
+        dword |= (x >= 0.0f ? 1u : 0u) << i;                      /* rtl_wmbus.c:1059 */
+        if (t2) {
+            float v = wmb_fmul(x, x);                             /* rtl_wmbus.c:1089 */
+            float h0;
+            h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a10, r.h10), wmb_fmul(a20, r.h20)));
+            v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b10, r.h10)), wmb_fmul(b20, r.h20));
+            r.h20 = r.h10; r.h10 = h0;
+            h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a11, r.h11), wmb_fmul(a21, r.h21)));
+            v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b11, r.h11)), wmb_fmul(b21, r.h21));
+            r.h21 = r.h11; r.h11 = h0;
+            h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a12, r.h12), wmb_fmul(a22, r.h22)));
+            v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b12, r.h12)), wmb_fmul(b22, r.h22));
+            r.h22 = r.h12; r.h12 = h0;
+            v = wmb_fmul(v, gain);
+            cword |= (v >= 0.0f ? 1u : 0u) << i;
+        }
+    }
+}
+
+WMB_D void k2a_load(float4 (&blk)[8], const float *src)
+{
+    const float4 *s4 = (const float4 *)src;
+#pragma unroll
+    for (int j = 0; j < 8; j++) blk[j] = s4[j];
+}
+
+WMB_D void k2a_save(IirState &st, const K2aRegs &r)
+{
+    st.dc_x = r.dcx; st.dc_y = r.dcy;
+    st.h[0] = r.h10; st.h[1] = r.h20; st.h[2] = r.h11; st.h[3] = r.h21; st.h[4] = r.h12; st.h[5] = r.h22;
+    st.clk3 = r.clk3; st.pad = 0;
+}
+
 template <class CH>
 WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
 {
     if (lane >= p.lanes) return;
-    const float *cf = (CH::ID == 0) ? c_iir_t1c1 : c_iir_s1;
     const int64_t s0 = (int64_t)lane * p.C;
     const int64_t e0 = (s0 + p.C < p.M) ? s0 + p.C : p.M;
     IirState st;
@@ -57,60 +118,31 @@ WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
         st = p.st_end[lane - 1];
         m = s0;
     }
-    /* registers */
-    float dcx = st.dc_x, dcy = st.dc_y;
-    float h10 = st.h[0], h20 = st.h[1], h11 = st.h[2], h21 = st.h[3], h12 = st.h[4], h22 = st.h[5];
-    uint32_t clk3 = st.clk3;
-    const float b10 = cf[0], b20 = cf[1], a10 = cf[2], a20 = cf[3];
-    const float b11 = cf[4], b21 = cf[5], a11 = cf[6], a21 = cf[7];
-    const float b12 = cf[8], b22 = cf[9], a12 = cf[10], a22 = cf[11];
-    const float gain = c_iir_gain;
-    const float alpha = 0.999f, cdc = (1.f + 0.999f) / 2.f;       /* rtl_wmbus.c:501 / :511 */
+    K2aRegs r;
+    r.dcx = st.dc_x; r.dcy = st.dc_y;
+    r.h10 = st.h[0]; r.h20 = st.h[1]; r.h11 = st.h[2]; r.h21 = st.h[3]; r.h12 = st.h[4]; r.h22 = st.h[5];
+    r.clk3 = st.clk3;
     bool saved_start = false;
 
+    /* each lane streams whole 128-byte lines of dphi; the next line is requested before the
+     * current one is processed so that the DRAM latency hides behind ~32 recurrence steps
+     * (reads may run up to 32 samples past the lane's end: the buffers carry that slack) */
+    float4 cur[8], nxt[8];
+    if (m < e0) k2a_load(cur, p.dphi + m);
     while (m < e0) {
-        if (m == s0 && !saved_start) {
-            st.dc_x = dcx; st.dc_y = dcy;
-            st.h[0] = h10; st.h[1] = h20; st.h[2] = h11; st.h[3] = h21; st.h[4] = h12; st.h[5] = h22;
-            st.clk3 = clk3;
-            p.st_start[lane] = st;
-            saved_start = true;
-        }
+        if (m + 32 < e0) k2a_load(nxt, p.dphi + m + 32);
+        if (m == s0 && !saved_start) { k2a_save(st, r); p.st_start[lane] = st; saved_start = true; }
         const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
-        uint32_t dword = 0, cword = 0;
-        const float *x4 = p.dphi + m;
-#pragma unroll 4
-        for (int i = 0; i < n; i++) {
-            float x = x4[i];
-            if (p.dc) {
-                const float y = wmb_fadd(wmb_fmul(cdc, wmb_fsub(x, dcx)), wmb_fmul(alpha, dcy));
-                dcx = x; dcy = y; x = y;
-            }
-            dword |= (x >= 0.0f ? 1u : 0u) << i;                  /* rtl_wmbus.c:1059 */
-            if (p.t2) {
-                float v = wmb_fmul(x, x);                         /* rtl_wmbus.c:1089 */
-                float h0;
-                h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a10, h10), wmb_fmul(a20, h20)));
-                v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b10, h10)), wmb_fmul(b20, h20));
-                h20 = h10; h10 = h0;
-                h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a11, h11), wmb_fmul(a21, h21)));
-                v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b11, h11)), wmb_fmul(b21, h21));
-                h21 = h11; h11 = h0;
-                h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a12, h12), wmb_fmul(a22, h22)));
-                v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b12, h12)), wmb_fmul(b22, h22));
-                h22 = h12; h12 = h0;
-                v = wmb_fmul(v, gain);
-                cword |= (v >= 0.0f ? 1u : 0u) << i;
-            }
-        }
+        uint32_t dword, cword;
+        k2a_block<CH>(cur, n, p.dc, p.t2, r, dword, cword);
         /* lock stencil on the whole word: sample the data bit where the clock reads
          * low, high, high, high at m-3..m (rtl_wmbus.c:1092-1111) */
-        const uint64_t hist3 = ((clk3 & 1u) << 2) | (clk3 & 2u) | ((clk3 >> 2) & 1u);   /* bit2 = m-1 */
+        const uint64_t hist3 = ((r.clk3 & 1u) << 2) | (r.clk3 & 2u) | ((r.clk3 >> 2) & 1u);   /* bit2 = m-1 */
         const uint64_t H = ((uint64_t)cword << 3) | hist3;
         const uint32_t sword = (uint32_t)((H >> 3) & (H >> 2) & (H >> 1) & ~H);
-        if (n == 32) clk3 = ((cword >> 31) & 1u) | (((cword >> 30) & 1u) << 1) | (((cword >> 29) & 1u) << 2);
+        if (n == 32) r.clk3 = ((cword >> 31) & 1u) | (((cword >> 30) & 1u) << 1) | (((cword >> 29) & 1u) << 2);
         else {
-            for (int i = 0; i < n; i++) clk3 = ((clk3 << 1) | ((cword >> i) & 1u)) & 7u;
+            for (int i = 0; i < n; i++) r.clk3 = ((r.clk3 << 1) | ((cword >> i) & 1u)) & 7u;
         }
         if (m >= s0) {
             const uint32_t keep = (n == 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
@@ -118,10 +150,10 @@ WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
             p.sbits[m >> 5] = sword & keep;
         }
         m += n;
+#pragma unroll
+        for (int j = 0; j < 8; j++) cur[j] = nxt[j];
     }
-    st.dc_x = dcx; st.dc_y = dcy;
-    st.h[0] = h10; st.h[1] = h20; st.h[2] = h11; st.h[3] = h21; st.h[4] = h12; st.h[5] = h22;
-    st.clk3 = clk3;
+    k2a_save(st, r);
     if (!saved_start) p.st_start[lane] = st;                      /* empty lane */
     p.st_end[lane] = st;
 }
@@ -344,7 +376,7 @@ WMB_D void k2m_edge(const K2mParams &p, RlState &s, uint32_t st, int64_t m, uint
             if (rl <= half) reset = true;
             else if (s.a <= 0) { reset = true; err |= 2u; }  /* the reference would spin here */
             else {
-                const uint32_t rssi = live ? p.rssi[m] : 0u;
+                const uint32_t rssi = 0u;                    /* filled in by k2c_compact */
                 while (rl > half) {
                     rl -= s.a;
                     s.sr = ((s.sr << 1) | level) & CH::CODE_MASK;
@@ -367,7 +399,7 @@ WMB_D void k2m_edge(const K2mParams &p, RlState &s, uint32_t st, int64_t m, uint
         else if (run <= half) reset = true;
         else {
             int rl = run;
-            const uint32_t rssi = live ? p.rssi[m] : 0u;
+            const uint32_t rssi = 0u;                        /* filled in by k2c_compact */
             while (rl > half) {
                 rl -= spb;
                 s.sr = ((s.sr << 1) | level) & CH::CODE_MASK;

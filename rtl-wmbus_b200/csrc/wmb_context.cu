@@ -645,7 +645,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
                 q.ev = s.ev; q.cnt = s.cnt; q.base = s.base; q.lanes = lanes; q.cap = km[ch].cap; q.C = C;
                 q.m_base = (int64_t)c->m_consumed;
                 q.ring = s.ring; q.ring_mask = s.ring_cap - 1; q.sd = s.sd; q.cand = s.cand; q.cand_cap = c->cand_cap;
-                q.agg = s.agg;
+                q.agg = s.agg; q.rssi = b.rssi + c->W;
                 TRY(launch_k2c(c, q));
             }
         }

@@ -332,6 +332,7 @@ struct K2cParams {
     StreamDev *sd;
     uint64_t *cand; uint32_t cand_cap;      /* out: ordinals of access-code matches        */
     uint64_t *agg;                  /* [SCAN_THREADS] scan scratch                         */
+    const uint8_t *rssi;            /* (unsigned)rssi, index 0 = batch sample 0            */
 };
 
 /* exclusive scan of the lane counts, same three-phase scheme as k2t_scan_* */
@@ -367,7 +368,9 @@ WMB_D void k2c_compact(const K2cParams &p, uint32_t lane, int tid, int nthr)
     for (uint32_t i = tid; i < n; i += nthr) {
         const uint32_t e = src[i];
         const uint64_t m = m_lane + (e >> 11);
-        const uint64_t g = (m << 24) | ((uint64_t)((e >> 3) & 0xFFu) << 16) | (e & 7u);
+        /* the run-length lanes leave the rssi field empty; it is looked up here, where the
+         * gather is wide and its latency hides (rtl_wmbus.c:1074: rssi of the edge sample) */
+        const uint64_t g = (m << 24) | ((uint64_t)p.rssi[(int64_t)(m - (uint64_t)p.m_base)] << 16) | (e & 7u);
         p.ring[(base + i) & p.ring_mask] = g;
         if (e & 2u) {
 #ifdef WMB_HOSTSIM
