@@ -173,6 +173,7 @@ typedef struct wmb_stats {
     double   demod_kernel_ms;     /* CUDA-event time of the demod kernel(s), last batch */
     double   bitsync_kernel_ms;   /* CUDA-event time of the bit-sync kernel(s), last batch */
     double   batch_device_ms;     /* CUDA-event time of the whole device pass, last batch */
+    uint64_t rl_fallbacks;        /* T1/C1 batches redone with the monolithic run-length lanes */
 } wmb_stats;
 
 int wmb_get_stats(wmb_ctx *c, wmb_stats *s);

@@ -490,3 +490,288 @@ WMB_D void k2m_verify_lane(const K2mParams &p, uint32_t lane, uint32_t *n_fail)
 #endif
     }
 }
+
+/* ------------------------------------------------------------------------------------- */
+/* K2p: two-phase run-length bit sync for the T1/C1 chain                                */
+/*                                                                                       */
+/* The reference's run-length algorithm (rtl_wmbus.c:729-803) mixes two time scales: a    */
+/* per-sample deglitch/edge detector whose only feedback is "runs shorter than 5 samples  */
+/* reset everything", and a per-run PI loop that turns run lengths into bits.  Phase 1    */
+/* keeps the per-sample part (a tiny state: 6 raw bits, level, run length, a pending-     */
+/* reset flag) and emits one RECORD per run of >= 5 samples; phase 2 walks the records.   */
+/* A record that follows a reset starts phase 2 from a known state, so phase 2 is exactly */
+/* segment-parallel.  The one coupling phase 1 cannot see is the reference's second reset */
+/* rule (run*256 <= bit_length/2 with run >= 5, :756-762), which needs a bit_length 25 %   */
+/* above nominal; phase 2 detects it and the batch falls back to the exact monolithic     */
+/* lanes (k2m_lane).                                                                      */
+/* ------------------------------------------------------------------------------------- */
+
+struct P1State { uint32_t raw, level, pend; int32_t run; };
+
+struct K2p1Params {
+    const uint32_t *dbits;
+    int64_t  M, hist;
+    uint32_t C, W, lanes;       /* multiples of 32 */
+    uint32_t cap;               /* records per lane */
+    uint64_t *rec;              /* [lanes * cap] lane-local records: run<<32 | off<<2 | level<<1 | rst */
+    uint32_t *cnt;              /* [lanes] */
+    P1State *st_start, *st_end;
+    const RlState *carry;
+    uint32_t *rerun;
+    uint32_t mode;
+};
+
+WMB_D void k2p1_lane(const K2p1Params &p, uint32_t lane)
+{
+    if (lane >= p.lanes) return;
+    const int64_t s0 = (int64_t)lane * p.C;
+    const int64_t e0 = (s0 + p.C < p.M) ? s0 + p.C : p.M;
+    uint32_t raw, level, pend;
+    int32_t run;
+    int64_t m;
+    if (p.mode == 0) {
+        if (lane == 0) {
+            const RlState c = *p.carry;
+            raw = c.raw; level = c.flags & 1u; pend = (c.flags >> 1) & 1u; run = c.run; m = 0;
+        } else {
+            raw = 0; level = 0; pend = 0; run = 0;
+            m = s0 - (int64_t)p.W;
+            if (m < -p.hist) m = -p.hist;
+        }
+    } else {
+        if (lane == 0 || !p.rerun[lane]) return;
+        const P1State c = p.st_end[lane - 1];
+        raw = c.raw; level = c.level; pend = c.pend; run = c.run; m = s0;
+    }
+    uint64_t *rec = p.rec + (size_t)lane * p.cap;
+    uint32_t n_rec = 0;
+    bool saved_start = false;
+    while (m < e0) {
+        if (m == s0 && !saved_start) {
+            P1State st = { raw, level, pend, run };
+            p.st_start[lane] = st; saved_start = true;
+        }
+        const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
+        const uint32_t word = p.dbits[m >> 5];
+        const bool live = m >= s0;
+        for (int i = 0; i < n; i++) {
+            const uint32_t bit = (word >> i) & 1u;
+            raw = ((raw << 1) | bit) & 0x3Fu;
+            const uint32_t st = (wmb_popc(raw) >= 3) ? 1u : 0u;         /* deglitch_filter_t1_c1 */
+            if (st == level) { run++; continue; }
+            if (run < 5) { raw = 0; pend = 1; }                         /* :742-748 */
+            else {
+                if (live && n_rec < p.cap)
+                    rec[n_rec] = ((uint64_t)(uint32_t)run << 32) | ((uint64_t)(uint32_t)(m + i - s0) << 2) | (level << 1) | pend;
+                if (live) n_rec++;
+                pend = 0;
+            }
+            level = st; run = 1;
+        }
+        m += n;
+    }
+    P1State st = { raw, level, pend, run };
+    if (!saved_start) p.st_start[lane] = st;
+    p.st_end[lane] = st;
+    p.cnt[lane] = n_rec < p.cap ? n_rec : p.cap;     /* cap = C/5 + 2 cannot overflow: runs are >= 5 samples */
+}
+
+WMB_D void k2p1_verify_lane(const K2p1Params &p, uint32_t lane, uint32_t *n_fail)
+{
+    if (lane >= p.lanes) return;
+    uint32_t bad = 0;
+    if (lane > 0) {
+        const P1State &a = p.st_start[lane], &b = p.st_end[lane - 1];
+        if (!(a.raw == b.raw && a.level == b.level && a.pend == b.pend && a.run == b.run)) bad = 1;
+    }
+    p.rerun[lane] = bad;
+    if (bad) {
+#ifdef WMB_HOSTSIM
+        (*n_fail)++;
+#else
+        atomicAdd(n_fail, 1u);
+#endif
+    }
+}
+
+/* records -> one global list per batch */
+struct K2pDev {                 /* device bookkeeping of the two-phase path */
+    uint64_t n_rec;             /* records in this batch                                   */
+    uint32_t fallback;          /* phase 2 met the second reset rule: redo with k2m_lane   */
+    uint32_t errors;
+};
+
+struct K2pcParams {
+    const uint64_t *rec; const uint32_t *cnt; uint64_t *base;
+    uint32_t lanes, cap, C;
+    uint32_t *rec_m, *rec_v;    /* out: batch-relative edge sample ; run<<2 | level<<1 | rst */
+    uint64_t *agg;
+    K2pDev *pd;
+};
+
+WMB_D void k2pc_scan_a(const K2pcParams &p, uint32_t t)
+{
+    const uint32_t per = scan_per_thread(p.lanes);
+    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
+    uint64_t cnt = 0;
+    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) cnt += p.cnt[l];
+    p.agg[t] = cnt;
+}
+WMB_D void k2pc_scan_b(const K2pcParams &p)
+{
+    uint64_t acc = 0;
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) { const uint64_t c = p.agg[t]; p.agg[t] = acc; acc += c; }
+    p.pd->n_rec = acc; p.pd->fallback = 0;
+}
+WMB_D void k2pc_scan_c(const K2pcParams &p, uint32_t t)
+{
+    const uint32_t per = scan_per_thread(p.lanes);
+    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
+    uint64_t acc = p.agg[t];
+    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) { p.base[l] = acc; acc += p.cnt[l]; }
+}
+WMB_D void k2pc_compact(const K2pcParams &p, uint32_t lane, int tid, int nthr)
+{
+    if (lane >= p.lanes) return;
+    const uint32_t n = p.cnt[lane];
+    const uint64_t base = p.base[lane];
+    const uint64_t *src = p.rec + (size_t)lane * p.cap;
+    for (uint32_t i = tid; i < n; i += nthr) {
+        const uint64_t r = src[i];
+        uint64_t run = r >> 32;
+        if (run > 0x3FFFFFFFu) run = 0x3FFFFFFFu;
+        p.rec_m[base + i] = (uint32_t)((uint64_t)lane * p.C + ((r >> 2) & 0x3FFFFFFFu));
+        p.rec_v[base + i] = (uint32_t)(run << 2) | (uint32_t)(r & 3u);
+    }
+}
+
+/* phase 2 */
+struct K2p2Params {
+    const uint32_t *rec_m, *rec_v;
+    const K2pDev *pd_in; K2pDev *pd;
+    uint32_t R;                 /* records per lane (nominal)                              */
+    uint32_t lanes;
+    uint32_t *cnt;              /* [lanes] events per lane                                 */
+    uint64_t *base;             /* [lanes]                                                 */
+    const uint8_t *rssi;
+    int64_t  m_base;
+    uint64_t *ring; uint64_t ring_mask;
+    StreamDev *sd;
+    uint64_t *cand; uint32_t cand_cap;
+    const RlState *carry;       /* exact state at batch start                               */
+    RlState *p2_out;            /* out: a/b/sr after the last record, run = 1 marks it valid */
+    uint32_t write;             /* 0: count pass, 1: write pass                            */
+    uint64_t *agg;
+};
+
+WMB_D void k2p2_lane(const K2p2Params &p, uint32_t lane)
+{
+    if (lane >= p.lanes) return;
+    const uint64_t N = p.pd->n_rec;
+    if (p.write && p.pd->fallback) return;
+    const uint64_t r0 = (uint64_t)lane * p.R, r1 = (r0 + p.R < N) ? r0 + p.R : N;
+    uint32_t n_ev = 0;
+    if (r0 < N) {
+        /* find this lane's first segment start: record 0 (carry state) or a record that follows a reset */
+        uint64_t i = r0;
+        int32_t a, b; uint32_t sr, pend;
+        bool have = false;
+        if (lane == 0) {
+            const RlState c = *p.carry;
+            a = c.a; b = c.b; sr = c.sr; pend = (c.flags >> 1) & 1u; have = true;
+        } else {
+            for (; i < r1; i++) if (p.rec_v[i] & 1u) { have = true; break; }
+            a = 8 * 256; b = 0; sr = 0; pend = 0;
+        }
+        uint64_t ord = p.write ? p.base[lane] : 0;
+        if (have) {
+            for (; i < N; i++) {
+                const uint32_t v = p.rec_v[i];
+                if (v & 1u) {
+                    if (i >= r1) break;                              /* next lane's segment */
+                    a = 8 * 256; b = 0; sr = 0; pend = 1;             /* runlength_algorithm_reset_t1_c1 */
+                }
+                const uint32_t level = (v >> 1) & 1u;
+                int rl = (int)((v >> 2) * 256u);
+                const int half = a / 2;
+                if (rl <= half || a <= 0) {                          /* rtl_wmbus.c:756-762 (or a spin) */
+                    if (!p.write) p.pd->fallback = 1;
+                    break;
+                }
+                int n = 0;
+                const uint32_t m = p.rec_m[i];
+                const uint32_t rssi = p.write ? p.rssi[m] : 0u;
+                while (rl > half) {                                  /* :765-779 */
+                    rl -= a;
+                    sr = ((sr << 1) | level) & 0xFFFFu;
+                    if (n < K2_EDGE_EMIT_CAP) {
+                        if (p.write) {
+                            const uint32_t sync = (sr == 0x543Du) ? 1u : 0u;
+                            p.ring[ord & p.ring_mask] = ((uint64_t)(p.m_base + m) << 24) | ((uint64_t)rssi << 16) |
+                                                        (pend << 2) | (sync << 1) | level;
+                            if (sync) {
+#ifdef WMB_HOSTSIM
+                                const uint32_t slot = p.sd->n_cand++;
+#else
+                                const uint32_t slot = atomicAdd(&p.sd->n_cand, 1u);
+#endif
+                                if (slot < p.cand_cap) p.cand[slot] = ord;
+                                else p.sd->cand_overflow = 1;
+                            }
+                            ord++;
+                        }
+                        n_ev++;
+                        pend = 0;
+                    }
+                    n++;
+                }
+                b += rl;                                             /* :792 */
+                a += (rl + b / 16) / (32 * n);                       /* :796 */
+            }
+            if (i >= N && p.write) {                                 /* this lane saw the last record */
+                RlState c;
+                c.run = 1; c.a = a; c.b = b; c.sr = sr; c.flags = pend << 1; c.raw = 0;
+                *p.p2_out = c;
+            }
+        }
+    }
+    if (!p.write) p.cnt[lane] = n_ev;
+}
+
+WMB_D void k2p2_scan_a(const K2p2Params &p, uint32_t t)
+{
+    const uint32_t per = scan_per_thread(p.lanes);
+    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
+    uint64_t cnt = 0;
+    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) cnt += p.cnt[l];
+    p.agg[t] = cnt;
+}
+WMB_D void k2p2_scan_b(const K2p2Params &p)
+{
+    if (p.pd->fallback) return;
+    uint64_t acc = p.sd->total;
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) { const uint64_t c = p.agg[t]; p.agg[t] = acc; acc += c; }
+    p.sd->total = acc;
+}
+WMB_D void k2p2_scan_c(const K2p2Params &p, uint32_t t)
+{
+    if (p.pd->fallback) return;
+    const uint32_t per = scan_per_thread(p.lanes);
+    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
+    uint64_t acc = p.agg[t];
+    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) { p.base[l] = acc; acc += p.cnt[l]; }
+}
+
+/* end of batch: compose the carried RlState from phase 1's end state (raw bits, level, run,
+ * "reset since the last record") and phase 2's state after the last record */
+WMB_D void k2p_fold(const P1State *p1_end, RlState *p2_out, RlState *carry, const K2pDev *pd)
+{
+    if (pd->fallback) return;
+    RlState c = *carry;
+    if (p2_out->run) { c.a = p2_out->a; c.b = p2_out->b; c.sr = p2_out->sr; }
+    c.raw = p1_end->raw; c.run = p1_end->run;
+    if (p1_end->pend) { c.a = 8 * 256; c.b = 0; c.sr = 0; }      /* runlength_algorithm_reset_t1_c1 */
+    c.flags = (p1_end->level & 1u) | ((p1_end->pend & 1u) << 1);
+    *carry = c;
+    p2_out->run = 0;
+}

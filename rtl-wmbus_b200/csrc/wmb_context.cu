@@ -86,6 +86,12 @@ struct ChainBuf {
     IirState *ia_start = nullptr, *ia_end = nullptr, *ia_carry = nullptr;
     RlState *rl_start = nullptr, *rl_end = nullptr, *rl_carry = nullptr;
     uint32_t *rerun = nullptr;
+    /* two-phase run-length path (T1/C1) */
+    uint64_t *p1_rec = nullptr; uint32_t *p1_cnt = nullptr; uint64_t *p1_base = nullptr;
+    P1State *p1_start = nullptr, *p1_end = nullptr; uint32_t *p1_rerun = nullptr;
+    uint32_t *rec_m = nullptr, *rec_v = nullptr;
+    uint32_t *p2_cnt = nullptr; uint64_t *p2_base = nullptr;
+    K2pDev *pd = nullptr; RlState *p2_out = nullptr;
     /* time2 lanes */
     uint32_t *t2_tail = nullptr, *t2_len = nullptr, *t2_sr = nullptr, *t2_agg_tail = nullptr, *t2_agg_len = nullptr;
     Stream s[WMB_N_ALGOS];
@@ -117,6 +123,10 @@ struct wmb_ctx {
     uint32_t C_fixed = 0;
     uint32_t lanes_max = 0;
     uint32_t t2_lanes_max = 0;
+    uint32_t p1_lanes_max = 0, p2_lanes_max = 0;
+    size_t rec_max = 0;
+    bool two_phase = true;
+    K2pDev *h_pd = nullptr;
     uint32_t cap_words_rl = 0;
     size_t ring_events = 0;
     std::vector<void *> dev_allocs, host_allocs;
@@ -209,6 +219,31 @@ static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p)
     k2m_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, c->cs>>>(p, c->d_nfail);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches += 2;
+    return WMB_OK;
+}
+
+static int launch_k2p1(wmb_ctx *c, const K2p1Params &p)
+{
+    k2p1_lanes_kernel<<<(p.lanes + 127) / 128, 128, 0, c->cs>>>(p);
+    k2p1_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, c->cs>>>(p, c->d_nfail);
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches += 2;
+    return WMB_OK;
+}
+
+static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, const P1State *p1_end_last, RlState *carry)
+{
+    k2pc_scan_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(pc);
+    k2pc_compact_kernel<<<pc.lanes, 128, 0, c->cs>>>(pc);
+    const unsigned grid = (p2.lanes + 127) / 128;
+    p2.write = 0;
+    k2p2_lanes_kernel<<<grid, 128, 0, c->cs>>>(p2);
+    k2p2_scan_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(p2);
+    p2.write = 1;
+    k2p2_lanes_kernel<<<grid, 128, 0, c->cs>>>(p2);
+    k2p_fold_kernel<<<1, 32, 0, c->cs>>>(p1_end_last, p2.p2_out, carry, p2.pd);
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches += 6;
     return WMB_OK;
 }
 
@@ -324,6 +359,10 @@ static int host_alloc(wmb_ctx *c, T **p, size_t count)
 #define TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 #define K2T_WORDS_PER_LANE 128u      /* 4096 decimated samples per time2 lane */
+#define K2P1_CHUNK 2048u             /* decimated samples per phase-1 run-length lane */
+#define K2P1_WARM  256u
+#define K2P1_CAP   (K2P1_CHUNK / 5 + 2)
+#define K2P2_RECORDS 512u            /* records per phase-2 lane (nominal) */
 
 static int ctx_alloc(wmb_ctx *c)
 {
@@ -336,6 +375,9 @@ static int ctx_alloc(wmb_ctx *c)
     const size_t words_rl = (size_t)c->M_max / 4 + (size_t)c->lanes_max * (K2_EDGE_EMIT_CAP + 8) + 1024;
     c->cap_words_rl = (uint32_t)std::min<size_t>(words_rl, 0xFFFFFFFFu);
     c->ring_events = next_pow2((size_t)c->M_max / 4 + 65536 + WMB_MAXBITS);
+    c->p1_lanes_max = (uint32_t)(c->M_max / K2P1_CHUNK + 2);
+    c->rec_max = (size_t)c->M_max / 5 + 2 * (size_t)c->p1_lanes_max + 64;
+    c->p2_lanes_max = (uint32_t)(c->rec_max / K2P2_RECORDS + 2);
 
     TRY(dev_alloc(c, &c->d_in[0], c->max_batch_bytes + 4096));
     TRY(dev_alloc(c, &c->d_in[1], c->max_batch_bytes + 4096));
@@ -349,6 +391,7 @@ static int ctx_alloc(wmb_ctx *c)
     TRY(dev_alloc(c, &c->d_words, c->frame_words_cap));
     TRY(host_alloc(c, &c->h_small, 16));
     TRY(host_alloc(c, &c->h_sd, 4));
+    TRY(host_alloc(c, &c->h_pd, 1));
     TRY(host_alloc(c, &c->h_cand, c->cand_cap));
     TRY(host_alloc(c, &c->h_hdr, c->cand_cap));
     TRY(host_alloc(c, &c->h_words, c->frame_words_cap));
@@ -383,6 +426,20 @@ static int ctx_alloc(wmb_ctx *c)
         TRY(dev_alloc(c, &b.rl_end, c->lanes_max));
         TRY(dev_alloc(c, &b.rl_carry, 1));
         TRY(dev_alloc(c, &b.rerun, c->lanes_max, true));
+        if (ch == 0 && c->two_phase && c->o.rla_enabled) {
+            TRY(dev_alloc(c, &b.p1_rec, (size_t)c->p1_lanes_max * K2P1_CAP));
+            TRY(dev_alloc(c, &b.p1_cnt, c->p1_lanes_max, true));
+            TRY(dev_alloc(c, &b.p1_base, c->p1_lanes_max));
+            TRY(dev_alloc(c, &b.p1_start, c->p1_lanes_max));
+            TRY(dev_alloc(c, &b.p1_end, c->p1_lanes_max));
+            TRY(dev_alloc(c, &b.p1_rerun, c->p1_lanes_max, true));
+            TRY(dev_alloc(c, &b.rec_m, c->rec_max));
+            TRY(dev_alloc(c, &b.rec_v, c->rec_max));
+            TRY(dev_alloc(c, &b.p2_cnt, c->p2_lanes_max, true));
+            TRY(dev_alloc(c, &b.p2_base, c->p2_lanes_max));
+            TRY(dev_alloc(c, &b.pd, 1, true));
+            TRY(dev_alloc(c, &b.p2_out, 1, true));
+        }
         TRY(dev_alloc(c, &b.t2_tail, c->t2_lanes_max));
         TRY(dev_alloc(c, &b.t2_len, c->t2_lanes_max));
         TRY(dev_alloc(c, &b.t2_sr, c->t2_lanes_max));
@@ -442,6 +499,7 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
     for (int ch = 0; ch < WMB_N_CHAINS; ch++)
         if ((c->chains & (1u << ch)) && o->rla_enabled) c->W = std::max(c->W, c->W_m[ch]);
     c->manual = o->manual_frames != 0;
+    c->two_phase = o->reserved[0] == 0;                  /* reserved[0] = 1: force the monolithic run-length lanes (tests) */
     c->C_fixed = o->chunk_samples ? (o->chunk_samples + 255) / 256 * 256 : 0;
     if (c->C_fixed && (c->C_fixed < 1024 || c->C_fixed > K2_MAX_CHUNK)) { delete c; return set_err(WMB_E_INVAL, "chunk_samples out of range"); }
     size_t mb = o->max_batch_mib ? (size_t)o->max_batch_mib * 1048576u : (size_t)256 * 1048576u;
@@ -610,43 +668,79 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             }
         }
 
-        /* ---- K2m: run-length lanes, verified; then compaction into the rings ---- */
+        /* ---- run-length bit sync ---- */
         if (c->o.rla_enabled) {
-            K2mParams km[WMB_N_CHAINS];
-            for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-                if (!(c->chains & (1u << ch))) continue;
-                ChainBuf &b = c->cb[ch];
-                K2mParams &p = km[ch];
-                memset(&p, 0, sizeof(p));
-                p.dbits = b.dbits + wofs; p.rssi = b.rssi + c->W; p.M = M; p.hist = c->hist_m;
-                p.C = C; p.W = c->W_m[ch]; p.lanes = lanes;
-                p.cap = C / 4 + K2_EDGE_EMIT_CAP + 8;
-                if ((uint64_t)lanes * p.cap > c->cap_words_rl) return set_err(WMB_E_INVAL, "internal: event buffers too small for C=%u", C);
-                p.ev = b.s[WMB_ALGO_RLA].ev; p.cnt = b.s[WMB_ALGO_RLA].cnt;
-                p.st_start = b.rl_start; p.st_end = b.rl_end; p.carry = b.rl_carry; p.rerun = b.rerun;
-                p.errors = c->d_errors;
-                c->st.lanes_run += lanes;
-            }
-            TRY(verified_pass(c, lanes, [&](uint32_t mode) {
-                for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-                    if (!(c->chains & (1u << ch))) continue;
-                    km[ch].mode = mode;
-                    TRY(launch_k2m(c, ch, km[ch]));
-                }
-                return (int)WMB_OK;
-            }));
-            for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-                if (!(c->chains & (1u << ch))) continue;
-                ChainBuf &b = c->cb[ch];
+            uint32_t mono = 0;                             /* chains that take the monolithic lanes */
+            if ((c->chains & 1u) && c->two_phase) {
+                /* T1/C1: phase 1 (per-sample, verified) -> records -> phase 2 (per-run) */
+                ChainBuf &b = c->cb[0];
                 Stream &s = b.s[WMB_ALGO_RLA];
-                CUDA_TRY(cudaMemcpyAsync(b.rl_carry, b.rl_end + (lanes - 1), sizeof(RlState), cudaMemcpyDeviceToDevice, c->cs));
-                K2cParams q;
-                memset(&q, 0, sizeof(q));
-                q.ev = s.ev; q.cnt = s.cnt; q.base = s.base; q.lanes = lanes; q.cap = km[ch].cap; q.C = C;
-                q.m_base = (int64_t)c->m_consumed;
-                q.ring = s.ring; q.ring_mask = s.ring_cap - 1; q.sd = s.sd; q.cand = s.cand; q.cand_cap = c->cand_cap;
-                q.agg = s.agg; q.rssi = b.rssi + c->W;
-                TRY(launch_k2c(c, q));
+                K2p1Params p1;
+                memset(&p1, 0, sizeof(p1));
+                p1.dbits = b.dbits + wofs; p1.M = M; p1.hist = c->hist_m;
+                p1.C = K2P1_CHUNK; p1.W = K2P1_WARM; p1.lanes = (uint32_t)((M + K2P1_CHUNK - 1) / K2P1_CHUNK);
+                p1.cap = K2P1_CAP; p1.rec = b.p1_rec; p1.cnt = b.p1_cnt;
+                p1.st_start = b.p1_start; p1.st_end = b.p1_end; p1.carry = b.rl_carry; p1.rerun = b.p1_rerun;
+                if (p1.lanes > c->p1_lanes_max) return set_err(WMB_E_INVAL, "internal: phase-1 lanes");
+                c->st.lanes_run += p1.lanes;
+                TRY(verified_pass(c, p1.lanes, [&](uint32_t mode) { p1.mode = mode; return launch_k2p1(c, p1); }));
+                K2pcParams pc;
+                memset(&pc, 0, sizeof(pc));
+                pc.rec = b.p1_rec; pc.cnt = b.p1_cnt; pc.base = b.p1_base; pc.lanes = p1.lanes; pc.cap = p1.cap; pc.C = p1.C;
+                pc.rec_m = b.rec_m; pc.rec_v = b.rec_v; pc.agg = s.agg; pc.pd = b.pd;
+                K2p2Params p2;
+                memset(&p2, 0, sizeof(p2));
+                p2.rec_m = b.rec_m; p2.rec_v = b.rec_v; p2.pd = b.pd; p2.R = K2P2_RECORDS;
+                p2.lanes = (uint32_t)(((uint64_t)M / 5 + 2 * (uint64_t)p1.lanes) / K2P2_RECORDS + 2);
+                if (p2.lanes > c->p2_lanes_max) return set_err(WMB_E_INVAL, "internal: phase-2 lanes");
+                p2.cnt = b.p2_cnt; p2.base = b.p2_base; p2.rssi = b.rssi + c->W; p2.m_base = (int64_t)c->m_consumed;
+                p2.ring = s.ring; p2.ring_mask = s.ring_cap - 1; p2.sd = s.sd; p2.cand = s.cand; p2.cand_cap = c->cand_cap;
+                p2.carry = b.rl_carry; p2.p2_out = b.p2_out; p2.agg = s.agg;
+                TRY(launch_k2p_rest(c, pc, p2, b.p1_end + (p1.lanes - 1), b.rl_carry));
+                CUDA_TRY(cudaMemcpyAsync(c->h_pd, b.pd, sizeof(K2pDev), cudaMemcpyDeviceToHost, c->cs));
+                CUDA_TRY(cudaStreamSynchronize(c->cs));
+                if (c->h_pd->fallback) { mono |= 1u; c->st.rl_fallbacks++; }
+            } else if (c->chains & 1u) mono |= 1u;
+            if (c->chains & 2u) mono |= 2u;
+
+            /* S1 (and T1/C1 batches in which the second reset rule fired): monolithic lanes */
+            if (mono) {
+                K2mParams km[WMB_N_CHAINS];
+                for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+                    if (!(mono & (1u << ch))) continue;
+                    ChainBuf &b = c->cb[ch];
+                    K2mParams &p = km[ch];
+                    memset(&p, 0, sizeof(p));
+                    p.dbits = b.dbits + wofs; p.rssi = b.rssi + c->W; p.M = M; p.hist = c->hist_m;
+                    p.C = C; p.W = c->W_m[ch]; p.lanes = lanes;
+                    p.cap = C / 4 + K2_EDGE_EMIT_CAP + 8;
+                    if ((uint64_t)lanes * p.cap > c->cap_words_rl) return set_err(WMB_E_INVAL, "internal: event buffers too small for C=%u", C);
+                    p.ev = b.s[WMB_ALGO_RLA].ev; p.cnt = b.s[WMB_ALGO_RLA].cnt;
+                    p.st_start = b.rl_start; p.st_end = b.rl_end; p.carry = b.rl_carry; p.rerun = b.rerun;
+                    p.errors = c->d_errors;
+                    c->st.lanes_run += lanes;
+                }
+                TRY(verified_pass(c, lanes, [&](uint32_t mode) {
+                    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+                        if (!(mono & (1u << ch))) continue;
+                        km[ch].mode = mode;
+                        TRY(launch_k2m(c, ch, km[ch]));
+                    }
+                    return (int)WMB_OK;
+                }));
+                for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+                    if (!(mono & (1u << ch))) continue;
+                    ChainBuf &b = c->cb[ch];
+                    Stream &s = b.s[WMB_ALGO_RLA];
+                    CUDA_TRY(cudaMemcpyAsync(b.rl_carry, b.rl_end + (lanes - 1), sizeof(RlState), cudaMemcpyDeviceToDevice, c->cs));
+                    K2cParams q;
+                    memset(&q, 0, sizeof(q));
+                    q.ev = s.ev; q.cnt = s.cnt; q.base = s.base; q.lanes = lanes; q.cap = km[ch].cap; q.C = C;
+                    q.m_base = (int64_t)c->m_consumed;
+                    q.ring = s.ring; q.ring_mask = s.ring_cap - 1; q.sd = s.sd; q.cand = s.cand; q.cand_cap = c->cand_cap;
+                    q.agg = s.agg; q.rssi = b.rssi + c->W;
+                    TRY(launch_k2c(c, q));
+                }
             }
         }
     }

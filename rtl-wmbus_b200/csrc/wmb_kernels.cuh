@@ -540,6 +540,30 @@ __global__ void k2m_verify_kernel(const K2mParams p, uint32_t *n_fail)
 {
     k2m_verify_lane(p, blockIdx.x * blockDim.x + threadIdx.x, n_fail);
 }
+__global__ void __launch_bounds__(128) k2p1_lanes_kernel(const K2p1Params p) { k2p1_lane(p, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void k2p1_verify_kernel(const K2p1Params p, uint32_t *n_fail) { k2p1_verify_lane(p, blockIdx.x * blockDim.x + threadIdx.x, n_fail); }
+__global__ void __launch_bounds__(SCAN_THREADS) k2pc_scan_kernel(const K2pcParams p)
+{
+    k2pc_scan_a(p, threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) k2pc_scan_b(p);
+    __syncthreads();
+    k2pc_scan_c(p, threadIdx.x);
+}
+__global__ void k2pc_compact_kernel(const K2pcParams p) { k2pc_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
+__global__ void __launch_bounds__(128) k2p2_lanes_kernel(const K2p2Params p) { k2p2_lane(p, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(SCAN_THREADS) k2p2_scan_kernel(const K2p2Params p)
+{
+    k2p2_scan_a(p, threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) k2p2_scan_b(p);
+    __syncthreads();
+    k2p2_scan_c(p, threadIdx.x);
+}
+__global__ void k2p_fold_kernel(const P1State *p1_end, RlState *p2_out, RlState *carry, const K2pDev *pd)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) k2p_fold(p1_end, p2_out, carry, pd);
+}
 __global__ void __launch_bounds__(SCAN_THREADS) k2c_scan_kernel(const K2cParams p)
 {
     k2c_scan_a(p, threadIdx.x);

@@ -58,6 +58,33 @@ static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p)
     return WMB_OK;
 }
 
+static int launch_k2p1(wmb_ctx *c, const K2p1Params &p)
+{
+    for (uint32_t lane = 0; lane < p.lanes; lane++) k2p1_lane(p, lane);
+    for (uint32_t lane = 0; lane < p.lanes; lane++) k2p1_verify_lane(p, lane, c->d_nfail);
+    c->st.kernel_launches += 2;
+    return WMB_OK;
+}
+
+static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, const P1State *p1_end_last, RlState *carry)
+{
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2pc_scan_a(pc, t);
+    k2pc_scan_b(pc);
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2pc_scan_c(pc, t);
+    for (uint32_t lane = 0; lane < pc.lanes; lane++)
+        for (int t = 0; t < 4; t++) k2pc_compact(pc, lane, t, 4);
+    p2.write = 0;
+    for (uint32_t lane = 0; lane < p2.lanes; lane++) k2p2_lane(p2, lane);
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2p2_scan_a(p2, t);
+    k2p2_scan_b(p2);
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2p2_scan_c(p2, t);
+    p2.write = 1;
+    for (uint32_t lane = 0; lane < p2.lanes; lane++) k2p2_lane(p2, lane);
+    k2p_fold(p1_end_last, p2.p2_out, carry, p2.pd);
+    c->st.kernel_launches += 6;
+    return WMB_OK;
+}
+
 template <class CH>
 static void hostsim_k2t(const K2tParams &p)
 {

@@ -117,3 +117,44 @@ def check_degenerate(pkg, lib, flags_list=("-v", "-v -o -d 3 -s", "-v -a -d 1"))
         for flags in flags_list:
             got, _ = run_lines(pkg, lib, cu8, flags, max_batch_mib=1)
             assert got == oracle_lines(cu8, flags), (name, flags)
+
+
+def type2_capture():
+    """A capture that drives the T1/C1 run-length tracker to a bit length ~37 % above nominal (runs of
+    11 samples) and then presents 5/6-sample runs: the reference's second reset rule
+    (rtl_wmbus.c:756-762) fires, which the two-phase path must hand to the monolithic lanes.
+    Real telegrams follow the pattern so that the fallback also has lines to get right."""
+    import math
+    synth = importlib.import_module("rtl-wmbus_b200.synth")
+    n_iq = 1 << 19
+    x = np.random.default_rng(4).normal(127.4, 4.0, (n_iq, 2))
+    x[:1 << 16] = np.random.default_rng(8).normal(127.4, 4.0, (1 << 16, 2))   # seed found by search: 2 hits
+    runs = [11] * 200 + [6] * 2 + [11] * 200 + [5] * 3 + [11] * 100
+    lev, f = 0, []
+    for r in runs:
+        f += [50e3 if lev else -50e3] * (r * 2)
+        lev ^= 1
+    phase = 2 * math.pi * np.cumsum(np.array(f)) / 1.6e6
+    s0 = 20000
+    x[s0:s0 + len(f), 0] += 80 * np.cos(phase)
+    x[s0:s0 + len(f), 1] += 80 * np.sin(phase)
+    for k, (mode, ident, at) in enumerate([("T1", 0x71200023, 100000), ("C1A", 0x20338739, 200000),
+                                           ("S1", 0x19131290, 300000), ("T1", 0x71200023, 420000)]):
+        e = synth.Emitter(mode, ident, amp=80.0, offset_hz=3e3, l_field=0x19, seed=40 + k)
+        b = synth.fsk_burst(e.chips(k), e.chip_rate, 1.6e6, e.dev_hz, e.offset_hz, e.amp)
+        x[at:at + len(b)] += b
+    return np.clip(np.round(x), 0, 255).astype(np.uint8).reshape(-1)
+
+
+def check_type2_fallback(pkg, lib):
+    cu8 = type2_capture()
+    want = oracle_lines(cu8, "-v")
+    assert len(want) >= 6
+    got, st = run_lines(pkg, lib, cu8, "-v")
+    assert got == want
+    assert st.rl_fallbacks >= 1, "the capture is meant to exercise the monolithic fallback"
+    got, st = run_lines(pkg, lib, cu8, "-v", max_batch_mib=1, pushes=[1 << 18] * 6)
+    assert got == want and st.rl_fallbacks >= 1
+    # forcing the monolithic lanes everywhere gives the same lines
+    got, st = run_lines(pkg, lib, cu8, "-v", reserved=(C.c_uint32 * 2)(1, 0))
+    assert got == want and st.rl_fallbacks == 0

@@ -67,6 +67,10 @@ def test_manual_frame_api(pkg, gpu_lib):
     pc.check_manual_frames(pkg, gpu_lib, load_fixture("synth_mixed_1m6.cu8"), "-v")
 
 
+def test_second_reset_rule_falls_back_to_monolithic_lanes(pkg, gpu_lib):
+    pc.check_type2_fallback(pkg, gpu_lib)
+
+
 def test_degenerate_inputs(pkg, gpu_lib):
     pc.check_degenerate(pkg, gpu_lib)
 

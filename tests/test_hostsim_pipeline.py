@@ -37,6 +37,10 @@ def test_manual_frame_api(pkg, hostsim_lib):
     pc.check_manual_frames(pkg, hostsim_lib, load_fixture("synth_mixed_1m6.cu8"), "-v")
 
 
+def test_second_reset_rule_falls_back_to_monolithic_lanes(pkg, hostsim_lib):
+    pc.check_type2_fallback(pkg, hostsim_lib)
+
+
 def test_degenerate_inputs(pkg, hostsim_lib):
     pc.check_degenerate(pkg, hostsim_lib)
 
