@@ -293,7 +293,10 @@ def main():
                          "k1_demod_ms": round(k1_ms / args.steps, 4), "k2_bitsync_ms": round(k2_ms / args.steps, 4),
                          "device_pass_ms": round(dev_ms / args.steps, 4)},
             "packets": {"lines": tot_lines, "crc_ok": tot_ok, "planted_per_gpu": len(plan)},
-            "lanes": {"run": int(st.lanes_run), "rerun": int(st.lanes_rerun)},
+            "lanes": {"run": int(st.lanes_run), "rerun": int(st.lanes_rerun), "rl_fallbacks": int(st.rl_fallbacks)},
+            "host_ms_per_step": {"batch": round(st.host_batch_ms / (args.steps + args.warmup), 3),
+                                 "gather": round(st.host_gather_ms / (args.steps + args.warmup), 3),
+                                 "decode": round(st.host_decode_ms / (args.steps + args.warmup), 3)},
         }
         if world == 1 and not args.no_cpu_baseline:
             sample = 64 << 20

@@ -174,6 +174,9 @@ typedef struct wmb_stats {
     double   bitsync_kernel_ms;   /* CUDA-event time of the bit-sync kernel(s), last batch */
     double   batch_device_ms;     /* CUDA-event time of the whole device pass, last batch */
     uint64_t rl_fallbacks;        /* T1/C1 batches redone with the monolithic run-length lanes */
+    double   host_batch_ms;       /* cumulative wall time in the enqueue+verify part of batches */
+    double   host_gather_ms;      /* cumulative wall time gathering candidate frames          */
+    double   host_decode_ms;      /* cumulative wall time in the host framers                 */
 } wmb_stats;
 
 int wmb_get_stats(wmb_ctx *c, wmb_stats *s);

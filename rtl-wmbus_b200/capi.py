@@ -29,7 +29,8 @@ class WmbStats(C.Structure):
                 ("candidates", (C.c_uint64 * 2) * 2), ("lines", (C.c_uint64 * 2) * 2),
                 ("lines_crc_ok", (C.c_uint64 * 2) * 2), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("demod_kernel_ms", C.c_double), ("bitsync_kernel_ms", C.c_double),
-                ("batch_device_ms", C.c_double), ("rl_fallbacks", C.c_uint64)]
+                ("batch_device_ms", C.c_double), ("rl_fallbacks", C.c_uint64), ("host_batch_ms", C.c_double),
+                ("host_gather_ms", C.c_double), ("host_decode_ms", C.c_double)]
 
 
 def library_path() -> str:

@@ -27,6 +27,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <time.h>
 
 #ifdef WMB_HOSTSIM
 #include "hostsim_cuda.h"
@@ -142,6 +143,8 @@ struct wmb_ctx {
     uint32_t *d_errors = nullptr, *d_nfail = nullptr, *d_nwords = nullptr;
     FrameHdr *d_hdr = nullptr;
     uint32_t *d_words = nullptr;
+    uint32_t *d_cut_n = nullptr;
+    uint64_t *d_k3_agg = nullptr;
 
     /* pinned host mirrors */
     uint32_t *h_small = nullptr;    /* [0] errors [1] nfail [2] nwords */
@@ -276,10 +279,11 @@ static int launch_k2c(wmb_ctx *c, const K2cParams &p)
 static int launch_k3(wmb_ctx *c, const K3Params &p)
 {
     k3_size_kernel<<<(p.n + 127) / 128, 128, 0, c->cs>>>(p);
-    k3_offsets_kernel<<<1, 32, 0, c->cs>>>(p);
+    k3_cut_kernel<<<p.n, 64, 0, c->cs>>>(p);
+    k3_offsets_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(p);
     k3_copy_kernel<<<p.n, 128, 0, c->cs>>>(p);
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 3;
+    c->st.kernel_launches += 4;
     return WMB_OK;
 }
 #endif
@@ -389,6 +393,8 @@ static int ctx_alloc(wmb_ctx *c)
     c->d_nwords = c->d_errors + 2;
     TRY(dev_alloc(c, &c->d_hdr, c->cand_cap));
     TRY(dev_alloc(c, &c->d_words, c->frame_words_cap));
+    TRY(dev_alloc(c, &c->d_cut_n, c->cand_cap));
+    TRY(dev_alloc(c, &c->d_k3_agg, SCAN_THREADS));
     TRY(host_alloc(c, &c->h_small, 16));
     TRY(host_alloc(c, &c->h_sd, 4));
     TRY(host_alloc(c, &c->h_pd, 1));
@@ -831,6 +837,7 @@ static int gather_frames(wmb_ctx *c, bool final)
     CUDA_TRY(cudaMemcpyAsync(c->d_hdr, c->h_hdr, hdr.size() * sizeof(FrameHdr), cudaMemcpyHostToDevice, c->cs));
     p.hdr = c->d_hdr; p.n = (uint32_t)hdr.size();
     p.words = c->d_words; p.words_cap = c->frame_words_cap; p.n_words = c->d_nwords; p.errors = c->d_errors;
+    p.cut_n = c->d_cut_n; p.agg = c->d_k3_agg;
     int rc = launch_k3(c, p);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->h_hdr, c->d_hdr, hdr.size() * sizeof(FrameHdr), cudaMemcpyDeviceToHost, c->cs));
@@ -883,13 +890,27 @@ struct FrameStore {
 
 static int process_device_batches(wmb_ctx *c, const uint8_t *dev, size_t nbytes, bool final);
 
+static double wall_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
 static int finish_batch(wmb_ctx *c, bool final)
 {
+    const double t0 = wall_ms();
     int rc = gather_frames(c, final);
     if (rc) return rc;
     read_timers(c);
+    const double t1 = wall_ms();
+    c->st.host_gather_ms += t1 - t0;
     if (c->out_frames.empty()) return WMB_OK;
-    if (!c->manual) return wmb_decode_frames(c, c->out_frames.data(), c->out_frames.size());
+    if (!c->manual) {
+        rc = wmb_decode_frames(c, c->out_frames.data(), c->out_frames.size());
+        c->st.host_decode_ms += wall_ms() - t1;
+        return rc;
+    }
     /* manual mode: keep the frames (newest version of a re-delivered partial one wins) for wmb_poll */
     for (const wmb_frame &f : c->out_frames) {
         wmb_ctx::Held *slot = nullptr;
@@ -928,8 +949,10 @@ static int process_device_batches(wmb_ctx *c, const uint8_t *dev, size_t nbytes,
             if (n % gran) n -= n % gran;
             if (n == 0) break;
         }
+        const double tb = wall_ms();
         int rc = run_batch(c, dev + off, n, false);
         if (rc) return rc;
+        c->st.host_batch_ms += wall_ms() - tb;
         rc = finish_batch(c, false);
         if (rc) return rc;
         off += n;
@@ -970,8 +993,10 @@ static int push_host_bytes(wmb_ctx *c, const uint8_t *p, size_t nbytes, bool fin
         }
         CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_h2d[idx], 0));
         c->buf_idx = idx;
+        const double tb = wall_ms();
         int rc = run_batch(c, c->d_in[idx], cur_n, true);
         if (rc) return rc;
+        c->st.host_batch_ms += wall_ms() - tb;
         c->st.h2d_bytes += cur_n;
         rc = finish_batch(c, false);
         if (rc) return rc;

@@ -408,6 +408,8 @@ struct K3Params {
     uint32_t n;
     uint32_t *words; uint32_t words_cap;
     uint32_t *n_words;              /* out: total words used                               */
+    uint32_t *cut_n;                /* [n] scratch: list length before the reset cut       */
+    uint64_t *agg;                  /* [SCAN_THREADS] scan scratch                         */
     uint32_t *errors;
 };
 
@@ -471,25 +473,66 @@ WMB_D void k3_size(const K3Params &p, uint32_t i)
     const uint64_t avail = total - h.ordinal;
     uint32_t need = k3_bits_needed(ring, mask, h.ordinal, total, h.chain);
     uint32_t n = (need == 0 || need > avail) ? (uint32_t)avail : need;
-    uint8_t complete = (need != 0 && need <= avail) ? 1 : 0, cut = 0;
-    /* the run-length algorithm resets its decoder when it resets itself: stop there */
-    for (uint32_t j = 1; j < n; j++) {
-        if (EVG_RESET(ring[(h.ordinal + j) & mask])) { n = j; complete = 1; cut = 1; break; }
-    }
-    h.nbits = n; h.complete = complete; h.cut = cut; h.overflow = 0;
+    const uint8_t complete = (need != 0 && need <= avail) ? 1 : 0;
+    h.nbits = n; h.complete = complete; h.cut = 0; h.overflow = 0;
+    p.cut_n[i] = n;
     h.sync_sample = EVG_M(ring[h.ordinal & mask]);
 }
 
-/* pass 2 (single thread): exclusive scan of nbits -> word offsets */
-WMB_D void k3_offsets(const K3Params &p)
+/* pass 1b (block per candidate, run-length streams only): the run-length algorithm resets its
+ * decoder when it resets itself (rtl_wmbus.c:717-726) -- cut the list at the first event that
+ * follows a reset.  Threads stride over the list; the earliest hit wins through an atomic min. */
+WMB_D void k3_cut(const K3Params &p, uint32_t i, int tid, int nthr)
+{
+    if (i >= p.n) return;
+    FrameHdr &h = p.hdr[i];
+    if (h.algo != 0) return;                                  /* time2 never resets */
+    const uint64_t *ring = p.ring[h.chain][h.algo];
+    const uint64_t mask = p.ring_mask[h.chain][h.algo];
+    const uint32_t n = p.cut_n[i];                            /* list length before cutting (k3_size) */
+    for (uint32_t j = 1 + tid; j < n; j += nthr) {
+        if (EVG_RESET(ring[(h.ordinal + j) & mask])) {
+#ifdef WMB_HOSTSIM
+            if (j < h.nbits) h.nbits = j;
+#else
+            atomicMin(&h.nbits, j);
+#endif
+            break;
+        }
+    }
+}
+
+/* pass 2: exclusive scan of nbits -> word offsets (three-phase block scan) */
+WMB_D void k3_offsets_a(const K3Params &p, uint32_t t)
+{
+    const uint32_t per = scan_per_thread(p.n);
+    const uint32_t i0 = t * per, i1 = (i0 + per < p.n) ? i0 + per : p.n;
+    uint64_t acc = 0;
+    for (uint32_t i = i0; i < i1 && i0 < p.n; i++) {
+        FrameHdr &h = p.hdr[i];
+        if (h.nbits < p.cut_n[i]) { h.complete = 1; h.cut = 1; }     /* k3_cut found a reset */
+        acc += h.nbits;
+    }
+    p.agg[t] = acc;
+}
+WMB_D void k3_offsets_b(const K3Params &p)
 {
     uint64_t acc = 0;
-    for (uint32_t i = 0; i < p.n; i++) {
-        if (acc + p.hdr[i].nbits > p.words_cap) { p.hdr[i].nbits = 0; p.hdr[i].complete = 0; *p.errors |= 4u; }
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) { const uint64_t c = p.agg[t]; p.agg[t] = acc; acc += c; }
+    if (acc > p.words_cap) { *p.errors |= 4u; acc = 0; }
+    *p.n_words = (uint32_t)acc;
+}
+WMB_D void k3_offsets_c(const K3Params &p, uint32_t t)
+{
+    const uint32_t per = scan_per_thread(p.n);
+    const uint32_t i0 = t * per, i1 = (i0 + per < p.n) ? i0 + per : p.n;
+    uint64_t acc = p.agg[t];
+    const bool overflow = (*p.n_words == 0);
+    for (uint32_t i = i0; i < i1 && i0 < p.n; i++) {
+        if (overflow) { p.hdr[i].nbits = 0; p.hdr[i].complete = 0; }
         p.hdr[i].word_off = (uint32_t)acc;
         acc += p.hdr[i].nbits;
     }
-    *p.n_words = (uint32_t)acc;
 }
 
 /* pass 3 (block per candidate): copy events as wmb_bit words */
@@ -574,6 +617,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k2c_scan_kernel(const K2cParams 
 }
 __global__ void k2c_compact_kernel(const K2cParams p) { k2c_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
 __global__ void k3_size_kernel(const K3Params p) { k3_size(p, blockIdx.x * blockDim.x + threadIdx.x); }
-__global__ void k3_offsets_kernel(const K3Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) k3_offsets(p); }
+__global__ void k3_cut_kernel(const K3Params p) { k3_cut(p, blockIdx.x, threadIdx.x, blockDim.x); }
+__global__ void __launch_bounds__(SCAN_THREADS) k3_offsets_kernel(const K3Params p)
+{
+    k3_offsets_a(p, threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) k3_offsets_b(p);
+    __syncthreads();
+    k3_offsets_c(p, threadIdx.x);
+}
 __global__ void k3_copy_kernel(const K3Params p) { k3_copy(p, blockIdx.x, threadIdx.x, blockDim.x); }
 #endif

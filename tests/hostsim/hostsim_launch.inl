@@ -98,7 +98,7 @@ static void hostsim_k2t(const K2tParams &p)
 static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
 {
     if (chain == 0) hostsim_k2t<ChainT1C1>(p); else hostsim_k2t<ChainS1>(p);
-    c->st.kernel_launches += 3;
+    c->st.kernel_launches += 4;
     return WMB_OK;
 }
 
@@ -116,9 +116,13 @@ static int launch_k2c(wmb_ctx *c, const K2cParams &p)
 static int launch_k3(wmb_ctx *c, const K3Params &p)
 {
     for (uint32_t i = 0; i < p.n; i++) k3_size(p, i);
-    k3_offsets(p);
+    for (uint32_t i = 0; i < p.n; i++)
+        for (int t = 0; t < 4; t++) k3_cut(p, i, t, 4);
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) k3_offsets_a(p, t);
+    k3_offsets_b(p);
+    for (uint32_t t = 0; t < SCAN_THREADS; t++) k3_offsets_c(p, t);
     for (uint32_t i = 0; i < p.n; i++)
         for (int t = 0; t < 4; t++) k3_copy(p, i, t, 4);
-    c->st.kernel_launches += 3;
+    c->st.kernel_launches += 4;
     return WMB_OK;
 }
