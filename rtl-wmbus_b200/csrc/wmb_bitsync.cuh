@@ -45,16 +45,14 @@ struct K2aRegs {
 
 /* 32 decimated samples (one 128-byte line of dphi, already in registers) through the DC block,
  * the slicer and the three biquads; returns the data-bit and clock-sign words */
-template <class CH>
-WMB_D void k2a_block(const float4 (&blk)[8], int n, uint32_t dc, uint32_t t2, K2aRegs &r,
-                     uint32_t &dword, uint32_t &cword)
+template <class CH, bool dc, bool t2>
+WMB_D void k2a_block(const float4 (&blk)[8], int n, K2aRegs &r, uint32_t &dword, uint32_t &cword)
 {
-    const float *cf = (CH::ID == 0) ? c_iir_t1c1 : c_iir_s1;
-    const float b10 = cf[0], b20 = cf[1], a10 = cf[2], a20 = cf[3];
-    const float b11 = cf[4], b21 = cf[5], a11 = cf[6], a21 = cf[7];
-    const float b12 = cf[8], b22 = cf[9], a12 = cf[10], a22 = cf[11];
-    const float gain = c_iir_gain;
-    const float alpha = 0.999f, cdc = (1.f + 0.999f) / 2.f;       /* rtl_wmbus.c:501 / :511 */
+    constexpr float b10 = CH::B10, b20 = CH::B20, a10 = CH::A10, a20 = CH::A20;
+    constexpr float b11 = CH::B11, b21 = CH::B21, a11 = CH::A11, a21 = CH::A21;
+    constexpr float b12 = CH::B12, b22 = CH::B22, a12 = CH::A12, a22 = CH::A22;
+    constexpr float gain = 1.874981046e-06;                       /* rtl_wmbus.c:338 */
+    constexpr float alpha = 0.999f, cdc = (1.f + 0.999f) / 2.f;   /* rtl_wmbus.c:501 / :511 */
     dword = 0; cword = 0;
 #pragma unroll
     for (int i = 0; i < 32; i++) {
@@ -98,8 +96,8 @@ WMB_D void k2a_save(IirState &st, const K2aRegs &r)
     st.clk3 = r.clk3; st.pad = 0;
 }
 
-template <class CH>
-WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
+template <class CH, bool DC, bool T2>
+WMB_D void k2a_lane_t(const K2aParams &p, uint32_t lane)
 {
     if (lane >= p.lanes) return;
     const int64_t s0 = (int64_t)lane * p.C;
@@ -134,7 +132,7 @@ WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
         if (m == s0 && !saved_start) { k2a_save(st, r); p.st_start[lane] = st; saved_start = true; }
         const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
         uint32_t dword, cword;
-        k2a_block<CH>(cur, n, p.dc, p.t2, r, dword, cword);
+        k2a_block<CH, DC, T2>(cur, n, r, dword, cword);
         /* lock stencil on the whole word: sample the data bit where the clock reads
          * low, high, high, high at m-3..m (rtl_wmbus.c:1092-1111) */
         const uint64_t hist3 = ((r.clk3 & 1u) << 2) | (r.clk3 & 2u) | ((r.clk3 >> 2) & 1u);   /* bit2 = m-1 */
@@ -156,6 +154,13 @@ WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
     k2a_save(st, r);
     if (!saved_start) p.st_start[lane] = st;                      /* empty lane */
     p.st_end[lane] = st;
+}
+
+template <class CH>
+WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
+{
+    if (p.dc) { if (p.t2) k2a_lane_t<CH, true, true>(p, lane); else k2a_lane_t<CH, true, false>(p, lane); }
+    else      { if (p.t2) k2a_lane_t<CH, false, true>(p, lane); else k2a_lane_t<CH, false, false>(p, lane); }
 }
 
 WMB_D bool iir_state_equal(const IirState &a, const IirState &b, uint32_t dc, uint32_t t2)

@@ -49,6 +49,11 @@ struct ChainT1C1 {
     static constexpr uint32_t CODE = 0x543Du;     /* rtl_wmbus.c:97  */
     static constexpr uint32_t CODE_MASK = 0xFFFFu;
     static constexpr uint32_t RAW_MASK = 0x3Fu;   /* rtl_wmbus.c:733 */
+    /* Chebyshev-I band-pass, per section {b1, b2, a1, a2} (rtl_wmbus.c:340-341); literals so that
+     * they become instruction immediates */
+    static constexpr float B10 = 1.999994649, B20 = 0.9999946492, A10 = -1.387139203, A20 = 0.9921518712;
+    static constexpr float B11 = -1.99999482, B21 = 0.9999948196, A11 = -1.403492665, A21 = 0.9845934971;
+    static constexpr float B12 = 1.703868036e-07, B22 = -1.000010531, A12 = -1.430055639, A22 = 0.9923856172;
 };
 
 struct ChainS1 {
@@ -58,6 +63,10 @@ struct ChainS1 {
     static constexpr uint32_t CODE = 0x547696u;   /* rtl_wmbus.c:101 */
     static constexpr uint32_t CODE_MASK = 0xFFFFFFu;
     static constexpr uint32_t RAW_MASK = 0xFu;    /* rtl_wmbus.c:644 */
+    /* rtl_wmbus.c:355-356 */
+    static constexpr float B10 = 1.999994187, B20 = 0.9999941867, A10 = -1.92151475, A20 = 0.9918135499;
+    static constexpr float B11 = -1.999994026, B21 = 0.9999940262, A11 = -1.922481015, A21 = 0.984593497;
+    static constexpr float B12 = -1.605750097e-07, B22 = -1.000011787, A12 = -1.937432099, A22 = 0.9927241336;
 };
 
 #ifdef WMB_HOSTSIM

@@ -329,8 +329,10 @@ static uint64_t next_pow2(uint64_t v)
 static uint32_t pick_chunk(const wmb_ctx *c, int64_t M)
 {
     if (c->C_fixed) return c->C_fixed;
-    /* aim for ~8192 lanes on big batches, never below 8192 samples per lane */
-    int64_t C = (M + 8191) / 8192;
+    /* The clock-recovery lanes are bound by the fp32 pipe of the scheduler they sit on, so a
+     * big batch is cut into about one warp per scheduler (148 SMs x 4 x 32 lanes); never
+     * below 8192 samples per lane (the warm-up is 32768) */
+    int64_t C = (M + 18943) / 18944;
     C = (C + 1023) / 1024 * 1024;
     if (C < 8192) C = 8192;
     if (C > 65536) C = 65536;
