@@ -653,7 +653,8 @@ WMB_D void k2pc_compact(const K2pcParams &p, uint32_t lane, int tid, int nthr)
 /* phase 2 */
 struct K2p2Params {
     const uint32_t *rec_m, *rec_v;
-    const K2pDev *pd_in; K2pDev *pd;
+    uint16_t *rec_n;            /* [records] bits emitted per record (pass A -> pass B)     */
+    K2pDev *pd;
     uint32_t R;                 /* records per lane (nominal)                              */
     uint32_t lanes;
     uint32_t *cnt;              /* [lanes] events per lane                                 */
@@ -665,82 +666,133 @@ struct K2p2Params {
     uint64_t *cand; uint32_t cand_cap;
     const RlState *carry;       /* exact state at batch start                               */
     RlState *p2_out;            /* out: a/b/sr after the last record, run = 1 marks it valid */
-    uint32_t write;             /* 0: count pass, 1: write pass                            */
     uint64_t *agg;
 };
 
-WMB_D void k2p2_lane(const K2p2Params &p, uint32_t lane)
+#define K2P2_BLK 8                   /* records fetched together (memory-level parallelism) */
+
+/* the lane's first record: record 0 (carry state) or the first record in [r0, r1) that follows a reset */
+WMB_D bool k2p2_start(const K2p2Params &p, uint32_t lane, uint64_t r0, uint64_t r1, uint64_t &i)
+{
+    i = r0;
+    if (lane == 0) return true;
+    for (; i < r1; i++) if (p.rec_v[i] & 1u) return true;
+    return false;
+}
+
+/* pass A (serial in the PI recurrence, nothing else): bits per record -> rec_n, events per lane -> cnt.
+ * Only rec_v is read; the next block of records is requested while the current one is processed. */
+WMB_D void k2p2_count(const K2p2Params &p, uint32_t lane)
 {
     if (lane >= p.lanes) return;
     const uint64_t N = p.pd->n_rec;
-    if (p.write && p.pd->fallback) return;
     const uint64_t r0 = (uint64_t)lane * p.R, r1 = (r0 + p.R < N) ? r0 + p.R : N;
     uint32_t n_ev = 0;
-    if (r0 < N) {
-        /* find this lane's first segment start: record 0 (carry state) or a record that follows a reset */
-        uint64_t i = r0;
-        int32_t a, b; uint32_t sr, pend;
-        bool have = false;
-        if (lane == 0) {
-            const RlState c = *p.carry;
-            a = c.a; b = c.b; sr = c.sr; pend = (c.flags >> 1) & 1u; have = true;
-        } else {
-            for (; i < r1; i++) if (p.rec_v[i] & 1u) { have = true; break; }
-            a = 8 * 256; b = 0; sr = 0; pend = 0;
-        }
-        uint64_t ord = p.write ? p.base[lane] : 0;
-        if (have) {
-            for (; i < N; i++) {
-                const uint32_t v = p.rec_v[i];
-                if (v & 1u) {
-                    if (i >= r1) break;                              /* next lane's segment */
-                    a = 8 * 256; b = 0; sr = 0; pend = 1;             /* runlength_algorithm_reset_t1_c1 */
+    uint64_t i;
+    if (r0 < N && k2p2_start(p, lane, r0, r1, i)) {
+        int32_t a = 8 * 256, b = 0;
+        if (lane == 0) { const RlState c = *p.carry; a = c.a; b = c.b; }
+        bool stop = false, ran_off_end = false;
+        uint32_t v[K2P2_BLK], vn[K2P2_BLK];
+#pragma unroll
+        for (int j = 0; j < K2P2_BLK; j++) v[j] = (i + j < N) ? p.rec_v[i + j] : 1u;
+        if (i >= N) ran_off_end = true;
+        while (!stop && i < N) {
+#pragma unroll
+            for (int j = 0; j < K2P2_BLK; j++) vn[j] = (i + K2P2_BLK + j < N) ? p.rec_v[i + K2P2_BLK + j] : 1u;
+#pragma unroll
+            for (int j = 0; j < K2P2_BLK; j++) {
+                if (stop) continue;
+                if (i + j >= N) { stop = true; ran_off_end = true; continue; }
+                const uint32_t vv = v[j];
+                if (vv & 1u) {
+                    if (i + j >= r1) { stop = true; continue; }      /* next lane's segment */
+                    a = 8 * 256; b = 0;                              /* runlength_algorithm_reset_t1_c1 */
                 }
-                const uint32_t level = (v >> 1) & 1u;
-                int rl = (int)((v >> 2) * 256u);
+                int rl = (int)((vv >> 2) * 256u);
                 const int half = a / 2;
                 if (rl <= half || a <= 0) {                          /* rtl_wmbus.c:756-762 (or a spin) */
-                    if (!p.write) p.pd->fallback = 1;
-                    break;
+                    p.pd->fallback = 1;
+                    stop = true; continue;
                 }
-                int n = 0;
-                const uint32_t m = p.rec_m[i];
-                const uint32_t rssi = p.write ? p.rssi[m] : 0u;
-                while (rl > half) {                                  /* :765-779 */
-                    rl -= a;
-                    sr = ((sr << 1) | level) & 0xFFFFu;
-                    if (n < K2_EDGE_EMIT_CAP) {
-                        if (p.write) {
-                            const uint32_t sync = (sr == 0x543Du) ? 1u : 0u;
-                            p.ring[ord & p.ring_mask] = ((uint64_t)(p.m_base + m) << 24) | ((uint64_t)rssi << 16) |
-                                                        (pend << 2) | (sync << 1) | level;
-                            if (sync) {
-#ifdef WMB_HOSTSIM
-                                const uint32_t slot = p.sd->n_cand++;
-#else
-                                const uint32_t slot = atomicAdd(&p.sd->n_cand, 1u);
-#endif
-                                if (slot < p.cand_cap) p.cand[slot] = ord;
-                                else p.sd->cand_overflow = 1;
-                            }
-                            ord++;
-                        }
-                        n_ev++;
-                        pend = 0;
-                    }
-                    n++;
-                }
+                /* n = number of bit periods in the run (:765-779): smallest n with rl - n*a <= half */
+                int n = (rl - half + a - 1) / a;
+                rl -= n * a;
                 b += rl;                                             /* :792 */
                 a += (rl + b / 16) / (32 * n);                       /* :796 */
+                const uint32_t ne = n < K2_EDGE_EMIT_CAP ? (uint32_t)n : (uint32_t)K2_EDGE_EMIT_CAP;
+                p.rec_n[i + j] = (uint16_t)ne;
+                n_ev += ne;
             }
-            if (i >= N && p.write) {                                 /* this lane saw the last record */
-                RlState c;
-                c.run = 1; c.a = a; c.b = b; c.sr = sr; c.flags = pend << 1; c.raw = 0;
-                *p.p2_out = c;
+            i += K2P2_BLK;
+            if (!stop && i >= N) ran_off_end = true;
+#pragma unroll
+            for (int j = 0; j < K2P2_BLK; j++) v[j] = vn[j];
+        }
+        if (ran_off_end) { p.p2_out->a = a; p.p2_out->b = b; }       /* exactly one lane sees the last record */
+    }
+    p.cnt[lane] = n_ev;
+}
+
+/* pass B: with the bit counts known, writing the events has no long dependency chain any more:
+ * records, sample indices and rssi values are fetched a block at a time */
+WMB_D void k2p2_write(const K2p2Params &p, uint32_t lane)
+{
+    if (lane >= p.lanes) return;
+    if (p.pd->fallback) return;
+    const uint64_t N = p.pd->n_rec;
+    const uint64_t r0 = (uint64_t)lane * p.R, r1 = (r0 + p.R < N) ? r0 + p.R : N;
+    uint64_t i;
+    if (!(r0 < N && k2p2_start(p, lane, r0, r1, i))) return;
+    uint32_t sr = 0, pend = 0;
+    if (lane == 0) { const RlState c = *p.carry; sr = c.sr; pend = (c.flags >> 1) & 1u; }
+    uint64_t ord = p.base[lane];
+    bool stop = false, ran_off_end = (i >= N);
+    while (!stop && i < N) {
+        uint32_t v[K2P2_BLK], m[K2P2_BLK], rs[K2P2_BLK];
+        uint16_t nn[K2P2_BLK];
+#pragma unroll
+        for (int j = 0; j < K2P2_BLK; j++) {
+            const bool ok = i + j < N;
+            v[j] = ok ? p.rec_v[i + j] : 1u;
+            m[j] = ok ? p.rec_m[i + j] : 0u;
+            nn[j] = ok ? p.rec_n[i + j] : (uint16_t)0;
+        }
+#pragma unroll
+        for (int j = 0; j < K2P2_BLK; j++) rs[j] = p.rssi[m[j]];
+#pragma unroll
+        for (int j = 0; j < K2P2_BLK; j++) {
+            if (stop) continue;
+            if (i + j >= N) { stop = true; ran_off_end = true; continue; }
+            if (v[j] & 1u) {
+                if (i + j >= r1) { stop = true; continue; }
+                sr = 0; pend = 1;
+            }
+            const uint32_t level = (v[j] >> 1) & 1u;
+            const uint64_t head = ((uint64_t)(p.m_base + m[j]) << 24) | ((uint64_t)rs[j] << 16) | level;
+            for (uint32_t k = 0; k < nn[j]; k++) {
+                sr = ((sr << 1) | level) & 0xFFFFu;
+                const uint32_t sync = (sr == 0x543Du) ? 1u : 0u;
+                p.ring[ord & p.ring_mask] = head | (pend << 2) | (sync << 1);
+                pend = 0;
+                if (sync) {
+#ifdef WMB_HOSTSIM
+                    const uint32_t slot = p.sd->n_cand++;
+#else
+                    const uint32_t slot = atomicAdd(&p.sd->n_cand, 1u);
+#endif
+                    if (slot < p.cand_cap) p.cand[slot] = ord;
+                    else p.sd->cand_overflow = 1;
+                }
+                ord++;
             }
         }
+        i += K2P2_BLK;
+        if (!stop && i >= N) ran_off_end = true;
     }
-    if (!p.write) p.cnt[lane] = n_ev;
+    if (ran_off_end) {                                               /* this lane saw the last record */
+        p.p2_out->sr = sr; p.p2_out->flags = pend << 1; p.p2_out->run = 1;
+    }
 }
 
 WMB_D void k2p2_scan_a(const K2p2Params &p, uint32_t t)

@@ -90,7 +90,7 @@ struct ChainBuf {
     /* two-phase run-length path (T1/C1) */
     uint64_t *p1_rec = nullptr; uint32_t *p1_cnt = nullptr; uint64_t *p1_base = nullptr;
     P1State *p1_start = nullptr, *p1_end = nullptr; uint32_t *p1_rerun = nullptr;
-    uint32_t *rec_m = nullptr, *rec_v = nullptr;
+    uint32_t *rec_m = nullptr, *rec_v = nullptr; uint16_t *rec_n = nullptr;
     uint32_t *p2_cnt = nullptr; uint64_t *p2_base = nullptr;
     K2pDev *pd = nullptr; RlState *p2_out = nullptr;
     /* time2 lanes */
@@ -239,11 +239,9 @@ static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, cons
     k2pc_scan_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(pc);
     k2pc_compact_kernel<<<pc.lanes, 128, 0, c->cs>>>(pc);
     const unsigned grid = (p2.lanes + 127) / 128;
-    p2.write = 0;
-    k2p2_lanes_kernel<<<grid, 128, 0, c->cs>>>(p2);
+    k2p2_count_kernel<<<grid, 128, 0, c->cs>>>(p2);
     k2p2_scan_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(p2);
-    p2.write = 1;
-    k2p2_lanes_kernel<<<grid, 128, 0, c->cs>>>(p2);
+    k2p2_write_kernel<<<grid, 128, 0, c->cs>>>(p2);
     k2p_fold_kernel<<<1, 32, 0, c->cs>>>(p1_end_last, p2.p2_out, carry, p2.pd);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches += 6;
@@ -443,6 +441,7 @@ static int ctx_alloc(wmb_ctx *c)
             TRY(dev_alloc(c, &b.p1_rerun, c->p1_lanes_max, true));
             TRY(dev_alloc(c, &b.rec_m, c->rec_max));
             TRY(dev_alloc(c, &b.rec_v, c->rec_max));
+            TRY(dev_alloc(c, &b.rec_n, c->rec_max));
             TRY(dev_alloc(c, &b.p2_cnt, c->p2_lanes_max, true));
             TRY(dev_alloc(c, &b.p2_base, c->p2_lanes_max));
             TRY(dev_alloc(c, &b.pd, 1, true));
@@ -698,7 +697,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
                 pc.rec_m = b.rec_m; pc.rec_v = b.rec_v; pc.agg = s.agg; pc.pd = b.pd;
                 K2p2Params p2;
                 memset(&p2, 0, sizeof(p2));
-                p2.rec_m = b.rec_m; p2.rec_v = b.rec_v; p2.pd = b.pd; p2.R = K2P2_RECORDS;
+                p2.rec_m = b.rec_m; p2.rec_v = b.rec_v; p2.rec_n = b.rec_n; p2.pd = b.pd; p2.R = K2P2_RECORDS;
                 p2.lanes = (uint32_t)(((uint64_t)M / 5 + 2 * (uint64_t)p1.lanes) / K2P2_RECORDS + 2);
                 if (p2.lanes > c->p2_lanes_max) return set_err(WMB_E_INVAL, "internal: phase-2 lanes");
                 p2.cnt = b.p2_cnt; p2.base = b.p2_base; p2.rssi = b.rssi + c->W; p2.m_base = (int64_t)c->m_consumed;

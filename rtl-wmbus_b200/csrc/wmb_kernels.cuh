@@ -150,6 +150,59 @@ WMB_D void k1_box(const K1Params &p, K1Smem &sm, int tid)
     }
 }
 
+/* ---- fast path for the common geometry: decimation 2, no mixer ------------------------
+ * One 32-bit word of input = I0 Q0 I1 Q1 = exactly one decimation step.  The truncation
+ * (int)(u8 - 127.5f) equals u8 - 127 - (u8 >= 128), so the per-word I and Q sums are two
+ * byte dot products (dp4a) minus the count of bytes with the top bit set.  Partial sums are
+ * stored biased (+512) and packed I | Q << 16, so box sums over 4 / 8 words are plain
+ * 32-bit adds without carries between the halves. */
+#define K1_PAIR_BIAS 512
+
+WMB_D int wmb_dp4a_u(uint32_t a, uint32_t b, int c)
+{
+#ifdef WMB_HOSTSIM
+    for (int i = 0; i < 4; i++) c += (int)((a >> (8 * i)) & 0xFFu) * (int)((b >> (8 * i)) & 0xFFu);
+    return c;
+#else
+    return (int)__dp4a(a, b, (unsigned)c);
+#endif
+}
+
+WMB_D void k1_convert_fast(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile, int tid)
+{
+    const int64_t k0 = k1_tile_k0(p, tile);
+    const int nw = (int)(k1_tile_iq(p.d) / 2);
+    const uint32_t *w32 = (const uint32_t *)raw;
+    for (int j = tid; j < nw; j += K1_THREADS) {
+        uint32_t packed = (uint32_t)K1_PAIR_BIAS | ((uint32_t)K1_PAIR_BIAS << 16);      /* two "zero" samples */
+        if (k0 + 2 * j >= -p.n_hist_iq) {
+            const uint32_t w = w32[j];
+            const uint32_t msb = (w >> 7) & 0x01010101u;
+            const int si = wmb_dp4a_u(w, 0x00010001u, 0) - wmb_dp4a_u(msb, 0x00010001u, 0) - 254 + K1_PAIR_BIAS;
+            const int sq = wmb_dp4a_u(w, 0x01000100u, 0) - wmb_dp4a_u(msb, 0x01000100u, 0) - 254 + K1_PAIR_BIAS;
+            packed = (uint32_t)si | ((uint32_t)sq << 16);
+        }
+        sm.v[j] = (int32_t)packed;
+    }
+}
+
+template <class CH>
+WMB_D void k1_box_fast(const K1Params &p, K1Smem &sm, int tid)
+{
+    const float inv = 1.0f / (float)CH::BOX;
+    constexpr int NW = CH::BOX / 2;                       /* words per box */
+    for (int r = tid; r < K1_TILE + K1_HALO; r += K1_THREADS) {
+        const int wend = r + K1_BOX_MAX / 2;              /* word holding the newest two samples */
+        uint32_t acc = 0;
+#pragma unroll
+        for (int b = 0; b < NW; b++) acc += (uint32_t)sm.v[wend - b];
+        const int si = (int)(acc & 0xFFFFu) - NW * K1_PAIR_BIAS;
+        const int sq = (int)(acc >> 16) - NW * K1_PAIR_BIAS;
+        sm.si[r] = wmb_fmul((float)si, inv);
+        sm.sq[r] = wmb_fmul((float)sq, inv);
+    }
+}
+
 WMB_HD int k1_pad(int r) { return r + (r >> 5); }
 
 /* phase C: discriminator and |s|   rtl_wmbus.c:1047, :1066 */
@@ -184,9 +237,11 @@ WMB_D void k1_fir_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
             acc = wmb_fadd(acc, wmb_fmul(b[t], sm.draw[K1_HALO + o - t]));
         out[m] = acc;
     }
-    if (tid < K1_TILE / K1_RSSI_SEG) {
-        /* one segment per thread, started K1_RSSI_WARM samples early from r = 0 */
-        const int o0 = tid * K1_RSSI_SEG;
+    if (tid >= K1_THREADS - K1_TILE / K1_RSSI_SEG) {
+        /* one segment per thread (the upper warps, so that the FIR loop above and the recurrence
+         * below overlap across warps), started K1_RSSI_WARM samples early from r = 0 */
+        const int seg = tid - (K1_THREADS - K1_TILE / K1_RSSI_SEG);
+        const int o0 = seg * K1_RSSI_SEG;
         const int r0 = K1_HALO + o0 - K1_RSSI_WARM;
         float rr = 0.0f;
         const float A = 0.6789f, B = 1.0f - 0.6789f;
@@ -275,8 +330,12 @@ template <class CH>
 __device__ __forceinline__ void k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile,
                                          int tid, bool need_convert)
 {
-    if (need_convert) { k1_convert<CH::ID>(p, sm, raw, tile, tid); __syncthreads(); }
-    k1_box<CH>(p, sm, tid);
+    const bool fast = (p.d == 2 && !p.mix);
+    if (need_convert) {
+        if (fast) k1_convert_fast(p, sm, raw, tile, tid); else k1_convert<CH::ID>(p, sm, raw, tile, tid);
+        __syncthreads();
+    }
+    if (fast) k1_box_fast<CH>(p, sm, tid); else k1_box<CH>(p, sm, tid);
     __syncthreads();
     k1_disc_mag(p, sm, tid);
     __syncthreads();
@@ -594,7 +653,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k2pc_scan_kernel(const K2pcParam
     k2pc_scan_c(p, threadIdx.x);
 }
 __global__ void k2pc_compact_kernel(const K2pcParams p) { k2pc_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
-__global__ void __launch_bounds__(128) k2p2_lanes_kernel(const K2p2Params p) { k2p2_lane(p, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(128) k2p2_count_kernel(const K2p2Params p) { k2p2_count(p, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(128) k2p2_write_kernel(const K2p2Params p) { k2p2_write(p, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(SCAN_THREADS) k2p2_scan_kernel(const K2p2Params p)
 {
     k2p2_scan_a(p, threadIdx.x);

@@ -8,8 +8,9 @@
 template <class CH>
 static void hostsim_k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile, bool need_convert)
 {
-    if (need_convert) for (int t = 0; t < K1_THREADS; t++) k1_convert<CH::ID>(p, sm, raw, tile, t);
-    for (int t = 0; t < K1_THREADS; t++) k1_box<CH>(p, sm, t);
+    const bool fast = (p.d == 2 && !p.mix);
+    if (need_convert) for (int t = 0; t < K1_THREADS; t++) { if (fast) k1_convert_fast(p, sm, raw, tile, t); else k1_convert<CH::ID>(p, sm, raw, tile, t); }
+    for (int t = 0; t < K1_THREADS; t++) { if (fast) k1_box_fast<CH>(p, sm, t); else k1_box<CH>(p, sm, t); }
     for (int t = 0; t < K1_THREADS; t++) k1_disc_mag(p, sm, t);
     for (int t = 0; t < K1_THREADS; t++) k1_fir_rssi<CH>(p, sm, tile, t);
     for (int t = 0; t < K1_THREADS; t++) k1_store_rssi<CH>(p, sm, tile, t);
@@ -73,13 +74,11 @@ static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, cons
     for (uint32_t t = 0; t < SCAN_THREADS; t++) k2pc_scan_c(pc, t);
     for (uint32_t lane = 0; lane < pc.lanes; lane++)
         for (int t = 0; t < 4; t++) k2pc_compact(pc, lane, t, 4);
-    p2.write = 0;
-    for (uint32_t lane = 0; lane < p2.lanes; lane++) k2p2_lane(p2, lane);
+    for (uint32_t lane = 0; lane < p2.lanes; lane++) k2p2_count(p2, lane);
     for (uint32_t t = 0; t < SCAN_THREADS; t++) k2p2_scan_a(p2, t);
     k2p2_scan_b(p2);
     for (uint32_t t = 0; t < SCAN_THREADS; t++) k2p2_scan_c(p2, t);
-    p2.write = 1;
-    for (uint32_t lane = 0; lane < p2.lanes; lane++) k2p2_lane(p2, lane);
+    for (uint32_t lane = 0; lane < p2.lanes; lane++) k2p2_write(p2, lane);
     k2p_fold(p1_end_last, p2.p2_out, carry, p2.pd);
     c->st.kernel_launches += 6;
     return WMB_OK;
