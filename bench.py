@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--workload", default="t1x2")
     ap.add_argument("--mib", type=int, default=1024)
     ap.add_argument("--batch-mib", type=int, default=0, help="device batch size (default: whole capture)")
-    ap.add_argument("--e2e-batch-mib", type=int, default=128)
+    ap.add_argument("--e2e-batch-mib", type=int, default=256)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--warm", type=int, default=0, help="bit-sync warm-up samples (default: library)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

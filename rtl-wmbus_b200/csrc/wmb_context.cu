@@ -27,6 +27,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <thread>
 #include <time.h>
 
 #ifdef WMB_HOSTSIM
@@ -1085,17 +1086,35 @@ extern "C" int wmb_decode_frames(wmb_ctx *c, const wmb_frame *frames, size_t n)
         if (a->algo != b->algo) return a->algo < b->algo;
         return a->ordinal < b->ordinal;
     });
+    for (const wmb_frame *f : v)
+        if (f->chain >= WMB_N_CHAINS || f->algo >= WMB_N_ALGOS) return set_err(WMB_E_INVAL, "bad frame");
+    /* The per-frame decode is pure, so it is spread over a few host threads; the stream-order
+     * bookkeeping below then only looks at the results. */
+    std::vector<wmb_decoded> dec(n);
+    {
+        unsigned nt = n >= 256 ? std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        auto work = [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) wmb_frame_decode(v[i], &dec[i]); };
+        if (nt <= 1) work(0, n);
+        else {
+            std::vector<std::thread> th;
+            const size_t per = (n + nt - 1) / nt;
+            for (unsigned t = 0; t < nt; t++) {
+                const size_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+                if (lo < hi) th.emplace_back(work, lo, hi);
+            }
+            for (auto &t : th) t.join();
+        }
+    }
     bool blocked[WMB_N_CHAINS][WMB_N_ALGOS] = {{false, false}, {false, false}};
     std::vector<QueuedLine> fresh;
-    for (const wmb_frame *f : v) {
-        if (f->chain >= WMB_N_CHAINS || f->algo >= WMB_N_ALGOS) return set_err(WMB_E_INVAL, "bad frame");
+    for (size_t fi = 0; fi < n; fi++) {
+        const wmb_frame *f = v[fi];
         Stream &s = c->cb[f->chain].s[f->algo];
         /* A decoder that is receiving ignores further access-code matches
          * (t1_c1_packet_decoder.h:272-278 honours the flag only in idle). */
         if (blocked[f->chain][f->algo]) continue;
         if ((int64_t)f->ordinal <= s.busy_until) continue;
-        wmb_decoded d;
-        wmb_frame_decode(f, &d);
+        const wmb_decoded &d = dec[fi];
         if (d.status == WMB_DEC_NEED_MORE) {
             if (f->reserved) { blocked[f->chain][f->algo] = true; continue; }   /* partial: comes again */
             if (!f->truncated) return set_err(WMB_E_STATE, "internal: frame shorter than its header demands");

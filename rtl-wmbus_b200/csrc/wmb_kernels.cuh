@@ -400,6 +400,7 @@ WMB_D void k2c_scan_a(const K2cParams &p, uint32_t t)
     const uint32_t per = scan_per_thread(p.lanes);
     const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
     uint64_t cnt = 0;
+#pragma unroll 8
     for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) cnt += p.cnt[l];
     p.agg[t] = cnt;
 }

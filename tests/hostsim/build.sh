@@ -10,5 +10,5 @@ gcc -O2 -std=gnu99 -fPIC -Wall -Wextra -I"$root/include" -c "$src/wmb_framer.c" 
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -Wextra -Wno-unused-parameter -Wno-unused-function -Wno-unknown-pragmas -Wno-stringop-overflow \
     -DWMB_HOSTSIM -DWMB_VERSION='"wmbus-b200 hostsim (TEST ONLY)"' \
     -I"$here" -I"$root/include" -I"$src" -x c++ -c "$src/wmb_context.cu" -o "$here/_build/wmb_context.o"
-g++ -shared -o "$here/_build/libwmbus_hostsim.so" "$here/_build/wmb_context.o" "$here/_build/wmb_framer.o" -lm
+g++ -shared -o "$here/_build/libwmbus_hostsim.so" "$here/_build/wmb_context.o" "$here/_build/wmb_framer.o" -lm -lpthread
 echo "built $here/_build/libwmbus_hostsim.so"
