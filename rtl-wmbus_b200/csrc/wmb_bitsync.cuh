@@ -301,7 +301,10 @@ WMB_D void k2t_scan_c(const K2tParams &p, uint32_t t)
     }
 }
 
-/* pass 2: write the events straight into the stream ring */
+/* pass 2: write the events straight into the stream ring.  Four words (128 samples) at a time:
+ * their strobe/data words and the 128 rssi bytes they may need are requested together. */
+struct u32x4 { uint32_t x, y, z, w; };
+
 template <class CH>
 WMB_D void k2t_write(const K2tParams &p, uint32_t lane)
 {
@@ -310,28 +313,48 @@ WMB_D void k2t_write(const K2tParams &p, uint32_t lane)
     const uint32_t w0 = lane * p.Cw, w1 = (w0 + p.Cw < nw) ? w0 + p.Cw : nw;
     uint32_t sr = p.sr_start[lane];
     uint64_t ord = p.base[lane];
-    for (uint32_t w = w0; w < w1; w++) {
-        uint32_t s = p.sbits[w];
-        const uint32_t d = p.dbits[w];
-        while (s) {
-            const int i = wmb_ffs(s) - 1;
-            s &= s - 1;
-            const uint32_t bit = (d >> i) & 1u;
-            sr = ((sr << 1) | bit) & CH::CODE_MASK;              /* rtl_wmbus.c:820 */
-            const uint32_t sync = (sr == CH::CODE) ? 1u : 0u;    /* rtl_wmbus.c:822 */
-            const int64_t m = (int64_t)w * 32 + i;
-            const uint64_t g = ((uint64_t)(p.m_base + m) << 24) | ((uint64_t)p.rssi[m] << 16) | (sync << 1) | bit;
-            p.ring[ord & p.ring_mask] = g;
-            if (sync) {
+    for (uint32_t wb = w0; wb < w1; wb += 4) {
+        uint32_t s4[4], d4[4];
+        u32x4 rs[8];
+        if (wb + 4 <= w1) {
+            const u32x4 sv = *(const u32x4 *)(p.sbits + wb), dv = *(const u32x4 *)(p.dbits + wb);
+            s4[0] = sv.x; s4[1] = sv.y; s4[2] = sv.z; s4[3] = sv.w;
+            d4[0] = dv.x; d4[1] = dv.y; d4[2] = dv.z; d4[3] = dv.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) { s4[q] = (wb + q < w1) ? p.sbits[wb + q] : 0u; d4[q] = (wb + q < w1) ? p.dbits[wb + q] : 0u; }
+        }
+        if ((s4[0] | s4[1] | s4[2] | s4[3]) == 0u) continue;
+        const u32x4 *r4 = (const u32x4 *)(p.rssi + (int64_t)wb * 32);   /* 32-byte aligned; slack behind M */
+#pragma unroll
+        for (int q = 0; q < 8; q++) rs[q] = r4[q];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t s = s4[q];
+            const uint32_t d = d4[q];
+            while (s) {
+                const int i = wmb_ffs(s) - 1;
+                s &= s - 1;
+                const uint32_t bit = (d >> i) & 1u;
+                sr = ((sr << 1) | bit) & CH::CODE_MASK;              /* rtl_wmbus.c:820 */
+                const uint32_t sync = (sr == CH::CODE) ? 1u : 0u;    /* rtl_wmbus.c:822 */
+                const int64_t m = (int64_t)(wb + q) * 32 + i;
+                const u32x4 rq = rs[2 * q + (i >> 4)];
+                const uint32_t rw = ((i >> 2) & 3) == 0 ? rq.x : ((i >> 2) & 3) == 1 ? rq.y : ((i >> 2) & 3) == 2 ? rq.z : rq.w;
+                const uint32_t rssi = (rw >> (8 * (i & 3))) & 0xFFu;
+                const uint64_t g = ((uint64_t)(p.m_base + m) << 24) | ((uint64_t)rssi << 16) | (sync << 1) | bit;
+                p.ring[ord & p.ring_mask] = g;
+                if (sync) {
 #ifdef WMB_HOSTSIM
-                const uint32_t slot = p.sd->n_cand++;
+                    const uint32_t slot = p.sd->n_cand++;
 #else
-                const uint32_t slot = atomicAdd(&p.sd->n_cand, 1u);
+                    const uint32_t slot = atomicAdd(&p.sd->n_cand, 1u);
 #endif
-                if (slot < p.cand_cap) p.cand[slot] = ord;
-                else p.sd->cand_overflow = 1;
+                    if (slot < p.cand_cap) p.cand[slot] = ord;
+                    else p.sd->cand_overflow = 1;
+                }
+                ord++;
             }
-            ord++;
         }
     }
 }
@@ -672,6 +695,23 @@ struct K2p2Params {
 
 #define K2P2_BLK 8                   /* records fetched together (memory-level parallelism) */
 
+/* C integer division (truncation toward zero) by 2^s and by a small positive n */
+WMB_D int wmb_div_pow2(int x, int s) { return (x + ((x >> 31) & ((1 << s) - 1))) >> s; }
+WMB_D int wmb_div_small(int x, int n)
+{
+    switch (n) {
+    case 1: return x;
+    case 2: return x / 2;
+    case 3: return x / 3;
+    case 4: return x / 4;
+    case 5: return x / 5;
+    case 6: return x / 6;
+    case 7: return x / 7;
+    case 8: return x / 8;
+    default: return x / n;
+    }
+}
+
 /* the lane's first record: record 0 (carry state) or the first record in [r0, r1) that follows a reset */
 WMB_D bool k2p2_start(const K2p2Params &p, uint32_t lane, uint64_t r0, uint64_t r1, uint64_t &i)
 {
@@ -716,11 +756,14 @@ WMB_D void k2p2_count(const K2p2Params &p, uint32_t lane)
                     p.pd->fallback = 1;
                     stop = true; continue;
                 }
-                /* n = number of bit periods in the run (:765-779): smallest n with rl - n*a <= half */
-                int n = (rl - half + a - 1) / a;
-                rl -= n * a;
+                /* n = number of bit periods in the run (:765-779): smallest n with rl - n*a <= half.
+                 * Telegram runs are 1-4 bits long: count them the reference's way and keep the
+                 * integer division for the rare long run. */
+                int n;
+                if (rl - half <= 8 * a) { n = 0; while (rl > half) { rl -= a; n++; } }
+                else { n = (rl - half + a - 1) / a; rl -= n * a; }
                 b += rl;                                             /* :792 */
-                a += (rl + b / 16) / (32 * n);                       /* :796 */
+                a += wmb_div_small(wmb_div_pow2(rl + wmb_div_pow2(b, 4), 5), n);   /* :796: x/(32 n) == (x/32)/n */
                 const uint32_t ne = n < K2_EDGE_EMIT_CAP ? (uint32_t)n : (uint32_t)K2_EDGE_EMIT_CAP;
                 p.rec_n[i + j] = (uint16_t)ne;
                 n_ev += ne;
@@ -749,18 +792,23 @@ WMB_D void k2p2_write(const K2p2Params &p, uint32_t lane)
     if (lane == 0) { const RlState c = *p.carry; sr = c.sr; pend = (c.flags >> 1) & 1u; }
     uint64_t ord = p.base[lane];
     bool stop = false, ran_off_end = (i >= N);
+    uint32_t v[K2P2_BLK], m[K2P2_BLK], rs[K2P2_BLK], vn[K2P2_BLK], mn[K2P2_BLK];
+    uint16_t nn[K2P2_BLK], nnn[K2P2_BLK];
+#pragma unroll
+    for (int j = 0; j < K2P2_BLK; j++) {
+        const bool ok = i + j < N;
+        v[j] = ok ? p.rec_v[i + j] : 1u; m[j] = ok ? p.rec_m[i + j] : 0u; nn[j] = ok ? p.rec_n[i + j] : (uint16_t)0;
+    }
+#pragma unroll
+    for (int j = 0; j < K2P2_BLK; j++) rs[j] = p.rssi[m[j]];
     while (!stop && i < N) {
-        uint32_t v[K2P2_BLK], m[K2P2_BLK], rs[K2P2_BLK];
-        uint16_t nn[K2P2_BLK];
+        /* request the next block's records while this one is written out */
 #pragma unroll
         for (int j = 0; j < K2P2_BLK; j++) {
-            const bool ok = i + j < N;
-            v[j] = ok ? p.rec_v[i + j] : 1u;
-            m[j] = ok ? p.rec_m[i + j] : 0u;
-            nn[j] = ok ? p.rec_n[i + j] : (uint16_t)0;
+            const bool ok = i + K2P2_BLK + j < N;
+            vn[j] = ok ? p.rec_v[i + K2P2_BLK + j] : 1u; mn[j] = ok ? p.rec_m[i + K2P2_BLK + j] : 0u;
+            nnn[j] = ok ? p.rec_n[i + K2P2_BLK + j] : (uint16_t)0;
         }
-#pragma unroll
-        for (int j = 0; j < K2P2_BLK; j++) rs[j] = p.rssi[m[j]];
 #pragma unroll
         for (int j = 0; j < K2P2_BLK; j++) {
             if (stop) continue;
@@ -790,6 +838,10 @@ WMB_D void k2p2_write(const K2p2Params &p, uint32_t lane)
         }
         i += K2P2_BLK;
         if (!stop && i >= N) ran_off_end = true;
+#pragma unroll
+        for (int j = 0; j < K2P2_BLK; j++) { v[j] = vn[j]; m[j] = mn[j]; nn[j] = nnn[j]; }
+#pragma unroll
+        for (int j = 0; j < K2P2_BLK; j++) rs[j] = p.rssi[m[j]];
     }
     if (ran_off_end) {                                               /* this lane saw the last record */
         p.p2_out->sr = sr; p.p2_out->flags = pend << 1; p.p2_out->run = 1;

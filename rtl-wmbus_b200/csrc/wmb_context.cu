@@ -421,7 +421,7 @@ static int ctx_alloc(wmb_ctx *c)
     for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
         if (!(c->chains & (1u << ch))) continue;
         ChainBuf &b = c->cb[ch];
-        const size_t n = (size_t)c->W + (size_t)c->M_max + 64;
+        const size_t n = (size_t)c->W + (size_t)c->M_max + 512;    /* slack: block loads may run past M */
         TRY(dev_alloc(c, &b.dphi, n));
         TRY(dev_alloc(c, &b.rssi, n));
         TRY(dev_alloc(c, &b.dbits, n / 32 + 4, true));

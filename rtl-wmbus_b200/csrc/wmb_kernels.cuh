@@ -216,7 +216,9 @@ WMB_D void k1_disc_mag(const K1Params &p, K1Smem &sm, int tid)
             dr = p.accurate ? wmb_discriminator(i, q, ip, qp) : wmb_discriminator_fast(i, q, ip, qp);
         }
         sm.draw[r] = dr;
-        sm.mag[k1_pad(r)] = wmb_fsqrt(wmb_fadd(wmb_fmul(i, i), wmb_fmul(q, q)));
+        /* the RSSI one-pole needs 0.6789f * |s| (rtl_wmbus.c:480); the product is formed here, in the
+         * wide phase, so that the serial recurrence below is one FMUL + one FADD per step */
+        sm.mag[k1_pad(r)] = wmb_fmul(0.6789f, wmb_fsqrt(wmb_fadd(wmb_fmul(i, i), wmb_fmul(q, q))));
     }
 }
 
@@ -244,10 +246,14 @@ WMB_D void k1_fir_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
         const int o0 = seg * K1_RSSI_SEG;
         const int r0 = K1_HALO + o0 - K1_RSSI_WARM;
         float rr = 0.0f;
-        const float A = 0.6789f, B = 1.0f - 0.6789f;
-        for (int j = 0; j < K1_RSSI_WARM + K1_RSSI_SEG; j++) {
-            rr = wmb_fadd(wmb_fmul(A, sm.mag[k1_pad(r0 + j)]), wmb_fmul(B, rr));
-            if (j >= K1_RSSI_WARM) sm.rs[o0 + j - K1_RSSI_WARM] = (uint8_t)(unsigned)rr;
+        const float B = 1.0f - 0.6789f;
+#pragma unroll 8
+        for (int j = 0; j < K1_RSSI_WARM; j++)
+            rr = wmb_fadd(sm.mag[k1_pad(r0 + j)], wmb_fmul(B, rr));
+#pragma unroll
+        for (int j = 0; j < K1_RSSI_SEG; j++) {
+            rr = wmb_fadd(sm.mag[k1_pad(r0 + K1_RSSI_WARM + j)], wmb_fmul(B, rr));
+            sm.rs[o0 + j] = (uint8_t)(unsigned)rr;
         }
     }
 }
