@@ -288,7 +288,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
                          "traffic": ncu_traffic(), "peak_source": peak_src,
-                         "kernel": "k1_demod_kernel + k2_lanes_kernel (the per-sample path; CUDA events on the launching stream)",
+                         "kernel": "k1_demod_kernel + k2a/k2t/k2p bit-sync kernels (the whole per-sample path; CUDA events on the launching stream)",
                          "algorithmic_bytes_per_step": int(abytes),
                          "k1_demod_ms": round(k1_ms / args.steps, 4), "k2_bitsync_ms": round(k2_ms / args.steps, 4),
                          "device_pass_ms": round(dev_ms / args.steps, 4)},

@@ -45,7 +45,7 @@ struct K2aRegs {
 
 /* 32 decimated samples (one 128-byte line of dphi, already in registers) through the DC block,
  * the slicer and the three biquads; returns the data-bit and clock-sign words */
-template <class CH, bool dc, bool t2>
+template <class CH, bool dc, bool t2, bool warm>
 WMB_D void k2a_block(const float4 (&blk)[8], int n, K2aRegs &r, uint32_t &dword, uint32_t &cword)
 {
     constexpr float b10 = CH::B10, b20 = CH::B20, a10 = CH::A10, a20 = CH::A20;
@@ -63,7 +63,7 @@ WMB_D void k2a_block(const float4 (&blk)[8], int n, K2aRegs &r, uint32_t &dword,
             const float y = wmb_fadd(wmb_fmul(cdc, wmb_fsub(x, r.dcx)), wmb_fmul(alpha, r.dcy));
             r.dcx = x; r.dcy = y; x = y;
         }
-        dword |= (x >= 0.0f ? 1u : 0u) << i;                      /* rtl_wmbus.c:1059 */
+        if (!warm) dword |= (x >= 0.0f ? 1u : 0u) << i;           /* rtl_wmbus.c:1059 */
         if (t2) {
             float v = wmb_fmul(x, x);                             /* rtl_wmbus.c:1089 */
             float h0;
@@ -74,10 +74,15 @@ WMB_D void k2a_block(const float4 (&blk)[8], int n, K2aRegs &r, uint32_t &dword,
             v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b11, r.h11)), wmb_fmul(b21, r.h21));
             r.h21 = r.h11; r.h11 = h0;
             h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a12, r.h12), wmb_fmul(a22, r.h22)));
-            v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b12, r.h12)), wmb_fmul(b22, r.h22));
+            /* a warm-up block only has to carry the state forward: the last section's output,
+             * the gain and the two comparisons are not part of it (only the final three clock
+             * signs are, and the block before the chunk start is computed in full) */
+            if (!warm) {
+                v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b12, r.h12)), wmb_fmul(b22, r.h22));
+                v = wmb_fmul(v, gain);
+                cword |= (v >= 0.0f ? 1u : 0u) << i;
+            }
             r.h22 = r.h12; r.h12 = h0;
-            v = wmb_fmul(v, gain);
-            cword |= (v >= 0.0f ? 1u : 0u) << i;
         }
     }
 }
@@ -132,7 +137,10 @@ WMB_D void k2a_lane_t(const K2aParams &p, uint32_t lane)
         if (m == s0 && !saved_start) { k2a_save(st, r); p.st_start[lane] = st; saved_start = true; }
         const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
         uint32_t dword, cword;
-        k2a_block<CH, DC, T2>(cur, n, r, dword, cword);
+        /* warm-up blocks skip the outputs, except the one right before the chunk start whose clock
+         * signs feed the lock stencil of the first owned word */
+        if (m + 32 < s0) k2a_block<CH, DC, T2, true>(cur, n, r, dword, cword);
+        else             k2a_block<CH, DC, T2, false>(cur, n, r, dword, cword);
         /* lock stencil on the whole word: sample the data bit where the clock reads
          * low, high, high, high at m-3..m (rtl_wmbus.c:1092-1111) */
         const uint64_t hist3 = ((r.clk3 & 1u) << 2) | (r.clk3 & 2u) | ((r.clk3 >> 2) & 1u);   /* bit2 = m-1 */
