@@ -855,7 +855,7 @@ static int gather_frames(wmb_ctx *c, bool final)
     c->st.d2h_bytes += (uint64_t)nwords * 4 + hdr.size() * sizeof(FrameHdr);
 
     c->out_hdr.assign(c->h_hdr, c->h_hdr + hdr.size());
-    c->out_words.assign(c->h_words, c->h_words + nwords);
+    /* frames point straight into the pinned copy; it stays valid until the next gather */
     for (const FrameHdr &h : c->out_hdr) {
         if (h.overflow) return set_err(WMB_E_OVERFLOW, "bit spacing exceeds 2^23 samples inside a frame");
         if (!h.complete && !final) c->cb[h.chain].s[h.algo].pending.push_back(h.ordinal);
@@ -866,7 +866,7 @@ static int gather_frames(wmb_ctx *c, bool final)
         f.truncated = (uint8_t)((h.complete && !h.cut) ? 0 : 1);
         f.reserved = (uint8_t)((!h.complete && !final) ? 1 : 0);      /* partial: will be re-delivered */
         f.nbits = h.nbits;
-        f.bits = c->out_words.data() + h.word_off;
+        f.bits = c->h_words + h.word_off;
         c->out_frames.push_back(f);
     }
     return WMB_OK;
