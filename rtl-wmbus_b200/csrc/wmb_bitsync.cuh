@@ -139,8 +139,8 @@ WMB_D void k2a_lane_t(const K2aParams &p, uint32_t lane)
         uint32_t dword, cword;
         /* warm-up blocks skip the outputs, except the one right before the chunk start whose clock
          * signs feed the lock stencil of the first owned word */
-        if (m + 32 < s0) k2a_block<CH, DC, T2, true>(cur, n, r, dword, cword);
-        else             k2a_block<CH, DC, T2, false>(cur, n, r, dword, cword);
+        if (wmb_all(m + 32 < s0)) k2a_block<CH, DC, T2, true>(cur, n, r, dword, cword);     /* warp-uniform choice */
+        else                      k2a_block<CH, DC, T2, false>(cur, n, r, dword, cword);
         /* lock stencil on the whole word: sample the data bit where the clock reads
          * low, high, high, high at m-3..m (rtl_wmbus.c:1092-1111) */
         const uint64_t hist3 = ((r.clk3 & 1u) << 2) | (r.clk3 & 2u) | ((r.clk3 >> 2) & 1u);   /* bit2 = m-1 */
