@@ -137,10 +137,9 @@ WMB_D void k2a_lane_t(const K2aParams &p, uint32_t lane)
         if (m == s0 && !saved_start) { k2a_save(st, r); p.st_start[lane] = st; saved_start = true; }
         const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
         uint32_t dword, cword;
-        /* warm-up blocks skip the outputs, except the one right before the chunk start whose clock
-         * signs feed the lock stencil of the first owned word */
-        if (wmb_all(m + 32 < s0)) k2a_block<CH, DC, T2, true>(cur, n, r, dword, cword);     /* warp-uniform choice */
-        else                      k2a_block<CH, DC, T2, false>(cur, n, r, dword, cword);
+        /* (a variant that skips the output-only arithmetic during the warm-up was measured slower:
+         * two 20 KB unrolled bodies thrash the instruction cache; profiles/README.md) */
+        k2a_block<CH, DC, T2, false>(cur, n, r, dword, cword);
         /* lock stencil on the whole word: sample the data bit where the clock reads
          * low, high, high, high at m-3..m (rtl_wmbus.c:1092-1111) */
         const uint64_t hist3 = ((r.clk3 & 1u) << 2) | (r.clk3 & 2u) | ((r.clk3 >> 2) & 1u);   /* bit2 = m-1 */
