@@ -190,13 +190,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module("rtl-wmbus_b200")
     synth = importlib.import_module("rtl-wmbus_b200.synth")
+    shard = importlib.import_module("rtl-wmbus_b200.shard")
     lib = pkg.load_library()                 # no fallback: raises when the CUDA library is missing
 
     n_bytes = args.mib << 20
     n_iq = n_bytes // 2
     # one independent capture per rank (weak scaling; BASELINE config 5's sharding rule)
     cap, plan = synth.synth_capture(n_bytes, fs=wl["fs"], emitters=synth.default_emitters(wl["emitters"]),
-                                    seed=0xB2000000 + 16 * 2 + rank, device="cuda")
+                                    seed=shard.capture_seed(2, rank), device="cuda")
     torch.cuda.synchronize()
     tune = dict(max_batch_mib=args.batch_mib or args.mib)
     if args.chunk: tune["chunk_samples"] = args.chunk
@@ -236,8 +237,6 @@ def main():
     clocks = sampler.stop()
     st = ctx.stats()
     launches = st.kernel_launches - launches0
-    n_lines = len(lines)
-    n_ok = sum(1 for l in lines if l.split(";")[1] == "1")      # MODE;CRC_OK;... (no -v prefix here)
     value = world * n_iq * args.steps / t_dev / 1e6
 
     # ---------------- host-input leg (e2e) ----------------
@@ -263,10 +262,7 @@ def main():
     assert e_lines == lines, "host-input and device-input legs disagree"
 
     # ---------------- packet counters: the only collective on this path ----------------
-    counts = torch.tensor([n_lines, n_ok], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)            # NCCL over NVLink
-    tot_lines, tot_ok = int(counts[0]), int(counts[1])
+    totals = shard.reduce_counts(shard.count_lines(lines), device="cuda")     # NCCL all-reduce over NVLink
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -292,7 +288,7 @@ def main():
                          "algorithmic_bytes_per_step": int(abytes),
                          "k1_demod_ms": round(k1_ms / args.steps, 4), "k2_bitsync_ms": round(k2_ms / args.steps, 4),
                          "device_pass_ms": round(dev_ms / args.steps, 4)},
-            "packets": {"lines": tot_lines, "crc_ok": tot_ok, "planted_per_gpu": len(plan)},
+            "packets": dict(totals, planted_per_gpu=len(plan)),
             "lanes": {"run": int(st.lanes_run), "rerun": int(st.lanes_rerun), "rl_fallbacks": int(st.rl_fallbacks)},
             "host_ms_per_step": {"batch": round(st.host_batch_ms / (args.steps + args.warmup), 3),
                                  "gather": round(st.host_gather_ms / (args.steps + args.warmup), 3),
