@@ -120,7 +120,7 @@ struct wmb_ctx {
     size_t max_batch_bytes = 0;
     int64_t M_max = 0;
     uint32_t W = 32768;             /* retained history (decimated samples) = max warm-up */
-    uint32_t W_a = 32768;           /* warm-up of the clock-recovery lanes               */
+    uint32_t W_a[WMB_N_CHAINS] = {32768, 98304};    /* warm-up of the clock-recovery lanes */
     uint32_t W_m[WMB_N_CHAINS] = {32768, 131072};   /* warm-up of the run-length lanes  */
     uint32_t C_fixed = 0;
     uint32_t lanes_max = 0;
@@ -498,14 +498,20 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
      * another ~18 k in front of them (A.6); a run-length lane must reach back past the
      * start of the telegram it may begin in (A.8: <= 28 k samples T1, <= 113 k S1). */
     if (o->warmup_samples) {
-        c->W_a = c->W_m[0] = c->W_m[1] = (o->warmup_samples + 255) / 256 * 256;
+        c->W_a[0] = c->W_a[1] = c->W_m[0] = c->W_m[1] = (o->warmup_samples + 255) / 256 * 256;
     } else {
-        c->W_a = o->remove_dc ? 98304u : 32768u;
+        /* measured re-join times of the biquad state (tools/ + DESIGN.md): T1/C1 filter <= 19 k samples,
+         * S1 filter (22-42 kHz band) <= 55 k; the DC block adds its own ~18 k in front */
+        c->W_a[0] = o->remove_dc ? 98304u : 32768u;
+        c->W_a[1] = o->remove_dc ? 163840u : 98304u;
         c->W_m[0] = 32768u; c->W_m[1] = 131072u;
     }
-    c->W = c->W_a;
-    for (int ch = 0; ch < WMB_N_CHAINS; ch++)
-        if ((c->chains & (1u << ch)) && o->rla_enabled) c->W = std::max(c->W, c->W_m[ch]);
+    c->W = 0;
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+        if (!(c->chains & (1u << ch))) continue;
+        c->W = std::max(c->W, c->W_a[ch]);
+        if (o->rla_enabled) c->W = std::max(c->W, c->W_m[ch]);
+    }
     c->manual = o->manual_frames != 0;
     c->two_phase = o->reserved[0] == 0;                  /* reserved[0] = 1: force the monolithic run-length lanes (tests) */
     c->C_fixed = o->chunk_samples ? (o->chunk_samples + 255) / 256 * 256 : 0;
@@ -636,7 +642,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             ChainBuf &b = c->cb[ch];
             K2aParams &p = ka[ch];
             memset(&p, 0, sizeof(p));
-            p.dphi = b.dphi + c->W; p.M = M; p.hist = c->hist_m; p.C = C; p.W = c->W_a; p.lanes = lanes;
+            p.dphi = b.dphi + c->W; p.M = M; p.hist = c->hist_m; p.C = C; p.W = c->W_a[ch]; p.lanes = lanes;
             p.dbits = b.dbits + wofs; p.sbits = b.sbits + wofs;
             p.st_start = b.ia_start; p.st_end = b.ia_end; p.carry = b.ia_carry; p.rerun = b.rerun;
             p.dc = c->o.remove_dc; p.t2 = c->o.t2_enabled;
