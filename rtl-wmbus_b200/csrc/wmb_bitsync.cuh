@@ -20,6 +20,8 @@
 #include "wmb_exact.cuh"
 #include "wmb_chain.cuh"
 
+struct u32x4 { uint32_t x, y, z, w; };
+
 /* ------------------------------------------------------------------------------------- */
 /* K2a: clock-recovery lanes                                                             */
 /* ------------------------------------------------------------------------------------- */
@@ -310,8 +312,6 @@ WMB_D void k2t_scan_c(const K2tParams &p, uint32_t t)
 
 /* pass 2: write the events straight into the stream ring.  Four words (128 samples) at a time:
  * their strobe/data words and the 128 rssi bytes they may need are requested together. */
-struct u32x4 { uint32_t x, y, z, w; };
-
 template <class CH>
 WMB_D void k2t_write(const K2tParams &p, uint32_t lane)
 {
@@ -526,31 +526,51 @@ WMB_D void k2m_lane(const K2mParams &p, uint32_t lane)
     uint32_t err = 0;
     bool saved_start = false;
     uint64_t H = k2m_hist_from_raw<CH>(s.raw);                 /* K history bits */
+    /* words are fetched eight at a time (one 32-byte sector per lane) and the next eight are requested
+     * before the current ones are walked: with one warp per scheduler a dependent load per word would
+     * expose the full DRAM latency 4600 times per lane */
+    uint32_t wcur[8], wnxt[8];
+    {
+        const u32x4 *src = (const u32x4 *)(p.dbits + (m >> 5));
+        const u32x4 a = src[0], c = src[1];
+        wcur[0] = a.x; wcur[1] = a.y; wcur[2] = a.z; wcur[3] = a.w; wcur[4] = c.x; wcur[5] = c.y; wcur[6] = c.z; wcur[7] = c.w;
+    }
     while (m < e0) {
-        if (m == s0 && !saved_start) {
-            s.raw = k2m_raw_from_hist<CH>(H);
-            p.st_start[lane] = s;
-            saved_start = true;
+        {
+            const u32x4 *src = (const u32x4 *)(p.dbits + (m >> 5) + 8);     /* slack behind M covers the over-read */
+            const u32x4 a = src[0], c = src[1];
+            wnxt[0] = a.x; wnxt[1] = a.y; wnxt[2] = a.z; wnxt[3] = a.w; wnxt[4] = c.x; wnxt[5] = c.y; wnxt[6] = c.z; wnxt[7] = c.w;
         }
-        const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
-        const uint32_t valid = (n == 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
-        const uint32_t word = p.dbits[m >> 5] & valid;
-        const bool live = m >= s0;
-        H = (H & ((1ull << K) - 1)) | ((uint64_t)word << K);
-        int pos = 0;                                           /* next unprocessed in-word position */
-        while (pos < n) {
-            const uint32_t D = k2m_deglitch_word<CH>(H);
-            const uint32_t lvl = (s.flags & 1u) ? 0xFFFFFFFFu : 0u;
-            const uint32_t x = (D ^ lvl) & (0xFFFFFFFFu << pos) & valid;
-            if (!x) { s.run += n - pos; break; }
-            const int e = wmb_ffs(x) - 1;
-            s.run += e - pos;                                  /* samples that kept the level */
-            const bool reset = k2m_edge<CH>(p, s, (D >> e) & 1u, m + e, (uint32_t)(m + e - s0), live, o, err);
-            if (reset) H &= ~((1ull << (K + e + 1)) - 1);      /* forget every bit up to and including e */
-            pos = e + 1;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (m >= e0) break;
+            if (m == s0 && !saved_start) {
+                s.raw = k2m_raw_from_hist<CH>(H);
+                p.st_start[lane] = s;
+                saved_start = true;
+            }
+            const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
+            const uint32_t valid = (n == 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+            const uint32_t word = wcur[q] & valid;
+            const bool live = m >= s0;
+            H = (H & ((1ull << K) - 1)) | ((uint64_t)word << K);
+            int pos = 0;                                       /* next unprocessed in-word position */
+            while (pos < n) {
+                const uint32_t D = k2m_deglitch_word<CH>(H);
+                const uint32_t lvl = (s.flags & 1u) ? 0xFFFFFFFFu : 0u;
+                const uint32_t x = (D ^ lvl) & (0xFFFFFFFFu << pos) & valid;
+                if (!x) { s.run += n - pos; break; }
+                const int e = wmb_ffs(x) - 1;
+                s.run += e - pos;                              /* samples that kept the level */
+                const bool reset = k2m_edge<CH>(p, s, (D >> e) & 1u, m + e, (uint32_t)(m + e - s0), live, o, err);
+                if (reset) H &= ~((1ull << (K + e + 1)) - 1);  /* forget every bit up to and including e */
+                pos = e + 1;
+            }
+            m += n;
+            H >>= n;                                           /* the newest K bits become the history */
         }
-        m += n;
-        H >>= n;                                               /* the newest K bits become the history */
+#pragma unroll
+        for (int q = 0; q < 8; q++) wcur[q] = wnxt[q];
     }
     s.raw = k2m_raw_from_hist<CH>(H);
     if (!saved_start) p.st_start[lane] = s;

@@ -424,8 +424,8 @@ static int ctx_alloc(wmb_ctx *c)
         const size_t n = (size_t)c->W + (size_t)c->M_max + 512;    /* slack: block loads may run past M */
         TRY(dev_alloc(c, &b.dphi, n));
         TRY(dev_alloc(c, &b.rssi, n));
-        TRY(dev_alloc(c, &b.dbits, n / 32 + 4, true));
-        TRY(dev_alloc(c, &b.sbits, n / 32 + 4, true));
+        TRY(dev_alloc(c, &b.dbits, n / 32 + 64, true));      /* slack: lanes prefetch 16 words ahead */
+        TRY(dev_alloc(c, &b.sbits, n / 32 + 64, true));
         TRY(dev_alloc(c, &b.ia_start, c->lanes_max));
         TRY(dev_alloc(c, &b.ia_end, c->lanes_max));
         TRY(dev_alloc(c, &b.ia_carry, 1));
