@@ -28,7 +28,6 @@
 #include <string>
 #include <vector>
 #include <thread>
-#include <memory>
 #include <time.h>
 
 #ifdef WMB_HOSTSIM
@@ -176,25 +175,7 @@ struct wmb_ctx {
     bool manual = false;
     std::vector<QueuedLine> lines;
     wmb_stats st;
-    /* host framers run on a worker thread, one batch behind the device (non-manual mode) */
-    std::thread decoder;
-    struct DecodeJob { std::vector<wmb_frame> frames; std::vector<uint32_t> words; };
-    std::unique_ptr<DecodeJob> job;
-    int decoder_rc = WMB_OK;
-    char decoder_err[256] = {0};
 };
-
-static int decode_frames_impl(wmb_ctx *c, const wmb_frame *frames, size_t n);
-
-/* wait for the framers of the previous batch; returns their status */
-static int join_decoder(wmb_ctx *c)
-{
-    if (c->decoder.joinable()) c->decoder.join();
-    c->job.reset();
-    const int rc = c->decoder_rc;
-    if (rc) { set_err(rc, "%s", c->decoder_err); c->decoder_rc = WMB_OK; }
-    return rc;
-}
 
 /* --------------------------------------------------------------------------- */
 /* launches                                                                    */
@@ -554,7 +535,6 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
 extern "C" void wmb_destroy(wmb_ctx *c)
 {
     if (!c) return;
-    join_decoder(c);
     cudaSetDevice(c->device);
     if (c->cs) cudaStreamSynchronize(c->cs);
     if (c->xs) cudaStreamSynchronize(c->xs);
@@ -935,32 +915,9 @@ static int finish_batch(wmb_ctx *c, bool final)
     c->st.host_gather_ms += t1 - t0;
     if (c->out_frames.empty()) return WMB_OK;
     if (!c->manual) {
-        /* the framers of this batch run while the device works on the next one: copy the frames out of
-         * the pinned buffer (the next gather overwrites it) and start the worker */
-        rc = join_decoder(c);
-        if (rc) return rc;
-        auto job = std::unique_ptr<wmb_ctx::DecodeJob>(new wmb_ctx::DecodeJob());
-        job->frames = c->out_frames;
-        size_t total = 0;
-        for (const wmb_frame &f : job->frames) total += f.nbits;
-        job->words.resize(total);
-        size_t off = 0;
-        for (wmb_frame &f : job->frames) {
-            memcpy(job->words.data() + off, f.bits, (size_t)f.nbits * 4);
-            f.bits = job->words.data() + off;
-            off += f.nbits;
-        }
-        c->job = std::move(job);
-        wmb_ctx::DecodeJob *jp = c->job.get();
-        c->decoder = std::thread([c, jp]() {
-            const double td = wall_ms();
-            const int r = decode_frames_impl(c, jp->frames.data(), jp->frames.size());
-            if (r) { c->decoder_rc = r; snprintf(c->decoder_err, sizeof(c->decoder_err), "%s", wmb_last_error()); }
-            c->st.host_decode_ms += wall_ms() - td;
-        });
-        c->st.host_gather_ms += wall_ms() - t1;
-        if (final) return join_decoder(c);
-        return WMB_OK;
+        rc = wmb_decode_frames(c, c->out_frames.data(), c->out_frames.size());
+        c->st.host_decode_ms += wall_ms() - t1;
+        return rc;
     }
     /* manual mode: keep the frames (newest version of a re-delivered partial one wins) for wmb_poll */
     for (const wmb_frame &f : c->out_frames) {
@@ -1128,13 +1085,6 @@ extern "C" int wmb_poll(wmb_ctx *c, wmb_frame *out, size_t cap, size_t *n, int f
 extern "C" int wmb_decode_frames(wmb_ctx *c, const wmb_frame *frames, size_t n)
 {
     if (!c || (!frames && n)) return set_err(WMB_E_INVAL, "null argument");
-    int rc = join_decoder(c);
-    if (rc) return rc;
-    return decode_frames_impl(c, frames, n);
-}
-
-static int decode_frames_impl(wmb_ctx *c, const wmb_frame *frames, size_t n)
-{
     std::vector<const wmb_frame *> v(n);
     for (size_t i = 0; i < n; i++) v[i] = &frames[i];
     std::sort(v.begin(), v.end(), [](const wmb_frame *a, const wmb_frame *b) {
@@ -1204,7 +1154,6 @@ extern "C" size_t wmb_take_lines(wmb_ctx *c, char *buf, size_t cap, size_t *n_li
     size_t len = 0, taken = 0;
     if (n_lines) *n_lines = 0;
     if (!c || !buf) return 0;
-    join_decoder(c);
     char ts[64];
     for (; taken < c->lines.size(); taken++) {
         const QueuedLine &q = c->lines[taken];
@@ -1259,7 +1208,6 @@ extern "C" long wmb_process_device(wmb_ctx *c, const void *dev_cu8, size_t nbyte
 extern "C" int wmb_reset(wmb_ctx *c)
 {
     if (!c) return set_err(WMB_E_INVAL, "null argument");
-    join_decoder(c);
     CUDA_TRY(cudaSetDevice(c->device));
     if (c->cs) CUDA_TRY(cudaStreamSynchronize(c->cs));
     if (c->xs) CUDA_TRY(cudaStreamSynchronize(c->xs));
@@ -1291,7 +1239,6 @@ extern "C" int wmb_reset(wmb_ctx *c)
 extern "C" int wmb_get_stats(wmb_ctx *c, wmb_stats *s)
 {
     if (!c || !s) return set_err(WMB_E_INVAL, "null argument");
-    join_decoder(c);
     *s = c->st;
     return WMB_OK;
 }
