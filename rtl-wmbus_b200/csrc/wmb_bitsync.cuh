@@ -526,41 +526,52 @@ WMB_D void k2m_lane(const K2mParams &p, uint32_t lane)
     uint32_t err = 0;
     bool saved_start = false;
     uint64_t H = k2m_hist_from_raw<CH>(s.raw);                 /* K history bits */
-    /* One event per loop iteration -- either "fetch the next word" or "handle the next edge" -- so that
-     * every lane of a warp advances in every iteration although their edges fall on different samples
-     * (a loop nest per word left most lanes idle while one of them worked through its edges). */
-    int n = 0, pos = 0;                                        /* valid bits / next position in the word */
-    uint32_t valid = 0;
-    bool live = false;
-    while (m < e0 || pos < n) {
-        if (pos >= n) {
-            /* next word; its sector stays in L1 for the following seven words of this lane */
-            if (n) H >>= n;                                    /* the newest K bits become the history */
+    /* words are fetched eight at a time (one 32-byte sector per lane) and the next eight are requested
+     * before the current ones are walked: with one warp per scheduler a dependent load per word would
+     * expose the full DRAM latency 4600 times per lane */
+    uint32_t wcur[8], wnxt[8];
+    {
+        const u32x4 *src = (const u32x4 *)(p.dbits + (m >> 5));
+        const u32x4 a = src[0], c = src[1];
+        wcur[0] = a.x; wcur[1] = a.y; wcur[2] = a.z; wcur[3] = a.w; wcur[4] = c.x; wcur[5] = c.y; wcur[6] = c.z; wcur[7] = c.w;
+    }
+    while (m < e0) {
+        {
+            const u32x4 *src = (const u32x4 *)(p.dbits + (m >> 5) + 8);     /* slack behind M covers the over-read */
+            const u32x4 a = src[0], c = src[1];
+            wnxt[0] = a.x; wnxt[1] = a.y; wnxt[2] = a.z; wnxt[3] = a.w; wnxt[4] = c.x; wnxt[5] = c.y; wnxt[6] = c.z; wnxt[7] = c.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (m >= e0) break;
             if (m == s0 && !saved_start) {
                 s.raw = k2m_raw_from_hist<CH>(H);
                 p.st_start[lane] = s;
                 saved_start = true;
             }
-            n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
-            valid = (n == 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
-            live = m >= s0;
-            H = (H & ((1ull << K) - 1)) | ((uint64_t)(wmb_ldg(p.dbits + (m >> 5)) & valid) << K);
-            m += n;                                            /* m now points behind the word */
-            pos = 0;
-            continue;
+            const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
+            const uint32_t valid = (n == 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+            const uint32_t word = wcur[q] & valid;
+            const bool live = m >= s0;
+            H = (H & ((1ull << K) - 1)) | ((uint64_t)word << K);
+            int pos = 0;                                       /* next unprocessed in-word position */
+            while (pos < n) {
+                const uint32_t D = k2m_deglitch_word<CH>(H);
+                const uint32_t lvl = (s.flags & 1u) ? 0xFFFFFFFFu : 0u;
+                const uint32_t x = (D ^ lvl) & (0xFFFFFFFFu << pos) & valid;
+                if (!x) { s.run += n - pos; break; }
+                const int e = wmb_ffs(x) - 1;
+                s.run += e - pos;                              /* samples that kept the level */
+                const bool reset = k2m_edge<CH>(p, s, (D >> e) & 1u, m + e, (uint32_t)(m + e - s0), live, o, err);
+                if (reset) H &= ~((1ull << (K + e + 1)) - 1);  /* forget every bit up to and including e */
+                pos = e + 1;
+            }
+            m += n;
+            H >>= n;                                           /* the newest K bits become the history */
         }
-        const uint32_t D = k2m_deglitch_word<CH>(H);
-        const uint32_t lvl = (s.flags & 1u) ? 0xFFFFFFFFu : 0u;
-        const uint32_t x = (D ^ lvl) & (0xFFFFFFFFu << pos) & valid;
-        if (!x) { s.run += n - pos; pos = n; continue; }
-        const int e = wmb_ffs(x) - 1;
-        s.run += e - pos;                                      /* samples that kept the level */
-        const int64_t me = m - n + e;                          /* sample index of the edge */
-        const bool reset = k2m_edge<CH>(p, s, (D >> e) & 1u, me, (uint32_t)(me - s0), live, o, err);
-        if (reset) H &= ~((1ull << (K + e + 1)) - 1);          /* forget every bit up to and including e */
-        pos = e + 1;
+#pragma unroll
+        for (int q = 0; q < 8; q++) wcur[q] = wnxt[q];
     }
-    if (n) H >>= n;
     s.raw = k2m_raw_from_hist<CH>(H);
     if (!saved_start) p.st_start[lane] = s;
     p.st_end[lane] = s;
