@@ -255,58 +255,140 @@ WMB_D void k2t_count(const K2tParams &p, uint32_t lane)
     p.cnt[lane] = cnt; p.tail[lane] = tail; p.tail_len[lane] = (uint32_t)len;
 }
 
-/* scan over lanes, three phases of one SCAN_THREADS-wide block: (A) every thread folds a
- * contiguous range of lanes, (B) one thread scans the per-thread aggregates, (C) every thread
- * writes its lanes' event ordinals and start registers.  The fold of (register, tail) pairs is
- * associative: appending `len` newer bits shifts the older ones up. */
-#define SCAN_THREADS 1024
+/* ---- device-wide exclusive scans over lanes -------------------------------------------------
+ * Three small kernels: (A) every block of SCAN_BLOCK threads reduces a tile of SCAN_TILE lanes
+ * (each thread a run of SCAN_ITEMS contiguous lanes), (B) one thread scans the tile aggregates,
+ * (C) every block scans its tile again and writes the lanes' bases.  `part` is the block's
+ * shared scratch (SCAN_BLOCK entries). */
+#ifdef WMB_HOSTSIM                   /* tiny tiles so that the CPU tests cross tile boundaries */
+#define SCAN_BLOCK 4
+#define SCAN_ITEMS 2
+#else
+#define SCAN_BLOCK 256
+#define SCAN_ITEMS 16
+#endif
+#define SCAN_TILE  (SCAN_BLOCK * SCAN_ITEMS)
+#define SCAN_THREADS 1024            /* k3_offsets keeps the single-block variant */
 
 WMB_HD uint32_t scan_per_thread(uint32_t n) { return (n + SCAN_THREADS - 1) / SCAN_THREADS; }
+WMB_HD uint32_t scan_tiles(uint32_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+struct CountScan {
+    const uint32_t *cnt; uint64_t *base; uint32_t n;
+    uint64_t *agg;                  /* [tiles] */
+    uint64_t *total;                /* in: ordinal of the first item; out: += sum of cnt */
+    const uint32_t *skip;           /* optional: nonzero -> leave everything untouched */
+    uint32_t *clear;                /* optional: word zeroed by phase B */
+    uint32_t from_zero;             /* ignore *total on input */
+};
+
+WMB_D void cscan_local(const CountScan &p, uint32_t tile, uint32_t tid, uint64_t *part)
+{
+    const uint32_t l0 = tile * SCAN_TILE + tid * SCAN_ITEMS;
+    uint64_t s = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < SCAN_ITEMS; i++) if (l0 + i < p.n) s += p.cnt[l0 + i];
+    part[tid] = s;
+}
+WMB_D void cscan_a_finish(const CountScan &p, uint32_t tile, const uint64_t *part)
+{
+    uint64_t s = 0;
+    for (uint32_t t = 0; t < SCAN_BLOCK; t++) s += part[t];
+    p.agg[tile] = s;
+}
+WMB_D void cscan_b(const CountScan &p)
+{
+    if (p.skip && *p.skip) return;
+    uint64_t acc = p.from_zero ? 0 : *p.total;
+    const uint32_t nt = scan_tiles(p.n);
+    for (uint32_t t = 0; t < nt; t++) { const uint64_t c = p.agg[t]; p.agg[t] = acc; acc += c; }
+    *p.total = acc;
+    if (p.clear) *p.clear = 0;
+}
+WMB_D void cscan_c_block(const CountScan &p, uint32_t tile, uint64_t *part)
+{
+    uint64_t acc = p.agg[tile];
+    for (uint32_t t = 0; t < SCAN_BLOCK; t++) { const uint64_t c = part[t]; part[t] = acc; acc += c; }
+}
+WMB_D void cscan_c_write(const CountScan &p, uint32_t tile, uint32_t tid, const uint64_t *part)
+{
+    if (p.skip && *p.skip) return;
+    const uint32_t l0 = tile * SCAN_TILE + tid * SCAN_ITEMS;
+    uint64_t acc = part[tid];
+#pragma unroll
+    for (uint32_t i = 0; i < SCAN_ITEMS; i++) if (l0 + i < p.n) { p.base[l0 + i] = acc; acc += p.cnt[l0 + i]; }
+}
+
+/* time2 variant: besides the strobe counts, the scan carries the shift register.  A lane contributes
+ * its last <= 24 strobed bits (tail, len); appending `len` newer bits shifts the older ones up, which
+ * is associative, so (register, tail) pairs fold like sums. */
+struct T2Fold { uint64_t cnt; uint32_t tail, len; };
 
 template <class CH>
-WMB_D void k2t_scan_a(const K2tParams &p, uint32_t t)
+WMB_D void t2_append(T2Fold &a, uint64_t cnt, uint32_t tail, uint32_t len)
 {
-    const uint32_t per = scan_per_thread(p.lanes);
-    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
-    uint64_t cnt = 0, tail = 0;
-    uint32_t len = 0;
-    const uint32_t NB = (CH::ID == 0) ? 16 : 24;
-    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) {
-        cnt += p.cnt[l];
-        const uint32_t ll = p.tail_len[l];
-        tail = ((tail << ll) | p.tail[l]) & CH::CODE_MASK;
-        len = (len + ll > NB) ? NB : len + ll;
-    }
-    p.agg_cnt[t] = cnt; p.agg_tail[t] = (uint32_t)tail; p.agg_len[t] = len;
+    constexpr uint32_t NB = (CH::ID == 0) ? 16 : 24;
+    a.cnt += cnt;
+    a.tail = (uint32_t)((((uint64_t)a.tail << len) | tail) & CH::CODE_MASK);
+    a.len = (a.len + len > NB) ? NB : a.len + len;
 }
 
 template <class CH>
-WMB_D void k2t_scan_b(const K2tParams &p)
+WMB_D void t2scan_local(const K2tParams &p, uint32_t tile, uint32_t tid, T2Fold *part)
+{
+    const uint32_t l0 = tile * SCAN_TILE + tid * SCAN_ITEMS;
+    T2Fold f = { 0, 0, 0 };
+#pragma unroll
+    for (uint32_t i = 0; i < SCAN_ITEMS; i++) if (l0 + i < p.lanes) t2_append<CH>(f, p.cnt[l0 + i], p.tail[l0 + i], p.tail_len[l0 + i]);
+    part[tid] = f;
+}
+template <class CH>
+WMB_D void t2scan_a_finish(const K2tParams &p, uint32_t tile, const T2Fold *part)
+{
+    T2Fold f = { 0, 0, 0 };
+    for (uint32_t t = 0; t < SCAN_BLOCK; t++) t2_append<CH>(f, part[t].cnt, part[t].tail, part[t].len);
+    p.agg_cnt[tile] = f.cnt; p.agg_tail[tile] = f.tail; p.agg_len[tile] = f.len;
+}
+template <class CH>
+WMB_D void t2scan_b(const K2tParams &p)
 {
     uint64_t acc = p.sd->total;
     uint64_t sr = p.sd->t2_sr;
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) {
+    const uint32_t nt = scan_tiles(p.lanes);
+    for (uint32_t t = 0; t < nt; t++) {
         const uint64_t c = p.agg_cnt[t];
         const uint32_t tl = p.agg_tail[t], ll = p.agg_len[t];
-        p.agg_cnt[t] = acc; p.agg_tail[t] = (uint32_t)sr;       /* exclusive prefixes */
+        p.agg_cnt[t] = acc; p.agg_tail[t] = (uint32_t)sr;            /* exclusive prefixes */
         acc += c;
         sr = ((sr << ll) | tl) & CH::CODE_MASK;
     }
     p.sd->total = acc;
     p.sd->t2_sr = (uint32_t)sr;
 }
-
 template <class CH>
-WMB_D void k2t_scan_c(const K2tParams &p, uint32_t t)
+WMB_D void t2scan_c_block(const K2tParams &p, uint32_t tile, T2Fold *part)
 {
-    const uint32_t per = scan_per_thread(p.lanes);
-    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
-    uint64_t acc = p.agg_cnt[t];
-    uint64_t sr = p.agg_tail[t];
-    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) {
-        p.base[l] = acc; p.sr_start[l] = (uint32_t)sr;
-        acc += p.cnt[l];
-        sr = ((sr << p.tail_len[l]) | p.tail[l]) & CH::CODE_MASK;
+    uint64_t acc = p.agg_cnt[tile];
+    uint64_t sr = p.agg_tail[tile];
+    for (uint32_t t = 0; t < SCAN_BLOCK; t++) {
+        const T2Fold f = part[t];
+        part[t].cnt = acc; part[t].tail = (uint32_t)sr;               /* exclusive prefixes */
+        acc += f.cnt;
+        sr = ((sr << f.len) | f.tail) & CH::CODE_MASK;
+    }
+}
+template <class CH>
+WMB_D void t2scan_c_write(const K2tParams &p, uint32_t tile, uint32_t tid, const T2Fold *part)
+{
+    const uint32_t l0 = tile * SCAN_TILE + tid * SCAN_ITEMS;
+    uint64_t acc = part[tid].cnt;
+    uint64_t sr = part[tid].tail;
+#pragma unroll
+    for (uint32_t i = 0; i < SCAN_ITEMS; i++) {
+        if (l0 + i >= p.lanes) break;
+        p.base[l0 + i] = acc; p.sr_start[l0 + i] = (uint32_t)sr;
+        acc += p.cnt[l0 + i];
+        sr = ((sr << p.tail_len[l0 + i]) | p.tail[l0 + i]) & CH::CODE_MASK;
     }
 }
 
@@ -722,28 +804,6 @@ struct K2pcParams {
     K2pDev *pd;
 };
 
-WMB_D void k2pc_scan_a(const K2pcParams &p, uint32_t t)
-{
-    const uint32_t per = scan_per_thread(p.lanes);
-    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
-    uint64_t cnt = 0;
-#pragma unroll 8
-    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) cnt += p.cnt[l];
-    p.agg[t] = cnt;
-}
-WMB_D void k2pc_scan_b(const K2pcParams &p)
-{
-    uint64_t acc = 0;
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) { const uint64_t c = p.agg[t]; p.agg[t] = acc; acc += c; }
-    p.pd->n_rec = acc; p.pd->fallback = 0;
-}
-WMB_D void k2pc_scan_c(const K2pcParams &p, uint32_t t)
-{
-    const uint32_t per = scan_per_thread(p.lanes);
-    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
-    uint64_t acc = p.agg[t];
-    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) { p.base[l] = acc; acc += p.cnt[l]; }
-}
 WMB_D void k2pc_compact(const K2pcParams &p, uint32_t lane, int tid, int nthr)
 {
     if (lane >= p.lanes) return;
@@ -931,31 +991,6 @@ WMB_D void k2p2_write(const K2p2Params &p, uint32_t lane)
     if (ran_off_end) {                                               /* this lane saw the last record */
         p.p2_out->sr = sr; p.p2_out->flags = pend << 1; p.p2_out->run = 1;
     }
-}
-
-WMB_D void k2p2_scan_a(const K2p2Params &p, uint32_t t)
-{
-    const uint32_t per = scan_per_thread(p.lanes);
-    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
-    uint64_t cnt = 0;
-#pragma unroll 8
-    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) cnt += p.cnt[l];
-    p.agg[t] = cnt;
-}
-WMB_D void k2p2_scan_b(const K2p2Params &p)
-{
-    if (p.pd->fallback) return;
-    uint64_t acc = p.sd->total;
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) { const uint64_t c = p.agg[t]; p.agg[t] = acc; acc += c; }
-    p.sd->total = acc;
-}
-WMB_D void k2p2_scan_c(const K2p2Params &p, uint32_t t)
-{
-    if (p.pd->fallback) return;
-    const uint32_t per = scan_per_thread(p.lanes);
-    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
-    uint64_t acc = p.agg[t];
-    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) { p.base[l] = acc; acc += p.cnt[l]; }
 }
 
 /* end of batch: compose the carried RlState from phase 1's end state (raw bits, level, run,

@@ -73,7 +73,7 @@ struct Stream {                     /* one (chain, algo) bit stream */
     uint64_t ring_cap = 0;          /* power of two                               */
     StreamDev *sd = nullptr;        /* device bookkeeping                         */
     uint64_t *cand = nullptr;       /* device candidate ordinals                  */
-    uint64_t *agg = nullptr;        /* scan scratch [SCAN_THREADS]                */
+    uint64_t *agg = nullptr;        /* scan scratch [tiles]                       */
     uint64_t total = 0;             /* host mirror of sd->total                   */
     std::vector<uint64_t> pending;  /* candidates not yet complete                */
     /* host framer bookkeeping */
@@ -235,43 +235,59 @@ static int launch_k2p1(wmb_ctx *c, const K2p1Params &p)
     return WMB_OK;
 }
 
+static void launch_cscan(wmb_ctx *c, const uint32_t *cnt, uint64_t *base, uint32_t n, uint64_t *agg, uint64_t *total,
+                         const uint32_t *skip = nullptr, uint32_t *clear = nullptr, uint32_t from_zero = 0)
+{
+    CountScan s;
+    s.cnt = cnt; s.base = base; s.n = n; s.agg = agg; s.total = total; s.skip = skip; s.clear = clear; s.from_zero = from_zero;
+    const unsigned tiles = scan_tiles(n);
+    cscan_a_kernel<<<tiles, SCAN_BLOCK, 0, c->cs>>>(s);
+    cscan_b_kernel<<<1, 32, 0, c->cs>>>(s);
+    cscan_c_kernel<<<tiles, SCAN_BLOCK, 0, c->cs>>>(s);
+    c->st.kernel_launches += 3;
+}
+
 static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, const P1State *p1_end_last, RlState *carry)
 {
-    k2pc_scan_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(pc);
+    launch_cscan(c, pc.cnt, pc.base, pc.lanes, pc.agg, &pc.pd->n_rec, nullptr, &pc.pd->fallback, 1);
     k2pc_compact_kernel<<<pc.lanes, 128, 0, c->cs>>>(pc);
     const unsigned grid = (p2.lanes + 127) / 128;
     k2p2_count_kernel<<<grid, 128, 0, c->cs>>>(p2);
-    k2p2_scan_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(p2);
+    launch_cscan(c, p2.cnt, p2.base, p2.lanes, p2.agg, &p2.sd->total, &p2.pd->fallback);
     k2p2_write_kernel<<<grid, 128, 0, c->cs>>>(p2);
     k2p_fold_kernel<<<1, 32, 0, c->cs>>>(p1_end_last, p2.p2_out, carry, p2.pd);
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 6;
+    c->st.kernel_launches += 4;
     return WMB_OK;
 }
 
 static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
 {
-    const unsigned grid = (p.lanes + 127) / 128;
+    const unsigned grid = (p.lanes + 127) / 128, tiles = scan_tiles(p.lanes);
     if (chain == 0) {
         k2t_count_kernel<ChainT1C1><<<grid, 128, 0, c->cs>>>(p);
-        k2t_scan_kernel<ChainT1C1><<<1, SCAN_THREADS, 0, c->cs>>>(p);
+        t2scan_a_kernel<ChainT1C1><<<tiles, SCAN_BLOCK, 0, c->cs>>>(p);
+        t2scan_b_kernel<ChainT1C1><<<1, 32, 0, c->cs>>>(p);
+        t2scan_c_kernel<ChainT1C1><<<tiles, SCAN_BLOCK, 0, c->cs>>>(p);
         k2t_write_kernel<ChainT1C1><<<grid, 128, 0, c->cs>>>(p);
     } else {
         k2t_count_kernel<ChainS1><<<grid, 128, 0, c->cs>>>(p);
-        k2t_scan_kernel<ChainS1><<<1, SCAN_THREADS, 0, c->cs>>>(p);
+        t2scan_a_kernel<ChainS1><<<tiles, SCAN_BLOCK, 0, c->cs>>>(p);
+        t2scan_b_kernel<ChainS1><<<1, 32, 0, c->cs>>>(p);
+        t2scan_c_kernel<ChainS1><<<tiles, SCAN_BLOCK, 0, c->cs>>>(p);
         k2t_write_kernel<ChainS1><<<grid, 128, 0, c->cs>>>(p);
     }
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 3;
+    c->st.kernel_launches += 5;
     return WMB_OK;
 }
 
 static int launch_k2c(wmb_ctx *c, const K2cParams &p)
 {
-    k2c_scan_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(p);
+    launch_cscan(c, p.cnt, p.base, p.lanes, p.agg, &p.sd->total);
     k2c_compact_kernel<<<p.lanes, 128, 0, c->cs>>>(p);
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 2;
+    c->st.kernel_launches += 1;
     return WMB_OK;
 }
 
@@ -363,11 +379,25 @@ static int host_alloc(wmb_ctx *c, T **p, size_t count)
 
 #define TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
-#define K2T_WORDS_PER_LANE 128u      /* 4096 decimated samples per time2 lane */
-#define K2P1_CHUNK 2048u             /* decimated samples per phase-1 run-length lane */
+/* lane geometry of the bit-sync kernels; WMBUS_B200_TUNE="t2words:p1chunk:p2records" overrides it for experiments */
+static uint32_t g_t2_words = 128u;       /* time2 lane = 32 * this many decimated samples */
+static uint32_t g_p1_chunk = 2048u;      /* decimated samples per phase-1 run-length lane */
+static uint32_t g_p2_records = 512u;     /* records per phase-2 lane (nominal) */
+#define K2T_WORDS_PER_LANE g_t2_words
+#define K2P1_CHUNK g_p1_chunk
 #define K2P1_WARM  256u
 #define K2P1_CAP   (K2P1_CHUNK / 5 + 2)
-#define K2P2_RECORDS 512u            /* records per phase-2 lane (nominal) */
+#define K2P2_RECORDS g_p2_records
+
+static void read_tuning()
+{
+    const char *e = getenv("WMBUS_B200_TUNE");
+    unsigned a = 0, b = 0, r = 0;
+    if (!e || sscanf(e, "%u:%u:%u", &a, &b, &r) != 3) return;
+    if (a >= 4 && a <= 4096 && a % 4 == 0) g_t2_words = a;
+    if (b >= 512 && b <= 65536 && b % 32 == 0) g_p1_chunk = b;
+    if (r >= 16 && r <= 65536) g_p2_records = r;
+}
 
 static int ctx_alloc(wmb_ctx *c)
 {
@@ -451,8 +481,12 @@ static int ctx_alloc(wmb_ctx *c)
         TRY(dev_alloc(c, &b.t2_tail, c->t2_lanes_max));
         TRY(dev_alloc(c, &b.t2_len, c->t2_lanes_max));
         TRY(dev_alloc(c, &b.t2_sr, c->t2_lanes_max));
-        TRY(dev_alloc(c, &b.t2_agg_tail, SCAN_THREADS));
-        TRY(dev_alloc(c, &b.t2_agg_len, SCAN_THREADS));
+        uint32_t scan_lanes = c->lanes_max > c->t2_lanes_max ? c->lanes_max : c->t2_lanes_max;
+        if (c->p1_lanes_max > scan_lanes) scan_lanes = c->p1_lanes_max;
+        if (c->p2_lanes_max > scan_lanes) scan_lanes = c->p2_lanes_max;
+        const size_t n_agg = scan_tiles(scan_lanes) + 1;
+        TRY(dev_alloc(c, &b.t2_agg_tail, n_agg));
+        TRY(dev_alloc(c, &b.t2_agg_len, n_agg));
         IirState ia;
         iir_state_init(ia);
         CUDA_TRY(cudaMemcpy(b.ia_carry, &ia, sizeof(ia), cudaMemcpyHostToDevice));
@@ -469,7 +503,7 @@ static int ctx_alloc(wmb_ctx *c)
             TRY(dev_alloc(c, &s.ring, s.ring_cap));
             TRY(dev_alloc(c, &s.sd, 1, true));
             TRY(dev_alloc(c, &s.cand, c->cand_cap));
-            TRY(dev_alloc(c, &s.agg, SCAN_THREADS));
+            TRY(dev_alloc(c, &s.agg, n_agg));
         }
     }
     c->allocated = true;
@@ -480,6 +514,7 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
 {
     if (!o || !out) return set_err(WMB_E_INVAL, "null argument");
     *out = nullptr;
+    read_tuning();
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return set_err(WMB_E_NODEVICE, "no CUDA device available (libwmbus_b200 has no CPU fallback)");

@@ -400,30 +400,6 @@ struct K2cParams {
     const uint8_t *rssi;            /* (unsigned)rssi, index 0 = batch sample 0            */
 };
 
-/* exclusive scan of the lane counts, same three-phase scheme as k2t_scan_* */
-WMB_D void k2c_scan_a(const K2cParams &p, uint32_t t)
-{
-    const uint32_t per = scan_per_thread(p.lanes);
-    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
-    uint64_t cnt = 0;
-#pragma unroll 8
-    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) cnt += p.cnt[l];
-    p.agg[t] = cnt;
-}
-WMB_D void k2c_scan_b(const K2cParams &p)
-{
-    uint64_t acc = p.sd->total;
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) { const uint64_t c = p.agg[t]; p.agg[t] = acc; acc += c; }
-    p.sd->total = acc;
-}
-WMB_D void k2c_scan_c(const K2cParams &p, uint32_t t)
-{
-    const uint32_t per = scan_per_thread(p.lanes);
-    const uint32_t l0 = t * per, l1 = (l0 + per < p.lanes) ? l0 + per : p.lanes;
-    uint64_t acc = p.agg[t];
-    for (uint32_t l = l0; l < l1 && l0 < p.lanes; l++) { p.base[l] = acc; acc += p.cnt[l]; }
-}
-
 WMB_D void k2c_compact(const K2cParams &p, uint32_t lane, int tid, int nthr)
 {
     if (lane >= p.lanes) return;
@@ -618,6 +594,43 @@ WMB_D void k3_copy(const K3Params &p, uint32_t i, int tid, int nthr)
 
 #ifndef WMB_HOSTSIM
 /* ---- __global__ wrappers ---- */
+__global__ void __launch_bounds__(SCAN_BLOCK) cscan_a_kernel(const CountScan p)
+{
+    __shared__ uint64_t part[SCAN_BLOCK];
+    cscan_local(p, blockIdx.x, threadIdx.x, part);
+    __syncthreads();
+    if (threadIdx.x == 0) cscan_a_finish(p, blockIdx.x, part);
+}
+__global__ void cscan_b_kernel(const CountScan p) { if (threadIdx.x == 0 && blockIdx.x == 0) cscan_b(p); }
+__global__ void __launch_bounds__(SCAN_BLOCK) cscan_c_kernel(const CountScan p)
+{
+    __shared__ uint64_t part[SCAN_BLOCK];
+    cscan_local(p, blockIdx.x, threadIdx.x, part);
+    __syncthreads();
+    if (threadIdx.x == 0) cscan_c_block(p, blockIdx.x, part);
+    __syncthreads();
+    cscan_c_write(p, blockIdx.x, threadIdx.x, part);
+}
+template <class CH>
+__global__ void __launch_bounds__(SCAN_BLOCK) t2scan_a_kernel(const K2tParams p)
+{
+    __shared__ T2Fold part[SCAN_BLOCK];
+    t2scan_local<CH>(p, blockIdx.x, threadIdx.x, part);
+    __syncthreads();
+    if (threadIdx.x == 0) t2scan_a_finish<CH>(p, blockIdx.x, part);
+}
+template <class CH>
+__global__ void t2scan_b_kernel(const K2tParams p) { if (threadIdx.x == 0 && blockIdx.x == 0) t2scan_b<CH>(p); }
+template <class CH>
+__global__ void __launch_bounds__(SCAN_BLOCK) t2scan_c_kernel(const K2tParams p)
+{
+    __shared__ T2Fold part[SCAN_BLOCK];
+    t2scan_local<CH>(p, blockIdx.x, threadIdx.x, part);
+    __syncthreads();
+    if (threadIdx.x == 0) t2scan_c_block<CH>(p, blockIdx.x, part);
+    __syncthreads();
+    t2scan_c_write<CH>(p, blockIdx.x, threadIdx.x, part);
+}
 template <class CH>
 __global__ void __launch_bounds__(K2_THREADS) k2a_lanes_kernel(const K2aParams p)
 {
@@ -629,15 +642,6 @@ __global__ void k2a_verify_kernel(const K2aParams p, uint32_t *n_fail)
 }
 template <class CH>
 __global__ void k2t_count_kernel(const K2tParams p) { k2t_count<CH>(p, blockIdx.x * blockDim.x + threadIdx.x); }
-template <class CH>
-__global__ void __launch_bounds__(SCAN_THREADS) k2t_scan_kernel(const K2tParams p)
-{
-    k2t_scan_a<CH>(p, threadIdx.x);
-    __syncthreads();
-    if (threadIdx.x == 0) k2t_scan_b<CH>(p);
-    __syncthreads();
-    k2t_scan_c<CH>(p, threadIdx.x);
-}
 template <class CH>
 __global__ void k2t_write_kernel(const K2tParams p) { k2t_write<CH>(p, blockIdx.x * blockDim.x + threadIdx.x); }
 template <class CH>
@@ -651,36 +655,12 @@ __global__ void k2m_verify_kernel(const K2mParams p, uint32_t *n_fail)
 }
 __global__ void __launch_bounds__(128) k2p1_lanes_kernel(const K2p1Params p) { k2p1_lane(p, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void k2p1_verify_kernel(const K2p1Params p, uint32_t *n_fail) { k2p1_verify_lane(p, blockIdx.x * blockDim.x + threadIdx.x, n_fail); }
-__global__ void __launch_bounds__(SCAN_THREADS) k2pc_scan_kernel(const K2pcParams p)
-{
-    k2pc_scan_a(p, threadIdx.x);
-    __syncthreads();
-    if (threadIdx.x == 0) k2pc_scan_b(p);
-    __syncthreads();
-    k2pc_scan_c(p, threadIdx.x);
-}
 __global__ void k2pc_compact_kernel(const K2pcParams p) { k2pc_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
 __global__ void __launch_bounds__(128) k2p2_count_kernel(const K2p2Params p) { k2p2_count(p, blockIdx.x * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(128) k2p2_write_kernel(const K2p2Params p) { k2p2_write(p, blockIdx.x * blockDim.x + threadIdx.x); }
-__global__ void __launch_bounds__(SCAN_THREADS) k2p2_scan_kernel(const K2p2Params p)
-{
-    k2p2_scan_a(p, threadIdx.x);
-    __syncthreads();
-    if (threadIdx.x == 0) k2p2_scan_b(p);
-    __syncthreads();
-    k2p2_scan_c(p, threadIdx.x);
-}
 __global__ void k2p_fold_kernel(const P1State *p1_end, RlState *p2_out, RlState *carry, const K2pDev *pd)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) k2p_fold(p1_end, p2_out, carry, pd);
-}
-__global__ void __launch_bounds__(SCAN_THREADS) k2c_scan_kernel(const K2cParams p)
-{
-    k2c_scan_a(p, threadIdx.x);
-    __syncthreads();
-    if (threadIdx.x == 0) k2c_scan_b(p);
-    __syncthreads();
-    k2c_scan_c(p, threadIdx.x);
 }
 __global__ void k2c_compact_kernel(const K2cParams p) { k2c_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
 __global__ void k3_size_kernel(const K3Params p) { k3_size(p, blockIdx.x * blockDim.x + threadIdx.x); }

@@ -67,20 +67,36 @@ static int launch_k2p1(wmb_ctx *c, const K2p1Params &p)
     return WMB_OK;
 }
 
+static void launch_cscan(wmb_ctx *c, const uint32_t *cnt, uint64_t *base, uint32_t n, uint64_t *agg, uint64_t *total,
+                         const uint32_t *skip = nullptr, uint32_t *clear = nullptr, uint32_t from_zero = 0)
+{
+    CountScan s;
+    s.cnt = cnt; s.base = base; s.n = n; s.agg = agg; s.total = total; s.skip = skip; s.clear = clear; s.from_zero = from_zero;
+    static uint64_t part[SCAN_BLOCK];
+    const uint32_t tiles = scan_tiles(n);
+    for (uint32_t b = 0; b < tiles; b++) {
+        for (uint32_t t = 0; t < SCAN_BLOCK; t++) cscan_local(s, b, t, part);
+        cscan_a_finish(s, b, part);
+    }
+    cscan_b(s);
+    for (uint32_t b = 0; b < tiles; b++) {
+        for (uint32_t t = 0; t < SCAN_BLOCK; t++) cscan_local(s, b, t, part);
+        cscan_c_block(s, b, part);
+        for (uint32_t t = 0; t < SCAN_BLOCK; t++) cscan_c_write(s, b, t, part);
+    }
+    c->st.kernel_launches += 3;
+}
+
 static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, const P1State *p1_end_last, RlState *carry)
 {
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2pc_scan_a(pc, t);
-    k2pc_scan_b(pc);
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2pc_scan_c(pc, t);
+    launch_cscan(c, pc.cnt, pc.base, pc.lanes, pc.agg, &pc.pd->n_rec, nullptr, &pc.pd->fallback, 1);
     for (uint32_t lane = 0; lane < pc.lanes; lane++)
         for (int t = 0; t < 4; t++) k2pc_compact(pc, lane, t, 4);
     for (uint32_t lane = 0; lane < p2.lanes; lane++) k2p2_count(p2, lane);
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2p2_scan_a(p2, t);
-    k2p2_scan_b(p2);
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2p2_scan_c(p2, t);
+    launch_cscan(c, p2.cnt, p2.base, p2.lanes, p2.agg, &p2.sd->total, &p2.pd->fallback);
     for (uint32_t lane = 0; lane < p2.lanes; lane++) k2p2_write(p2, lane);
     k2p_fold(p1_end_last, p2.p2_out, carry, p2.pd);
-    c->st.kernel_launches += 6;
+    c->st.kernel_launches += 4;
     return WMB_OK;
 }
 
@@ -88,27 +104,34 @@ template <class CH>
 static void hostsim_k2t(const K2tParams &p)
 {
     for (uint32_t lane = 0; lane < p.lanes; lane++) k2t_count<CH>(p, lane);
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2t_scan_a<CH>(p, t);
-    k2t_scan_b<CH>(p);
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2t_scan_c<CH>(p, t);
+    static T2Fold part[SCAN_BLOCK];
+    const uint32_t tiles = scan_tiles(p.lanes);
+    for (uint32_t b = 0; b < tiles; b++) {
+        for (uint32_t t = 0; t < SCAN_BLOCK; t++) t2scan_local<CH>(p, b, t, part);
+        t2scan_a_finish<CH>(p, b, part);
+    }
+    t2scan_b<CH>(p);
+    for (uint32_t b = 0; b < tiles; b++) {
+        for (uint32_t t = 0; t < SCAN_BLOCK; t++) t2scan_local<CH>(p, b, t, part);
+        t2scan_c_block<CH>(p, b, part);
+        for (uint32_t t = 0; t < SCAN_BLOCK; t++) t2scan_c_write<CH>(p, b, t, part);
+    }
     for (uint32_t lane = 0; lane < p.lanes; lane++) k2t_write<CH>(p, lane);
 }
 
 static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
 {
     if (chain == 0) hostsim_k2t<ChainT1C1>(p); else hostsim_k2t<ChainS1>(p);
-    c->st.kernel_launches += 4;
+    c->st.kernel_launches += 5;
     return WMB_OK;
 }
 
 static int launch_k2c(wmb_ctx *c, const K2cParams &p)
 {
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2c_scan_a(p, t);
-    k2c_scan_b(p);
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) k2c_scan_c(p, t);
+    launch_cscan(c, p.cnt, p.base, p.lanes, p.agg, &p.sd->total);
     for (uint32_t lane = 0; lane < p.lanes; lane++)
         for (int t = 0; t < 4; t++) k2c_compact(p, lane, t, 4);
-    c->st.kernel_launches += 2;
+    c->st.kernel_launches += 1;
     return WMB_OK;
 }
 
