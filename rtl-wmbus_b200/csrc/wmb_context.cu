@@ -515,6 +515,7 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
     if (!o || !out) return set_err(WMB_E_INVAL, "null argument");
     *out = nullptr;
     read_tuning();
+    g_trace = getenv("WMBUS_B200_TRACE") != nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return set_err(WMB_E_NODEVICE, "no CUDA device available (libwmbus_b200 has no CPU fallback)");
@@ -624,8 +625,23 @@ static int verified_pass(wmb_ctx *c, uint32_t lanes, F launch)
 }
 
 /* Enqueue the whole device pass for one batch whose bytes are at `src` (device memory). */
+static double wall_ms();
+/* WMBUS_B200_TRACE=1: host wall-clock marks of one batch on stderr (debugging aid) */
+static bool g_trace = false;
+static std::vector<std::pair<const char *, double>> g_marks;
+static inline void tr(const char *name) { if (g_trace) g_marks.emplace_back(name, wall_ms()); }
+static void tr_dump()
+{
+    if (!g_trace || g_marks.empty()) return;
+    fprintf(stderr, "[trace]");
+    for (size_t i = 1; i < g_marks.size(); i++) fprintf(stderr, " %s %.3f", g_marks[i].first, g_marks[i].second - g_marks[i - 1].second);
+    fprintf(stderr, " | total %.3f ms\n", g_marks.back().second - g_marks.front().second);
+    g_marks.clear();
+}
+
 static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_ctx_buffer)
 {
+    tr("batch-start");
     const uint32_t d = c->d;
     const int64_t n_iq = (int64_t)(nbytes / 2);
     const int64_t M = n_iq / d;
@@ -694,6 +710,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             }
             return (int)WMB_OK;
         }));
+        tr("k1+k2a");
         for (int ch = 0; ch < WMB_N_CHAINS; ch++)
             if (c->chains & (1u << ch))
                 CUDA_TRY(cudaMemcpyAsync(c->cb[ch].ia_carry, c->cb[ch].ia_end + (lanes - 1), sizeof(IirState),
@@ -751,6 +768,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
                 TRY(launch_k2p_rest(c, pc, p2, b.p1_end + (p1.lanes - 1), b.rl_carry));
                 CUDA_TRY(cudaMemcpyAsync(c->h_pd, b.pd, sizeof(K2pDev), cudaMemcpyDeviceToHost, c->cs));
                 CUDA_TRY(cudaStreamSynchronize(c->cs));
+                tr("k2t+p1+p2");
                 if (c->h_pd->fallback) { mono |= 1u; c->st.rl_fallbacks++; }
             } else if (c->chains & 1u) mono |= 1u;
             if (c->chains & 2u) mono |= 2u;
@@ -798,6 +816,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
     }
     CUDA_TRY(cudaEventRecord(c->ev_t[2], c->cs));
 
+    tr("mono");
     /* slide the histories: the last W samples move in front of index 0 */
     for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
         if (!(c->chains & (1u << ch))) continue;
@@ -841,6 +860,7 @@ static int gather_frames(wmb_ctx *c, bool final)
     }
     CUDA_TRY(cudaMemcpyAsync(&c->h_small[0], c->d_errors, 4, cudaMemcpyDeviceToHost, c->cs));
     CUDA_TRY(cudaStreamSynchronize(c->cs));
+    tr("g-sd");
     if (c->h_small[0] & 1u) return set_err(WMB_E_OVERFLOW, "bit event buffer overflow (pathological input)");
     if (c->h_small[0] & 2u) return set_err(WMB_E_OVERFLOW, "run-length tracker left its defined range (the reference would spin here)");
 
@@ -868,6 +888,7 @@ static int gather_frames(wmb_ctx *c, bool final)
         }
         s.pending.clear();
     }
+    tr("g-cand");
     c->out_hdr.clear(); c->out_words.clear(); c->out_frames.clear();
     if (hdr.empty()) return WMB_OK;
     if (hdr.size() > c->cand_cap) return set_err(WMB_E_OVERFLOW, "too many pending candidates");
@@ -890,12 +911,14 @@ static int gather_frames(wmb_ctx *c, bool final)
     CUDA_TRY(cudaMemcpyAsync(&c->h_small[2], c->d_nwords, 4, cudaMemcpyDeviceToHost, c->cs));
     CUDA_TRY(cudaMemcpyAsync(&c->h_small[0], c->d_errors, 4, cudaMemcpyDeviceToHost, c->cs));
     CUDA_TRY(cudaStreamSynchronize(c->cs));
+    tr("g-k3");
     if (c->h_small[0] & 4u) return set_err(WMB_E_OVERFLOW, "frame buffer overflow");
     const uint32_t nwords = c->h_small[2];
     if (nwords) {
         CUDA_TRY(cudaMemcpyAsync(c->h_words, c->d_words, (size_t)nwords * 4, cudaMemcpyDeviceToHost, c->cs));
         CUDA_TRY(cudaStreamSynchronize(c->cs));
     }
+    tr("g-d2h");
     c->st.d2h_bytes += (uint64_t)nwords * 4 + hdr.size() * sizeof(FrameHdr);
 
     c->out_hdr.assign(c->h_hdr, c->h_hdr + hdr.size());
@@ -953,8 +976,11 @@ static int finish_batch(wmb_ctx *c, bool final)
     c->st.host_gather_ms += t1 - t0;
     if (c->out_frames.empty()) return WMB_OK;
     if (!c->manual) {
+        tr("g-frames");
         rc = wmb_decode_frames(c, c->out_frames.data(), c->out_frames.size());
         c->st.host_decode_ms += wall_ms() - t1;
+        tr("decode");
+        tr_dump();
         return rc;
     }
     /* manual mode: keep the frames (newest version of a re-delivered partial one wins) for wmb_poll */
