@@ -389,6 +389,20 @@ static uint32_t g_p2_records = 512u;     /* records per phase-2 lane (nominal) *
 #define K2P1_CAP   (K2P1_CHUNK / 5 + 2)
 #define K2P2_RECORDS g_p2_records
 
+static double wall_ms();
+/* WMBUS_B200_TRACE=1: host wall-clock marks of one batch on stderr (debugging aid) */
+static bool g_trace = false;
+static std::vector<std::pair<const char *, double>> g_marks;
+static inline void tr(const char *name) { if (g_trace) g_marks.emplace_back(name, wall_ms()); }
+static void tr_dump()
+{
+    if (!g_trace || g_marks.empty()) return;
+    fprintf(stderr, "[trace]");
+    for (size_t i = 1; i < g_marks.size(); i++) fprintf(stderr, " %s %.3f", g_marks[i].first, g_marks[i].second - g_marks[i - 1].second);
+    fprintf(stderr, " | total %.3f ms\n", g_marks.back().second - g_marks.front().second);
+    g_marks.clear();
+}
+
 static void read_tuning()
 {
     const char *e = getenv("WMBUS_B200_TUNE");
@@ -625,20 +639,6 @@ static int verified_pass(wmb_ctx *c, uint32_t lanes, F launch)
 }
 
 /* Enqueue the whole device pass for one batch whose bytes are at `src` (device memory). */
-static double wall_ms();
-/* WMBUS_B200_TRACE=1: host wall-clock marks of one batch on stderr (debugging aid) */
-static bool g_trace = false;
-static std::vector<std::pair<const char *, double>> g_marks;
-static inline void tr(const char *name) { if (g_trace) g_marks.emplace_back(name, wall_ms()); }
-static void tr_dump()
-{
-    if (!g_trace || g_marks.empty()) return;
-    fprintf(stderr, "[trace]");
-    for (size_t i = 1; i < g_marks.size(); i++) fprintf(stderr, " %s %.3f", g_marks[i].first, g_marks[i].second - g_marks[i - 1].second);
-    fprintf(stderr, " | total %.3f ms\n", g_marks.back().second - g_marks.front().second);
-    g_marks.clear();
-}
-
 static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_ctx_buffer)
 {
     tr("batch-start");
