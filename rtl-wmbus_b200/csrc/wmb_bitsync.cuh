@@ -89,6 +89,63 @@ WMB_D void k2a_block(const float4 (&blk)[8], int n, K2aRegs &r, uint32_t &dword,
     }
 }
 
+/* The same arithmetic for a full block of 32 samples, software-pipelined across the cascade: in
+ * step t the DC block works on sample t, the first biquad on sample t - o1, the second on t - o2
+ * and the third on t - o3.  Every sample still sees exactly the operations of k2a_block in the
+ * same order (the results are bit-identical); only independent work of neighbouring samples is
+ * now adjacent in the instruction stream, which a single in-order warp needs to keep the FP pipe
+ * busy (one sample alone is a chain of ~10 dependent 4-cycle operations). */
+template <class CH, bool dc, bool t2>
+WMB_D void k2a_block32(const float4 (&blk)[8], K2aRegs &r, uint32_t &dword, uint32_t &cword)
+{
+    constexpr float b10 = CH::B10, b20 = CH::B20, a10 = CH::A10, a20 = CH::A20;
+    constexpr float b11 = CH::B11, b21 = CH::B21, a11 = CH::A11, a21 = CH::A21;
+    constexpr float b12 = CH::B12, b22 = CH::B22, a12 = CH::A12, a22 = CH::A22;
+    constexpr float gain = 1.874981046e-06;
+    constexpr float alpha = 0.999f, cdc = (1.f + 0.999f) / 2.f;
+    constexpr int o1 = dc ? 1 : 0, o2 = o1 + 1, o3 = o2 + 1;
+    constexpr int steps = t2 ? 32 + o3 : 32;
+    dword = 0; cword = 0;
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f;      /* pipeline registers between the stages */
+#pragma unroll
+    for (int t = 0; t < steps; t++) {
+        if (t2 && t >= o3 && t - o3 < 32) {
+            const float h0 = wmb_fsub(q2, wmb_fadd(wmb_fmul(a12, r.h12), wmb_fmul(a22, r.h22)));
+            float v = wmb_fadd(wmb_fadd(h0, wmb_fmul(b12, r.h12)), wmb_fmul(b22, r.h22));
+            v = wmb_fmul(v, gain);
+            cword |= (v >= 0.0f ? 1u : 0u) << (t - o3);
+            r.h22 = r.h12; r.h12 = h0;
+        }
+        if (t2 && t >= o2 && t - o2 < 32) {
+            const float h0 = wmb_fsub(q1, wmb_fadd(wmb_fmul(a11, r.h11), wmb_fmul(a21, r.h21)));
+            q2 = wmb_fadd(wmb_fadd(h0, wmb_fmul(b11, r.h11)), wmb_fmul(b21, r.h21));
+            r.h21 = r.h11; r.h11 = h0;
+        }
+        if (t2 && t >= o1 && t - o1 < 32) {
+            float x;
+            if (dc) x = q0;
+            else {
+                const float4 q = blk[t >> 2];
+                x = (t & 3) == 0 ? q.x : (t & 3) == 1 ? q.y : (t & 3) == 2 ? q.z : q.w;
+            }
+            const float v = wmb_fmul(x, x);
+            const float h0 = wmb_fsub(v, wmb_fadd(wmb_fmul(a10, r.h10), wmb_fmul(a20, r.h20)));
+            q1 = wmb_fadd(wmb_fadd(h0, wmb_fmul(b10, r.h10)), wmb_fmul(b20, r.h20));
+            r.h20 = r.h10; r.h10 = h0;
+        }
+        if (t < 32) {
+            const float4 q = blk[t >> 2];
+            float x = (t & 3) == 0 ? q.x : (t & 3) == 1 ? q.y : (t & 3) == 2 ? q.z : q.w;
+            if (dc) {
+                const float y = wmb_fadd(wmb_fmul(cdc, wmb_fsub(x, r.dcx)), wmb_fmul(alpha, r.dcy));
+                r.dcx = x; r.dcy = y; x = y;
+                q0 = y;
+            }
+            dword |= (x >= 0.0f ? 1u : 0u) << t;
+        }
+    }
+}
+
 WMB_D void k2a_load(float4 (&blk)[8], const float *src)
 {
     const float4 *s4 = (const float4 *)src;
@@ -141,7 +198,8 @@ WMB_D void k2a_lane_t(const K2aParams &p, uint32_t lane)
         uint32_t dword, cword;
         /* (a variant that skips the output-only arithmetic during the warm-up was measured slower:
          * two 20 KB unrolled bodies thrash the instruction cache; profiles/README.md) */
-        k2a_block<CH, DC, T2, false>(cur, n, r, dword, cword);
+        if (n == 32) k2a_block32<CH, DC, T2>(cur, r, dword, cword);
+        else k2a_block<CH, DC, T2, false>(cur, n, r, dword, cword);
         /* lock stencil on the whole word: sample the data bit where the clock reads
          * low, high, high, high at m-3..m (rtl_wmbus.c:1092-1111) */
         const uint64_t hist3 = ((r.clk3 & 1u) << 2) | (r.clk3 & 2u) | ((r.clk3 >> 2) & 1u);   /* bit2 = m-1 */
