@@ -152,6 +152,10 @@ struct wmb_ctx {
     StreamDev *h_sd = nullptr;      /* 4 entries */
     uint64_t *h_cand = nullptr;
     FrameHdr *h_hdr = nullptr;
+    DecHdr *d_dec = nullptr, *h_dec = nullptr;       /* K4 results, one per candidate */
+    uint8_t *d_pool = nullptr, *h_pool = nullptr;    /* CRC-stripped datagrams */
+    uint32_t pool_cap = 0;
+    uint32_t *d_pool_n = nullptr;
     uint32_t *h_words = nullptr;
 
     /* stream position */
@@ -168,6 +172,7 @@ struct wmb_ctx {
     std::vector<FrameHdr> out_hdr;
     std::vector<uint32_t> out_words;
     std::vector<wmb_frame> out_frames;
+    bool out_final = false;
     /* manual mode (opts.manual_frames): frames wait here for wmb_poll */
     struct Held { wmb_frame f; std::vector<uint32_t> words; };
     std::vector<Held> held, held_prev;
@@ -299,6 +304,14 @@ static int launch_k3(wmb_ctx *c, const K3Params &p)
     k3_copy_kernel<<<p.n, 128, 0, c->cs>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches += 4;
+    return WMB_OK;
+}
+
+static int launch_k4(wmb_ctx *c, const K4Params &p)
+{
+    k4_decode_kernel<<<p.n, K4_THREADS, 0, c->cs>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches += 1;
     return WMB_OK;
 }
 #endif
@@ -436,6 +449,7 @@ static int ctx_alloc(wmb_ctx *c)
     TRY(dev_alloc(c, &c->d_errors, 16, true));
     c->d_nfail = c->d_errors + 1;
     c->d_nwords = c->d_errors + 2;
+    c->d_pool_n = c->d_errors + 3;
     TRY(dev_alloc(c, &c->d_hdr, c->cand_cap));
     TRY(dev_alloc(c, &c->d_words, c->frame_words_cap));
     TRY(dev_alloc(c, &c->d_cut_n, c->cand_cap));
@@ -445,6 +459,11 @@ static int ctx_alloc(wmb_ctx *c)
     TRY(host_alloc(c, &c->h_pd, 1));
     TRY(host_alloc(c, &c->h_cand, c->cand_cap));
     TRY(host_alloc(c, &c->h_hdr, c->cand_cap));
+    c->pool_cap = c->frame_words_cap / 8 + 4 * c->cand_cap;    /* a datagram byte takes >= 8 shipped bit words */
+    TRY(dev_alloc(c, &c->d_dec, c->cand_cap));
+    TRY(host_alloc(c, &c->h_dec, c->cand_cap));
+    TRY(dev_alloc(c, &c->d_pool, c->pool_cap));
+    TRY(host_alloc(c, &c->h_pool, c->pool_cap));
     TRY(host_alloc(c, &c->h_words, c->frame_words_cap));
 
     /* mixer look-up tables, built with the host libm exactly like the reference
@@ -907,26 +926,50 @@ static int gather_frames(wmb_ctx *c, bool final)
     p.cut_n = c->d_cut_n; p.agg = c->d_k3_agg;
     int rc = launch_k3(c, p);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(c->h_hdr, c->d_hdr, hdr.size() * sizeof(FrameHdr), cudaMemcpyDeviceToHost, c->cs));
+    const size_t nf = hdr.size();
+    const bool dev_decode = !c->manual;
+    if (dev_decode) {
+        /* K4: decode every candidate on the device; only the verdicts and the datagrams travel */
+        CUDA_TRY(cudaMemsetAsync(c->d_pool_n, 0, 4, c->cs));
+        K4Params q;
+        memset(&q, 0, sizeof(q));
+        q.hdr = c->d_hdr; q.n = (uint32_t)nf; q.words = c->d_words; q.dec = c->d_dec;
+        q.pool = c->d_pool; q.pool_cap = c->pool_cap; q.pool_n = c->d_pool_n; q.errors = c->d_errors;
+        rc = launch_k4(c, q);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->h_dec, c->d_dec, nf * sizeof(DecHdr), cudaMemcpyDeviceToHost, c->cs));
+        CUDA_TRY(cudaMemcpyAsync(&c->h_small[3], c->d_pool_n, 4, cudaMemcpyDeviceToHost, c->cs));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_hdr, c->d_hdr, nf * sizeof(FrameHdr), cudaMemcpyDeviceToHost, c->cs));
     CUDA_TRY(cudaMemcpyAsync(&c->h_small[2], c->d_nwords, 4, cudaMemcpyDeviceToHost, c->cs));
     CUDA_TRY(cudaMemcpyAsync(&c->h_small[0], c->d_errors, 4, cudaMemcpyDeviceToHost, c->cs));
     CUDA_TRY(cudaStreamSynchronize(c->cs));
     tr("g-k3");
     if (c->h_small[0] & 4u) return set_err(WMB_E_OVERFLOW, "frame buffer overflow");
+    if (c->h_small[0] & 8u) return set_err(WMB_E_OVERFLOW, "datagram pool overflow");
     const uint32_t nwords = c->h_small[2];
-    if (nwords) {
+    c->st.d2h_bytes += nf * sizeof(FrameHdr);
+    if (dev_decode) {
+        const uint32_t npool = c->h_small[3];
+        if (npool) {
+            CUDA_TRY(cudaMemcpyAsync(c->h_pool, c->d_pool, npool, cudaMemcpyDeviceToHost, c->cs));
+            CUDA_TRY(cudaStreamSynchronize(c->cs));
+        }
+        c->st.d2h_bytes += npool + nf * sizeof(DecHdr);
+    } else if (nwords) {
         CUDA_TRY(cudaMemcpyAsync(c->h_words, c->d_words, (size_t)nwords * 4, cudaMemcpyDeviceToHost, c->cs));
         CUDA_TRY(cudaStreamSynchronize(c->cs));
+        c->st.d2h_bytes += (uint64_t)nwords * 4;
     }
     tr("g-d2h");
-    c->st.d2h_bytes += (uint64_t)nwords * 4 + hdr.size() * sizeof(FrameHdr);
 
-    c->out_hdr.assign(c->h_hdr, c->h_hdr + hdr.size());
+    c->out_hdr.assign(c->h_hdr, c->h_hdr + nf);
+    c->out_final = final;
     /* frames point straight into the pinned copy; it stays valid until the next gather */
     for (const FrameHdr &h : c->out_hdr) {
         if (h.overflow) return set_err(WMB_E_OVERFLOW, "bit spacing exceeds 2^23 samples inside a frame");
         if (!h.complete && !final) c->cb[h.chain].s[h.algo].pending.push_back(h.ordinal);
-        if (h.nbits == 0) continue;
+        if (h.nbits == 0 || dev_decode) continue;
         wmb_frame f;
         memset(&f, 0, sizeof(f));
         f.sync_sample = h.sync_sample; f.ordinal = h.ordinal; f.chain = h.chain; f.algo = h.algo;
@@ -966,6 +1009,8 @@ static double wall_ms()
     return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
 }
 
+static int book_device_frames(wmb_ctx *c);
+
 static int finish_batch(wmb_ctx *c, bool final)
 {
     const double t0 = wall_ms();
@@ -974,15 +1019,14 @@ static int finish_batch(wmb_ctx *c, bool final)
     read_timers(c);
     const double t1 = wall_ms();
     c->st.host_gather_ms += t1 - t0;
-    if (c->out_frames.empty()) return WMB_OK;
     if (!c->manual) {
-        tr("g-frames");
-        rc = wmb_decode_frames(c, c->out_frames.data(), c->out_frames.size());
+        rc = book_device_frames(c);
         c->st.host_decode_ms += wall_ms() - t1;
         tr("decode");
         tr_dump();
         return rc;
     }
+    if (c->out_frames.empty()) return WMB_OK;
     /* manual mode: keep the frames (newest version of a re-delivered partial one wins) for wmb_poll */
     for (const wmb_frame &f : c->out_frames) {
         wmb_ctx::Held *slot = nullptr;
@@ -1146,6 +1190,137 @@ extern "C" int wmb_poll(wmb_ctx *c, wmb_frame *out, size_t cap, size_t *n, int f
 /* host framers: stream-order bookkeeping around wmb_frame_decode()            */
 /* --------------------------------------------------------------------------- */
 
+/* Stream-order bookkeeping over decoded candidates (sorted by chain, algorithm, ordinal): a decoder
+ * that is receiving ignores further access-code matches (t1_c1_packet_decoder.h:272-278 honours the
+ * flag only in idle), so a candidate inside the telegram of an earlier one is dropped; the rest
+ * become lines, queued in the order the reference prints them. */
+struct FrameMeta { uint8_t chain, algo, partial, truncated; uint64_t ordinal; };
+struct DecLite { int status; uint32_t consumed; uint64_t end_sample; uint8_t crc_ok; };
+
+template <class Meta, class Lite, class Fill>
+static int book_frames(wmb_ctx *c, size_t n, Meta meta, Lite lite, Fill fill)
+{
+    bool blocked[WMB_N_CHAINS][WMB_N_ALGOS] = {{false, false}, {false, false}};
+    std::vector<QueuedLine> fresh;
+    for (size_t fi = 0; fi < n; fi++) {
+        const FrameMeta f = meta(fi);
+        Stream &s = c->cb[f.chain].s[f.algo];
+        if (blocked[f.chain][f.algo]) continue;
+        if ((int64_t)f.ordinal <= s.busy_until) continue;
+        const DecLite d = lite(fi);
+        if (d.status == WMB_DEC_NEED_MORE) {
+            if (f.partial) { blocked[f.chain][f.algo] = true; continue; }   /* comes again */
+            if (!f.truncated) return set_err(WMB_E_STATE, "internal: frame shorter than its header demands");
+            /* cut by a run-length reset or by the end of input: the reference's decoder is reset too */
+            s.busy_until = (int64_t)(f.ordinal + d.consumed - 1);
+            continue;
+        }
+        s.busy_until = (int64_t)(f.ordinal + d.consumed - 1);
+        if (d.status == WMB_DEC_LINE) {
+            fresh.emplace_back();
+            QueuedLine &q = fresh.back();
+            q.end_sample = d.end_sample;
+            q.prio = f.chain * 2 + (f.algo == WMB_ALGO_T2A ? 1 : 0);
+            q.algo = f.algo;
+            fill(fi, q.d);
+            c->st.lines[f.chain][f.algo]++;
+            if (d.crc_ok) c->st.lines_crc_ok[f.chain][f.algo]++;
+        }
+    }
+    /* the reference prints in the order the per-sample state machines finish:
+     * sample index, then T1/C1-rla, T1/C1-t2a, S1-rla, S1-t2a (rtl_wmbus.c:1354-1355) */
+    std::stable_sort(fresh.begin(), fresh.end(), [](const QueuedLine &a, const QueuedLine &b) {
+        if (a.end_sample != b.end_sample) return a.end_sample < b.end_sample;
+        return a.prio < b.prio;
+    });
+    c->lines.insert(c->lines.end(), fresh.begin(), fresh.end());
+    return WMB_OK;
+}
+
+/* candidates of the last gather, decoded by K4 (already in stream order) */
+static int book_device_frames(wmb_ctx *c)
+{
+    static const char modes[3][3] = { "T1", "C1", "S1" };
+    const size_t n = c->out_hdr.size();
+    const FrameHdr *hdr = c->out_hdr.data();
+    const DecHdr *dec = c->h_dec;
+    const bool final = c->out_final;
+    /* frames without any bit (candidate at the very end of the stream) are not decoded at all */
+    std::vector<uint32_t> idx;
+    idx.reserve(n);
+    for (size_t i = 0; i < n; i++) if (hdr[i].nbits) idx.push_back((uint32_t)i);
+    return book_frames(c, idx.size(),
+        [&](size_t k) {
+            const FrameHdr &h = hdr[idx[k]];
+            FrameMeta m;
+            m.chain = h.chain; m.algo = h.algo; m.ordinal = h.ordinal;
+            m.partial = (uint8_t)((!h.complete && !final) ? 1 : 0);
+            m.truncated = (uint8_t)((h.complete && !h.cut) ? 0 : 1);
+            return m;
+        },
+        [&](size_t k) {
+            const DecHdr &d = dec[idx[k]];
+            DecLite l;
+            l.status = d.status; l.consumed = d.consumed; l.end_sample = hdr[idx[k]].sync_sample + d.end_off; l.crc_ok = d.crc_ok;
+            return l;
+        },
+        [&](size_t k, wmb_decoded &o) {
+            const DecHdr &d = dec[idx[k]];
+            memset(&o, 0, sizeof(o));
+            o.status = WMB_DEC_LINE; o.consumed = d.consumed; o.end_sample = hdr[idx[k]].sync_sample + d.end_off;
+            memcpy(o.mode, modes[d.mode < 3 ? d.mode : 0], 3);
+            o.crc_ok = d.crc_ok; o.ok_3of6 = d.ok_3of6; o.packet_rssi = d.packet_rssi; o.current_rssi = d.current_rssi;
+            o.serial = d.serial; o.len = d.len;
+            memcpy(o.datagram, c->h_pool + d.data_off, d.len);
+        });
+}
+
+/* Test hook (declared in wmb_framer.h, not part of the public ABI): run K4 on caller-made frames so
+ * that the device framer can be compared with its host twin candidate by candidate. */
+extern "C" int wmb_frame_decode_device(wmb_ctx *c, const wmb_frame *frames, size_t n, wmb_decoded *out)
+{
+    if (!c || !frames || !out) return set_err(WMB_E_INVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(ctx_alloc(c));
+    if (n > c->cand_cap) return set_err(WMB_E_INVAL, "too many frames");
+    size_t words = 0;
+    for (size_t i = 0; i < n; i++) {
+        FrameHdr &h = c->h_hdr[i];
+        memset(&h, 0, sizeof(h));
+        h.ordinal = frames[i].ordinal; h.sync_sample = frames[i].sync_sample; h.nbits = frames[i].nbits;
+        h.word_off = (uint32_t)words; h.chain = frames[i].chain; h.algo = frames[i].algo; h.complete = 1;
+        if (words + h.nbits > c->frame_words_cap) return set_err(WMB_E_INVAL, "frames too large");
+        memcpy(c->h_words + words, frames[i].bits, (size_t)h.nbits * 4);
+        words += h.nbits;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_hdr, c->h_hdr, n * sizeof(FrameHdr), cudaMemcpyHostToDevice, c->cs));
+    CUDA_TRY(cudaMemcpyAsync(c->d_words, c->h_words, words * 4, cudaMemcpyHostToDevice, c->cs));
+    CUDA_TRY(cudaMemsetAsync(c->d_pool_n, 0, 4, c->cs));
+    K4Params q;
+    memset(&q, 0, sizeof(q));
+    q.hdr = c->d_hdr; q.n = (uint32_t)n; q.words = c->d_words; q.dec = c->d_dec;
+    q.pool = c->d_pool; q.pool_cap = c->pool_cap; q.pool_n = c->d_pool_n; q.errors = c->d_errors;
+    TRY(launch_k4(c, q));
+    CUDA_TRY(cudaMemcpyAsync(c->h_dec, c->d_dec, n * sizeof(DecHdr), cudaMemcpyDeviceToHost, c->cs));
+    CUDA_TRY(cudaMemcpyAsync(c->h_pool, c->d_pool, c->pool_cap < (1u << 24) ? c->pool_cap : (1u << 24), cudaMemcpyDeviceToHost, c->cs));
+    CUDA_TRY(cudaStreamSynchronize(c->cs));
+    static const char modes[3][3] = { "T1", "C1", "S1" };
+    for (size_t i = 0; i < n; i++) {
+        const DecHdr &d = c->h_dec[i];
+        wmb_decoded &o = out[i];
+        memset(&o, 0, sizeof(o));
+        o.status = d.status == K4_SKIP ? WMB_DEC_NEED_MORE : d.status;
+        o.consumed = d.consumed;
+        o.end_sample = d.status == K4_SKIP ? 0 : frames[i].sync_sample + d.end_off;
+        if (d.status != K4_LINE) continue;
+        memcpy(o.mode, modes[d.mode < 3 ? d.mode : 0], 3);
+        o.crc_ok = d.crc_ok; o.ok_3of6 = d.ok_3of6; o.packet_rssi = d.packet_rssi; o.current_rssi = d.current_rssi;
+        o.serial = d.serial; o.len = d.len;
+        memcpy(o.datagram, c->h_pool + d.data_off, d.len);
+    }
+    return WMB_OK;
+}
+
 extern "C" int wmb_decode_frames(wmb_ctx *c, const wmb_frame *frames, size_t n)
 {
     if (!c || (!frames && n)) return set_err(WMB_E_INVAL, "null argument");
@@ -1158,8 +1333,8 @@ extern "C" int wmb_decode_frames(wmb_ctx *c, const wmb_frame *frames, size_t n)
     });
     for (const wmb_frame *f : v)
         if (f->chain >= WMB_N_CHAINS || f->algo >= WMB_N_ALGOS) return set_err(WMB_E_INVAL, "bad frame");
-    /* The per-frame decode is pure, so it is spread over a few host threads; the stream-order
-     * bookkeeping below then only looks at the results. */
+    /* frames handed in by the caller are decoded by the host twin of K4 (wmb_framer.c); the
+     * per-frame decode is pure, so it is spread over a few host threads */
     std::vector<wmb_decoded> dec(n);
     {
         unsigned nt = n >= 256 ? std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
@@ -1175,42 +1350,19 @@ extern "C" int wmb_decode_frames(wmb_ctx *c, const wmb_frame *frames, size_t n)
             for (auto &t : th) t.join();
         }
     }
-    bool blocked[WMB_N_CHAINS][WMB_N_ALGOS] = {{false, false}, {false, false}};
-    std::vector<QueuedLine> fresh;
-    for (size_t fi = 0; fi < n; fi++) {
-        const wmb_frame *f = v[fi];
-        Stream &s = c->cb[f->chain].s[f->algo];
-        /* A decoder that is receiving ignores further access-code matches
-         * (t1_c1_packet_decoder.h:272-278 honours the flag only in idle). */
-        if (blocked[f->chain][f->algo]) continue;
-        if ((int64_t)f->ordinal <= s.busy_until) continue;
-        const wmb_decoded &d = dec[fi];
-        if (d.status == WMB_DEC_NEED_MORE) {
-            if (f->reserved) { blocked[f->chain][f->algo] = true; continue; }   /* partial: comes again */
-            if (!f->truncated) return set_err(WMB_E_STATE, "internal: frame shorter than its header demands");
-            /* cut by a run-length reset or by the end of input: the reference's decoder is reset too */
-            s.busy_until = (int64_t)(f->ordinal + d.consumed - 1);
-            continue;
-        }
-        s.busy_until = (int64_t)(f->ordinal + d.consumed - 1);
-        if (d.status == WMB_DEC_LINE) {
-            QueuedLine q;
-            q.end_sample = d.end_sample;
-            q.prio = f->chain * 2 + (f->algo == WMB_ALGO_T2A ? 1 : 0);
-            q.d = d; q.algo = f->algo;
-            fresh.push_back(q);
-            c->st.lines[f->chain][f->algo]++;
-            if (d.crc_ok) c->st.lines_crc_ok[f->chain][f->algo]++;
-        }
-    }
-    /* the reference prints in the order the per-sample state machines finish:
-     * sample index, then T1/C1-rla, T1/C1-t2a, S1-rla, S1-t2a (rtl_wmbus.c:1354-1355) */
-    std::stable_sort(fresh.begin(), fresh.end(), [](const QueuedLine &a, const QueuedLine &b) {
-        if (a.end_sample != b.end_sample) return a.end_sample < b.end_sample;
-        return a.prio < b.prio;
-    });
-    c->lines.insert(c->lines.end(), fresh.begin(), fresh.end());
-    return WMB_OK;
+    return book_frames(c, n,
+        [&](size_t i) {
+            FrameMeta m;
+            m.chain = v[i]->chain; m.algo = v[i]->algo; m.ordinal = v[i]->ordinal;
+            m.partial = v[i]->reserved; m.truncated = v[i]->truncated;
+            return m;
+        },
+        [&](size_t i) {
+            DecLite l;
+            l.status = dec[i].status; l.consumed = dec[i].consumed; l.end_sample = dec[i].end_sample; l.crc_ok = dec[i].crc_ok;
+            return l;
+        },
+        [&](size_t i, wmb_decoded &o) { o = dec[i]; });
 }
 
 extern "C" size_t wmb_take_lines(wmb_ctx *c, char *buf, size_t cap, size_t *n_lines, int timestamp_mode)

@@ -36,6 +36,10 @@ typedef struct wmb_decoded {
  * framer is still receiving. */
 void wmb_frame_decode(const wmb_frame *f, wmb_decoded *out);
 
+/* test hook: the same decode done by the device framer (kernel K4), n frames at once */
+struct wmb_ctx;
+int wmb_frame_decode_device(struct wmb_ctx *ctx, const wmb_frame *frames, size_t n, wmb_decoded *out);
+
 uint16_t wmb_crc16(const uint8_t *data, size_t n);
 unsigned wmb_tlg_length_format_a(unsigned l_field);
 

@@ -592,6 +592,264 @@ WMB_D void k3_copy(const K3Params &p, uint32_t i, int tid, int nthr)
     }
 }
 
+
+/* =========================================================================== */
+/* K4: frame decode (3-out-of-6 / NRZ / Manchester, L-field, RSSI abort, CRCs)  */
+/* =========================================================================== */
+/* One thread block per gathered candidate.  The reference walks a telegram bit by bit
+ * (t1_c1_packet_decoder.h:272-460 and :649-712, s1_packet_decoder.h:132-282) and stops at the
+ * first of: an rssi below the capture threshold on any bit but the telegram's last one (:703-710),
+ * a Manchester violation, a mode word that is neither a 3-out-of-6 L-field nor a C1 pattern, a
+ * wrong C1 trailer, or the end of the bits there are.  Each of these is tied to a bit index, so the
+ * block looks for the smallest such index in parallel, then decodes all bytes in parallel, checks
+ * one CRC block per thread (:463-536) and writes the CRC-stripped datagram (:551-636) into a byte
+ * pool.  (wmb_framer.c is the host twin behind wmb_decode_frames(); tests compare the two.) */
+#define K4_THREADS 32
+#define K4_CAPTURE_THRESHOLD 5u     /* PACKET_CAPTURE_THRESHOLD, t1_c1_packet_decoder.h:36 */
+enum { K4_ABORT = 0, K4_LINE = 1, K4_NEED_MORE = 2, K4_SKIP = 3 };
+
+struct DecHdr {                     /* one per candidate, device -> host                   */
+    uint32_t consumed;              /* bits consumed including the flagged one             */
+    uint32_t end_off;               /* sample offset (from sync_sample) of the last consumed bit */
+    uint32_t serial;
+    uint32_t data_off;              /* byte offset of the datagram in the pool             */
+    uint16_t len;                   /* datagram bytes after the CRC strip                  */
+    uint8_t  status, mode;          /* K4_* ; 0 T1, 1 C1, 2 S1                             */
+    uint8_t  crc_ok, ok_3of6, packet_rssi, current_rssi;
+};
+
+struct K4Params {
+    const FrameHdr *hdr; uint32_t n;
+    const uint32_t *words;
+    DecHdr *dec;
+    uint8_t *pool; uint32_t pool_cap; uint32_t *pool_n;
+    uint32_t *errors;
+};
+
+struct K4Smem {
+    uint8_t pkt[296];
+    int stop_idx;
+    uint32_t flags;                 /* 1: 3-out-of-6 error, 2: CRC error */
+    uint32_t data_off;
+};
+
+#ifdef WMB_HOSTSIM
+#define K4_SYNC() do { } while (0)
+static inline void k4_smin(int *a, int v) { if (v < *a) *a = v; }
+static inline void k4_sor(uint32_t *a, uint32_t v) { *a |= v; }
+static inline uint32_t k4_gadd(uint32_t *a, uint32_t v) { const uint32_t o = *a; *a += v; return o; }
+#else
+#define K4_SYNC() __syncthreads()
+WMB_D void k4_smin(int *a, int v) { atomicMin(a, v); }
+WMB_D void k4_sor(uint32_t *a, uint32_t v) { atomicOr(a, v); }
+WMB_D uint32_t k4_gadd(uint32_t *a, uint32_t v) { return atomicAdd(a, v); }
+#endif
+
+/* first stop event in bits [lo, hi): returns true and (status, pos) if the decoder stops there */
+WMB_D bool k4_scan(const uint32_t *b, uint32_t nbits, uint32_t lo, uint32_t hi, uint32_t exempt, bool manch,
+                   K4Smem &sm, int tid, int nthr, uint32_t &status, uint32_t &pos)
+{
+    const uint32_t he = hi < nbits ? hi : nbits;
+    if (tid == 0) sm.stop_idx = 0x7FFFFFFF;
+    K4_SYNC();
+    int best = 0x7FFFFFFF;
+    for (uint32_t i = lo + (uint32_t)tid; i < he; i += (uint32_t)nthr) {
+        const uint32_t w = b[i];
+        bool bad = WMB_BIT_RSSI(w) < K4_CAPTURE_THRESHOLD && i != exempt;
+        if (manch && !(i & 1u)) bad = bad || (WMB_BIT_DATA(w) == WMB_BIT_DATA(b[i - 1]));   /* "01"/"10" only */
+        if (bad && (int)i < best) best = (int)i;
+    }
+    if (best != 0x7FFFFFFF) k4_smin(&sm.stop_idx, best);
+    K4_SYNC();
+    const int s = sm.stop_idx;
+    K4_SYNC();
+    if (s != 0x7FFFFFFF) { status = K4_ABORT; pos = (uint32_t)s; return true; }
+    if (hi > nbits) { status = K4_NEED_MORE; pos = nbits - 1; return true; }
+    return false;
+}
+
+WMB_D uint32_t k4_bits(const uint32_t *b, uint32_t first, uint32_t n)     /* MSB first */
+{
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < n; k++) v = (v << 1) | WMB_BIT_DATA(b[first + k]);
+    return v;
+}
+
+WMB_D uint32_t k4_crc16(const uint8_t *d, uint32_t n)                      /* polynomial 0x3D65, :463-469 */
+{
+    uint32_t crc = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        crc ^= (uint32_t)d[i] << 8;
+        for (int k = 0; k < 8; k++) crc = (crc & 0x8000u) ? ((crc << 1) ^ 0x3D65u) : (crc << 1);
+        crc &= 0xFFFFu;
+    }
+    return ~crc & 0xFFFFu;
+}
+
+WMB_D bool k4_block_ok(const uint8_t *q, uint32_t n)                       /* n includes the CRC bytes */
+{
+    if (n < 2) return false;
+    return k4_crc16(q, n - 2) == (((uint32_t)q[n - 2] << 8) | q[n - 1]);
+}
+
+WMB_D void k4_decode(const K4Params &p, uint32_t f, int tid, int nthr, K4Smem &sm)
+{
+    if (f >= p.n) return;
+    const FrameHdr h = p.hdr[f];
+    const uint32_t *b = p.words + h.word_off;
+    const uint32_t nbits = h.nbits;
+    DecHdr d;
+    d.consumed = 0; d.end_off = 0; d.serial = 0; d.data_off = 0; d.len = 0; d.status = K4_SKIP; d.mode = 0;
+    d.crc_ok = 0; d.ok_3of6 = 0; d.packet_rssi = 0; d.current_rssi = 0;
+    if (nbits == 0) { if (tid == 0) p.dec[f] = d; return; }
+
+    for (int i = tid; i < 296; i += nthr) sm.pkt[i] = 0;
+    if (tid == 0) sm.flags = 0;
+    K4_SYNC();
+
+    uint32_t status = K4_LINE, pos = 0, len = 0, mode = 0;
+    bool bframe = false;
+    /* the flagged bit: the idle handler keeps the state, then the rssi check (:703-710) */
+    if (WMB_BIT_RSSI(b[0]) < K4_CAPTURE_THRESHOLD) { status = K4_ABORT; pos = 0; }
+    else if (h.chain == WMB_CHAIN_T1C1) {
+        if (!k4_scan(b, nbits, 1, 13, 0xFFFFFFFFu, false, sm, tid, nthr, status, pos)) {
+            const uint32_t hi6 = k4_bits(b, 1, 6), lo6 = k4_bits(b, 7, 6);
+            const uint32_t hi = wmb_dec3of6(hi6), lo = wmb_dec3of6(lo6);
+            const uint32_t word = (hi6 << 6) | lo6;
+            if (hi != 0xFFu && lo != 0xFFu) {
+                /* T1: 3-out-of-6 coded L-field and data (:298-392) */
+                const uint32_t L = (hi << 4) | lo;
+                len = wmb_tlg_len_a(L);
+                const uint32_t P = 1 + 12 * len;
+                if (!k4_scan(b, nbits, 13, P, P - 1, false, sm, tid, nthr, status, pos)) {
+                    if (tid == 0) sm.pkt[0] = (uint8_t)L;
+                    for (uint32_t l = 1 + (uint32_t)tid; l < len; l += (uint32_t)nthr) {
+                        const uint32_t hh = wmb_dec3of6(k4_bits(b, 1 + 12 * l, 6)), ll = wmb_dec3of6(k4_bits(b, 7 + 12 * l, 6));
+                        if (hh == 0xFFu || ll == 0xFFu) k4_sor(&sm.flags, 1u);
+                        sm.pkt[l] = (uint8_t)((hh == 0xFFu ? 0xFFu : hh << 4) | ll);
+                    }
+                    pos = P - 1; mode = 0;
+                }
+            } else if (word != 0x54Cu && word != 0x543u) {          /* neither L-field nor C1 mode word (:334-337) */
+                status = K4_ABORT; pos = 12;
+            } else {
+                /* C1: 4-bit trailer, 8-bit L, NRZ bytes (:399-460) */
+                bframe = (word == 0x543u);
+                if (!k4_scan(b, nbits, 13, 17, 0xFFFFFFFFu, false, sm, tid, nthr, status, pos)) {
+                    if (k4_bits(b, 13, 4) != 0xDu) { status = K4_ABORT; pos = 16; }
+                    else if (!k4_scan(b, nbits, 17, 25, 0xFFFFFFFFu, false, sm, tid, nthr, status, pos)) {
+                        const uint32_t L = k4_bits(b, 17, 8);
+                        len = bframe ? 1 + L : wmb_tlg_len_a(L);
+                        const uint32_t after = (len > 2 ? len : 2) - 1;       /* the byte loop runs at least once */
+                        const uint32_t P = 25 + 8 * after;
+                        if (!k4_scan(b, nbits, 25, P, P - 1, false, sm, tid, nthr, status, pos)) {
+                            if (tid == 0) sm.pkt[0] = (uint8_t)L;
+                            for (uint32_t l = 1 + (uint32_t)tid; l <= after; l += (uint32_t)nthr)
+                                sm.pkt[l] = (uint8_t)k4_bits(b, 25 + 8 * (l - 1), 8);
+                            pos = P - 1; mode = 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        /* S1: Manchester coded bytes, chips "01" = 1, "10" = 0 (s1_packet_decoder.h:35-37, :152-168) */
+        if (!k4_scan(b, nbits, 1, 17, 0xFFFFFFFFu, true, sm, tid, nthr, status, pos)) {
+            uint32_t L = 0;
+            for (uint32_t k = 0; k < 8; k++) L = (L << 1) | WMB_BIT_DATA(b[2 + 2 * k]);
+            len = wmb_tlg_len_a(L);
+            const uint32_t P = 1 + 16 * len;
+            if (!k4_scan(b, nbits, 17, P, P - 1, true, sm, tid, nthr, status, pos)) {
+                if (tid == 0) sm.pkt[0] = (uint8_t)L;
+                for (uint32_t l = 1 + (uint32_t)tid; l < len; l += (uint32_t)nthr) {
+                    uint32_t v = 0;
+                    for (uint32_t k = 0; k < 8; k++) v = (v << 1) | WMB_BIT_DATA(b[2 + 16 * l + 2 * k]);
+                    sm.pkt[l] = (uint8_t)v;
+                }
+                pos = P - 1; mode = 2;
+            }
+        }
+    }
+    K4_SYNC();
+
+    d.status = (uint8_t)status;
+    d.consumed = pos + 1;
+    d.end_off = WMB_BIT_OFFSET(b[pos]);
+    if (status != K4_LINE) { if (tid == 0) p.dec[f] = d; return; }
+
+    /* block CRCs, one block per thread */
+    const uint32_t n = len;
+    uint32_t out_len = 0, nblk = 0;
+    if (!bframe) {
+        /* format A: 12-byte first block, 18-byte blocks after it (:471-506, strip :551-592) */
+        if (n < 12) { if (tid == 0) sm.flags |= 2u; }
+        else {
+            nblk = 1 + (n - 12 + 17) / 18;
+            for (uint32_t j = (uint32_t)tid; j < nblk; j += (uint32_t)nthr) {
+                const uint32_t off = j ? 12 + 18 * (j - 1) : 0;
+                const uint32_t blk = j ? ((n - off >= 18) ? 18 : n - off) : 12;
+                if (!k4_block_ok(sm.pkt + off, blk)) k4_sor(&sm.flags, 2u);
+            }
+            if (sm.pkt[0] != 0) out_len = n - 2 * nblk;
+        }
+    } else {
+        /* format B: CRC over the first 126 bytes, then over the rest (:508-536, strip :595-636) */
+        if (n < 12) { if (tid == 0) sm.flags |= 2u; }
+        else {
+            nblk = (n + 127) / 128;
+            for (uint32_t j = (uint32_t)tid; j < nblk; j += (uint32_t)nthr) {
+                const uint32_t off = 128 * j;
+                const uint32_t blk = (n - off >= 128) ? 128 : n - off;
+                if (!k4_block_ok(sm.pkt + off, blk)) k4_sor(&sm.flags, 2u);
+            }
+            if (sm.pkt[0] >= 2) {
+                uint32_t stripped = 0;
+                for (uint32_t j = 0; j < nblk; j++) {
+                    const uint32_t blk = (n - 128 * j >= 128) ? 128 : n - 128 * j;
+                    if (blk < 2) break;                       /* the reference reads out of bounds here */
+                    out_len += blk - 2; stripped++;
+                }
+                nblk = stripped;
+            }
+        }
+    }
+    if (tid == 0) {
+        const uint32_t room = (out_len + 3u) & ~3u;
+        uint32_t off = room ? k4_gadd(p.pool_n, room) : 0;
+        if (room && (off > p.pool_cap || room > p.pool_cap - off)) {
+#ifdef WMB_HOSTSIM
+            *p.errors |= 8u;
+#else
+            atomicOr(p.errors, 8u);
+#endif
+            off = 0xFFFFFFFFu;
+        }
+        sm.data_off = off;
+    }
+    K4_SYNC();
+    const uint32_t flags = sm.flags, data_off = sm.data_off;
+    if (data_off != 0xFFFFFFFFu) {
+        uint8_t *out = p.pool + data_off;
+        for (uint32_t i = (uint32_t)tid; i < out_len; i += (uint32_t)nthr) {
+            uint32_t v;
+            if (!bframe) v = i < 10 ? sm.pkt[i] : sm.pkt[12 + 18 * ((i - 10) / 16) + (i - 10) % 16];
+            else v = i == 0 ? (uint32_t)(uint8_t)(sm.pkt[0] - 2 * nblk) : sm.pkt[i + 2 * (i / 126)];
+            out[i] = (uint8_t)v;
+        }
+    }
+    if (tid == 0) {
+        d.mode = (uint8_t)mode;
+        d.crc_ok = (flags & 2u) ? 0 : 1;
+        d.ok_3of6 = (flags & 1u) ? 0 : 1;
+        d.packet_rssi = (uint8_t)WMB_BIT_RSSI(b[1]);            /* rssi at the first bit after sync (:295) */
+        d.current_rssi = (uint8_t)WMB_BIT_RSSI(b[pos]);
+        d.serial = (uint32_t)sm.pkt[4] | ((uint32_t)sm.pkt[5] << 8) | ((uint32_t)sm.pkt[6] << 16) | ((uint32_t)sm.pkt[7] << 24);
+        d.len = (uint16_t)out_len;
+        d.data_off = data_off == 0xFFFFFFFFu ? 0 : data_off;
+        p.dec[f] = d;
+    }
+}
+
 #ifndef WMB_HOSTSIM
 /* ---- __global__ wrappers ---- */
 __global__ void __launch_bounds__(SCAN_BLOCK) cscan_a_kernel(const CountScan p)
@@ -674,4 +932,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k3_offsets_kernel(const K3Params
     k3_offsets_c(p, threadIdx.x);
 }
 __global__ void k3_copy_kernel(const K3Params p) { k3_copy(p, blockIdx.x, threadIdx.x, blockDim.x); }
+__global__ void __launch_bounds__(K4_THREADS) k4_decode_kernel(const K4Params p)
+{
+    __shared__ K4Smem sm;
+    k4_decode(p, blockIdx.x, threadIdx.x, blockDim.x, sm);
+}
 #endif

@@ -148,3 +148,11 @@ static int launch_k3(wmb_ctx *c, const K3Params &p)
     c->st.kernel_launches += 4;
     return WMB_OK;
 }
+
+static int launch_k4(wmb_ctx *c, const K4Params &p)
+{
+    static K4Smem sm;                   /* the block's phases need real barriers: one simulated thread */
+    for (uint32_t i = 0; i < p.n; i++) k4_decode(p, i, 0, 1, sm);
+    c->st.kernel_launches += 1;
+    return WMB_OK;
+}

@@ -108,3 +108,87 @@ def test_framer_on_random_bits(hostsim_lib, pkg, orc_mod):
             assert oline is None and oc == n
         else:
             assert (consumed, line) == (oc, oline), (trial, chain)
+
+
+# ---- device framer (kernel K4) vs its host twin, candidate by candidate ----------------------------
+
+def framer_cases(synth, n_random=1500):
+    """(chain, bits, rssi) of crafted, corrupted, truncated and random candidates."""
+    rng = np.random.default_rng(17)
+    cases = []
+    for chain, chips in frames_for_tests(synth):
+        chips = chips.astype(np.uint8)
+        for trial in range(40):
+            bits = chips.copy()
+            rssi = rng.integers(20, 200, len(bits)).astype(np.uint8)
+            if trial % 4 == 1:
+                for i in rng.integers(1, len(bits), rng.integers(1, 4)):
+                    bits[i] ^= 1
+            if trial % 4 == 2:
+                rssi[rng.integers(0, len(bits))] = rng.integers(0, 5)
+            if trial % 4 == 3:                      # low rssi exactly on / next to the telegram's last bit
+                rssi[len(bits) - 17 + int(rng.integers(-1, 2))] = 1
+            if trial % 10 == 9:
+                cut = rng.integers(1, len(bits))
+                bits, rssi = bits[:cut], rssi[:cut]
+            cases.append((chain, bits, rssi))
+    for trial in range(n_random):
+        chain = trial & 1
+        n = int(rng.integers(1, 400))
+        bits = rng.integers(0, 2, n).astype(np.uint8)
+        if trial % 4 == 0 and chain == 0 and n > 30:
+            word = "010101001100" if trial % 8 == 0 else "010101000011"
+            bits[1:13] = np.frombuffer(word.encode(), np.uint8) - 48
+            bits[13:17] = [1, 1, 0, 1]
+            bits[17:25] = [0, 0, 0, 0, 0, 0, int(rng.integers(0, 2)), int(rng.integers(0, 2))]
+        if trial % 4 == 1 and chain == 1:                # valid Manchester prefix of random length
+            k = int(rng.integers(1, n // 2 + 1))
+            v = rng.integers(0, 2, k).astype(np.uint8)
+            bits[1:1 + 2 * k:2][:len(bits[1:1 + 2 * k:2])] = (1 - v)[:len(bits[1:1 + 2 * k:2])]
+            bits[2:2 + 2 * k:2][:len(bits[2:2 + 2 * k:2])] = v[:len(bits[2:2 + 2 * k:2])]
+        rssi = rng.integers(3, 60, n).astype(np.uint8)
+        cases.append((chain, bits, rssi))
+    return cases
+
+
+def check_device_framer(lib, pkg, synth):
+    cases = framer_cases(synth)
+    n = len(cases)
+    frames = (pkg.WmbFrame * n)()
+    keep = []
+    for i, (chain, bits, rssi) in enumerate(cases):
+        k = len(bits)
+        words = (np.arange(k, dtype=np.uint32) * 3 << 9) | (rssi.astype(np.uint32) << 1) | bits.astype(np.uint32)
+        words = np.ascontiguousarray(words, np.uint32)
+        keep.append(words)
+        f = frames[i]
+        f.sync_sample = 1000 + i; f.ordinal = i; f.chain = chain; f.algo = i & 1; f.nbits = k
+        f.bits = words.ctypes.data_as(C.POINTER(C.c_uint32))
+    host = (Decoded * n)()
+    dev = (Decoded * n)()
+    lib.wmb_frame_decode.argtypes = [C.POINTER(pkg.WmbFrame), C.POINTER(Decoded)]
+    for i in range(n):
+        lib.wmb_frame_decode(C.byref(frames[i]), C.byref(host[i]))
+    with pkg.WmbusB200("-v", lib=lib) as ctx:
+        lib.wmb_frame_decode_device.argtypes = [C.c_void_p, C.POINTER(pkg.WmbFrame), C.c_size_t, C.POINTER(Decoded)]
+        rc = lib.wmb_frame_decode_device(ctx._ctx, frames, n, dev)
+        assert rc == 0, lib.wmb_last_error()
+    seen = {0: 0, 1: 0, 2: 0}
+    for i in range(n):
+        h, d = host[i], dev[i]
+        assert (h.status, h.consumed, h.end_sample) == (d.status, d.consumed, d.end_sample), (i, cases[i][0])
+        seen[h.status] += 1
+        if h.status == 1:
+            assert (h.mode, h.crc_ok, h.ok_3of6, h.packet_rssi, h.current_rssi, h.serial, h.len) == \
+                   (d.mode, d.crc_ok, d.ok_3of6, d.packet_rssi, d.current_rssi, d.serial, d.len), i
+            assert bytes(h.datagram[:h.len]) == bytes(d.datagram[:d.len]), i
+    assert seen[0] > 500 and seen[1] > 100 and seen[2] > 10, seen
+
+
+def test_device_framer_matches_host_twin_hostsim(hostsim_lib, pkg):
+    check_device_framer(hostsim_lib, pkg, importlib.import_module("rtl-wmbus_b200.synth"))
+
+
+@pytest.mark.gpu
+def test_device_framer_matches_host_twin_gpu(gpu_lib, pkg):
+    check_device_framer(gpu_lib, pkg, importlib.import_module("rtl-wmbus_b200.synth"))
