@@ -897,22 +897,20 @@ struct K2p2Params {
 };
 
 #define K2P2_BLK 8                   /* records fetched together (memory-level parallelism) */
+#define K2P2W_THREADS 128            /* write pass: one block per lane of records */
+#define K2P2W_ITEMS 4                /* consecutive records per thread (K2P2W_THREADS * K2P2W_ITEMS >= R) */
 
 /* C integer division (truncation toward zero) by 2^s and by a small positive n */
 WMB_D int wmb_div_pow2(int x, int s) { return (x + ((x >> 31) & ((1 << s) - 1))) >> s; }
+/* x / n for 1 <= n <= 8 and |x| < 2^29 without a divide or a jump table: |x| * ceil(2^35 / n) >> 35
+ * is exact as long as |x| < 2^35 / n */
 WMB_D int wmb_div_small(int x, int n)
 {
-    switch (n) {
-    case 1: return x;
-    case 2: return x / 2;
-    case 3: return x / 3;
-    case 4: return x / 4;
-    case 5: return x / 5;
-    case 6: return x / 6;
-    case 7: return x / 7;
-    case 8: return x / 8;
-    default: return x / n;
-    }
+    static const uint64_t magic[9] = { 0, 1ull << 35, 1ull << 34, 11453246123ull, 1ull << 33, 6871947674ull, 5726623062ull,
+                                4908534053ull, 1ull << 32 };
+    const uint32_t ax = (uint32_t)(x < 0 ? -x : x);
+    const int q = (int)(((uint64_t)ax * magic[n]) >> 35);
+    return x < 0 ? -q : q;
 }
 
 /* the lane's first record: record 0 (carry state) or the first record in [r0, r1) that follows a reset */
@@ -924,130 +922,181 @@ WMB_D bool k2p2_start(const K2p2Params &p, uint32_t lane, uint64_t r0, uint64_t 
     return false;
 }
 
-/* pass A (serial in the PI recurrence, nothing else): bits per record -> rec_n, events per lane -> cnt.
+/* pass A (serial in the PI recurrence, nothing else): bits per record -> rec_n.  A lane owns the
+ * records from the first reset in its range up to the first reset of a later range, so a telegram
+ * (which has no reset inside) is one dependent chain; the step is therefore written for latency:
+ * no loop and no jump table on the way from one bit-length estimate to the next.
  * Only rec_v is read; the next block of records is requested while the current one is processed. */
 WMB_D void k2p2_count(const K2p2Params &p, uint32_t lane)
 {
     if (lane >= p.lanes) return;
     const uint64_t N = p.pd->n_rec;
     const uint64_t r0 = (uint64_t)lane * p.R, r1 = (r0 + p.R < N) ? r0 + p.R : N;
-    uint32_t n_ev = 0;
-    uint64_t i;
-    if (r0 < N && k2p2_start(p, lane, r0, r1, i)) {
-        int32_t a = 8 * 256, b = 0;
-        if (lane == 0) { const RlState c = *p.carry; a = c.a; b = c.b; }
-        bool stop = false, ran_off_end = false;
-        uint32_t v[K2P2_BLK], vn[K2P2_BLK];
-#pragma unroll
-        for (int j = 0; j < K2P2_BLK; j++) v[j] = (i + j < N) ? p.rec_v[i + j] : 1u;
-        if (i >= N) ran_off_end = true;
-        while (!stop && i < N) {
-#pragma unroll
-            for (int j = 0; j < K2P2_BLK; j++) vn[j] = (i + K2P2_BLK + j < N) ? p.rec_v[i + K2P2_BLK + j] : 1u;
-#pragma unroll
-            for (int j = 0; j < K2P2_BLK; j++) {
-                if (stop) continue;
-                if (i + j >= N) { stop = true; ran_off_end = true; continue; }
-                const uint32_t vv = v[j];
-                if (vv & 1u) {
-                    if (i + j >= r1) { stop = true; continue; }      /* next lane's segment */
-                    a = 8 * 256; b = 0;                              /* runlength_algorithm_reset_t1_c1 */
-                }
-                int rl = (int)((vv >> 2) * 256u);
-                const int half = a / 2;
-                if (rl <= half || a <= 0) {                          /* rtl_wmbus.c:756-762 (or a spin) */
-                    p.pd->fallback = 1;
-                    stop = true; continue;
-                }
-                /* n = number of bit periods in the run (:765-779): smallest n with rl - n*a <= half.
-                 * Telegram runs are 1-4 bits long: count them the reference's way and keep the
-                 * integer division for the rare long run. */
-                int n;
-                if (rl - half <= 8 * a) { n = 0; while (rl > half) { rl -= a; n++; } }
-                else { n = (rl - half + a - 1) / a; rl -= n * a; }
-                b += rl;                                             /* :792 */
-                a += wmb_div_small(wmb_div_pow2(rl + wmb_div_pow2(b, 4), 5), n);   /* :796: x/(32 n) == (x/32)/n */
-                const uint32_t ne = n < K2_EDGE_EMIT_CAP ? (uint32_t)n : (uint32_t)K2_EDGE_EMIT_CAP;
-                p.rec_n[i + j] = (uint16_t)ne;
-                n_ev += ne;
-            }
-            i += K2P2_BLK;
-            if (!stop && i >= N) ran_off_end = true;
-#pragma unroll
-            for (int j = 0; j < K2P2_BLK; j++) v[j] = vn[j];
-        }
-        if (ran_off_end) { p.p2_out->a = a; p.p2_out->b = b; }       /* exactly one lane sees the last record */
-    }
-    p.cnt[lane] = n_ev;
-}
-
-/* pass B: with the bit counts known, writing the events has no long dependency chain any more:
- * records, sample indices and rssi values are fetched a block at a time */
-WMB_D void k2p2_write(const K2p2Params &p, uint32_t lane)
-{
-    if (lane >= p.lanes) return;
-    if (p.pd->fallback) return;
-    const uint64_t N = p.pd->n_rec;
-    const uint64_t r0 = (uint64_t)lane * p.R, r1 = (r0 + p.R < N) ? r0 + p.R : N;
     uint64_t i;
     if (!(r0 < N && k2p2_start(p, lane, r0, r1, i))) return;
-    uint32_t sr = 0, pend = 0;
-    if (lane == 0) { const RlState c = *p.carry; sr = c.sr; pend = (c.flags >> 1) & 1u; }
-    uint64_t ord = p.base[lane];
-    bool stop = false, ran_off_end = (i >= N);
-    uint32_t v[K2P2_BLK], m[K2P2_BLK], rs[K2P2_BLK], vn[K2P2_BLK], mn[K2P2_BLK];
-    uint16_t nn[K2P2_BLK], nnn[K2P2_BLK];
+    int32_t a = 8 * 256, b = 0;
+    if (lane == 0) { const RlState c = *p.carry; a = c.a; b = c.b; }
+    bool stop = false, ran_off_end = false;
+    uint32_t v[K2P2_BLK], vn[K2P2_BLK];
 #pragma unroll
-    for (int j = 0; j < K2P2_BLK; j++) {
-        const bool ok = i + j < N;
-        v[j] = ok ? p.rec_v[i + j] : 1u; m[j] = ok ? p.rec_m[i + j] : 0u; nn[j] = ok ? p.rec_n[i + j] : (uint16_t)0;
-    }
-#pragma unroll
-    for (int j = 0; j < K2P2_BLK; j++) rs[j] = p.rssi[m[j]];
+    for (int j = 0; j < K2P2_BLK; j++) v[j] = (i + j < N) ? p.rec_v[i + j] : 1u;
+    if (i >= N) ran_off_end = true;
     while (!stop && i < N) {
-        /* request the next block's records while this one is written out */
 #pragma unroll
-        for (int j = 0; j < K2P2_BLK; j++) {
-            const bool ok = i + K2P2_BLK + j < N;
-            vn[j] = ok ? p.rec_v[i + K2P2_BLK + j] : 1u; mn[j] = ok ? p.rec_m[i + K2P2_BLK + j] : 0u;
-            nnn[j] = ok ? p.rec_n[i + K2P2_BLK + j] : (uint16_t)0;
-        }
+        for (int j = 0; j < K2P2_BLK; j++) vn[j] = (i + K2P2_BLK + j < N) ? p.rec_v[i + K2P2_BLK + j] : 1u;
 #pragma unroll
         for (int j = 0; j < K2P2_BLK; j++) {
             if (stop) continue;
             if (i + j >= N) { stop = true; ran_off_end = true; continue; }
-            if (v[j] & 1u) {
-                if (i + j >= r1) { stop = true; continue; }
-                sr = 0; pend = 1;
+            const uint32_t vv = v[j];
+            if (vv & 1u) {
+                if (i + j >= r1) { stop = true; continue; }          /* next lane's segment */
+                a = 8 * 256; b = 0;                                  /* runlength_algorithm_reset_t1_c1 */
             }
-            const uint32_t level = (v[j] >> 1) & 1u;
-            const uint64_t head = ((uint64_t)(p.m_base + m[j]) << 24) | ((uint64_t)rs[j] << 16) | level;
-            for (uint32_t k = 0; k < nn[j]; k++) {
-                sr = ((sr << 1) | level) & 0xFFFFu;
-                const uint32_t sync = (sr == 0x543Du) ? 1u : 0u;
-                p.ring[ord & p.ring_mask] = head | (pend << 2) | (sync << 1);
-                pend = 0;
-                if (sync) {
-#ifdef WMB_HOSTSIM
-                    const uint32_t slot = p.sd->n_cand++;
-#else
-                    const uint32_t slot = atomicAdd(&p.sd->n_cand, 1u);
-#endif
-                    if (slot < p.cand_cap) p.cand[slot] = ord;
-                    else p.sd->cand_overflow = 1;
-                }
-                ord++;
+            int rl = (int)((vv >> 2) * 256u);
+            const int half = a / 2;
+            if (rl <= half || a <= 0) {                              /* rtl_wmbus.c:756-762 (or a spin) */
+                p.pd->fallback = 1;
+                stop = true; continue;
             }
+            /* n = number of bit periods in the run (:765-779): the smallest n with rl - n*a <= half.
+             * Telegram runs are 1-4 bits long: compare against all of half + k*a at once and keep the
+             * integer division for the rare long run. */
+            int n;
+            if (rl - half <= 8 * a) {
+                n = 1;
+#pragma unroll
+                for (int k = 1; k < 8; k++) n += (rl > half + k * a) ? 1 : 0;
+                rl -= n * a;
+                b += rl;                                             /* :792 */
+                a += wmb_div_small(wmb_div_pow2(rl + wmb_div_pow2(b, 4), 5), n);   /* :796: x/(32 n) == (x/32)/n */
+            } else {
+                n = (rl - half + a - 1) / a; rl -= n * a;
+                b += rl;
+                a += wmb_div_pow2(rl + wmb_div_pow2(b, 4), 5) / n;
+            }
+            p.rec_n[i + j] = (uint16_t)(n < K2_EDGE_EMIT_CAP ? n : K2_EDGE_EMIT_CAP);
         }
         i += K2P2_BLK;
         if (!stop && i >= N) ran_off_end = true;
 #pragma unroll
-        for (int j = 0; j < K2P2_BLK; j++) { v[j] = vn[j]; m[j] = mn[j]; nn[j] = nnn[j]; }
-#pragma unroll
-        for (int j = 0; j < K2P2_BLK; j++) rs[j] = p.rssi[m[j]];
+        for (int j = 0; j < K2P2_BLK; j++) v[j] = vn[j];
     }
-    if (ran_off_end) {                                               /* this lane saw the last record */
-        p.p2_out->sr = sr; p.p2_out->flags = pend << 1; p.p2_out->run = 1;
+    if (ran_off_end) { p.p2_out->a = a; p.p2_out->b = b; }           /* exactly one lane sees the last record */
+}
+
+/* pass B: with the bit counts known nothing is serial any more.  One block per lane of R records,
+ * K2P2W_ITEMS consecutive records per thread: (a) per-thread bit counts, (b) their exclusive scan,
+ * (c) every thread rebuilds the 16-bit shift register in front of its first record from the
+ * preceding records (at most 16 of them, or the carried register at the start of the batch) and
+ * writes its records' events with the access-code test. */
+WMB_D void k2p2w_a(const K2p2Params &p, uint32_t lane, uint32_t tid, uint32_t *part)
+{
+    uint32_t s = 0;
+    if (!p.pd->fallback) {
+        const uint64_t N = p.pd->n_rec;
+        const uint64_t r0 = (uint64_t)lane * p.R, r1 = (r0 + p.R < N) ? r0 + p.R : N;
+        const uint64_t i0 = r0 + (uint64_t)tid * K2P2W_ITEMS;
+#pragma unroll
+        for (int j = 0; j < K2P2W_ITEMS; j++) if (i0 + j < r1) s += p.rec_n[i0 + j];
+    }
+    part[tid] = s;
+}
+
+/* events per lane of records = sum of part[] after k2p2w_a */
+WMB_D void k2p2_sum_finish(const K2p2Params &p, uint32_t lane, const uint32_t *part)
+{
+    uint32_t n_ev = 0;
+    for (uint32_t t = 0; t < K2P2W_THREADS; t++) n_ev += part[t];
+    p.cnt[lane] = n_ev;
+}
+
+/* exclusive scan of part[0 .. K2P2W_THREADS) */
+#ifdef WMB_HOSTSIM
+static inline void k2p2w_b(uint32_t *part, uint32_t)
+{
+    uint32_t acc = 0;
+    for (uint32_t t = 0; t < K2P2W_THREADS; t++) { const uint32_t c = part[t]; part[t] = acc; acc += c; }
+}
+#else
+WMB_D void k2p2w_b(uint32_t *part, uint32_t tid)
+{
+    if (tid >= 32) return;
+    constexpr int PER = K2P2W_THREADS / 32;
+    uint32_t loc[PER], tot = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { loc[k] = tot; tot += part[tid * PER + k]; }
+    uint32_t inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if ((int)tid >= d) inc += o; }
+    const uint32_t excl = inc - tot;
+#pragma unroll
+    for (int k = 0; k < PER; k++) part[tid * PER + k] = excl + loc[k];
+}
+#endif
+
+WMB_D void k2p2w_c(const K2p2Params &p, uint32_t lane, uint32_t tid, const uint32_t *part)
+{
+    if (p.pd->fallback) return;
+    const uint64_t N = p.pd->n_rec;
+    const uint64_t r0 = (uint64_t)lane * p.R, r1 = (r0 + p.R < N) ? r0 + p.R : N;
+    const uint64_t i0 = r0 + (uint64_t)tid * K2P2W_ITEMS;
+    if (i0 >= r1) return;
+    uint32_t v[K2P2W_ITEMS], m[K2P2W_ITEMS], nn[K2P2W_ITEMS], rs[K2P2W_ITEMS];
+#pragma unroll
+    for (int j = 0; j < K2P2W_ITEMS; j++) {
+        const bool ok = i0 + j < r1;
+        v[j] = ok ? p.rec_v[i0 + j] : 1u; m[j] = ok ? p.rec_m[i0 + j] : 0u; nn[j] = ok ? p.rec_n[i0 + j] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < K2P2W_ITEMS; j++) rs[j] = p.rssi[m[j]];
+    /* the register in front of record i0: the bits since the last reset, zero-extended */
+    uint32_t sr = 0, pend = 0;
+    if (!(v[0] & 1u)) {
+        uint32_t have = 0;
+        uint64_t k = i0;
+        while (true) {
+            if (k == 0) {                                            /* start of the batch: the carried state */
+                const RlState c = *p.carry;
+                sr |= c.sr << have;
+                if (i0 == 0) pend = (c.flags >> 1) & 1u;
+                break;
+            }
+            k--;
+            const uint32_t pv = p.rec_v[k], pn = p.rec_n[k];
+            const uint32_t take = pn < 16u - have ? pn : 16u - have;
+            if (pv & 2u) sr |= ((1u << take) - 1u) << have;
+            have += take;
+            if (have >= 16u || (pv & 1u)) break;                     /* nothing older than a reset counts */
+        }
+        sr &= 0xFFFFu;
+    }
+    uint64_t ord = p.base[lane] + part[tid];
+#pragma unroll
+    for (int j = 0; j < K2P2W_ITEMS; j++) {
+        if (i0 + j >= r1) break;
+        if (v[j] & 1u) { sr = 0; pend = 1; }
+        const uint32_t level = (v[j] >> 1) & 1u;
+        const uint64_t head = ((uint64_t)(p.m_base + m[j]) << 24) | ((uint64_t)rs[j] << 16) | level;
+        for (uint32_t k = 0; k < nn[j]; k++) {
+            sr = ((sr << 1) | level) & 0xFFFFu;
+            const uint32_t sync = (sr == 0x543Du) ? 1u : 0u;
+            p.ring[ord & p.ring_mask] = head | (pend << 2) | (sync << 1);
+            pend = 0;
+            if (sync) {
+#ifdef WMB_HOSTSIM
+                const uint32_t slot = p.sd->n_cand++;
+#else
+                const uint32_t slot = atomicAdd(&p.sd->n_cand, 1u);
+#endif
+                if (slot < p.cand_cap) p.cand[slot] = ord;
+                else p.sd->cand_overflow = 1;
+            }
+            ord++;
+        }
+        if (i0 + j + 1 == N) {                                       /* the last record of the batch */
+            p.p2_out->sr = sr; p.p2_out->flags = pend << 1; p.p2_out->run = 1;
+        }
     }
 }
 

@@ -258,11 +258,12 @@ static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, cons
     k2pc_compact_kernel<<<pc.lanes, 128, 0, c->cs>>>(pc);
     const unsigned grid = (p2.lanes + 127) / 128;
     k2p2_count_kernel<<<grid, 128, 0, c->cs>>>(p2);
+    k2p2_sum_kernel<<<p2.lanes, K2P2W_THREADS, 0, c->cs>>>(p2);
     launch_cscan(c, p2.cnt, p2.base, p2.lanes, p2.agg, &p2.sd->total, &p2.pd->fallback);
-    k2p2_write_kernel<<<grid, 128, 0, c->cs>>>(p2);
+    k2p2_write_kernel<<<p2.lanes, K2P2W_THREADS, 0, c->cs>>>(p2);
     k2p_fold_kernel<<<1, 32, 0, c->cs>>>(p1_end_last, p2.p2_out, carry, p2.pd);
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 4;
+    c->st.kernel_launches += 5;
     return WMB_OK;
 }
 
@@ -423,7 +424,7 @@ static void read_tuning()
     if (!e || sscanf(e, "%u:%u:%u", &a, &b, &r) != 3) return;
     if (a >= 4 && a <= 4096 && a % 4 == 0) g_t2_words = a;
     if (b >= 512 && b <= 65536 && b % 32 == 0) g_p1_chunk = b;
-    if (r >= 16 && r <= 65536) g_p2_records = r;
+    if (r >= 32 && r <= K2P2W_THREADS * K2P2W_ITEMS) g_p2_records = r;
 }
 
 static int ctx_alloc(wmb_ctx *c)

@@ -915,7 +915,27 @@ __global__ void __launch_bounds__(128) k2p1_lanes_kernel(const K2p1Params p) { k
 __global__ void k2p1_verify_kernel(const K2p1Params p, uint32_t *n_fail) { k2p1_verify_lane(p, blockIdx.x * blockDim.x + threadIdx.x, n_fail); }
 __global__ void k2pc_compact_kernel(const K2pcParams p) { k2pc_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
 __global__ void __launch_bounds__(128) k2p2_count_kernel(const K2p2Params p) { k2p2_count(p, blockIdx.x * blockDim.x + threadIdx.x); }
-__global__ void __launch_bounds__(128) k2p2_write_kernel(const K2p2Params p) { k2p2_write(p, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(K2P2W_THREADS) k2p2_sum_kernel(const K2p2Params p)
+{
+    __shared__ uint32_t part[K2P2W_THREADS];
+    k2p2w_a(p, blockIdx.x, threadIdx.x, part);
+    __syncthreads();
+    if (threadIdx.x < 32) {                       /* warp 0 adds the block's partial sums */
+        uint32_t s = 0;
+        for (uint32_t t = threadIdx.x; t < K2P2W_THREADS; t += 32) s += part[t];
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+        if (threadIdx.x == 0) p.cnt[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(K2P2W_THREADS) k2p2_write_kernel(const K2p2Params p)
+{
+    __shared__ uint32_t part[K2P2W_THREADS];
+    k2p2w_a(p, blockIdx.x, threadIdx.x, part);
+    __syncthreads();
+    k2p2w_b(part, threadIdx.x);
+    __syncthreads();
+    k2p2w_c(p, blockIdx.x, threadIdx.x, part);
+}
 __global__ void k2p_fold_kernel(const P1State *p1_end, RlState *p2_out, RlState *carry, const K2pDev *pd)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) k2p_fold(p1_end, p2_out, carry, pd);

@@ -93,10 +93,24 @@ static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, cons
     for (uint32_t lane = 0; lane < pc.lanes; lane++)
         for (int t = 0; t < 4; t++) k2pc_compact(pc, lane, t, 4);
     for (uint32_t lane = 0; lane < p2.lanes; lane++) k2p2_count(p2, lane);
+    {
+        static uint32_t part[K2P2W_THREADS];
+        for (uint32_t lane = 0; lane < p2.lanes; lane++) {
+            for (uint32_t t = 0; t < K2P2W_THREADS; t++) k2p2w_a(p2, lane, t, part);
+            k2p2_sum_finish(p2, lane, part);
+        }
+    }
     launch_cscan(c, p2.cnt, p2.base, p2.lanes, p2.agg, &p2.sd->total, &p2.pd->fallback);
-    for (uint32_t lane = 0; lane < p2.lanes; lane++) k2p2_write(p2, lane);
+    {
+        static uint32_t part[K2P2W_THREADS];
+        for (uint32_t lane = 0; lane < p2.lanes; lane++) {
+            for (uint32_t t = 0; t < K2P2W_THREADS; t++) k2p2w_a(p2, lane, t, part);
+            k2p2w_b(part, 0);
+            for (uint32_t t = 0; t < K2P2W_THREADS; t++) k2p2w_c(p2, lane, t, part);
+        }
+    }
     k2p_fold(p1_end_last, p2.p2_out, carry, p2.pd);
-    c->st.kernel_launches += 4;
+    c->st.kernel_launches += 5;
     return WMB_OK;
 }
 
