@@ -1411,13 +1411,19 @@ extern "C" long wmb_process_device(wmb_ctx *c, const void *dev_cu8, size_t nbyte
     CUDA_TRY(cudaSetDevice(c->device));
     int rc = ctx_alloc(c);
     if (rc) return rc;
+    tr("enter");
     rc = process_device_batches(c, (const uint8_t *)dev_cu8, nbytes, flush != 0);
     if (rc) return rc;
+    tr("batches");
     if (flush) {
         rc = flush_input(c);
         if (rc) return rc;
     }
-    return (long)wmb_take_lines(c, out, outcap, n_lines, timestamp_mode);
+    tr("flush");
+    const long len = (long)wmb_take_lines(c, out, outcap, n_lines, timestamp_mode);
+    tr("lines");
+    tr_dump();
+    return len;
 }
 
 /* Back to the state right after wmb_create (a new capture starts): filter memories, stream

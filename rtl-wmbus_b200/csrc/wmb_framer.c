@@ -268,12 +268,23 @@ void wmb_frame_decode(const wmb_frame *f, wmb_decoded *d)
 
 void wmb_make_time_string(char *ts, size_t n)
 {
+    /* the calendar part only changes once a second: localtime_r/strftime are redone when tv_sec moves */
+    static __thread time_t cached_sec = (time_t)-1;
+    static __thread char cached_fmt[64];
     struct timeval tv;
-    struct tm tmv;
-    if (gettimeofday(&tv, NULL) != 0 || localtime_r(&tv.tv_sec, &tmv) == NULL) { if (n) ts[0] = 0; return; }
-    char fmt[64];
-    strftime(fmt, sizeof(fmt), "%Y-%m-%d %H:%M:%S.%%06u", &tmv);
-    snprintf(ts, n, fmt, (unsigned)tv.tv_usec);
+    if (gettimeofday(&tv, NULL) != 0) { if (n) ts[0] = 0; return; }
+    if (tv.tv_sec != cached_sec) {
+        struct tm tmv;
+        if (localtime_r(&tv.tv_sec, &tmv) == NULL) { if (n) ts[0] = 0; return; }
+        strftime(cached_fmt, sizeof(cached_fmt), "%Y-%m-%d %H:%M:%S.", &tmv);
+        cached_sec = tv.tv_sec;
+    }
+    const size_t l = strlen(cached_fmt);
+    if (n < l + 7) { if (n) ts[0] = 0; return; }
+    memcpy(ts, cached_fmt, l);
+    unsigned us = (unsigned)tv.tv_usec;
+    for (int i = 5; i >= 0; i--) { ts[l + (size_t)i] = (char)('0' + us % 10u); us /= 10u; }
+    ts[l + 6] = 0;
 }
 
 size_t wmb_format_line(const wmb_decoded *d, const char *algo_prefix, const char *timestamp,

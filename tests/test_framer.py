@@ -192,3 +192,15 @@ def test_device_framer_matches_host_twin_hostsim(hostsim_lib, pkg):
 @pytest.mark.gpu
 def test_device_framer_matches_host_twin_gpu(gpu_lib, pkg):
     check_device_framer(gpu_lib, pkg, importlib.import_module("rtl-wmbus_b200.synth"))
+
+
+def test_time_string_format(hostsim_lib):
+    import re
+    buf = C.create_string_buffer(64)
+    hostsim_lib.wmb_make_time_string.argtypes = [C.c_char_p, C.c_size_t]
+    hostsim_lib.wmb_make_time_string.restype = None
+    for _ in range(3):
+        hostsim_lib.wmb_make_time_string(buf, 64)
+        assert re.fullmatch(r"\d{4}-\d\d-\d\d \d\d:\d\d:\d\d\.\d{6}", buf.value.decode()), buf.value
+    hostsim_lib.wmb_make_time_string(buf, 8)          # too small: empty string, no overflow
+    assert buf.value == b""
