@@ -120,7 +120,7 @@ struct wmb_ctx {
     size_t max_batch_bytes = 0;
     int64_t M_max = 0;
     uint32_t W = 32768;             /* retained history (decimated samples) = max warm-up */
-    uint32_t W_a[WMB_N_CHAINS] = {32768, 98304};    /* warm-up of the clock-recovery lanes */
+    uint32_t W_a[WMB_N_CHAINS] = {24576, 98304};    /* warm-up of the clock-recovery lanes */
     uint32_t W_m[WMB_N_CHAINS] = {32768, 65536};    /* warm-up of the run-length lanes  */
     uint32_t C_fixed = 0;
     uint32_t lanes_max = 0;
@@ -572,7 +572,7 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
     } else {
         /* measured re-join times of the biquad state (tools/ + DESIGN.md): T1/C1 filter <= 19 k samples,
          * S1 filter (22-42 kHz band) <= 55 k; the DC block adds its own ~18 k in front */
-        c->W_a[0] = o->remove_dc ? 98304u : 32768u;
+        c->W_a[0] = o->remove_dc ? 98304u : 24576u;    /* measured re-join <= 19k samples; a miss only costs a re-run */
         c->W_a[1] = o->remove_dc ? 163840u : 98304u;
         /* run-length lanes: a cold start re-joins at the first reset both trajectories share, i.e. at the
          * latest when the telegram it started in is over (T1 <= 28 k samples; S1 <= 113 k, typically < 40 k:
@@ -1310,7 +1310,7 @@ extern "C" int wmb_frame_decode_device(wmb_ctx *c, const wmb_frame *frames, size
         const DecHdr &d = c->h_dec[i];
         wmb_decoded &o = out[i];
         memset(&o, 0, sizeof(o));
-        o.status = d.status == K4_SKIP ? WMB_DEC_NEED_MORE : d.status;
+        o.status = d.status == K4_SKIP ? (int)WMB_DEC_NEED_MORE : (int)d.status;
         o.consumed = d.consumed;
         o.end_sample = d.status == K4_SKIP ? 0 : frames[i].sync_sample + d.end_off;
         if (d.status != K4_LINE) continue;

@@ -287,19 +287,48 @@ void wmb_make_time_string(char *ts, size_t n)
     ts[l + 6] = 0;
 }
 
+static size_t put_str(char *buf, size_t len, size_t cap, const char *s)
+{
+    while (*s && len + 1 < cap) buf[len++] = *s++;
+    return len;
+}
+
+static size_t put_u32(char *buf, size_t len, size_t cap, uint32_t v)
+{
+    char tmp[10];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10u); v /= 10u; } while (v);
+    while (n && len + 1 < cap) buf[len++] = tmp[--n];
+    return len;
+}
+
+/* hand-rolled (no printf machinery): a batch can carry thousands of lines */
 size_t wmb_format_line(const wmb_decoded *d, const char *algo_prefix, const char *timestamp,
                        char *buf, size_t cap)
 {
-    static const char hexd[] = "0123456789abcdef";
-    int n = snprintf(buf, cap, "%s%s;%u;%u;%s;%u;%u;%08X;0x", algo_prefix ? algo_prefix : "", d->mode,
-                     (unsigned)d->crc_ok, (unsigned)d->ok_3of6, timestamp, d->packet_rssi, d->current_rssi,
-                     d->serial);
-    if (n < 0) return 0;
-    size_t len = (size_t)n;
+    static const char hexd[] = "0123456789abcdef", hexu[] = "0123456789ABCDEF";
+    if (cap < 2) return 0;
+    size_t len = 0;
+    if (algo_prefix) len = put_str(buf, len, cap, algo_prefix);
+    len = put_str(buf, len, cap, d->mode);
+    if (len + 1 < cap) buf[len++] = ';';
+    len = put_u32(buf, len, cap, d->crc_ok);
+    if (len + 1 < cap) buf[len++] = ';';
+    len = put_u32(buf, len, cap, d->ok_3of6);
+    if (len + 1 < cap) buf[len++] = ';';
+    len = put_str(buf, len, cap, timestamp);
+    if (len + 1 < cap) buf[len++] = ';';
+    len = put_u32(buf, len, cap, d->packet_rssi);
+    if (len + 1 < cap) buf[len++] = ';';
+    len = put_u32(buf, len, cap, d->current_rssi);
+    if (len + 1 < cap) buf[len++] = ';';
+    for (int sh = 28; sh >= 0 && len + 1 < cap; sh -= 4) buf[len++] = hexu[(d->serial >> sh) & 15u];   /* %08X */
+    len = put_str(buf, len, cap, ";0x");
     for (uint32_t i = 0; i < d->len && len + 3 < cap; i++) {
         buf[len++] = hexd[d->datagram[i] >> 4];
         buf[len++] = hexd[d->datagram[i] & 15];
     }
-    if (len + 1 < cap) { buf[len++] = '\n'; buf[len] = 0; }
+    if (len + 1 < cap) buf[len++] = '\n';
+    buf[len] = 0;
     return len;
 }
