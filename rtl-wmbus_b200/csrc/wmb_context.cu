@@ -198,12 +198,14 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     if (!sm_count) {
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device);
     }
-    CUDA_TRY(cudaFuncSetAttribute(k1_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k1_demod_kernel, K1_THREADS, smem));
+    const bool six = getenv("WMBUS_B200_K1_SIX") != nullptr;
+    auto kern = six ? k1_demod_kernel6 : k1_demod_kernel;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, K1_THREADS, smem));
     if (blocks_per_sm < 1) return set_err(WMB_E_INVAL, "decimation %u needs %zu B shared memory per CTA", p.d, smem);
     int64_t grid = (int64_t)sm_count * blocks_per_sm;      /* persistent: whole waves of resident CTAs */
     if (grid > ntiles) grid = ntiles;
-    k1_demod_kernel<<<(unsigned)grid, K1_THREADS, smem, c->cs>>>(p);
+    kern<<<(unsigned)grid, K1_THREADS, smem, c->cs>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches++;
     return WMB_OK;

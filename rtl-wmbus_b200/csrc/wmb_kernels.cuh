@@ -230,14 +230,42 @@ WMB_D void k1_fir_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
     const float *b = (CH::ID == 0) ? c_fir_t1c1 : c_fir_s1;
     const int64_t m0 = tile * K1_TILE;
     float *out = p.dphi[CH::ID];
-    for (int o = tid; o < K1_TILE; o += K1_THREADS) {
-        const int64_t m = m0 + o;
-        if (m >= p.M) break;
-        float acc = 0.0f;
+    if (CH::NTAPS <= 16) {
+        /* four consecutive outputs per thread: their taps overlap, so the window is read once with
+         * 128-bit shared loads and the results leave as one 128-bit store */
+        constexpr int BACK = (CH::NTAPS - 1 + 3) / 4 * 4, WIN = BACK + 4;
+        for (int o = 4 * tid; o < K1_TILE; o += 4 * K1_THREADS) {
+            const int64_t m = m0 + o;
+            if (m >= p.M) break;
+            float w[WIN];
+            const float4 *src = (const float4 *)(sm.draw + K1_HALO + o - BACK);
 #pragma unroll
-        for (int t = 0; t < CH::NTAPS; t++)
-            acc = wmb_fadd(acc, wmb_fmul(b[t], sm.draw[K1_HALO + o - t]));
-        out[m] = acc;
+            for (int q = 0; q < WIN / 4; q++) { const float4 v = src[q]; w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+            float acc[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float a = 0.0f;
+#pragma unroll
+                for (int t = 0; t < CH::NTAPS; t++) a = wmb_fadd(a, wmb_fmul(b[t], w[BACK + k - t]));
+                acc[k] = a;
+            }
+            if (m + 3 < p.M) {
+                float4 v; v.x = acc[0]; v.y = acc[1]; v.z = acc[2]; v.w = acc[3];
+                *(float4 *)(out + m) = v;
+            } else {
+                for (int k = 0; k < 4; k++) if (m + k < p.M) out[m + k] = acc[k];
+            }
+        }
+    } else {
+        for (int o = tid; o < K1_TILE; o += K1_THREADS) {
+            const int64_t m = m0 + o;
+            if (m >= p.M) break;
+            float acc = 0.0f;
+#pragma unroll
+            for (int t = 0; t < CH::NTAPS; t++)
+                acc = wmb_fadd(acc, wmb_fmul(b[t], sm.draw[K1_HALO + o - t]));
+            out[m] = acc;
+        }
     }
     if (tid >= K1_THREADS - K1_TILE / K1_RSSI_SEG) {
         /* one segment per thread (the upper warps, so that the FIR loop above and the recurrence
@@ -351,7 +379,7 @@ __device__ __forceinline__ void k1_chain(const K1Params &p, K1Smem &sm, const ui
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(K1_THREADS) k1_demod_kernel(const K1Params p)
+WMB_D void k1_demod_body(const K1Params &p)
 {
     extern __shared__ __align__(128) uint8_t k1_smem_raw[];
     K1Smem sm;
@@ -378,6 +406,10 @@ __global__ void __launch_bounds__(K1_THREADS) k1_demod_kernel(const K1Params p)
         if (p.chains & 2u) k1_chain<ChainS1>(p, sm, raw, tile, tid, p.mix || !(p.chains & 1u));
     }
 }
+
+__global__ void __launch_bounds__(K1_THREADS) k1_demod_kernel(const K1Params p) { k1_demod_body(p); }
+/* experiment: one more resident CTA per SM (40 registers per thread) */
+__global__ void __launch_bounds__(K1_THREADS, 6) k1_demod_kernel6(const K1Params p) { k1_demod_body(p); }
 #endif /* !WMB_HOSTSIM */
 
 #include "wmb_bitsync.cuh"
