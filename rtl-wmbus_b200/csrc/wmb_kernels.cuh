@@ -408,8 +408,7 @@ WMB_D void k1_demod_body(const K1Params &p)
 }
 
 __global__ void __launch_bounds__(K1_THREADS) k1_demod_kernel(const K1Params p) { k1_demod_body(p); }
-/* experiment: one more resident CTA per SM (40 registers per thread) */
-__global__ void __launch_bounds__(K1_THREADS, 6) k1_demod_kernel6(const K1Params p) { k1_demod_body(p); }
+
 #endif /* !WMB_HOSTSIM */
 
 #include "wmb_bitsync.cuh"
