@@ -112,6 +112,8 @@ struct wmb_ctx {
     uint32_t d = 2;                 /* effective decimation (>= 1) */
     uint32_t chains = 3;
     cudaStream_t cs = nullptr, xs = nullptr;       /* compute, copy */
+    cudaStream_t ts = nullptr;                     /* time2 bit streams, beside the run-length chain on cs */
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k1done[2] = {nullptr, nullptr};
     cudaEvent_t ev_t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool allocated = false;
@@ -272,17 +274,17 @@ static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
 {
     const unsigned grid = (p.lanes + 127) / 128, tiles = scan_tiles(p.lanes);
     if (chain == 0) {
-        k2t_count_kernel<ChainT1C1><<<grid, 128, 0, c->cs>>>(p);
-        t2scan_a_kernel<ChainT1C1><<<tiles, SCAN_BLOCK, 0, c->cs>>>(p);
-        t2scan_b_kernel<ChainT1C1><<<1, 32, 0, c->cs>>>(p);
-        t2scan_c_kernel<ChainT1C1><<<tiles, SCAN_BLOCK, 0, c->cs>>>(p);
-        k2t_write_kernel<ChainT1C1><<<grid, 128, 0, c->cs>>>(p);
+        k2t_count_kernel<ChainT1C1><<<grid, 128, 0, c->ts>>>(p);
+        t2scan_a_kernel<ChainT1C1><<<tiles, SCAN_BLOCK, 0, c->ts>>>(p);
+        t2scan_b_kernel<ChainT1C1><<<1, 32, 0, c->ts>>>(p);
+        t2scan_c_kernel<ChainT1C1><<<tiles, SCAN_BLOCK, 0, c->ts>>>(p);
+        k2t_write_kernel<ChainT1C1><<<grid, 128, 0, c->ts>>>(p);
     } else {
-        k2t_count_kernel<ChainS1><<<grid, 128, 0, c->cs>>>(p);
-        t2scan_a_kernel<ChainS1><<<tiles, SCAN_BLOCK, 0, c->cs>>>(p);
-        t2scan_b_kernel<ChainS1><<<1, 32, 0, c->cs>>>(p);
-        t2scan_c_kernel<ChainS1><<<tiles, SCAN_BLOCK, 0, c->cs>>>(p);
-        k2t_write_kernel<ChainS1><<<grid, 128, 0, c->cs>>>(p);
+        k2t_count_kernel<ChainS1><<<grid, 128, 0, c->ts>>>(p);
+        t2scan_a_kernel<ChainS1><<<tiles, SCAN_BLOCK, 0, c->ts>>>(p);
+        t2scan_b_kernel<ChainS1><<<1, 32, 0, c->ts>>>(p);
+        t2scan_c_kernel<ChainS1><<<tiles, SCAN_BLOCK, 0, c->ts>>>(p);
+        k2t_write_kernel<ChainS1><<<grid, 128, 0, c->ts>>>(p);
     }
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches += 5;
@@ -596,12 +598,15 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
     c->max_batch_bytes = mb;
     memset(&c->st, 0, sizeof(c->st));
     if (cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->xs, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&c->xs, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->ts, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return set_err(WMB_E_CUDA, "cannot create CUDA streams");
     }
     for (int i = 0; i < 2; i++) { cudaEventCreate(&c->ev_h2d[i]); cudaEventCreate(&c->ev_k1done[i]); }
     for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev_t[i]);
+    cudaEventCreate(&c->ev_fork);
+    cudaEventCreate(&c->ev_join);
     *out = c;
     return WMB_OK;
 }
@@ -616,6 +621,9 @@ extern "C" void wmb_destroy(wmb_ctx *c)
     for (void *p : c->host_allocs) cudaFreeHost(p);
     for (int i = 0; i < 2; i++) { if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]); if (c->ev_k1done[i]) cudaEventDestroy(c->ev_k1done[i]); }
     for (int i = 0; i < 6; i++) if (c->ev_t[i]) cudaEventDestroy(c->ev_t[i]);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ts) cudaStreamDestroy(c->ts);
     if (c->cs) cudaStreamDestroy(c->cs);
     if (c->xs) cudaStreamDestroy(c->xs);
     delete c;
@@ -737,8 +745,11 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
                 CUDA_TRY(cudaMemcpyAsync(c->cb[ch].ia_carry, c->cb[ch].ia_end + (lanes - 1), sizeof(IirState),
                                          cudaMemcpyDeviceToDevice, c->cs));
 
-        /* ---- K2t: time2 bit streams straight into the rings ---- */
+        /* ---- K2t: time2 bit streams straight into the rings (own stream: independent of the
+         *      run-length kernels below, and both leave most of the GPU idle on their own) ---- */
         if (c->o.t2_enabled) {
+            CUDA_TRY(cudaEventRecord(c->ev_fork, c->cs));
+            CUDA_TRY(cudaStreamWaitEvent(c->ts, c->ev_fork, 0));
             for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
                 if (!(c->chains & (1u << ch))) continue;
                 ChainBuf &b = c->cb[ch];
@@ -756,6 +767,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
                 p.ring = s.ring; p.ring_mask = s.ring_cap - 1; p.sd = s.sd; p.cand = s.cand; p.cand_cap = c->cand_cap;
                 TRY(launch_k2t(c, ch, p));
             }
+            CUDA_TRY(cudaEventRecord(c->ev_join, c->ts));
         }
 
         /* ---- run-length bit sync ---- */
@@ -835,6 +847,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             }
         }
     }
+    if (any_sync && c->o.t2_enabled) CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_join, 0));
     CUDA_TRY(cudaEventRecord(c->ev_t[2], c->cs));
 
     tr("mono");
