@@ -1,4 +1,4 @@
-"""Host wall-clock trace of device-resident steps (WMBUS_B200_TRACE): python tools/trace_step.py [mib] [batch_mib]"""
+"""Host wall-clock trace of device-resident steps (WMBUS_B200_TRACE): python tools/trace_step.py [mib] [batch_mib] [workload]"""
 import importlib, os, sys, time
 sys.path.insert(0, '.')
 os.environ["WMBUS_B200_TRACE"] = "1"
@@ -8,9 +8,11 @@ lib = pkg.load_library()
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 bm = int(sys.argv[2]) if len(sys.argv) > 2 else mib
 n = mib << 20
-cap, plan = synth.synth_capture(n, emitters=synth.default_emitters("t1x2"), seed=0xB2000020, device="cuda")
+workload = sys.argv[3] if len(sys.argv) > 3 else "t1x2"
+flags = {"t1x2": "-p S", "s1": "-p T", "both": ""}[workload]
+cap, plan = synth.synth_capture(n, emitters=synth.default_emitters("mixed" if workload == "both" else workload), seed=0xB2000020, device="cuda")
 torch.cuda.synchronize()
-ctx = pkg.WmbusB200("-p S", lib=lib, max_batch_mib=bm)
+ctx = pkg.WmbusB200(flags, lib=lib, max_batch_mib=bm)
 for i in range(4):
     t0 = time.perf_counter(); ctx.reset(); t1 = time.perf_counter()
     lines = ctx.process_device(cap.data_ptr(), n, flush=True)

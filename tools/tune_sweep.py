@@ -13,7 +13,7 @@ pkg = importlib.import_module("rtl-wmbus_b200")
 synth = importlib.import_module("rtl-wmbus_b200.synth")
 lib = pkg.load_library()
 workload = sys.argv[1] if len(sys.argv) > 1 else "t1x2"
-flags = {"t1x2": "-p S", "s1": "-p T", "both": "-s"}[workload]
+flags = {"t1x2": "-p S", "s1": "-p T", "both": ""}[workload]
 n = 1 << 30
 cap, plan = synth.synth_capture(n, emitters=synth.default_emitters("mixed" if workload == "both" else workload),
                                 seed=0xB2000020, device="cuda")
