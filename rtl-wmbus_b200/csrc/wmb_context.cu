@@ -1215,8 +1215,9 @@ struct DecLite { int status; uint32_t consumed; uint64_t end_sample; uint8_t crc
 template <class Meta, class Lite, class Fill>
 static int book_frames(wmb_ctx *c, size_t n, Meta meta, Lite lite, Fill fill)
 {
+    struct Key { uint64_t end_sample; uint32_t prio, seq; size_t fi; uint8_t algo; };
     bool blocked[WMB_N_CHAINS][WMB_N_ALGOS] = {{false, false}, {false, false}};
-    std::vector<QueuedLine> fresh;
+    std::vector<Key> fresh;
     for (size_t fi = 0; fi < n; fi++) {
         const FrameMeta f = meta(fi);
         Stream &s = c->cb[f.chain].s[f.algo];
@@ -1232,23 +1233,30 @@ static int book_frames(wmb_ctx *c, size_t n, Meta meta, Lite lite, Fill fill)
         }
         s.busy_until = (int64_t)(f.ordinal + d.consumed - 1);
         if (d.status == WMB_DEC_LINE) {
-            fresh.emplace_back();
-            QueuedLine &q = fresh.back();
-            q.end_sample = d.end_sample;
-            q.prio = f.chain * 2 + (f.algo == WMB_ALGO_T2A ? 1 : 0);
-            q.algo = f.algo;
-            fill(fi, q.d);
+            Key k;
+            k.end_sample = d.end_sample;
+            k.prio = (uint32_t)(f.chain * 2 + (f.algo == WMB_ALGO_T2A ? 1 : 0));
+            k.seq = (uint32_t)fresh.size(); k.fi = fi; k.algo = f.algo;
+            fresh.push_back(k);
             c->st.lines[f.chain][f.algo]++;
             if (d.crc_ok) c->st.lines_crc_ok[f.chain][f.algo]++;
         }
     }
     /* the reference prints in the order the per-sample state machines finish:
-     * sample index, then T1/C1-rla, T1/C1-t2a, S1-rla, S1-t2a (rtl_wmbus.c:1354-1355) */
-    std::stable_sort(fresh.begin(), fresh.end(), [](const QueuedLine &a, const QueuedLine &b) {
+     * sample index, then T1/C1-rla, T1/C1-t2a, S1-rla, S1-t2a (rtl_wmbus.c:1354-1355).
+     * Only the small keys are sorted; the datagrams are materialised once, in print order. */
+    std::sort(fresh.begin(), fresh.end(), [](const Key &a, const Key &b) {
         if (a.end_sample != b.end_sample) return a.end_sample < b.end_sample;
-        return a.prio < b.prio;
+        if (a.prio != b.prio) return a.prio < b.prio;
+        return a.seq < b.seq;
     });
-    c->lines.insert(c->lines.end(), fresh.begin(), fresh.end());
+    const size_t base = c->lines.size();
+    c->lines.resize(base + fresh.size());
+    for (size_t i = 0; i < fresh.size(); i++) {
+        QueuedLine &q = c->lines[base + i];
+        q.end_sample = fresh[i].end_sample; q.prio = (int)fresh[i].prio; q.algo = fresh[i].algo;
+        fill(fresh[i].fi, q.d);
+    }
     return WMB_OK;
 }
 
