@@ -186,13 +186,14 @@ WMB_D void k2a_lane_t(const K2aParams &p, uint32_t lane)
     r.clk3 = st.clk3;
     bool saved_start = false;
 
-    /* each lane streams whole 128-byte lines of dphi; the next line is requested before the
-     * current one is processed so that the DRAM latency hides behind ~32 recurrence steps
+    /* each lane streams whole 128-byte lines of dphi; a line is requested two blocks before it is
+     * processed so that the DRAM latency under load hides behind ~64 recurrence steps
      * (reads may run up to 32 samples past the lane's end: the buffers carry that slack) */
-    float4 cur[8], nxt[8];
+    float4 cur[8], nxt[8], nx2[8];
     if (m < e0) k2a_load(cur, p.dphi + m);
+    if (m + 32 < e0) k2a_load(nxt, p.dphi + m + 32);
     while (m < e0) {
-        if (m + 32 < e0) k2a_load(nxt, p.dphi + m + 32);
+        if (m + 64 < e0) k2a_load(nx2, p.dphi + m + 64);        /* two lines ahead: ~2 us of recurrence steps */
         if (m == s0 && !saved_start) { k2a_save(st, r); p.st_start[lane] = st; saved_start = true; }
         const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
         uint32_t dword, cword;
@@ -216,7 +217,7 @@ WMB_D void k2a_lane_t(const K2aParams &p, uint32_t lane)
         }
         m += n;
 #pragma unroll
-        for (int j = 0; j < 8; j++) cur[j] = nxt[j];
+        for (int j = 0; j < 8; j++) { cur[j] = nxt[j]; nxt[j] = nx2[j]; }
     }
     k2a_save(st, r);
     if (!saved_start) p.st_start[lane] = st;                      /* empty lane */
@@ -799,30 +800,48 @@ WMB_D void k2p1_lane(const K2p1Params &p, uint32_t lane)
     uint64_t *rec = p.rec + (size_t)lane * p.cap;
     uint32_t n_rec = 0;
     bool saved_start = false;
+    /* edge driven like k2m_lane: the deglitched level of a whole word comes from a few bitwise
+     * operations (recomputed only after a reset, which clears the raw history), then the lane jumps
+     * from edge to edge.  The state keeps the K = 5 raw bits that can still matter. */
+    constexpr int K = 5;
+    uint64_t H = k2m_hist_from_raw<ChainT1C1>(raw);
+    uint32_t wnext = (m < e0) ? p.dbits[m >> 5] : 0u;
     while (m < e0) {
         if (m == s0 && !saved_start) {
-            P1State st = { raw, level, pend, run };
+            P1State st = { k2m_raw_from_hist<ChainT1C1>(H), level, pend, run };
             p.st_start[lane] = st; saved_start = true;
         }
         const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
-        const uint32_t word = p.dbits[m >> 5];
+        const uint32_t valid = (n == 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+        const uint32_t word = wnext & valid;
+        if (m + 32 < e0) wnext = p.dbits[(m >> 5) + 1];              /* request the next word early */
         const bool live = m >= s0;
-        for (int i = 0; i < n; i++) {
-            const uint32_t bit = (word >> i) & 1u;
-            raw = ((raw << 1) | bit) & 0x3Fu;
-            const uint32_t st = (wmb_popc(raw) >= 3) ? 1u : 0u;         /* deglitch_filter_t1_c1 */
-            if (st == level) { run++; continue; }
-            if (run < 5) { raw = 0; pend = 1; }                         /* :742-748 */
-            else {
+        H = (H & ((1ull << K) - 1)) | ((uint64_t)word << K);
+        uint32_t D = k2m_deglitch_word<ChainT1C1>(H);
+        int pos = 0;
+        while (pos < n) {
+            const uint32_t x = (D ^ (level ? 0xFFFFFFFFu : 0u)) & (0xFFFFFFFFu << pos) & valid;
+            if (!x) { run += n - pos; break; }
+            const int e = wmb_ffs(x) - 1;
+            run += e - pos;                                          /* samples that kept the level */
+            const uint32_t st = (D >> e) & 1u;
+            if (run < 5) {                                           /* :742-748: forget every bit up to and including e */
+                H &= ~((1ull << (K + e + 1)) - 1);
+                D = k2m_deglitch_word<ChainT1C1>(H);
+                pend = 1;
+            } else {
                 if (live && n_rec < p.cap)
-                    rec[n_rec] = ((uint64_t)(uint32_t)run << 32) | ((uint64_t)(uint32_t)(m + i - s0) << 2) | (level << 1) | pend;
+                    rec[n_rec] = ((uint64_t)(uint32_t)run << 32) | ((uint64_t)(uint32_t)(m + e - s0) << 2) | (level << 1) | pend;
                 if (live) n_rec++;
                 pend = 0;
             }
             level = st; run = 1;
+            pos = e + 1;
         }
         m += n;
+        H >>= n;                                                     /* the newest K bits become the history */
     }
+    raw = k2m_raw_from_hist<ChainT1C1>(H);
     P1State st = { raw, level, pend, run };
     if (!saved_start) p.st_start[lane] = st;
     p.st_end[lane] = st;
