@@ -187,6 +187,30 @@ int wmb_get_stats(wmb_ctx *c, wmb_stats *s);
  * Returns the number of samples copied or a negative error. */
 long wmb_debug_copy_stage(wmb_ctx *c, int chain, float *dphi, uint8_t *rssi, size_t cap);
 
+/* ---- time-chunk sharding of one capture (several contexts / GPUs on one stream) ----
+ * The reference has no counterpart: it is one sequential loop (rtl_wmbus.c:1298-1357).  A worker that
+ * owns the decimated samples [lo, hi) of a capture (1) seeks its context to a position a warm-up halo
+ * before lo, (2) pushes the halo, takes wmb_boundary_state() and compares it with the state its left
+ * neighbour took after pushing up to the same sample -- equal bytes mean that every recurrence, shift
+ * register and telegram in flight is bit-identical from there on, so the chunk decodes exactly as in
+ * the sequential run; a mismatch means the halo was too short (retry with a longer one; position 0 is
+ * exact by definition), (3) pushes its chunk and a right halo of one maximum telegram and keeps only
+ * the lines whose access-code match lies in [lo, hi). */
+
+/* wmb_reset() plus: the next byte pushed is IQ sample `first_iq_sample` of the capture (mixer and
+ * decimation phases, sample indices).  Must be a multiple of 2048 * decimation. */
+int wmb_seek(wmb_ctx *c, uint64_t first_iq_sample);
+
+/* Only telegrams whose access-code match falls on a decimated sample in [sync_lo, sync_hi) produce
+ * lines (default: all).  The others are still decoded: they keep the decoders busy as in the reference. */
+int wmb_set_line_window(wmb_ctx *c, uint64_t sync_lo, uint64_t sync_hi);
+
+/* Everything that couples the samples pushed so far to the output still to come: the carried filter,
+ * clock and run-length states, the shift registers, and the bit events of every telegram in flight
+ * (absolute sample indices, so two contexts that started at different positions can be compared).
+ * Valid after a push of whole batch granules.  Returns the number of bytes written or a negative error. */
+long wmb_boundary_state(wmb_ctx *c, uint8_t *buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

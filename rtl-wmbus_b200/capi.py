@@ -68,12 +68,17 @@ def _bind(lib):
     lib.wmb_get_stats.argtypes = [C.c_void_p, C.POINTER(WmbStats)]
     lib.wmb_debug_copy_stage.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.wmb_debug_copy_stage.restype = C.c_long
+    lib.wmb_seek.argtypes = [C.c_void_p, C.c_uint64]
+    lib.wmb_set_line_window.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    lib.wmb_boundary_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.wmb_boundary_state.restype = C.c_long
     return lib
 
 
 EXPORTS = ["wmb_reset", "wmb_host_alloc", "wmb_host_free", "wmb_default_opts", "wmb_abi_version", "wmb_last_error", "wmb_version_string", "wmb_create",
            "wmb_destroy", "wmb_push", "wmb_push_device", "wmb_poll", "wmb_decode_frames", "wmb_take_lines",
-           "wmb_process", "wmb_process_device", "wmb_get_stats", "wmb_debug_copy_stage"]
+           "wmb_process", "wmb_process_device", "wmb_get_stats", "wmb_debug_copy_stage",
+           "wmb_seek", "wmb_set_line_window", "wmb_boundary_state"]
 
 
 def load_library(path: str | None = None):
@@ -176,6 +181,11 @@ class WmbusB200:
         self._check(self.lib.wmb_poll(self._ctx, arr, cap, C.byref(n), int(flush)))
         return arr, n.value
 
+    def poll_flush(self):
+        """end of input: process what is buffered and finish the telegrams in flight (lines stay queued)"""
+        n = C.c_size_t(0)
+        self._check(self.lib.wmb_poll(self._ctx, None, 0, C.byref(n), 1))
+
     def decode_frames(self, arr, n):
         self._check(self.lib.wmb_decode_frames(self._ctx, arr, n))
 
@@ -191,6 +201,18 @@ class WmbusB200:
 
     def reset(self):
         self._check(self.lib.wmb_reset(self._ctx))
+
+    def seek(self, first_iq_sample: int):
+        """reset + position the stream at an absolute IQ sample of the capture (time-chunk sharding)"""
+        self._check(self.lib.wmb_seek(self._ctx, first_iq_sample))
+
+    def set_line_window(self, sync_lo: int, sync_hi: int):
+        self._check(self.lib.wmb_set_line_window(self._ctx, sync_lo, sync_hi))
+
+    def boundary_state(self) -> bytes:
+        buf = C.create_string_buffer(1 << 22)
+        n = self._check(self.lib.wmb_boundary_state(self._ctx, buf, len(buf)))
+        return buf.raw[:n]
 
     def stats(self) -> WmbStats:
         s = WmbStats()

@@ -175,6 +175,7 @@ struct wmb_ctx {
     std::vector<uint32_t> out_words;
     std::vector<wmb_frame> out_frames;
     bool out_final = false;
+    uint64_t win_lo = 0, win_hi = ~0ull;             /* line window (access-code match sample) */
     /* manual mode (opts.manual_frames): frames wait here for wmb_poll */
     struct Held { wmb_frame f; std::vector<uint32_t> words; };
     std::vector<Held> held, held_prev;
@@ -1209,7 +1210,7 @@ extern "C" int wmb_poll(wmb_ctx *c, wmb_frame *out, size_t cap, size_t *n, int f
  * that is receiving ignores further access-code matches (t1_c1_packet_decoder.h:272-278 honours the
  * flag only in idle), so a candidate inside the telegram of an earlier one is dropped; the rest
  * become lines, queued in the order the reference prints them. */
-struct FrameMeta { uint8_t chain, algo, partial, truncated; uint64_t ordinal; };
+struct FrameMeta { uint8_t chain, algo, partial, truncated; uint64_t ordinal, sync_sample; };
 struct DecLite { int status; uint32_t consumed; uint64_t end_sample; uint8_t crc_ok; };
 
 template <class Meta, class Lite, class Fill>
@@ -1232,7 +1233,7 @@ static int book_frames(wmb_ctx *c, size_t n, Meta meta, Lite lite, Fill fill)
             continue;
         }
         s.busy_until = (int64_t)(f.ordinal + d.consumed - 1);
-        if (d.status == WMB_DEC_LINE) {
+        if (d.status == WMB_DEC_LINE && f.sync_sample >= c->win_lo && f.sync_sample < c->win_hi) {
             Key k;
             k.end_sample = d.end_sample;
             k.prio = (uint32_t)(f.chain * 2 + (f.algo == WMB_ALGO_T2A ? 1 : 0));
@@ -1276,7 +1277,7 @@ static int book_device_frames(wmb_ctx *c)
         [&](size_t k) {
             const FrameHdr &h = hdr[idx[k]];
             FrameMeta m;
-            m.chain = h.chain; m.algo = h.algo; m.ordinal = h.ordinal;
+            m.chain = h.chain; m.algo = h.algo; m.ordinal = h.ordinal; m.sync_sample = h.sync_sample;
             m.partial = (uint8_t)((!h.complete && !final) ? 1 : 0);
             m.truncated = (uint8_t)((h.complete && !h.cut) ? 0 : 1);
             return m;
@@ -1376,7 +1377,7 @@ extern "C" int wmb_decode_frames(wmb_ctx *c, const wmb_frame *frames, size_t n)
     return book_frames(c, n,
         [&](size_t i) {
             FrameMeta m;
-            m.chain = v[i]->chain; m.algo = v[i]->algo; m.ordinal = v[i]->ordinal;
+            m.chain = v[i]->chain; m.algo = v[i]->algo; m.ordinal = v[i]->ordinal; m.sync_sample = v[i]->sync_sample;
             m.partial = v[i]->reserved; m.truncated = v[i]->truncated;
             return m;
         },
@@ -1479,6 +1480,84 @@ extern "C" int wmb_reset(wmb_ctx *c)
         CUDA_TRY(cudaStreamSynchronize(c->cs));
     }
     return WMB_OK;
+}
+
+extern "C" int wmb_seek(wmb_ctx *c, uint64_t first_iq_sample)
+{
+    if (!c) return set_err(WMB_E_INVAL, "null argument");
+    if (first_iq_sample % (2048ull * c->d)) return set_err(WMB_E_INVAL, "seek position must be a multiple of 2048 * decimation IQ samples");
+    int rc = wmb_reset(c);
+    if (rc) return rc;
+    c->iq_consumed = first_iq_sample;
+    c->m_consumed = first_iq_sample / c->d;
+    return WMB_OK;
+}
+
+extern "C" int wmb_set_line_window(wmb_ctx *c, uint64_t sync_lo, uint64_t sync_hi)
+{
+    if (!c || sync_lo > sync_hi) return set_err(WMB_E_INVAL, "bad window");
+    c->win_lo = sync_lo; c->win_hi = sync_hi;
+    return WMB_OK;
+}
+
+extern "C" long wmb_boundary_state(wmb_ctx *c, uint8_t *buf, size_t cap)
+{
+    if (!c || !buf) return set_err(WMB_E_INVAL, "null argument");
+    if (!c->remainder.empty()) return set_err(WMB_E_STATE, "boundary state needs whole batch granules");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ctx_alloc(c);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->cs));
+    std::vector<uint8_t> out;
+    auto put = [&](const void *p, size_t n) { const uint8_t *b = (const uint8_t *)p; out.insert(out.end(), b, b + n); };
+    const uint64_t pos[2] = { c->iq_consumed, c->m_consumed };
+    put(pos, sizeof(pos));
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+        if (!(c->chains & (1u << ch))) continue;
+        ChainBuf &b = c->cb[ch];
+        IirState ia;
+        RlState rl;
+        CUDA_TRY(cudaMemcpy(&ia, b.ia_carry, sizeof(ia), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(&rl, b.rl_carry, sizeof(rl), cudaMemcpyDeviceToHost));
+        if (!c->o.remove_dc) { ia.dc_x = 0.f; ia.dc_y = 0.f; }        /* unused without -o */
+        if (!c->o.t2_enabled) memset(&ia, 0, sizeof(ia));
+        if (!c->o.rla_enabled) memset(&rl, 0, sizeof(rl));
+        ia.pad = 0;
+        put(&ia, sizeof(ia));
+        put(&rl, sizeof(rl));
+        for (int a = 0; a < WMB_N_ALGOS; a++) {
+            if ((a == WMB_ALGO_RLA && !c->o.rla_enabled) || (a == WMB_ALGO_T2A && !c->o.t2_enabled)) continue;
+            Stream &s = b.s[a];
+            StreamDev sd;
+            CUDA_TRY(cudaMemcpy(&sd, s.sd, sizeof(sd), cudaMemcpyDeviceToHost));
+            const uint32_t sr = (a == WMB_ALGO_T2A) ? sd.t2_sr : 0u;
+            put(&sr, 4);
+            /* telegrams in flight: their bit events so far (sample, rssi, flags, bit are all in the word) */
+            std::vector<uint64_t> pend(s.pending);
+            std::sort(pend.begin(), pend.end());
+            const uint32_t np = (uint32_t)pend.size();
+            put(&np, 4);
+            for (uint64_t ord : pend) {
+                if (ord >= sd.total) return set_err(WMB_E_STATE, "internal: pending candidate beyond the stream");
+                const uint64_t n = sd.total - ord;
+                if (n > WMB_MAXBITS + 64) return set_err(WMB_E_STATE, "internal: pending candidate older than a telegram");
+                std::vector<uint64_t> ev((size_t)n);
+                for (uint64_t i = 0; i < n;) {                         /* the ring wraps */
+                    const uint64_t at = (ord + i) & (s.ring_cap - 1);
+                    const uint64_t run = std::min<uint64_t>(n - i, s.ring_cap - at);
+                    CUDA_TRY(cudaMemcpy(ev.data() + i, s.ring + at, (size_t)run * 8, cudaMemcpyDeviceToHost));
+                    i += run;
+                }
+                /* a match inside a telegram that is already decoded will be ignored (busy decoder) */
+                const uint32_t n32 = (uint32_t)n | (((int64_t)ord <= s.busy_until) ? 0x80000000u : 0u);
+                put(&n32, 4);
+                put(ev.data(), ev.size() * 8);
+            }
+        }
+    }
+    if (out.size() > cap) return set_err(WMB_E_INVAL, "buffer too small (%zu bytes needed)", out.size());
+    memcpy(buf, out.data(), out.size());
+    return (long)out.size();
 }
 
 extern "C" int wmb_get_stats(wmb_ctx *c, wmb_stats *s)

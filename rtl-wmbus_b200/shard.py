@@ -1,6 +1,10 @@
-"""Multi-GPU sharding rule of the path: one independent capture per rank, no data-path
-collective; the only exchange is the all-reduce of the packet counters.  Used by bench.py (NCCL) and by the
-world_size-2 gloo test on CPU."""
+"""Multi-GPU sharding rules of the path.
+
+* Independent captures (BASELINE config 5): one capture per rank, no data-path collective; the only exchange is
+  the all-reduce of the packet counters.  Used by bench.py (NCCL) and by the world_size-2 gloo test on CPU.
+* Time chunks of ONE capture (config 4): rank g owns the decimated samples [S_g, S_g+1), warm-starts a
+  halo earlier and proves that it re-joined the sequential run by comparing `wmb_boundary_state()` with its left
+  neighbour's (an all-gather of two digests); a rank whose halo was too short repeats with a longer one."""
 from __future__ import annotations
 
 import torch
@@ -33,3 +37,81 @@ def reduce_counts(counts: torch.Tensor, device=None) -> dict:
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return dict(zip(COUNTER_FIELDS, (int(v) for v in t.cpu())))
+
+
+# ---- time chunks of one capture ---------------------------------------------------------------------
+
+MAX_TELEGRAM_M = 1 << 17        # right halo, decimated samples: the longest S1 telegram is ~113,300 + preamble
+
+
+def chunk_bounds(n_bytes: int, d: int, world: int):
+    """IQ-sample boundaries [k_0 .. k_world] of `world` time chunks, multiples of the batch granule."""
+    gran = 2048 * d                                   # IQ samples per 4096*d input bytes
+    n_iq = (n_bytes // 2) // gran * gran
+    return [min(n_iq, (n_iq * g // world) // gran * gran) for g in range(world)] + [n_iq]
+
+
+def decode_time_chunk(ctx, push, n_bytes: int, d: int, rank: int, world: int, halo_m: int = 1 << 18):
+    """Decode rank `rank`'s chunk of a capture of n_bytes cu8 bytes.  `push(byte_lo, byte_hi)` feeds that byte
+    range of the capture to ctx (host or device memory: the caller's business).
+    Returns (lines, digest_start, digest_end, halo_start_iq): digest_start is None for a chunk that starts at 0."""
+    import hashlib
+    k = chunk_bounds(n_bytes, d, world)
+    lo, hi = k[rank], k[rank + 1]
+    gran = 2048 * d
+    start = max(0, lo - (halo_m * d + gran - 1) // gran * gran)
+    ctx.seek(start)
+    ctx.set_line_window(lo // d, hi // d if rank + 1 < world else (1 << 63))
+    lines = []
+    dig_start = None
+    if start < lo:
+        push(2 * start, 2 * lo)
+        lines += ctx.take_lines()
+    if lo > 0:
+        dig_start = hashlib.sha256(ctx.boundary_state()).digest()
+    push(2 * lo, 2 * hi)
+    lines += ctx.take_lines()
+    dig_end = hashlib.sha256(ctx.boundary_state()).digest()
+    if rank + 1 < world:                              # finish the telegrams that started in the chunk
+        tail = min(k[world], hi + (MAX_TELEGRAM_M * d + gran - 1) // gran * gran)
+        push(2 * hi, 2 * tail)
+        ctx.poll_flush()
+    else:
+        if n_bytes > 2 * hi:
+            push(2 * hi, n_bytes)                     # the ragged end of the capture (the reference drops a short item)
+        ctx.poll_flush()
+    lines += ctx.take_lines()
+    return lines, dig_start, dig_end, start
+
+
+def decode_time_sharded(ctx, push, n_bytes: int, d: int, halo_m: int = 1 << 18):
+    """All ranks: decode one capture in time chunks, exact by construction (see module docstring).
+    Returns (my_lines, rounds)."""
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rounds = 0
+    lines = None
+    redo = True
+    while True:
+        rounds += 1
+        if redo:
+            lines, ds, de, start = decode_time_chunk(ctx, push, n_bytes, d, rank, world, halo_m)
+        mine = torch.zeros(65, dtype=torch.uint8)
+        mine[:32] = torch.frombuffer(bytearray(ds or bytes(32)), dtype=torch.uint8)
+        mine[32:64] = torch.frombuffer(bytearray(de), dtype=torch.uint8)
+        mine[64] = 1 if (ds is None or start == 0) else 0          # started from the true beginning: exact
+        if world > 1:
+            backend = dist.get_backend()
+            dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+            allv = [torch.zeros(65, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(allv, mine.to(dev))
+            allv = [v.cpu() for v in allv]
+        else:
+            allv = [mine]
+        bad = [g for g in range(1, world)
+               if not allv[g][64] and not torch.equal(allv[g][:32], allv[g - 1][32:64])]
+        if not bad:
+            return lines, rounds
+        redo = rank in bad
+        if redo:
+            halo_m *= 4                                 # too short: the neighbour's state was not reached yet

@@ -1,0 +1,101 @@
+"""Time-chunk sharding of one capture: every chunk is decoded by its own context
+from a warm-up halo, the boundary states must chain, and the union of the chunks' lines must be exactly the
+sequential run's lines.  `not gpu`: through the C ABI of the CPU-simulation build (host logic + kernels' phase
+functions; test infrastructure), single process and two ranks over gloo."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import HOSTSIM_SO, ROOT
+
+
+def _capture(nbytes, seed=0xB2000047, emitters="mixed"):
+    synth = importlib.import_module("rtl-wmbus_b200.synth")
+    buf, _ = synth.synth_capture(nbytes, emitters=synth.default_emitters(emitters), seed=seed)
+    return np.ascontiguousarray(buf.numpy())
+
+
+def _pusher(ctx, cu8):
+    return lambda lo, hi: ctx.push(cu8.ctypes.data + lo, hi - lo)
+
+
+def check_time_chunks(pkg, lib, cu8, flags, world, halo_m, d=2):
+    shard = importlib.import_module("rtl-wmbus_b200.shard")
+    with pkg.WmbusB200(flags, lib=lib) as ctx:
+        want = ctx.process(cu8.ctypes.data, len(cu8), flush=True)
+    got, ends, retries = [], [], 0
+    for rank in range(world):
+        h = halo_m
+        while True:
+            with pkg.WmbusB200(flags, lib=lib, max_batch_mib=1) as ctx:
+                lines, ds, de, start = shard.decode_time_chunk(ctx, _pusher(ctx, cu8), len(cu8), d, rank, world, h)
+            if rank == 0 or start == 0 or ds == ends[rank - 1]:
+                break
+            h *= 4
+            retries += 1
+        ends.append(de)
+        got.append(lines)
+    flat = [l for part in got for l in part]
+    assert sorted(flat) == sorted(want)
+    assert len(flat) == len(want) and len(want) > 10
+    assert all(len(part) > 0 for part in got)
+    return retries
+
+
+def test_time_chunks_match_the_sequential_run(hostsim_lib, pkg):
+    cu8 = _capture(6 << 20)
+    retries = check_time_chunks(pkg, hostsim_lib, cu8, "-v", world=3, halo_m=1 << 18)
+    assert retries == 0
+
+
+def test_short_halo_is_detected_and_repeated(hostsim_lib, pkg):
+    cu8 = _capture(4 << 20, seed=0xB2000048)
+    retries = check_time_chunks(pkg, hostsim_lib, cu8, "-v", world=2, halo_m=1 << 10)
+    assert retries >= 1, "a 1024-sample halo cannot re-join the clock-recovery filters"
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = importlib.import_module("rtl-wmbus_b200")
+    shard = importlib.import_module("rtl-wmbus_b200.shard")
+    lib = pkg.load_library(HOSTSIM_SO)
+    cu8 = _capture(4 << 20, seed=0xB2000049)
+    with pkg.WmbusB200("-v", lib=lib, max_batch_mib=1) as ctx:
+        lines, rounds = shard.decode_time_sharded(ctx, _pusher(ctx, cu8), len(cu8), 2, halo_m=1 << 12)
+    counts = shard.reduce_counts(shard.count_lines(lines))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, lines)
+    if rank == 0:
+        with pkg.WmbusB200("-v", lib=lib) as ctx:
+            want = ctx.process(cu8.ctypes.data, len(cu8), flush=True)
+        out.put((gathered, want, counts, rounds))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_time_sharded_gloo(hostsim_lib):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + os.getpid() % 40
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered, want, counts, rounds = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    flat = [l for part in gathered for l in part]
+    assert sorted(flat) == sorted(want) and len(want) > 10
+    assert counts["lines"] == len(want)
+    assert rounds >= 2, "the 4096-sample halo must have been rejected once"
+    assert all(len(part) > 0 for part in gathered)
