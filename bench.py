@@ -160,6 +160,78 @@ def run_reference_arm(args, wl):
     }))
 
 
+def run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local):
+    """Strong scaling: ONE capture, rank g decodes the time chunk [S_g, S_g+1) from a warm-up halo and proves the
+    re-join with its left neighbour's boundary state (two digests per rank, all-gathered)."""
+    import torch
+    import torch.distributed as dist
+    n_bytes = args.mib << 20
+    n_iq = n_bytes // 2
+    d = wl["d"]
+    host = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+    host.copy_(cap)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    results = {}
+    for leg, base, push_name in (("device", cap.data_ptr(), "push_device"), ("host", host.data_ptr(), "push")):
+        ctx = pkg.WmbusB200(wl["flags"], device=local, lib=lib,
+                            max_batch_mib=(args.batch_mib or args.mib) if leg == "device" else args.e2e_batch_mib)
+        push = lambda lo, hi, c=ctx, b=base, f=push_name: getattr(c, f)(b + lo, hi - lo)
+        lines, rounds = None, 0
+        for _ in range(max(1, args.warmup)):
+            lines, rounds = shard.decode_time_sharded(ctx, push, n_bytes, d)
+        l0 = ctx.stats().kernel_launches
+        sampler = ClockSampler(local) if leg == "device" else None
+        if sampler: sampler.start()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            lines, rounds = shard.decode_time_sharded(ctx, push, n_bytes, d)
+        barrier()
+        t = max_over_ranks(time.perf_counter() - t0)
+        results[leg] = dict(t=t, lines=lines, rounds=rounds, launches=ctx.stats().kernel_launches - l0,
+                            clocks=sampler.stop() if sampler else None, st=ctx.stats())
+        ctx.close()
+    assert results["device"]["lines"] == results["host"]["lines"], "host-input and device-input legs disagree"
+    totals = shard.reduce_counts(shard.count_lines(results["device"]["lines"]), device="cuda")
+    if rank == 0:
+        dv, hv = results["device"], results["host"]
+        k = shard.chunk_bounds(n_bytes, d, world)
+        out = {
+            "metric": METRIC, "value": round(n_iq * args.steps / dv["t"] / 1e6, 1), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dv["t"] / args.steps, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "flags": wl["flags"], "capture_mib_total": args.mib,
+                       "sharding": "time chunks of ONE capture: halo warm start, boundary states compared over "
+                                   "all_gather (2 x 32 B per rank), NCCL all-reduce of packet counters",
+                       "chunk_bounds_iq": k, "halo_rounds": dv["rounds"],
+                       "l2": "input and intermediates are larger than L2; no flush needed"},
+            "clocks": dv["clocks"],
+            "e2e": {"value": round(n_iq * args.steps / hv["t"] / 1e6, 1), "unit": UNIT,
+                    "h2d_bytes_per_step": int((hv["st"].h2d_bytes) // (args.steps + max(1, args.warmup))),
+                    "d2h_bytes_per_step": int((hv["st"].d2h_bytes) // (args.steps + max(1, args.warmup))),
+                    "ms_per_step": round(1e3 * hv["t"] / args.steps, 3)},
+            "gpu_launches": int(dv["launches"]),
+            "packets": dict(totals, planted=len(plan)),
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -173,6 +245,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--warm", type=int, default=0, help="bit-sync warm-up samples (default: library)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharding", default="captures", choices=["captures", "time"],
+                    help="N>1: one independent capture per GPU (weak scaling, default) or time chunks of ONE capture "
+                         "(strong scaling, SURVEY 8e / BASELINE config 4)")
     args = ap.parse_args()
     wl = workload_def(args.workload)
     if args.impl == "reference":
@@ -195,10 +270,15 @@ def main():
 
     n_bytes = args.mib << 20
     n_iq = n_bytes // 2
-    # one independent capture per rank (weak scaling; BASELINE config 5's sharding rule)
+    time_sharded = args.sharding == "time"
+    # one independent capture per rank (weak scaling; BASELINE config 5's sharding rule), or the same capture on
+    # every rank, of which each decodes its time chunk (strong scaling; config 4's rule)
     cap, plan = synth.synth_capture(n_bytes, fs=wl["fs"], emitters=synth.default_emitters(wl["emitters"]),
-                                    seed=shard.capture_seed(2, rank), device="cuda")
+                                    seed=shard.capture_seed(4 if time_sharded else 2, 0 if time_sharded else rank),
+                                    device="cuda")
     torch.cuda.synchronize()
+    if time_sharded:
+        return run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local)
     tune = dict(max_batch_mib=args.batch_mib or args.mib)
     if args.chunk: tune["chunk_samples"] = args.chunk
     if args.warm: tune["warmup_samples"] = args.warm

@@ -171,6 +171,9 @@ class WmbusB200:
     def push(self, host_ptr, nbytes):
         self._check(self.lib.wmb_push(self._ctx, host_ptr, nbytes))
 
+    def push_device(self, dev_ptr: int, nbytes: int):
+        self._check(self.lib.wmb_push_device(self._ctx, dev_ptr, nbytes))
+
     def push_bytes(self, data: bytes):
         buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
         self.push(C.cast(buf, C.c_void_p), len(data))

@@ -99,3 +99,26 @@ def test_two_ranks_time_sharded_gloo(hostsim_lib):
     assert counts["lines"] == len(want)
     assert rounds >= 2, "the 4096-sample halo must have been rejected once"
     assert all(len(part) > 0 for part in gathered)
+
+
+@pytest.mark.gpu
+def test_time_chunks_on_the_gpu(gpu_lib, pkg):
+    """Same property through the CUDA library: 64 MiB, three chunks, host pushes (H2D path) and device pushes."""
+    synth = importlib.import_module("rtl-wmbus_b200.synth")
+    shard = importlib.import_module("rtl-wmbus_b200.shard")
+    n = 64 << 20
+    cap, _ = synth.synth_capture(n, emitters=synth.default_emitters("mixed"), seed=0xB200004A, device="cuda")
+    cu8 = np.ascontiguousarray(cap.cpu().numpy())
+    assert check_time_chunks(pkg, gpu_lib, cu8, "-v", world=3, halo_m=1 << 18) == 0
+    with pkg.WmbusB200("", lib=gpu_lib) as ctx:
+        want = ctx.process_device(cap.data_ptr(), n, flush=True)
+    got = []
+    ends = []
+    for rank in range(4):
+        with pkg.WmbusB200("", lib=gpu_lib, max_batch_mib=8) as ctx:
+            push = lambda lo, hi, c=ctx: c.push_device(cap.data_ptr() + lo, hi - lo)
+            lines, ds, de, start = shard.decode_time_chunk(ctx, push, n, 2, rank, 4)
+        assert rank == 0 or ds == ends[-1]
+        ends.append(de)
+        got += lines
+    assert sorted(got) == sorted(want) and len(want) > 100
