@@ -582,6 +582,7 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
          * latest when the telegram it started in is over (T1 <= 28 k samples; S1 <= 113 k, typically < 40 k:
          * longer S1 telegrams cost a verified re-run of the lanes they cover, never a wrong bit) */
         c->W_m[0] = 32768u; c->W_m[1] = 65536u;
+        if (const char *e = getenv("WMBUS_B200_WM_S1")) { const unsigned v = (unsigned)atoi(e); if (v >= 256) c->W_m[1] = (v + 255) / 256 * 256; }   /* experiment */
     }
     c->W = 0;
     for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
