@@ -114,6 +114,8 @@ struct wmb_ctx {
     cudaStream_t cs = nullptr, xs = nullptr;       /* compute, copy */
     cudaStream_t ts = nullptr;                     /* time2 bit streams, beside the run-length chain on cs */
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t s2 = nullptr;                     /* the S1 chain's lanes, beside the T1/C1 chain's on cs */
+    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k1done[2] = {nullptr, nullptr};
     cudaEvent_t ev_t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool allocated = false;
@@ -213,23 +215,23 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     return WMB_OK;
 }
 
-static int launch_k2a(wmb_ctx *c, int chain, const K2aParams &p)
+static int launch_k2a(wmb_ctx *c, int chain, const K2aParams &p, cudaStream_t st)
 {
     const unsigned grid = (p.lanes + K2_THREADS - 1) / K2_THREADS;
-    if (chain == 0) k2a_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, c->cs>>>(p);
-    else            k2a_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, c->cs>>>(p);
-    k2a_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, c->cs>>>(p, c->d_nfail);
+    if (chain == 0) k2a_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, st>>>(p);
+    else            k2a_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, st>>>(p);
+    k2a_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, c->d_nfail);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches += 2;
     return WMB_OK;
 }
 
-static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p)
+static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p, cudaStream_t st)
 {
     const unsigned grid = (p.lanes + K2_THREADS - 1) / K2_THREADS;
-    if (chain == 0) k2m_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, c->cs>>>(p);
-    else            k2m_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, c->cs>>>(p);
-    k2m_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, c->cs>>>(p, c->d_nfail);
+    if (chain == 0) k2m_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, st>>>(p);
+    else            k2m_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, st>>>(p);
+    k2m_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, c->d_nfail);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches += 2;
     return WMB_OK;
@@ -245,14 +247,15 @@ static int launch_k2p1(wmb_ctx *c, const K2p1Params &p)
 }
 
 static void launch_cscan(wmb_ctx *c, const uint32_t *cnt, uint64_t *base, uint32_t n, uint64_t *agg, uint64_t *total,
-                         const uint32_t *skip = nullptr, uint32_t *clear = nullptr, uint32_t from_zero = 0)
+                         const uint32_t *skip = nullptr, uint32_t *clear = nullptr, uint32_t from_zero = 0, cudaStream_t st = nullptr)
 {
+    if (!st) st = c->cs;
     CountScan s;
     s.cnt = cnt; s.base = base; s.n = n; s.agg = agg; s.total = total; s.skip = skip; s.clear = clear; s.from_zero = from_zero;
     const unsigned tiles = scan_tiles(n);
-    cscan_a_kernel<<<tiles, SCAN_BLOCK, 0, c->cs>>>(s);
-    cscan_b_kernel<<<1, 32, 0, c->cs>>>(s);
-    cscan_c_kernel<<<tiles, SCAN_BLOCK, 0, c->cs>>>(s);
+    cscan_a_kernel<<<tiles, SCAN_BLOCK, 0, st>>>(s);
+    cscan_b_kernel<<<1, 32, 0, st>>>(s);
+    cscan_c_kernel<<<tiles, SCAN_BLOCK, 0, st>>>(s);
     c->st.kernel_launches += 3;
 }
 
@@ -292,10 +295,10 @@ static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
     return WMB_OK;
 }
 
-static int launch_k2c(wmb_ctx *c, const K2cParams &p)
+static int launch_k2c(wmb_ctx *c, const K2cParams &p, cudaStream_t st)
 {
-    launch_cscan(c, p.cnt, p.base, p.lanes, p.agg, &p.sd->total);
-    k2c_compact_kernel<<<p.lanes, 128, 0, c->cs>>>(p);
+    launch_cscan(c, p.cnt, p.base, p.lanes, p.agg, &p.sd->total, nullptr, nullptr, 0, st);
+    k2c_compact_kernel<<<p.lanes, 128, 0, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches += 1;
     return WMB_OK;
@@ -602,7 +605,8 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
     memset(&c->st, 0, sizeof(c->st));
     if (cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->xs, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->ts, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&c->ts, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return set_err(WMB_E_CUDA, "cannot create CUDA streams");
     }
@@ -610,6 +614,8 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
     for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev_t[i]);
     cudaEventCreate(&c->ev_fork);
     cudaEventCreate(&c->ev_join);
+    cudaEventCreate(&c->ev_fork2);
+    cudaEventCreate(&c->ev_join2);
     *out = c;
     return WMB_OK;
 }
@@ -627,6 +633,9 @@ extern "C" void wmb_destroy(wmb_ctx *c)
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ts) cudaStreamDestroy(c->ts);
+    if (c->ev_fork2) cudaEventDestroy(c->ev_fork2);
+    if (c->ev_join2) cudaEventDestroy(c->ev_join2);
+    if (c->s2) cudaStreamDestroy(c->s2);
     if (c->cs) cudaStreamDestroy(c->cs);
     if (c->xs) cudaStreamDestroy(c->xs);
     delete c;
@@ -734,12 +743,27 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             p.dc = c->o.remove_dc; p.t2 = c->o.t2_enabled;
             c->st.lanes_run += lanes;
         }
+        /* the two chains' lanes are independent and each leaves the schedulers half idle: chain 1 runs on its
+         * own stream (forked after whatever cs holds, joined before the verdict is read) */
+        auto fork2 = [&]() -> int {
+            CUDA_TRY(cudaEventRecord(c->ev_fork2, c->cs));
+            CUDA_TRY(cudaStreamWaitEvent(c->s2, c->ev_fork2, 0));
+            return WMB_OK;
+        };
+        auto join2 = [&]() -> int {
+            CUDA_TRY(cudaEventRecord(c->ev_join2, c->s2));
+            CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_join2, 0));
+            return WMB_OK;
+        };
+        const bool both = (c->chains & 3u) == 3u;
         TRY(verified_pass(c, lanes, [&](uint32_t mode) {
+            if (both) TRY(fork2());
             for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
                 if (!(c->chains & (1u << ch))) continue;
                 ka[ch].mode = mode;
-                TRY(launch_k2a(c, ch, ka[ch]));
+                TRY(launch_k2a(c, ch, ka[ch], (both && ch == 1) ? c->s2 : c->cs));
             }
+            if (both) TRY(join2());
             return (int)WMB_OK;
         }));
         tr("k1+k2a");
@@ -775,20 +799,70 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
 
         /* ---- run-length bit sync ---- */
         if (c->o.rla_enabled) {
-            uint32_t mono = 0;                             /* chains that take the monolithic lanes */
-            if ((c->chains & 1u) && c->two_phase) {
+            const bool two = (c->chains & 1u) && c->two_phase;
+            /* chains that take the monolithic lanes: S1 always, T1/C1 when forced (tests) */
+            uint32_t mono = (c->chains & 2u) | (((c->chains & 1u) && !two) ? 1u : 0u);
+            K2p1Params p1;
+            K2mParams km[WMB_N_CHAINS];
+            memset(&p1, 0, sizeof(p1));
+            auto setup_mono = [&](int ch) -> int {
+                ChainBuf &b = c->cb[ch];
+                K2mParams &p = km[ch];
+                memset(&p, 0, sizeof(p));
+                p.dbits = b.dbits + wofs; p.rssi = b.rssi + c->W; p.M = M; p.hist = c->hist_m;
+                p.C = C; p.W = c->W_m[ch]; p.lanes = lanes;
+                p.cap = C / 4 + K2_EDGE_EMIT_CAP + 8;
+                if ((uint64_t)lanes * p.cap > c->cap_words_rl) return set_err(WMB_E_INVAL, "internal: event buffers too small for C=%u", C);
+                p.ev = b.s[WMB_ALGO_RLA].ev; p.cnt = b.s[WMB_ALGO_RLA].cnt;
+                p.st_start = b.rl_start; p.st_end = b.rl_end; p.carry = b.rl_carry; p.rerun = b.rerun;
+                p.errors = c->d_errors;
+                c->st.lanes_run += lanes;
+                return WMB_OK;
+            };
+            auto finish_mono = [&](int ch, cudaStream_t st) -> int {          /* carry + compaction into the ring */
+                ChainBuf &b = c->cb[ch];
+                Stream &s = b.s[WMB_ALGO_RLA];
+                CUDA_TRY(cudaMemcpyAsync(b.rl_carry, b.rl_end + (lanes - 1), sizeof(RlState), cudaMemcpyDeviceToDevice, st));
+                K2cParams q;
+                memset(&q, 0, sizeof(q));
+                q.ev = s.ev; q.cnt = s.cnt; q.base = s.base; q.lanes = lanes; q.cap = km[ch].cap; q.C = C;
+                q.m_base = (int64_t)c->m_consumed;
+                q.ring = s.ring; q.ring_mask = s.ring_cap - 1; q.sd = s.sd; q.cand = s.cand; q.cand_cap = c->cand_cap;
+                q.agg = s.agg; q.rssi = b.rssi + c->W;
+                return launch_k2c(c, q, st);
+            };
+            if (two) {
                 /* T1/C1: phase 1 (per-sample, verified) -> records -> phase 2 (per-run) */
                 ChainBuf &b = c->cb[0];
-                Stream &s = b.s[WMB_ALGO_RLA];
-                K2p1Params p1;
-                memset(&p1, 0, sizeof(p1));
                 p1.dbits = b.dbits + wofs; p1.M = M; p1.hist = c->hist_m;
                 p1.C = K2P1_CHUNK; p1.W = K2P1_WARM; p1.lanes = (uint32_t)((M + K2P1_CHUNK - 1) / K2P1_CHUNK);
                 p1.cap = K2P1_CAP; p1.rec = b.p1_rec; p1.cnt = b.p1_cnt;
                 p1.st_start = b.p1_start; p1.st_end = b.p1_end; p1.carry = b.rl_carry; p1.rerun = b.p1_rerun;
                 if (p1.lanes > c->p1_lanes_max) return set_err(WMB_E_INVAL, "internal: phase-1 lanes");
                 c->st.lanes_run += p1.lanes;
-                TRY(verified_pass(c, p1.lanes, [&](uint32_t mode) { p1.mode = mode; return launch_k2p1(c, p1); }));
+            }
+            for (int ch = 0; ch < WMB_N_CHAINS; ch++) if (mono & (1u << ch)) TRY(setup_mono(ch));
+            /* one verified pass for everything that speculates: phase 1 of T1/C1 on cs, the S1 lanes beside it */
+            const bool s1_beside = two && (mono & 2u);
+            if (two || mono) {
+                TRY(verified_pass(c, std::max(lanes, p1.lanes), [&](uint32_t mode) {
+                    if (s1_beside) TRY(fork2());
+                    if (two) { p1.mode = mode; TRY(launch_k2p1(c, p1)); }
+                    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+                        if (!(mono & (1u << ch))) continue;
+                        km[ch].mode = mode;
+                        TRY(launch_k2m(c, ch, km[ch], (s1_beside && ch == 1) ? c->s2 : c->cs));
+                    }
+                    if (s1_beside) TRY(join2());
+                    return (int)WMB_OK;
+                }));
+            }
+            if (s1_beside) TRY(fork2());
+            for (int ch = 0; ch < WMB_N_CHAINS; ch++)
+                if (mono & (1u << ch)) TRY(finish_mono(ch, (s1_beside && ch == 1) ? c->s2 : c->cs));
+            if (two) {
+                ChainBuf &b = c->cb[0];
+                Stream &s = b.s[WMB_ALGO_RLA];
                 K2pcParams pc;
                 memset(&pc, 0, sizeof(pc));
                 pc.rec = b.p1_rec; pc.cnt = b.p1_cnt; pc.base = b.p1_base; pc.lanes = p1.lanes; pc.cap = p1.cap; pc.C = p1.C;
@@ -803,51 +877,17 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
                 p2.carry = b.rl_carry; p2.p2_out = b.p2_out; p2.agg = s.agg;
                 TRY(launch_k2p_rest(c, pc, p2, b.p1_end + (p1.lanes - 1), b.rl_carry));
                 CUDA_TRY(cudaMemcpyAsync(c->h_pd, b.pd, sizeof(K2pDev), cudaMemcpyDeviceToHost, c->cs));
+                if (s1_beside) TRY(join2());
                 CUDA_TRY(cudaStreamSynchronize(c->cs));
                 tr("k2t+p1+p2");
-                if (c->h_pd->fallback) { mono |= 1u; c->st.rl_fallbacks++; }
-            } else if (c->chains & 1u) mono |= 1u;
-            if (c->chains & 2u) mono |= 2u;
-
-            /* S1 (and T1/C1 batches in which the second reset rule fired): monolithic lanes */
-            if (mono) {
-                K2mParams km[WMB_N_CHAINS];
-                for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-                    if (!(mono & (1u << ch))) continue;
-                    ChainBuf &b = c->cb[ch];
-                    K2mParams &p = km[ch];
-                    memset(&p, 0, sizeof(p));
-                    p.dbits = b.dbits + wofs; p.rssi = b.rssi + c->W; p.M = M; p.hist = c->hist_m;
-                    p.C = C; p.W = c->W_m[ch]; p.lanes = lanes;
-                    p.cap = C / 4 + K2_EDGE_EMIT_CAP + 8;
-                    if ((uint64_t)lanes * p.cap > c->cap_words_rl) return set_err(WMB_E_INVAL, "internal: event buffers too small for C=%u", C);
-                    p.ev = b.s[WMB_ALGO_RLA].ev; p.cnt = b.s[WMB_ALGO_RLA].cnt;
-                    p.st_start = b.rl_start; p.st_end = b.rl_end; p.carry = b.rl_carry; p.rerun = b.rerun;
-                    p.errors = c->d_errors;
-                    c->st.lanes_run += lanes;
+                if (c->h_pd->fallback) {
+                    /* the second reset rule fired in this batch: redo T1/C1 with the exact monolithic lanes */
+                    c->st.rl_fallbacks++;
+                    TRY(setup_mono(0));
+                    TRY(verified_pass(c, lanes, [&](uint32_t mode) { km[0].mode = mode; return launch_k2m(c, 0, km[0], c->cs); }));
+                    TRY(finish_mono(0, c->cs));
                 }
-                TRY(verified_pass(c, lanes, [&](uint32_t mode) {
-                    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-                        if (!(mono & (1u << ch))) continue;
-                        km[ch].mode = mode;
-                        TRY(launch_k2m(c, ch, km[ch]));
-                    }
-                    return (int)WMB_OK;
-                }));
-                for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-                    if (!(mono & (1u << ch))) continue;
-                    ChainBuf &b = c->cb[ch];
-                    Stream &s = b.s[WMB_ALGO_RLA];
-                    CUDA_TRY(cudaMemcpyAsync(b.rl_carry, b.rl_end + (lanes - 1), sizeof(RlState), cudaMemcpyDeviceToDevice, c->cs));
-                    K2cParams q;
-                    memset(&q, 0, sizeof(q));
-                    q.ev = s.ev; q.cnt = s.cnt; q.base = s.base; q.lanes = lanes; q.cap = km[ch].cap; q.C = C;
-                    q.m_base = (int64_t)c->m_consumed;
-                    q.ring = s.ring; q.ring_mask = s.ring_cap - 1; q.sd = s.sd; q.cand = s.cand; q.cand_cap = c->cand_cap;
-                    q.agg = s.agg; q.rssi = b.rssi + c->W;
-                    TRY(launch_k2c(c, q));
-                }
-            }
+            } else if (s1_beside) TRY(join2());
         }
     }
     if (any_sync && c->o.t2_enabled) CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_join, 0));

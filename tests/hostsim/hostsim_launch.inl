@@ -37,7 +37,7 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     return WMB_OK;
 }
 
-static int launch_k2a(wmb_ctx *c, int chain, const K2aParams &p)
+static int launch_k2a(wmb_ctx *c, int chain, const K2aParams &p, cudaStream_t)
 {
     for (uint32_t lane = 0; lane < p.lanes; lane++) {
         if (chain == 0) k2a_lane<ChainT1C1>(p, lane);
@@ -48,7 +48,7 @@ static int launch_k2a(wmb_ctx *c, int chain, const K2aParams &p)
     return WMB_OK;
 }
 
-static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p)
+static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p, cudaStream_t)
 {
     for (uint32_t lane = 0; lane < p.lanes; lane++) {
         if (chain == 0) k2m_lane<ChainT1C1>(p, lane);
@@ -68,7 +68,7 @@ static int launch_k2p1(wmb_ctx *c, const K2p1Params &p)
 }
 
 static void launch_cscan(wmb_ctx *c, const uint32_t *cnt, uint64_t *base, uint32_t n, uint64_t *agg, uint64_t *total,
-                         const uint32_t *skip = nullptr, uint32_t *clear = nullptr, uint32_t from_zero = 0)
+                         const uint32_t *skip = nullptr, uint32_t *clear = nullptr, uint32_t from_zero = 0, cudaStream_t = nullptr)
 {
     CountScan s;
     s.cnt = cnt; s.base = base; s.n = n; s.agg = agg; s.total = total; s.skip = skip; s.clear = clear; s.from_zero = from_zero;
@@ -140,7 +140,7 @@ static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
     return WMB_OK;
 }
 
-static int launch_k2c(wmb_ctx *c, const K2cParams &p)
+static int launch_k2c(wmb_ctx *c, const K2cParams &p, cudaStream_t)
 {
     launch_cscan(c, p.cnt, p.base, p.lanes, p.agg, &p.sd->total);
     for (uint32_t lane = 0; lane < p.lanes; lane++)
