@@ -755,7 +755,8 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_join2, 0));
             return WMB_OK;
         };
-        const bool both = (c->chains & 3u) == 3u;
+        static const int s2_mode = getenv("WMBUS_B200_S2") ? atoi(getenv("WMBUS_B200_S2")) : 3;   /* experiment: bit0 K2a, bit1 run-length */
+        const bool both = (c->chains & 3u) == 3u && (s2_mode & 1);
         TRY(verified_pass(c, lanes, [&](uint32_t mode) {
             if (both) TRY(fork2());
             for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
@@ -843,7 +844,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             }
             for (int ch = 0; ch < WMB_N_CHAINS; ch++) if (mono & (1u << ch)) TRY(setup_mono(ch));
             /* one verified pass for everything that speculates: phase 1 of T1/C1 on cs, the S1 lanes beside it */
-            const bool s1_beside = two && (mono & 2u);
+            const bool s1_beside = two && (mono & 2u) && (s2_mode & 2);
             if (two || mono) {
                 TRY(verified_pass(c, std::max(lanes, p1.lanes), [&](uint32_t mode) {
                     if (s1_beside) TRY(fork2());
