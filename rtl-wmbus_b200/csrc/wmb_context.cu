@@ -743,8 +743,8 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             p.dc = c->o.remove_dc; p.t2 = c->o.t2_enabled;
             c->st.lanes_run += lanes;
         }
-        /* the two chains' lanes are independent and each leaves the schedulers half idle: chain 1 runs on its
-         * own stream (forked after whatever cs holds, joined before the verdict is read) */
+        /* chain 1's run-length lanes can run on their own stream (forked after whatever cs holds, joined before
+         * the verdict is read) */
         auto fork2 = [&]() -> int {
             CUDA_TRY(cudaEventRecord(c->ev_fork2, c->cs));
             CUDA_TRY(cudaStreamWaitEvent(c->s2, c->ev_fork2, 0));
@@ -755,8 +755,9 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_join2, 0));
             return WMB_OK;
         };
-        static const int s2_mode = getenv("WMBUS_B200_S2") ? atoi(getenv("WMBUS_B200_S2")) : 3;   /* experiment: bit0 K2a, bit1 run-length */
-        const bool both = (c->chains & 3u) == 3u && (s2_mode & 1);
+        /* (measured: the two chains' clock lanes side by side are SLOWER, 8.3 vs 7.2 ms of bit sync per GiB --
+         * each already fills the fp32 pipe of its scheduler; only the run-length lanes below share the GPU) */
+        const bool both = false;
         TRY(verified_pass(c, lanes, [&](uint32_t mode) {
             if (both) TRY(fork2());
             for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
@@ -844,7 +845,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             }
             for (int ch = 0; ch < WMB_N_CHAINS; ch++) if (mono & (1u << ch)) TRY(setup_mono(ch));
             /* one verified pass for everything that speculates: phase 1 of T1/C1 on cs, the S1 lanes beside it */
-            const bool s1_beside = two && (mono & 2u) && (s2_mode & 2);
+            const bool s1_beside = two && (mono & 2u);
             if (two || mono) {
                 TRY(verified_pass(c, std::max(lanes, p1.lanes), [&](uint32_t mode) {
                     if (s1_beside) TRY(fork2());
