@@ -148,8 +148,10 @@ class WmbusB200:
         return rc
 
     def _lines(self, n):
-        txt = self._out.raw[:n].decode()
-        return [l for l in txt.split("\n") if l]
+        if n <= 0:
+            return []
+        txt = C.string_at(self._out, n).decode("ascii")      # (.raw would copy the whole 4 MiB buffer)
+        return txt.split("\n")[:-1] if txt.endswith("\n") else [l for l in txt.split("\n") if l]
 
     def process(self, host_ptr, nbytes, flush=True, timestamp_mode=1):
         """host_ptr: int address / ctypes pointer of cu8 bytes in host memory."""
