@@ -54,6 +54,12 @@ def test_time_chunks_match_the_sequential_run(hostsim_lib, pkg):
     assert retries == 0
 
 
+def test_time_chunks_with_mixer_decimation_and_dc_block(hostsim_lib, pkg):
+    """-d 3 -s -o: the mixer LUT phase and the decimation phase must stay global after wmb_seek."""
+    cu8 = np.fromfile(os.path.join(ROOT, "tests", "golden", "synth_mixed_2m4_shift.cu8"), np.uint8)
+    check_time_chunks(pkg, hostsim_lib, cu8, "-v -d 3 -s -o", world=2, halo_m=1 << 16, d=3)
+
+
 def test_short_halo_is_detected_and_repeated(hostsim_lib, pkg):
     cu8 = _capture(4 << 20, seed=0xB2000048)
     retries = check_time_chunks(pkg, hostsim_lib, cu8, "-v", world=2, halo_m=1 << 10)
