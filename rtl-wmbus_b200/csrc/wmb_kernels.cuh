@@ -222,6 +222,46 @@ WMB_D void k1_disc_mag(const K1Params &p, K1Smem &sm, int tid)
     }
 }
 
+/* phases B + C of the d = 2 fast path in one: every thread owns four consecutive rows; it reads the pair
+ * sums its box windows cover with 128-bit shared loads, slides the (packed I|Q) box sum from row to row
+ * and goes straight on to the discriminator and |s| -- the box outputs never touch shared memory. */
+struct alignas(16) K1Word4 { uint32_t x, y, z, w; };
+
+template <class CH>
+WMB_D void k1_box_disc_fast(const K1Params &p, K1Smem &sm, int tid)
+{
+    constexpr int NW = CH::BOX / 2;                       /* pair-sum words per box */
+    constexpr int NLOAD = NW + 4;                         /* windows of rows r0-1 .. r0+3 */
+    const float inv = 1.0f / (float)CH::BOX;
+    for (int r0 = 4 * tid; r0 < K1_TILE + K1_HALO; r0 += 4 * K1_THREADS) {
+        uint32_t w[NLOAD];
+        const K1Word4 *src = (const K1Word4 *)(sm.v + r0 + K1_BOX_MAX / 2 - NW);   /* first word of row r0-1's window */
+#pragma unroll
+        for (int q = 0; q < NLOAD / 4; q++) { const K1Word4 v = src[q]; w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+        uint32_t acc = 0;
+#pragma unroll
+        for (int b = 0; b < NW; b++) acc += w[b];
+        float si[5], sq[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            if (k > 0) acc = acc - w[k - 1] + w[k - 1 + NW];          /* both halves stay non-negative: no borrow */
+            si[k] = wmb_fmul((float)((int)(acc & 0xFFFFu) - NW * K1_PAIR_BIAS), inv);
+            sq[k] = wmb_fmul((float)((int)(acc >> 16) - NW * K1_PAIR_BIAS), inv);
+        }
+        float dr[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int r = r0 + k;
+            dr[k] = 0.f;
+            if (r > 0) dr[k] = p.accurate ? wmb_discriminator(si[k + 1], sq[k + 1], si[k], sq[k])
+                                          : wmb_discriminator_fast(si[k + 1], sq[k + 1], si[k], sq[k]);
+            sm.mag[k1_pad(r)] = wmb_fmul(0.6789f, wmb_fsqrt(wmb_fadd(wmb_fmul(si[k + 1], si[k + 1]), wmb_fmul(sq[k + 1], sq[k + 1]))));
+        }
+        float4 o; o.x = dr[0]; o.y = dr[1]; o.z = dr[2]; o.w = dr[3];
+        *(float4 *)(sm.draw + r0) = o;
+    }
+}
+
 /* phase D: FIR (fir.h:56-67: newest sample first, accumulate from 0) and RSSI one-pole
  * (rtl_wmbus.c:475-484) */
 template <class CH>
@@ -369,9 +409,12 @@ __device__ __forceinline__ void k1_chain(const K1Params &p, K1Smem &sm, const ui
         if (fast) k1_convert_fast(p, sm, raw, tile, tid); else k1_convert<CH::ID>(p, sm, raw, tile, tid);
         __syncthreads();
     }
-    if (fast) k1_box_fast<CH>(p, sm, tid); else k1_box<CH>(p, sm, tid);
-    __syncthreads();
-    k1_disc_mag(p, sm, tid);
+    if (fast) k1_box_disc_fast<CH>(p, sm, tid);
+    else {
+        k1_box<CH>(p, sm, tid);
+        __syncthreads();
+        k1_disc_mag(p, sm, tid);
+    }
     __syncthreads();
     k1_fir_rssi<CH>(p, sm, tile, tid);
     __syncthreads();
