@@ -318,26 +318,19 @@ WMB_D void k1_fir_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
 #pragma unroll 8
         for (int j = 0; j < K1_RSSI_WARM; j++)
             rr = wmb_fadd(sm.mag[k1_pad(r0 + j)], wmb_fmul(B, rr));
+        /* the segment's 16 bytes leave as one 128-bit store (consecutive threads, consecutive segments) */
+        uint32_t pk[K1_RSSI_SEG / 4] = { 0, 0, 0, 0 };
 #pragma unroll
         for (int j = 0; j < K1_RSSI_SEG; j++) {
             rr = wmb_fadd(sm.mag[k1_pad(r0 + K1_RSSI_WARM + j)], wmb_fmul(B, rr));
-            sm.rs[o0 + j] = (uint8_t)(unsigned)rr;
+            pk[j >> 2] |= ((uint32_t)(unsigned)rr & 0xFFu) << (8 * (j & 3));
         }
-    }
-}
-
-/* phase E: coalesced store of the rssi bytes */
-template <class CH>
-WMB_D void k1_store_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
-{
-    const int64_t m0 = tile * K1_TILE;
-    uint8_t *out = p.rssi[CH::ID];
-    for (int o = tid * 4; o < K1_TILE; o += K1_THREADS * 4) {
-        const int64_t m = m0 + o;
-        if (m + 3 < p.M) {
-            *(uint32_t *)(out + m) = *(const uint32_t *)(sm.rs + o);
+        uint8_t *dst = p.rssi[CH::ID] + m0 + o0;
+        if (m0 + o0 + K1_RSSI_SEG <= p.M) {
+            K1Word4 v; v.x = pk[0]; v.y = pk[1]; v.z = pk[2]; v.w = pk[3];
+            *(K1Word4 *)dst = v;
         } else {
-            for (int j = 0; j < 4; j++) if (m + j < p.M) out[m + j] = sm.rs[o + j];
+            for (int j = 0; j < K1_RSSI_SEG; j++) if (m0 + o0 + j < p.M) dst[j] = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
         }
     }
 }
@@ -417,8 +410,6 @@ __device__ __forceinline__ void k1_chain(const K1Params &p, K1Smem &sm, const ui
     }
     __syncthreads();
     k1_fir_rssi<CH>(p, sm, tile, tid);
-    __syncthreads();
-    k1_store_rssi<CH>(p, sm, tile, tid);
     __syncthreads();
 }
 
