@@ -265,33 +265,6 @@ WMB_D void k1_box_disc_fast(const K1Params &p, K1Smem &sm, int tid)
     }
 }
 
-/* one RSSI segment: outputs [16 * (2u + PAR), +16) of the tile (rtl_wmbus.c:475-484) */
-template <class CH, int PAR>
-WMB_D void k1_rssi_segment(const K1Params &p, K1Smem &sm, int64_t m0, int u)
-{
-    constexpr int CP = K1_HALO - K1_RSSI_WARM + K1_RSSI_SEG * PAR;   /* first row of the warm-up, modulo 32 u */
-    const int o0 = 32 * u + K1_RSSI_SEG * PAR;
-    const float *mag = sm.mag + 33 * u;                              /* k1_pad(32 u) */
-    float rr = 0.0f;
-    const float B = 1.0f - 0.6789f;
-#pragma unroll
-    for (int j = 0; j < K1_RSSI_WARM; j++)
-        rr = wmb_fadd(mag[CP + j + ((CP + j) >> 5)], wmb_fmul(B, rr));
-    uint32_t pk[K1_RSSI_SEG / 4] = { 0, 0, 0, 0 };
-#pragma unroll
-    for (int j = 0; j < K1_RSSI_SEG; j++) {
-        rr = wmb_fadd(mag[CP + K1_RSSI_WARM + j + ((CP + K1_RSSI_WARM + j) >> 5)], wmb_fmul(B, rr));
-        pk[j >> 2] |= ((uint32_t)(unsigned)rr & 0xFFu) << (8 * (j & 3));
-    }
-    uint8_t *dst = p.rssi[CH::ID] + m0 + o0;
-    if (m0 + o0 + K1_RSSI_SEG <= p.M) {
-        K1Word4 v; v.x = pk[0]; v.y = pk[1]; v.z = pk[2]; v.w = pk[3];
-        *(K1Word4 *)dst = v;                                         /* 16 bytes, 16-byte aligned */
-    } else {
-        for (int j = 0; j < K1_RSSI_SEG; j++) if (m0 + o0 + j < p.M) dst[j] = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
-    }
-}
-
 /* phase D: FIR (fir.h:56-67: newest sample first, accumulate from 0) and RSSI one-pole
  * (rtl_wmbus.c:475-484) */
 template <class CH>
@@ -337,18 +310,39 @@ WMB_D void k1_fir_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
             out[m] = acc;
         }
     }
-    /* RSSI: one 16-output segment per thread, started K1_RSSI_WARM samples early from r = 0.  The last two
-     * warps take them (so that the FIR loop above and the recurrence overlap across warps): warp 6 the even
-     * segments, warp 7 the odd ones -- with the parity fixed per warp the padded shared-memory index of every
-     * step is a per-thread base plus a compile-time constant.  (32-output segments in one warp measured
-     * slower: 80 dependent steps hold the barrier.) */
-    static_assert(K1_RSSI_SEG == 16 && K1_TILE % 32 == 0 && K1_HALO >= K1_RSSI_WARM && K1_THREADS == 256, "RSSI segment geometry");
-    constexpr int NPAIR = K1_TILE / 32;                        /* segments per parity */
-    const int lane = tid & 31, warp = tid >> 5;
-    if (warp >= 6 && lane >= 32 - NPAIR) {
-        const int u = lane - (32 - NPAIR);
-        if (warp == 6) k1_rssi_segment<CH, 0>(p, sm, m0, u);
-        else           k1_rssi_segment<CH, 1>(p, sm, m0, u);
+    if (tid >= K1_THREADS - K1_TILE / K1_RSSI_SEG) {
+        /* one segment per thread (the last warp, so that the FIR loop above and the recurrence below
+         * overlap across warps), started K1_RSSI_WARM samples early from r = 0.  A segment starts on a
+         * multiple of 32 outputs, so the padded index of every step is the segment's base plus a constant. */
+        static_assert(K1_RSSI_SEG % 32 == 0 && K1_HALO >= K1_RSSI_WARM && K1_TILE % K1_RSSI_SEG == 0, "RSSI segment geometry");
+        constexpr int C0 = K1_HALO - K1_RSSI_WARM;
+        const int seg = tid - (K1_THREADS - K1_TILE / K1_RSSI_SEG);
+        const int o0 = seg * K1_RSSI_SEG;
+        const float *mag = sm.mag + o0 + (o0 >> 5);
+        float rr = 0.0f;
+        const float B = 1.0f - 0.6789f;
+#pragma unroll
+        for (int j = 0; j < K1_RSSI_WARM; j++)
+            rr = wmb_fadd(mag[C0 + j + ((C0 + j) >> 5)], wmb_fmul(B, rr));
+        /* the segment's bytes leave as 128-bit stores (consecutive threads, consecutive segments) */
+        uint32_t pk[K1_RSSI_SEG / 4];
+#pragma unroll
+        for (int q = 0; q < K1_RSSI_SEG / 4; q++) pk[q] = 0;
+#pragma unroll
+        for (int j = 0; j < K1_RSSI_SEG; j++) {
+            rr = wmb_fadd(mag[K1_HALO + j + ((K1_HALO + j) >> 5)], wmb_fmul(B, rr));
+            pk[j >> 2] |= ((uint32_t)(unsigned)rr & 0xFFu) << (8 * (j & 3));
+        }
+        uint8_t *dst = p.rssi[CH::ID] + m0 + o0;
+        if (m0 + o0 + K1_RSSI_SEG <= p.M) {
+#pragma unroll
+            for (int q = 0; q < K1_RSSI_SEG / 16; q++) {
+                K1Word4 v; v.x = pk[4 * q]; v.y = pk[4 * q + 1]; v.z = pk[4 * q + 2]; v.w = pk[4 * q + 3];
+                ((K1Word4 *)dst)[q] = v;
+            }
+        } else {
+            for (int j = 0; j < K1_RSSI_SEG; j++) if (m0 + o0 + j < p.M) dst[j] = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
+        }
     }
 }
 
