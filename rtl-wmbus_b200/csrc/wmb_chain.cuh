@@ -16,7 +16,7 @@
 #define K1_THREADS   256
 #define K1_TILE      960       /* decimated samples produced per tile: TILE + HALO = 4 rows per thread exactly */
 #define K1_HALO      64        /* decimated samples recomputed left of each tile */
-#define K1_RSSI_SEG  32        /* outputs per RSSI recurrence segment (a multiple of 32: constant padded offsets) */
+#define K1_RSSI_SEG  16        /* outputs per RSSI recurrence segment            */
 #define K1_RSSI_WARM 48        /* warm-up steps before each segment (contraction 0.32 per step) */
 #define K1_BOX_MAX   16
 

@@ -173,12 +173,9 @@ WMB_D void k1_convert_fast(const K1Params &p, K1Smem &sm, const uint8_t *raw, in
     const int64_t k0 = k1_tile_k0(p, tile);
     const int nw = (int)(k1_tile_iq(p.d) / 2);
     const uint32_t *w32 = (const uint32_t *)raw;
-    /* words before the start of the stream (first tile only) read as two "zero" samples */
-    const int64_t first = (-p.n_hist_iq - k0 + 1) >> 1;          /* smallest j with k0 + 2j >= -n_hist_iq */
-    const int jmin = first > 0 ? (first < nw ? (int)first : nw) : 0;
     for (int j = tid; j < nw; j += K1_THREADS) {
         uint32_t packed = (uint32_t)K1_PAIR_BIAS | ((uint32_t)K1_PAIR_BIAS << 16);      /* two "zero" samples */
-        if (j >= jmin) {
+        if (k0 + 2 * j >= -p.n_hist_iq) {
             const uint32_t w = w32[j];
             const uint32_t msb = (w >> 7) & 0x01010101u;
             const int si = wmb_dp4a_u(w, 0x00010001u, 0) - wmb_dp4a_u(msb, 0x00010001u, 0) - 254 + K1_PAIR_BIAS;
@@ -311,35 +308,27 @@ WMB_D void k1_fir_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
         }
     }
     if (tid >= K1_THREADS - K1_TILE / K1_RSSI_SEG) {
-        /* one segment per thread (the last warp, so that the FIR loop above and the recurrence below
-         * overlap across warps), started K1_RSSI_WARM samples early from r = 0.  A segment starts on a
-         * multiple of 32 outputs, so the padded index of every step is the segment's base plus a constant. */
-        static_assert(K1_RSSI_SEG % 32 == 0 && K1_HALO >= K1_RSSI_WARM && K1_TILE % K1_RSSI_SEG == 0, "RSSI segment geometry");
-        constexpr int C0 = K1_HALO - K1_RSSI_WARM;
+        /* one segment per thread (the upper warps, so that the FIR loop above and the recurrence
+         * below overlap across warps), started K1_RSSI_WARM samples early from r = 0 */
         const int seg = tid - (K1_THREADS - K1_TILE / K1_RSSI_SEG);
         const int o0 = seg * K1_RSSI_SEG;
-        const float *mag = sm.mag + o0 + (o0 >> 5);
+        const int r0 = K1_HALO + o0 - K1_RSSI_WARM;
         float rr = 0.0f;
         const float B = 1.0f - 0.6789f;
-#pragma unroll
+#pragma unroll 8
         for (int j = 0; j < K1_RSSI_WARM; j++)
-            rr = wmb_fadd(mag[C0 + j + ((C0 + j) >> 5)], wmb_fmul(B, rr));
-        /* the segment's bytes leave as 128-bit stores (consecutive threads, consecutive segments) */
-        uint32_t pk[K1_RSSI_SEG / 4];
-#pragma unroll
-        for (int q = 0; q < K1_RSSI_SEG / 4; q++) pk[q] = 0;
+            rr = wmb_fadd(sm.mag[k1_pad(r0 + j)], wmb_fmul(B, rr));
+        /* the segment's 16 bytes leave as one 128-bit store (consecutive threads, consecutive segments) */
+        uint32_t pk[K1_RSSI_SEG / 4] = { 0, 0, 0, 0 };
 #pragma unroll
         for (int j = 0; j < K1_RSSI_SEG; j++) {
-            rr = wmb_fadd(mag[K1_HALO + j + ((K1_HALO + j) >> 5)], wmb_fmul(B, rr));
+            rr = wmb_fadd(sm.mag[k1_pad(r0 + K1_RSSI_WARM + j)], wmb_fmul(B, rr));
             pk[j >> 2] |= ((uint32_t)(unsigned)rr & 0xFFu) << (8 * (j & 3));
         }
         uint8_t *dst = p.rssi[CH::ID] + m0 + o0;
         if (m0 + o0 + K1_RSSI_SEG <= p.M) {
-#pragma unroll
-            for (int q = 0; q < K1_RSSI_SEG / 16; q++) {
-                K1Word4 v; v.x = pk[4 * q]; v.y = pk[4 * q + 1]; v.z = pk[4 * q + 2]; v.w = pk[4 * q + 3];
-                ((K1Word4 *)dst)[q] = v;
-            }
+            K1Word4 v; v.x = pk[0]; v.y = pk[1]; v.z = pk[2]; v.w = pk[3];
+            *(K1Word4 *)dst = v;
         } else {
             for (int j = 0; j < K1_RSSI_SEG; j++) if (m0 + o0 + j < p.M) dst[j] = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
         }
