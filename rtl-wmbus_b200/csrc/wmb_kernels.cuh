@@ -173,9 +173,12 @@ WMB_D void k1_convert_fast(const K1Params &p, K1Smem &sm, const uint8_t *raw, in
     const int64_t k0 = k1_tile_k0(p, tile);
     const int nw = (int)(k1_tile_iq(p.d) / 2);
     const uint32_t *w32 = (const uint32_t *)raw;
+    /* words before the start of the stream (first tile only) read as two "zero" samples */
+    const int64_t first = (-p.n_hist_iq - k0 + 1) >> 1;          /* smallest j with k0 + 2j >= -n_hist_iq */
+    const int jmin = first > 0 ? (first < nw ? (int)first : nw) : 0;
     for (int j = tid; j < nw; j += K1_THREADS) {
         uint32_t packed = (uint32_t)K1_PAIR_BIAS | ((uint32_t)K1_PAIR_BIAS << 16);      /* two "zero" samples */
-        if (k0 + 2 * j >= -p.n_hist_iq) {
+        if (j >= jmin) {
             const uint32_t w = w32[j];
             const uint32_t msb = (w >> 7) & 0x01010101u;
             const int si = wmb_dp4a_u(w, 0x00010001u, 0) - wmb_dp4a_u(msb, 0x00010001u, 0) - 254 + K1_PAIR_BIAS;
