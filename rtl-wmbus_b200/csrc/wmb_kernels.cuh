@@ -168,24 +168,36 @@ WMB_D int wmb_dp4a_u(uint32_t a, uint32_t b, int c)
 #endif
 }
 
+struct alignas(16) K1Word4 { uint32_t x, y, z, w; };
+
+/* one raw word (I0 Q0 I1 Q1) -> packed biased pair sums (I0+I1 | Q0+Q1 << 16) of the truncated samples:
+ * (int)(u - 127.5f) = u - 127 for u < 128 and u - 128 above (rtl_wmbus.c:1312-1313, moving_average_filter.h:47) */
+WMB_D uint32_t k1_pair_sums(uint32_t w)
+{
+    const uint32_t msb = (w >> 7) & 0x01010101u;
+    const int si = wmb_dp4a_u(w, 0x00010001u, 0) - wmb_dp4a_u(msb, 0x00010001u, 0) - 254 + K1_PAIR_BIAS;
+    const int sq = wmb_dp4a_u(w, 0x01000100u, 0) - wmb_dp4a_u(msb, 0x01000100u, 0) - 254 + K1_PAIR_BIAS;
+    return (uint32_t)si | ((uint32_t)sq << 16);
+}
+
 WMB_D void k1_convert_fast(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile, int tid)
 {
     const int64_t k0 = k1_tile_k0(p, tile);
-    const int nw = (int)(k1_tile_iq(p.d) / 2);
-    const uint32_t *w32 = (const uint32_t *)raw;
+    const int nw = (int)(k1_tile_iq(p.d) / 2);             /* a multiple of 4 */
     /* words before the start of the stream (first tile only) read as two "zero" samples */
     const int64_t first = (-p.n_hist_iq - k0 + 1) >> 1;          /* smallest j with k0 + 2j >= -n_hist_iq */
     const int jmin = first > 0 ? (first < nw ? (int)first : nw) : 0;
-    for (int j = tid; j < nw; j += K1_THREADS) {
-        uint32_t packed = (uint32_t)K1_PAIR_BIAS | ((uint32_t)K1_PAIR_BIAS << 16);      /* two "zero" samples */
-        if (j >= jmin) {
-            const uint32_t w = w32[j];
-            const uint32_t msb = (w >> 7) & 0x01010101u;
-            const int si = wmb_dp4a_u(w, 0x00010001u, 0) - wmb_dp4a_u(msb, 0x00010001u, 0) - 254 + K1_PAIR_BIAS;
-            const int sq = wmb_dp4a_u(w, 0x01000100u, 0) - wmb_dp4a_u(msb, 0x01000100u, 0) - 254 + K1_PAIR_BIAS;
-            packed = (uint32_t)si | ((uint32_t)sq << 16);
-        }
-        sm.v[j] = (int32_t)packed;
+    const uint32_t zero = (uint32_t)K1_PAIR_BIAS | ((uint32_t)K1_PAIR_BIAS << 16);
+    const K1Word4 *src = (const K1Word4 *)raw;
+    K1Word4 *dst = (K1Word4 *)sm.v;
+    for (int g = tid; g < nw / 4; g += K1_THREADS) {           /* four words per step: 128-bit shared accesses */
+        const K1Word4 w = src[g];
+        K1Word4 o;
+        o.x = 4 * g + 0 >= jmin ? k1_pair_sums(w.x) : zero;
+        o.y = 4 * g + 1 >= jmin ? k1_pair_sums(w.y) : zero;
+        o.z = 4 * g + 2 >= jmin ? k1_pair_sums(w.z) : zero;
+        o.w = 4 * g + 3 >= jmin ? k1_pair_sums(w.w) : zero;
+        dst[g] = o;
     }
 }
 
@@ -228,8 +240,6 @@ WMB_D void k1_disc_mag(const K1Params &p, K1Smem &sm, int tid)
 /* phases B + C of the d = 2 fast path in one: every thread owns four consecutive rows; it reads the pair
  * sums its box windows cover with 128-bit shared loads, slides the (packed I|Q) box sum from row to row
  * and goes straight on to the discriminator and |s| -- the box outputs never touch shared memory. */
-struct alignas(16) K1Word4 { uint32_t x, y, z, w; };
-
 template <class CH>
 WMB_D void k1_box_disc_fast(const K1Params &p, K1Smem &sm, int tid)
 {
