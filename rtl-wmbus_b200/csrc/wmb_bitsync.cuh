@@ -160,6 +160,8 @@ WMB_D void k2a_save(IirState &st, const K2aRegs &r)
     st.clk3 = r.clk3; st.pad = 0;
 }
 
+#define K2A_L2_AHEAD 16
+
 template <class CH, bool DC, bool T2>
 WMB_D void k2a_lane_t(const K2aParams &p, uint32_t lane)
 {
@@ -194,6 +196,11 @@ WMB_D void k2a_lane_t(const K2aParams &p, uint32_t lane)
     if (m + 32 < e0) k2a_load(nxt, p.dphi + m + 32);
     while (m < e0) {
         if (m + 64 < e0) k2a_load(nx2, p.dphi + m + 64);        /* two lines ahead: ~2 us of recurrence steps */
+#ifndef WMB_HOSTSIM
+        /* and the line 16 blocks ahead is pulled into L2 (no register cost), so that the register loads above
+         * see L2 latency even when DRAM is busy with the other 18 k lanes */
+        if (m + 32 * K2A_L2_AHEAD < e0) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.dphi + m + 32 * K2A_L2_AHEAD));
+#endif
         if (m == s0 && !saved_start) { k2a_save(st, r); p.st_start[lane] = st; saved_start = true; }
         const int n = (e0 - m >= 32) ? 32 : (int)(e0 - m);
         uint32_t dword, cword;
