@@ -372,8 +372,8 @@ def main():
                          # says bounds the two largest kernels instead of HBM (static: from the committed capture)
                          "k1_only": {"achieved": round(abytes / (k1_ms / args.steps / 1e3) / 1e9, 1) if k1_ms else None,
                                      "frac": round(abytes / (k1_ms / args.steps / 1e3) / 1e9 / peak, 4) if k1_ms else None},
-                         "issue_bound_ncu": {"k1_issue_active_pct": 73.7, "k2a_issue_active_pct_one_warp_per_scheduler": 55.1,
-                                             "k1_dram_pct": 10.4, "source": "profiles/r1w_ncu_full_summary.txt"}},
+                         "issue_bound_ncu": {"k1_issue_active_pct": 76.0, "k2a_issue_active_pct_one_warp_per_scheduler": 64.5,
+                                             "k1_dram_pct": 10.6, "source": "profiles/r1z_ncu_full_summary.txt"}},
             "packets": dict(totals, planted_per_gpu=len(plan)),
             "lanes": {"run": int(st.lanes_run), "rerun": int(st.lanes_rerun), "rl_fallbacks": int(st.rl_fallbacks)},
             "host_ms_per_step": {"batch": round(st.host_batch_ms / (args.steps + args.warmup), 3),
