@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the rtl-wmbus hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload t1x2|s1|both]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload t1x2|s1|both|d3|d3s]
 
 One step = one pass of the hot path (cu8 -> ... -> datagram lines) over one synthetic capture:
 BASELINE.json config 2 by default -- 1 GiB of 1.6 MS/s cu8 with two T1 emitters, T1+C1 chain
@@ -49,6 +49,12 @@ def workload_def(name):
     if name == "both":
         return dict(emitters="mixed", flags="", chains=2, d=2, fs=1.6e6,
                     desc="1 GiB synthetic 1.6 MS/s cu8, T1/C1/S1 emitters, both chains (default flags)")
+    if name == "d3":         # BASELINE config 4's signal: 2.4 MS/s, decimation 3 (general front end, no d = 2 fast path)
+        return dict(emitters="mixed", flags="-d 3", chains=2, d=3, fs=2.4e6,
+                    desc="1 GiB synthetic 2.4 MS/s cu8, T1/C1/S1 emitters, both chains, -d 3")
+    if name == "d3s":        # ... its -s variant: capture centred on 868.625 MHz, T1/C1 at +325 kHz, S1 at -325 kHz
+        return dict(emitters="mixed", flags="-d 3 -s", chains=2, d=3, fs=2.4e6, shift=325e3,
+                    desc="1 GiB synthetic 2.4 MS/s cu8 centred on 868.625 MHz, T1/C1/S1 emitters, both chains, -d 3 -s")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -275,7 +281,7 @@ def main():
     # every rank, of which each decodes its time chunk (strong scaling; config 4's rule)
     cap, plan = synth.synth_capture(n_bytes, fs=wl["fs"], emitters=synth.default_emitters(wl["emitters"]),
                                     seed=shard.capture_seed(4 if time_sharded else 2, 0 if time_sharded else rank),
-                                    device="cuda")
+                                    device="cuda", center_shift_hz=wl.get("shift", 0.0))
     torch.cuda.synchronize()
     if time_sharded:
         return run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local)
