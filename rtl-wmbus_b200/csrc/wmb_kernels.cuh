@@ -103,31 +103,54 @@ WMB_HD int64_t k1_tile_k0(const K1Params &p, int64_t t)
     return (int64_t)p.d * (t * K1_TILE - K1_HALO) - K1_BOX_MAX;
 }
 
-/* phase A: cu8 -> float-127.5 -> (mix) -> truncate to int   rtl_wmbus.c:1312-1334 */
+/* phase A: cu8 -> float-127.5 -> (mix) -> truncate to int   rtl_wmbus.c:1312-1334
+ * The truncated I and Q are stored biased (+K1_SAMPLE_BIAS) and packed I | Q << 16, so that the box filter
+ * can add whole words: |value| <= 181 behind the mixer (127.5 * sqrt 2), 16 of them stay below 2^16. */
+#define K1_SAMPLE_BIAS 256
 template <int CHAIN>
 WMB_D void k1_convert(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile, int tid)
 {
     const int64_t k0 = k1_tile_k0(p, tile);
     const int n = (int)k1_tile_iq(p.d);
-    for (int j = tid; j < n; j += K1_THREADS) {
-        const int64_t k = k0 + j;
-        int vi = 0, vq = 0;
-        if (k >= -p.n_hist_iq) {
-            float xi = wmb_fsub((float)raw[2 * j], 127.5f);
-            float xq = wmb_fsub((float)raw[2 * j + 1], 127.5f);
-            if (p.mix) {
-                /* shift_freq_plus_minus325, rtl_wmbus.c:997-1031 */
-                int64_t idx = ((int64_t)p.lut_phase0 + 13 * (k % (int64_t)p.lut_n)) % (int64_t)p.lut_n;
-                if (idx < 0) idx += p.lut_n;
-                const float c = p.lut_cos[idx], z = p.lut_msin[idx];
-                const float ix = wmb_fmul(xi, c), qx = wmb_fmul(xq, c);
-                const float iz = wmb_fmul(xi, z), qz = wmb_fmul(xq, z);
-                if (CHAIN == 0) { xi = wmb_fsub(ix, qz); xq = wmb_fadd(qx, iz); }
-                else            { xi = wmb_fadd(ix, qz); xq = wmb_fsub(qx, iz); }
-            }
-            vi = (int)xi; vq = (int)xq;             /* float -> int parameter of mavgi() */
+    /* samples before the start of the stream (first tile only) are zero */
+    const int64_t first = -p.n_hist_iq - k0;
+    const int jmin = first > 0 ? (first < n ? (int)first : n) : 0;
+    const uint32_t zero = (uint32_t)K1_SAMPLE_BIAS | ((uint32_t)K1_SAMPLE_BIAS << 16);
+    const uint16_t *raw16 = (const uint16_t *)raw;                      /* one IQ sample per 16-bit load */
+    if (!p.mix) {
+        /* (int)(u - 127.5f) == u - 127 - (u >= 128): no float needed */
+        for (int j = tid; j < n; j += K1_THREADS) {
+            const uint32_t w = raw16[j];
+            const uint32_t ui = w & 0xFFu, uq = w >> 8;
+            const uint32_t packed = (ui - 127u - (ui >> 7) + K1_SAMPLE_BIAS) | ((uq - 127u - (uq >> 7) + K1_SAMPLE_BIAS) << 16);
+            sm.v[j] = (int32_t)(j >= jmin ? packed : zero);
         }
-        sm.v[j] = (int32_t)(((uint32_t)vi & 0xFFFFu) | ((uint32_t)vq << 16));
+        return;
+    }
+    /* shift_freq_plus_minus325, rtl_wmbus.c:997-1031: LUT index (13 k) mod n_max, kept incrementally
+     * (the thread's samples are K1_THREADS apart) */
+    const uint32_t ln = p.lut_n;
+    int64_t km = k0 % (int64_t)ln;
+    if (km < 0) km += ln;
+    uint32_t idx = (uint32_t)(((uint64_t)p.lut_phase0 + 13ull * (uint64_t)km + 13ull * (uint64_t)tid) % ln);
+    const uint32_t step = (13u * K1_THREADS) % ln;
+    for (int j = tid; j < n; j += K1_THREADS) {
+        uint32_t packed = zero;
+        if (j >= jmin) {
+            const uint32_t w = raw16[j];
+            float xi = wmb_fsub((float)(w & 0xFFu), 127.5f);
+            float xq = wmb_fsub((float)(w >> 8), 127.5f);
+            const float c = p.lut_cos[idx], z = p.lut_msin[idx];
+            const float ix = wmb_fmul(xi, c), qx = wmb_fmul(xq, c);
+            const float iz = wmb_fmul(xi, z), qz = wmb_fmul(xq, z);
+            if (CHAIN == 0) { xi = wmb_fsub(ix, qz); xq = wmb_fadd(qx, iz); }
+            else            { xi = wmb_fadd(ix, qz); xq = wmb_fsub(qx, iz); }
+            const int vi = (int)xi, vq = (int)xq;                       /* float -> int parameter of mavgi() */
+            packed = (uint32_t)(vi + K1_SAMPLE_BIAS) | ((uint32_t)(vq + K1_SAMPLE_BIAS) << 16);
+        }
+        sm.v[j] = (int32_t)packed;
+        idx += step;
+        if (idx >= ln) idx -= ln;
     }
 }
 
@@ -138,13 +161,11 @@ WMB_D void k1_box(const K1Params &p, K1Smem &sm, int tid)
     const float inv = 1.0f / (float)CH::BOX;
     for (int r = tid; r < K1_TILE + K1_HALO; r += K1_THREADS) {
         const int jend = (int)p.d * r + (int)p.d - 1 + K1_BOX_MAX;
-        int si = 0, sq = 0;
+        uint32_t acc = 0;
 #pragma unroll
-        for (int b = 0; b < CH::BOX; b++) {
-            const int32_t w = sm.v[jend - b];
-            si += (int)(int16_t)(w & 0xFFFF);
-            sq += w >> 16;
-        }
+        for (int b = 0; b < CH::BOX; b++) acc += (uint32_t)sm.v[jend - b];
+        const int si = (int)(acc & 0xFFFFu) - CH::BOX * K1_SAMPLE_BIAS;
+        const int sq = (int)(acc >> 16) - CH::BOX * K1_SAMPLE_BIAS;
         sm.si[r] = wmb_fmul((float)si, inv);
         sm.sq[r] = wmb_fmul((float)sq, inv);
     }
