@@ -53,7 +53,6 @@ struct K1Smem {
     float   *si, *sq;       /* decimated box-filter outputs, TILE+HALO           */
     float   *draw;          /* discriminator output, TILE+HALO                   */
     float   *mag;           /* |s|, padded                                       */
-    uint8_t *rs;            /* (unsigned)rssi, TILE                              */
     uint64_t *bar;          /* two mbarriers                                     */
 };
 
@@ -78,7 +77,7 @@ size_t k1_smem_bytes(uint32_t d)
 {
     const size_t nb = (size_t)2 * k1_tile_iq(d);
     const size_t n = K1_TILE + K1_HALO;
-    return 2 * nb + 4 * (size_t)k1_tile_iq(d) + 3 * 4 * n + 4 * (n + n / 32 + 1) + K1_TILE + 64 + 16;
+    return 2 * nb + 4 * (size_t)k1_tile_iq(d) + 3 * 4 * n + 4 * (n + n / 32 + 1) + 64 + 16;
 }
 
 WMB_HD void k1_carve(K1Smem &sm, uint8_t *base, uint32_t d)
@@ -94,7 +93,6 @@ WMB_HD void k1_carve(K1Smem &sm, uint8_t *base, uint32_t d)
     sm.sq = (float *)(base + off); off += 4 * n;
     sm.draw = (float *)(base + off); off += 4 * n;
     sm.mag = (float *)(base + off); off += 4 * (n + n / 32 + 1);
-    sm.rs = base + off;
 }
 
 /* first IQ sample (batch-relative, may be negative) held by tile `t` */
@@ -219,23 +217,6 @@ WMB_D void k1_convert_fast(const K1Params &p, K1Smem &sm, const uint8_t *raw, in
         o.z = 4 * g + 2 >= jmin ? k1_pair_sums(w.z) : zero;
         o.w = 4 * g + 3 >= jmin ? k1_pair_sums(w.w) : zero;
         dst[g] = o;
-    }
-}
-
-template <class CH>
-WMB_D void k1_box_fast(const K1Params &p, K1Smem &sm, int tid)
-{
-    const float inv = 1.0f / (float)CH::BOX;
-    constexpr int NW = CH::BOX / 2;                       /* words per box */
-    for (int r = tid; r < K1_TILE + K1_HALO; r += K1_THREADS) {
-        const int wend = r + K1_BOX_MAX / 2;              /* word holding the newest two samples */
-        uint32_t acc = 0;
-#pragma unroll
-        for (int b = 0; b < NW; b++) acc += (uint32_t)sm.v[wend - b];
-        const int si = (int)(acc & 0xFFFFu) - NW * K1_PAIR_BIAS;
-        const int sq = (int)(acc >> 16) - NW * K1_PAIR_BIAS;
-        sm.si[r] = wmb_fmul((float)si, inv);
-        sm.sq[r] = wmb_fmul((float)sq, inv);
     }
 }
 
