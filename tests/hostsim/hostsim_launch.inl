@@ -172,3 +172,9 @@ static int launch_k4(wmb_ctx *c, const K4Params &p)
     c->st.kernel_launches += 1;
     return WMB_OK;
 }
+
+/* ---- test hooks into the device arithmetic (CPU build only) ---- */
+extern "C" float hostsim_atan2f_bounded(float y, float x) { return wmb_atan2f_t<true>(y, x); }
+extern "C" float hostsim_atan2f_general(float y, float x) { return wmb_atan2f_t<false>(y, x); }
+extern "C" int hostsim_div_small(int x, int n) { return wmb_div_small(x, n); }
+extern "C" int hostsim_div_pow2(int x, int s) { return wmb_div_pow2(x, s); }
