@@ -1144,9 +1144,20 @@ static int push_host_bytes(wmb_ctx *c, const uint8_t *p, size_t nbytes, bool fin
     size_t off = 0;
     /* enqueue the first H2D, then for each batch: enqueue the next H2D before computing */
     size_t cur_n = 0;
+    /* Batch sizes: the maximum while plenty is left, then a taper (7/16 of what is left, not below half a
+     * batch): the copy of batch i+1 hides behind the kernels of batch i, so what a caller waits for after the
+     * last byte has crossed PCIe is the LAST batch's kernels -- a smaller last batch shortens that, as long as
+     * every batch still computes faster than the next one copies (fixed lane warm-ups: about 1.6 ms + 5.6 us
+     * per MiB against 18.8 us per MiB of copy). */
     auto next_size = [&](size_t at) {
-        size_t n = std::min(nbytes - at, c->max_batch_bytes);
+        const size_t rem = nbytes - at, mx = c->max_batch_bytes, half = mx / 2;
+        size_t n;
+        if (rem > 2 * mx) n = mx;
+        else if (rem <= half + half / 2) n = rem;
+        else if (rem <= 2 * half) n = rem - half;
+        else n = std::min(mx, std::max(half, rem / 16 * 7));
         if (!(final && at + n == nbytes)) n -= n % gran;
+        if (n == 0 && rem >= gran) n = gran;
         return n;
     };
     cur_n = next_size(0);
