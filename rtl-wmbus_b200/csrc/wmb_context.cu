@@ -124,7 +124,7 @@ struct wmb_ctx {
     size_t max_batch_bytes = 0;
     int64_t M_max = 0;
     uint32_t W = 32768;             /* retained history (decimated samples) = max warm-up */
-    uint32_t W_a[WMB_N_CHAINS] = {24576, 98304};    /* warm-up of the clock-recovery lanes */
+    uint32_t W_a[WMB_N_CHAINS] = {24576, 81920};    /* warm-up of the clock-recovery lanes */
     uint32_t W_m[WMB_N_CHAINS] = {32768, 8192};    /* warm-up of the run-length lanes  */
     uint32_t C_fixed = 0;
     uint32_t lanes_max = 0;
@@ -580,7 +580,7 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
         /* measured re-join times of the biquad state (tools/ + DESIGN.md): T1/C1 filter <= 19 k samples,
          * S1 filter (22-42 kHz band) <= 55 k; the DC block adds its own ~18 k in front */
         c->W_a[0] = o->remove_dc ? 98304u : 24576u;    /* measured re-join <= 19k samples; a miss only costs a re-run */
-        c->W_a[1] = o->remove_dc ? 163840u : 98304u;
+        c->W_a[1] = o->remove_dc ? 163840u : 81920u;   /* 0 / 32 / 96 re-runs of 0.3 M lanes at 81920 / 65536 / 57344 */
         /* run-length lanes.  T1/C1: the PI bit-length tracker remembers the whole reset-free stretch, so a cold
          * start re-joins at the first reset both trajectories share, at the latest when the telegram it started
          * in is over (<= 28 k samples).  S1: the state is the average run length of the last low and the last
