@@ -193,7 +193,7 @@ def run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local):
     results = {}
     for leg, base, push_name in (("device", cap.data_ptr(), "push_device"), ("host", host.data_ptr(), "push")):
         ctx = pkg.WmbusB200(wl["flags"], device=local, lib=lib,
-                            max_batch_mib=(args.batch_mib or args.mib) if leg == "device" else args.e2e_batch_mib)
+                            max_batch_mib=(args.batch_mib or min(args.mib, 1024)) if leg == "device" else args.e2e_batch_mib)
         push = lambda lo, hi, c=ctx, b=base, f=push_name: getattr(c, f)(b + lo, hi - lo)
         lines, rounds = None, 0
         for _ in range(max(1, args.warmup)):
@@ -285,7 +285,7 @@ def main():
     torch.cuda.synchronize()
     if time_sharded:
         return run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local)
-    tune = dict(max_batch_mib=args.batch_mib or args.mib)
+    tune = dict(max_batch_mib=args.batch_mib or min(args.mib, 1024))      # rings and candidate lists are sized for <= 1 GiB batches
     if args.chunk: tune["chunk_samples"] = args.chunk
     if args.warm: tune["warmup_samples"] = args.warm
     ctx = pkg.WmbusB200(wl["flags"], device=local, lib=lib, **tune)
