@@ -448,6 +448,12 @@ static int ctx_alloc(wmb_ctx *c)
     c->p1_lanes_max = (uint32_t)(c->M_max / K2P1_CHUNK + 2);
     c->rec_max = (size_t)c->M_max / 5 + 2 * (size_t)c->p1_lanes_max + 64;
     c->p2_lanes_max = (uint32_t)(c->rec_max / K2P2_RECORDS + 2);
+    /* access-code matches and gathered frame bits scale with the batch (sized for dense traffic at 1 GiB, d = 2) */
+    if (c->M_max > ((int64_t)1 << 28)) {
+        const uint64_t k = ((uint64_t)c->M_max + (1ull << 28) - 1) >> 28;
+        c->cand_cap = (uint32_t)std::min<uint64_t>((uint64_t)(1u << 20) * k, 1u << 24);
+        c->frame_words_cap = (uint32_t)std::min<uint64_t>((uint64_t)(1u << 24) * k, 1u << 28);
+    }
 
     TRY(dev_alloc(c, &c->d_in[0], c->max_batch_bytes + 4096));
     TRY(dev_alloc(c, &c->d_in[1], c->max_batch_bytes + 4096));
