@@ -99,6 +99,8 @@ struct ChainBuf {
     Stream s[WMB_N_ALGOS];
 };
 
+static uint32_t g_p2_block = 128u;       /* threads per block of the phase-2 count pass (WMBUS_B200_P2BLK, experiments) */
+
 struct QueuedLine {
     uint64_t end_sample;
     int prio;                       /* chain*2 + (algo == T2A) */
@@ -263,8 +265,7 @@ static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, cons
 {
     launch_cscan(c, pc.cnt, pc.base, pc.lanes, pc.agg, &pc.pd->n_rec, nullptr, &pc.pd->fallback, 1);
     k2pc_compact_kernel<<<pc.lanes, 128, 0, c->cs>>>(pc);
-    const unsigned grid = (p2.lanes + 127) / 128;
-    k2p2_count_kernel<<<grid, 128, 0, c->cs>>>(p2);
+    k2p2_count_kernel<<<(p2.lanes + g_p2_block - 1) / g_p2_block, g_p2_block, 0, c->cs>>>(p2);
     k2p2_sum_kernel<<<p2.lanes, K2P2W_THREADS, 0, c->cs>>>(p2);
     launch_cscan(c, p2.cnt, p2.base, p2.lanes, p2.agg, &p2.sd->total, &p2.pd->fallback);
     k2p2_write_kernel<<<p2.lanes, K2P2W_THREADS, 0, c->cs>>>(p2);
@@ -426,6 +427,7 @@ static void tr_dump()
 
 static void read_tuning()
 {
+    if (const char *b = getenv("WMBUS_B200_P2BLK")) { const unsigned v = (unsigned)atoi(b); if (v == 32 || v == 64 || v == 128) g_p2_block = v; }
     const char *e = getenv("WMBUS_B200_TUNE");
     unsigned a = 0, b = 0, r = 0;
     if (!e || sscanf(e, "%u:%u:%u", &a, &b, &r) != 3) return;
