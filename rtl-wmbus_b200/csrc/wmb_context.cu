@@ -205,7 +205,7 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     if (!sm_count) {
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device);
     }
-    auto kern = k1_demod_kernel;      /* (a 6-CTA/SM build, 40 registers, measured the same: 3.06 vs 3.07 ms) */
+    auto kern = p.chains == 1u ? k1_demod_kernel<1u> : p.chains == 2u ? k1_demod_kernel<2u> : k1_demod_kernel<3u>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, K1_THREADS, smem));
     if (blocks_per_sm < 1) return set_err(WMB_E_INVAL, "decimation %u needs %zu B shared memory per CTA", p.d, smem);

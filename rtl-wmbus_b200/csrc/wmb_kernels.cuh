@@ -312,14 +312,40 @@ WMB_D void k1_fir_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
             }
         }
     } else {
-        for (int o = tid; o < K1_TILE; o += K1_THREADS) {
+        /* long filter (S1: 46 taps): four consecutive outputs per thread again, the taps walked four at a time
+         * over a rolling window of two 128-bit shared loads (12 loads instead of 184 for the four outputs);
+         * every output still accumulates its taps in the order t = 0, 1, 2, ... */
+        constexpr int NCHUNK = (CH::NTAPS + 3) / 4;
+        static_assert(K1_HALO >= 4 * NCHUNK, "halo shorter than the filter");
+        for (int o = 4 * tid; o < K1_TILE; o += 4 * K1_THREADS) {
             const int64_t m = m0 + o;
             if (m >= p.M) break;
-            float acc = 0.0f;
+            const float4 *src = (const float4 *)(sm.draw + K1_HALO + o);
+            float4 v = src[0];
+            float w[8];
+            w[4] = v.x; w[5] = v.y; w[6] = v.z; w[7] = v.w;
+            float acc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
 #pragma unroll
-            for (int t = 0; t < CH::NTAPS; t++)
-                acc = wmb_fadd(acc, wmb_fmul(b[t], sm.draw[K1_HALO + o - t]));
-            out[m] = acc;
+            for (int j = 0; j < NCHUNK; j++) {
+                v = src[-(j + 1)];
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;          /* w[i] = draw[HALO + o - 4 j - 4 + i] */
+#pragma unroll
+                for (int tt = 0; tt < 4; tt++) {
+                    const int tap = 4 * j + tt;
+                    if (tap < CH::NTAPS) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) acc[k] = wmb_fadd(acc[k], wmb_fmul(b[tap], w[4 + k - tt]));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) w[4 + i] = w[i];
+            }
+            if (m + 3 < p.M) {
+                float4 r; r.x = acc[0]; r.y = acc[1]; r.z = acc[2]; r.w = acc[3];
+                *(float4 *)(out + m) = r;
+            } else {
+                for (int k = 0; k < 4; k++) if (m + k < p.M) out[m + k] = acc[k];
+            }
         }
     }
     if (tid >= K1_THREADS - K1_TILE / K1_RSSI_SEG) {
@@ -428,6 +454,9 @@ __device__ __forceinline__ void k1_chain(const K1Params &p, K1Smem &sm, const ui
     __syncthreads();
 }
 
+/* CHAINS (bit 0 T1/C1, bit 1 S1) is a template parameter so that a one-chain run does not carry the other
+ * chain's registers: the S1 filter's unrolled taps would cost the T1/C1-only kernel a resident CTA per SM */
+template <uint32_t CHAINS>
 WMB_D void k1_demod_body(const K1Params &p)
 {
     extern __shared__ __align__(128) uint8_t k1_smem_raw[];
@@ -451,12 +480,13 @@ WMB_D void k1_demod_body(const K1Params &p)
         mbar_wait(&sm.bar[buf], phase[buf]);
         phase[buf] ^= 1;
         const uint8_t *raw = sm.bytes[buf];
-        if (p.chains & 1u) k1_chain<ChainT1C1>(p, sm, raw, tile, tid, true);
-        if (p.chains & 2u) k1_chain<ChainS1>(p, sm, raw, tile, tid, p.mix || !(p.chains & 1u));
+        if (CHAINS & 1u) k1_chain<ChainT1C1>(p, sm, raw, tile, tid, true);
+        if (CHAINS & 2u) k1_chain<ChainS1>(p, sm, raw, tile, tid, p.mix || !(CHAINS & 1u));
     }
 }
 
-__global__ void __launch_bounds__(K1_THREADS) k1_demod_kernel(const K1Params p) { k1_demod_body(p); }
+template <uint32_t CHAINS>
+__global__ void __launch_bounds__(K1_THREADS) k1_demod_kernel(const K1Params p) { k1_demod_body<CHAINS>(p); }
 
 #endif /* !WMB_HOSTSIM */
 
