@@ -239,29 +239,36 @@ WMB_D void k1_disc_mag(const K1Params &p, K1Smem &sm, int tid)
     }
 }
 
-/* phases B + C of the d = 2 fast path in one: every thread owns four consecutive rows; it reads the pair
- * sums its box windows cover with 128-bit shared loads, slides the (packed I|Q) box sum from row to row
- * and goes straight on to the discriminator and |s| -- the box outputs never touch shared memory. */
-template <class CH>
-WMB_D void k1_box_disc_fast(const K1Params &p, K1Smem &sm, int tid)
+/* phases B + C in one: every thread owns four consecutive rows; it reads the words its box windows cover with
+ * 128-bit shared loads, slides the (packed I|Q) box sum from row to row and goes straight on to the discriminator
+ * and |s| -- the box outputs never touch shared memory.  FAST: the d = 2 fast path, one pair-sum word per row;
+ * otherwise DW = d sample words per row (d = 1, 2, 3; other decimations keep the separate phases). */
+template <class CH, int DW, bool FAST>
+WMB_D void k1_box_disc(const K1Params &p, K1Smem &sm, int tid)
 {
-    constexpr int NW = CH::BOX / 2;                       /* pair-sum words per box */
-    constexpr int NLOAD = NW + 4;                         /* windows of rows r0-1 .. r0+3 */
+    constexpr int NWIN = FAST ? CH::BOX / 2 : CH::BOX;    /* words per box window */
+    constexpr int START = FAST ? K1_BOX_MAX / 2 - NWIN : K1_BOX_MAX - CH::BOX;
+    constexpr int BIASW = FAST ? K1_PAIR_BIAS : K1_SAMPLE_BIAS;
+    constexpr int NLOAD = NWIN + 4 * DW;                  /* windows of rows r0-1 .. r0+3 */
+    static_assert(NLOAD % 4 == 0 && START % 4 == 0, "box windows are read as 128-bit words");
     const float inv = 1.0f / (float)CH::BOX;
     for (int r0 = 4 * tid; r0 < K1_TILE + K1_HALO; r0 += 4 * K1_THREADS) {
         uint32_t w[NLOAD];
-        const K1Word4 *src = (const K1Word4 *)(sm.v + r0 + K1_BOX_MAX / 2 - NW);   /* first word of row r0-1's window */
+        const K1Word4 *src = (const K1Word4 *)(sm.v + DW * r0 + START);   /* first word of row r0-1's window */
 #pragma unroll
         for (int q = 0; q < NLOAD / 4; q++) { const K1Word4 v = src[q]; w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
         uint32_t acc = 0;
 #pragma unroll
-        for (int b = 0; b < NW; b++) acc += w[b];
+        for (int b = 0; b < NWIN; b++) acc += w[b];
         float si[5], sq[5];
 #pragma unroll
         for (int k = 0; k < 5; k++) {
-            if (k > 0) acc = acc - w[k - 1] + w[k - 1 + NW];          /* both halves stay non-negative: no borrow */
-            si[k] = wmb_fmul((float)((int)(acc & 0xFFFFu) - NW * K1_PAIR_BIAS), inv);
-            sq[k] = wmb_fmul((float)((int)(acc >> 16) - NW * K1_PAIR_BIAS), inv);
+            if (k > 0) {
+#pragma unroll
+                for (int i = 0; i < DW; i++) acc = acc - w[(k - 1) * DW + i] + w[(k - 1) * DW + i + NWIN];   /* both halves stay non-negative */
+            }
+            si[k] = wmb_fmul((float)((int)(acc & 0xFFFFu) - NWIN * BIASW), inv);
+            sq[k] = wmb_fmul((float)((int)(acc >> 16) - NWIN * BIASW), inv);
         }
         float dr[4];
 #pragma unroll
@@ -443,7 +450,10 @@ __device__ __forceinline__ void k1_chain(const K1Params &p, K1Smem &sm, const ui
         if (fast) k1_convert_fast(p, sm, raw, tile, tid); else k1_convert<CH::ID>(p, sm, raw, tile, tid);
         __syncthreads();
     }
-    if (fast) k1_box_disc_fast<CH>(p, sm, tid);
+    if (fast) k1_box_disc<CH, 1, true>(p, sm, tid);
+    else if (p.d == 3) k1_box_disc<CH, 3, false>(p, sm, tid);
+    else if (p.d == 2) k1_box_disc<CH, 2, false>(p, sm, tid);
+    else if (p.d == 1) k1_box_disc<CH, 1, false>(p, sm, tid);
     else {
         k1_box<CH>(p, sm, tid);
         __syncthreads();

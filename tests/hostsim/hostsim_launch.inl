@@ -10,7 +10,10 @@ static void hostsim_k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, 
 {
     const bool fast = (p.d == 2 && !p.mix);
     if (need_convert) for (int t = 0; t < K1_THREADS; t++) { if (fast) k1_convert_fast(p, sm, raw, tile, t); else k1_convert<CH::ID>(p, sm, raw, tile, t); }
-    if (fast) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc_fast<CH>(p, sm, t); }
+    if (fast) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 1, true>(p, sm, t); }
+    else if (p.d == 3) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 3, false>(p, sm, t); }
+    else if (p.d == 2) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 2, false>(p, sm, t); }
+    else if (p.d == 1) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 1, false>(p, sm, t); }
     else {
         for (int t = 0; t < K1_THREADS; t++) k1_box<CH>(p, sm, t);
         for (int t = 0; t < K1_THREADS; t++) k1_disc_mag(p, sm, t);
