@@ -147,7 +147,9 @@ int  wmb_decode_frames(wmb_ctx *c, const wmb_frame *frames, size_t n);
 /* Copy queued lines ('\n'-terminated, concatenated) into buf; returns the number of
  * bytes written (0 when none); *n_lines (optional) receives the line count.  Lines
  * that do not fit stay queued.  timestamp_mode: 0 = wall clock at delivery
- * (rtl_wmbus_util.h:10-39 format), 1 = the literal TS. */
+ * (rtl_wmbus_util.h:10-39 format), 1 = the literal TS, 2 = the stream position at which the
+ * reference would print the line, "@<decimated sample of the telegram's last bit>.<chain*2 + (algo == t2a)>":
+ * sorting by it merges lines of several contexts (time-chunk sharding) into the reference's print order. */
 size_t wmb_take_lines(wmb_ctx *c, char *buf, size_t cap, size_t *n_lines, int timestamp_mode);
 
 /* Convenience for offline captures: push + flush + decode + take_lines in one call.

@@ -153,12 +153,16 @@ class WmbusB200:
         txt = C.string_at(self._out, n).decode("ascii")      # (.raw would copy the whole 4 MiB buffer)
         return txt.split("\n")[:-1] if txt.endswith("\n") else [l for l in txt.split("\n") if l]
 
+    def _drain(self, taken, timestamp_mode):
+        """wmb_process* hands out only the lines that fit the buffer; the rest stay queued -- fetch them too"""
+        return self.take_lines(timestamp_mode) if taken else []
+
     def process(self, host_ptr, nbytes, flush=True, timestamp_mode=1):
         """host_ptr: int address / ctypes pointer of cu8 bytes in host memory."""
         nl = C.c_size_t(0)
         n = self._check(self.lib.wmb_process(self._ctx, host_ptr, nbytes, int(flush), self._out,
                                              len(self._out), C.byref(nl), timestamp_mode))
-        return self._lines(n)
+        return self._lines(n) + self._drain(nl.value, timestamp_mode)
 
     def process_bytes(self, data: bytes, flush=True, timestamp_mode=1):
         buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
@@ -168,7 +172,7 @@ class WmbusB200:
         nl = C.c_size_t(0)
         n = self._check(self.lib.wmb_process_device(self._ctx, C.c_void_p(dev_ptr), nbytes, int(flush),
                                                     self._out, len(self._out), C.byref(nl), timestamp_mode))
-        return self._lines(n)
+        return self._lines(n) + self._drain(nl.value, timestamp_mode)
 
     def push(self, host_ptr, nbytes):
         self._check(self.lib.wmb_push(self._ctx, host_ptr, nbytes))

@@ -1461,6 +1461,7 @@ extern "C" size_t wmb_take_lines(wmb_ctx *c, char *buf, size_t cap, size_t *n_li
     for (; taken < c->lines.size(); taken++) {
         const QueuedLine &q = c->lines[taken];
         if (timestamp_mode == 1) snprintf(ts, sizeof(ts), "TS");
+        else if (timestamp_mode == 2) snprintf(ts, sizeof(ts), "@%014llu.%d", (unsigned long long)q.end_sample, q.prio);
         else wmb_make_time_string(ts, sizeof(ts));
         const char *prefix = c->o.show_algorithm ? (q.algo == WMB_ALGO_RLA ? "rla;" : "t2a;") : "";
         char line[1024];

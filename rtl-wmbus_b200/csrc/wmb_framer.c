@@ -110,7 +110,7 @@ static uint8_t nibble_3of6(unsigned c)
     return v < 0 ? 0xFF : (uint8_t)v;
 }
 
-unsigned wmb_tlg_length_format_a(unsigned L)      /* t1_c1_packet_decoder.h:68-96 */
+static unsigned wmb_tlg_length_format_a(unsigned L)      /* t1_c1_packet_decoder.h:68-96 */
 {
     return 1 + L + 2 * (1 + (L > 9 ? (L - 9 + 15) / 16 : 0));
 }

@@ -41,7 +41,34 @@ def reduce_counts(counts: torch.Tensor, device=None) -> dict:
 
 # ---- time chunks of one capture ---------------------------------------------------------------------
 
-MAX_TELEGRAM_M = 1 << 17        # right halo, decimated samples: the longest S1 telegram is ~113,300 + preamble
+# right halo, decimated samples.  The run-length tracker of the S1 chain accepts up to just under 36 samples per chip
+# (rtl_wmbus.c:659; nominal 24.4), so the longest telegram it can deliver -- (16 * 290 + 17) chips -- spans up to
+# 4657 * 36 = 167,652 samples; T1/C1: (12 * 290 + 13) chips * 8 * 1.25 < 35,000.
+MAX_TELEGRAM_M = 1 << 18
+
+
+def line_key(line: str):
+    """(end sample, stream priority) of a line taken with timestamp_mode=2 ("@<sample>.<prio>" in the TIMESTAMP
+    column): the position at which the reference prints it (rtl_wmbus.c:1354-1355)."""
+    f = line.split(";")
+    ts = f[4 if f[0] in ("rla", "t2a") else 3]
+    a, b = ts[1:].split(".")
+    return int(a), int(b)
+
+
+def blank_position(line: str) -> str:
+    f = line.split(";")
+    f[4 if f[0] in ("rla", "t2a") else 3] = "TS"
+    return ";".join(f)
+
+
+def merge_lines(parts):
+    """Lines of several time chunks (each taken with timestamp_mode=2) -> the sequential run's print order, with the
+    TIMESTAMP column blanked.  Within one chunk the order is already right; across chunks a telegram that started in
+    chunk g may finish after one that started in chunk g+1, so the merge is by print position (stable)."""
+    flat = [l for part in parts for l in part]
+    flat.sort(key=line_key)
+    return [blank_position(l) for l in flat]
 
 
 def chunk_bounds(n_bytes: int, d: int, world: int):
@@ -54,7 +81,8 @@ def chunk_bounds(n_bytes: int, d: int, world: int):
 def decode_time_chunk(ctx, push, n_bytes: int, d: int, rank: int, world: int, halo_m: int = 1 << 18):
     """Decode rank `rank`'s chunk of a capture of n_bytes cu8 bytes.  `push(byte_lo, byte_hi)` feeds that byte
     range of the capture to ctx (host or device memory: the caller's business).
-    Returns (lines, digest_start, digest_end, halo_start_iq): digest_start is None for a chunk that starts at 0."""
+    Returns (lines, digest_start, digest_end, halo_start_iq): digest_start is None for a chunk that starts at 0.
+    The lines carry their print position in the TIMESTAMP column (timestamp_mode 2) for merge_lines()."""
     import hashlib
     k = chunk_bounds(n_bytes, d, world)
     lo, hi = k[rank], k[rank + 1]
@@ -66,11 +94,11 @@ def decode_time_chunk(ctx, push, n_bytes: int, d: int, rank: int, world: int, ha
     dig_start = None
     if start < lo:
         push(2 * start, 2 * lo)
-        lines += ctx.take_lines()
+        lines += ctx.take_lines(2)
     if lo > 0:
         dig_start = hashlib.sha256(ctx.boundary_state()).digest()
     push(2 * lo, 2 * hi)
-    lines += ctx.take_lines()
+    lines += ctx.take_lines(2)
     dig_end = hashlib.sha256(ctx.boundary_state()).digest()
     if rank + 1 < world:                              # finish the telegrams that started in the chunk
         tail = min(k[world], hi + (MAX_TELEGRAM_M * d + gran - 1) // gran * gran)
@@ -80,7 +108,7 @@ def decode_time_chunk(ctx, push, n_bytes: int, d: int, rank: int, world: int, ha
         if n_bytes > 2 * hi:
             push(2 * hi, n_bytes)                     # the ragged end of the capture (the reference drops a short item)
         ctx.poll_flush()
-    lines += ctx.take_lines()
+    lines += ctx.take_lines(2)
     return lines, dig_start, dig_end, start
 
 

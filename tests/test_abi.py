@@ -10,10 +10,19 @@ from conftest import ROOT, has_gpu
 
 
 def declared_functions():
-    hdr = open(os.path.join(ROOT, "include", "wmbus_b200.h")).read()
-    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    names = re.findall(r"\b(wmb_[a-z_0-9]+)\s*\(", hdr)
-    return sorted(set(names))
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for h in sorted(os.listdir(inc)):
+        hdr = open(os.path.join(inc, h)).read()
+        hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+        names |= set(re.findall(r"\b(wmb_[a-z_0-9]+)\s*\(", hdr))
+    return sorted(names)
+
+
+def exported_symbols(path):
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    return sorted(l.split()[-1] for l in out.splitlines() if l.split()[1:2] and l.split()[1] in "TDBR")
 
 
 def test_header_declares_expected_surface():
@@ -31,6 +40,9 @@ def test_library_exports_every_declared_symbol(pkg):
     for n in declared_functions():
         assert hasattr(lib, n), f"{n} missing from {path}"
     assert lib.wmb_abi_version() == 1
+    # ... and nothing else: the dynamic symbol table is exactly the declared surface (csrc/wmb_exports.map)
+    extra = [s for s in exported_symbols(path) if s not in declared_functions()]
+    assert extra == [], f"exported but not declared in include/*.h: {extra}"
 
 
 @pytest.mark.skipif(has_gpu(), reason="only meaningful on a box without a GPU")

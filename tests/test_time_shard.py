@@ -12,6 +12,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+import pipeline_checks as pc
 from conftest import HOSTSIM_SO, ROOT
 
 
@@ -27,8 +28,7 @@ def _pusher(ctx, cu8):
 
 def check_time_chunks(pkg, lib, cu8, flags, world, halo_m, d=2):
     shard = importlib.import_module("rtl-wmbus_b200.shard")
-    with pkg.WmbusB200(flags, lib=lib) as ctx:
-        want = ctx.process(cu8.ctypes.data, len(cu8), flush=True)
+    want = pc.oracle_lines(cu8, flags)                        # the CPU oracle, not the library itself
     got, ends, retries = [], [], 0
     for rank in range(world):
         h = halo_m
@@ -41,9 +41,9 @@ def check_time_chunks(pkg, lib, cu8, flags, world, halo_m, d=2):
             retries += 1
         ends.append(de)
         got.append(lines)
-    flat = [l for part in got for l in part]
-    assert sorted(flat) == sorted(want)
-    assert len(flat) == len(want) and len(want) > 10
+    flat = shard.merge_lines(got)                             # the sequential run's print order
+    assert flat == want
+    assert len(want) > 10
     assert all(len(part) > 0 for part in got)
     return retries
 
@@ -82,9 +82,8 @@ def _worker(rank, world, port, out):
     gathered = [None] * world
     dist.all_gather_object(gathered, lines)
     if rank == 0:
-        with pkg.WmbusB200("-v", lib=lib) as ctx:
-            want = ctx.process(cu8.ctypes.data, len(cu8), flush=True)
-        out.put((gathered, want, counts, rounds))
+        import pipeline_checks as pc
+        out.put((shard.merge_lines(gathered), [len(g) for g in gathered], pc.oracle_lines(cu8, "-v"), counts, rounds))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -96,15 +95,14 @@ def test_two_ranks_time_sharded_gloo(hostsim_lib):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    gathered, want, counts, rounds = q.get(timeout=600)
+    flat, per_rank, want, counts, rounds = q.get(timeout=600)
     for p in procs:
         p.join(timeout=600)
         assert p.exitcode == 0
-    flat = [l for part in gathered for l in part]
-    assert sorted(flat) == sorted(want) and len(want) > 10
+    assert flat == want and len(want) > 10                    # merged in print order == the oracle's sequential run
     assert counts["lines"] == len(want)
     assert rounds >= 2, "the 4096-sample halo must have been rejected once"
-    assert all(len(part) > 0 for part in gathered)
+    assert all(n > 0 for n in per_rank)
 
 
 @pytest.mark.gpu
@@ -116,8 +114,7 @@ def test_time_chunks_on_the_gpu(gpu_lib, pkg):
     cap, _ = synth.synth_capture(n, emitters=synth.default_emitters("mixed"), seed=0xB200004A, device="cuda")
     cu8 = np.ascontiguousarray(cap.cpu().numpy())
     assert check_time_chunks(pkg, gpu_lib, cu8, "-v", world=3, halo_m=1 << 18) == 0
-    with pkg.WmbusB200("", lib=gpu_lib) as ctx:
-        want = ctx.process_device(cap.data_ptr(), n, flush=True)
+    want = pc.oracle_lines(cu8, "")
     got = []
     ends = []
     for rank in range(4):
@@ -126,5 +123,5 @@ def test_time_chunks_on_the_gpu(gpu_lib, pkg):
             lines, ds, de, start = shard.decode_time_chunk(ctx, push, n, 2, rank, 4)
         assert rank == 0 or ds == ends[-1]
         ends.append(de)
-        got += lines
-    assert sorted(got) == sorted(want) and len(want) > 100
+        got.append(lines)
+    assert shard.merge_lines(got) == want and len(want) > 100
