@@ -14,7 +14,10 @@ BASELINE.json config 2 by default -- 1 GiB of 1.6 MS/s cu8 with two T1 emitters,
   cpu_baseline  the reference's own -O3 build (oracle/_ref/rtl_wmbus) on a bounded prefix of the
              same capture, one process (the reference is single-threaded)
 
---impl reference times the reference CPU implementation with every host core (one process per core,
+  strong     BASELINE config 4 in the same run: ONE 4 GiB 2.4 MS/s capture, -d 3, decoded in time chunks by the
+             N ranks (strong scaling; `value`/`e2e` as above, for that capture)
+
+--impl reference times the reference CPU implementation with every usable host CPU (one process per CPU,
 each decoding its own copy of a bounded slice of the workload).
 """
 import argparse
@@ -95,6 +98,43 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
+def host_cpus():
+    """CPUs this process may really use: min(cpu_count, scheduler affinity, cgroup CPU quota)."""
+    n = os.cpu_count() or 1
+    detail = {"cpu_count": n}
+    try:
+        a = len(os.sched_getaffinity(0))
+        detail["affinity"] = a
+        n = min(n, a)
+    except (AttributeError, OSError):
+        pass
+    quota = None
+    try:                                                        # cgroup v2
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(p)
+    except (OSError, ValueError):
+        try:                                                    # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and p > 0:
+                quota = q / p
+        except (OSError, ValueError):
+            pass
+    if quota is not None:
+        detail["cgroup_quota"] = round(quota, 2)
+        n = min(n, max(1, int(quota + 0.5)))
+    return max(1, n), detail
+
+
+def config_dict(args, wl):
+    """`config` of the JSON line -- the same dict in both arms (ours and --impl reference)."""
+    return {"workload": wl["desc"], "flags": wl["flags"], "capture_mib_per_gpu": args.mib,
+            "sharding": "one independent capture per GPU; NCCL all-reduce of packet counters only",
+            "l2": "input (1 GiB) and intermediates are larger than L2; no flush needed",
+            "device_batch_mib": args.batch_mib or min(args.mib, 1024), "e2e_batch_mib": args.e2e_batch_mib}
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -102,12 +142,19 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the per-sample kernels from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get("traffic_bytes_per_step")
-    return None
+def ncu_step():
+    """What the committed ncu capture of one 1 GiB step says (profiles/ncu_step.json, written by profiles/ncu_extract.py
+    from the `ncu --page raw --csv` dump -- nothing in it is typed in by hand): DRAM bytes per step over the captured
+    kernels, and issue-active / DRAM percentages of the two largest kernels."""
+    p = os.path.join(ROOT, "profiles", "ncu_step.json")
+    if not os.path.exists(p):
+        return None, None
+    j = json.load(open(p))
+    top = sorted(j.get("kernels", {}).items(), key=lambda kv: -kv[1].get("ms", 0.0))[:2]
+    brief = {name: {k: v.get(k) for k in ("ms", "issue_active_pct", "dram_pct", "warps_active_pct", "threads_per_inst")}
+             for name, v in top}
+    brief["source"] = "profiles/ncu_step.json <- " + str(j.get("source"))
+    return j.get("traffic_bytes_per_step"), brief
 
 
 def ref_binary():
@@ -132,46 +179,69 @@ def time_reference(path_to_capture, flags, procs):
 
 
 def run_reference_arm(args, wl):
+    """The reference's own CPU implementation of the path on the box's host cores: P = the CPUs this process may use
+    (affinity and cgroup quota, not the machine's core count), one single-threaded reference process per CPU, each
+    decoding its own copy of a slice of the workload.  The slice is 256 MiB (spawn cost < 0.1 %) unless
+    (steps + warmup) of those would run longer than ~3 minutes, then it shrinks (not below 64 MiB)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     synth = importlib.import_module("rtl-wmbus_b200.synth")
-    cores = os.cpu_count() or 1
-    slice_bytes = 32 << 20
-    buf, _ = synth.synth_capture(slice_bytes, fs=wl["fs"], emitters=synth.default_emitters(wl["emitters"]),
-                                 seed=0xB2000000 + 16 * 2, device="cpu")
+    procs, cpu_detail = host_cpus()
     shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     path = os.path.join(shm, f"wmbus_ref_slice_{os.getpid()}.cu8")
+    full = 256 << 20
+    buf, _ = synth.synth_capture(full, fs=wl["fs"], emitters=synth.default_emitters(wl["emitters"]),
+                                 seed=0xB2000000 + 16 * 2, device="cpu", center_shift_hz=wl.get("shift", 0.0))
     buf.numpy().tofile(path)
     try:
+        # calibrate: one process on the first 32 MiB
+        cal = os.path.join(shm, f"wmbus_ref_cal_{os.getpid()}.cu8")
+        buf[:32 << 20].numpy().tofile(cal)
+        t_cal = min(time_reference(cal, wl["flags"], 1) for _ in range(2))
+        os.unlink(cal)
+        solo_rate = (32 << 20) / 2 / t_cal                                  # IQ samples/s of one process alone
+        budget_s = 170.0
+        slice_bytes = full
+        while slice_bytes > (64 << 20) and (args.steps + args.warmup) * (slice_bytes / 2 / solo_rate) * 1.15 > budget_s:
+            slice_bytes //= 2
+        if slice_bytes != full:
+            buf[:slice_bytes].numpy().tofile(path)
         for _ in range(args.warmup):
-            time_reference(path, wl["flags"], cores)
+            time_reference(path, wl["flags"], procs)
         t = 0.0
         for _ in range(args.steps):
-            t += time_reference(path, wl["flags"], cores)
+            t += time_reference(path, wl["flags"], procs)
     finally:
-        os.unlink(path)
-    n_iq = slice_bytes // 2 * cores
+        if os.path.exists(path):
+            os.unlink(path)
+    n_iq = slice_bytes // 2 * procs
     value = n_iq * args.steps / t / 1e6
     _, kind = ref_binary()
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "flags": wl["flags"]},
-        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{cores} processes x {slice_bytes >> 20} MiB slice of the workload per step "
-                                   f"(the reference is single-threaded: one process per host core)"},
+        "config": config_dict(args, wl),
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": procs, "kind": kind,
+                         "sample": f"{procs} processes x {slice_bytes >> 20} MiB slice of the workload per step (the reference "
+                                   f"is single-threaded: one process per usable host CPU; {cpu_detail})",
+                         "per_process_msamples_s": round(value / procs, 3),
+                         "one_process_alone_msamples_s": round(solo_rate / 1e6, 3)},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local):
+def run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local, mib=None, steps=None, warmup=None):
     """Strong scaling: ONE capture, rank g decodes the time chunk [S_g, S_g+1) from a warm-up halo and proves the
-    re-join with its left neighbour's boundary state (two digests per rank, all-gathered)."""
+    re-join with its left neighbour's boundary state (two digests per rank, all-gathered).  Returns the JSON object
+    (rank 0) or None."""
     import torch
     import torch.distributed as dist
-    n_bytes = args.mib << 20
+    mib = mib or args.mib
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
+    n_bytes = mib << 20
     n_iq = n_bytes // 2
     d = wl["d"]
     host = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
@@ -193,49 +263,47 @@ def run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local):
     results = {}
     for leg, base, push_name in (("device", cap.data_ptr(), "push_device"), ("host", host.data_ptr(), "push")):
         ctx = pkg.WmbusB200(wl["flags"], device=local, lib=lib,
-                            max_batch_mib=(args.batch_mib or min(args.mib, 1024)) if leg == "device" else args.e2e_batch_mib)
+                            max_batch_mib=(args.batch_mib or min(mib, 1024)) if leg == "device" else args.e2e_batch_mib)
         push = lambda lo, hi, c=ctx, b=base, f=push_name: getattr(c, f)(b + lo, hi - lo)
         lines, rounds = None, 0
-        for _ in range(max(1, args.warmup)):
+        for _ in range(max(1, warmup)):
             lines, rounds = shard.decode_time_sharded(ctx, push, n_bytes, d)
         l0 = ctx.stats().kernel_launches
         sampler = ClockSampler(local) if leg == "device" else None
         if sampler: sampler.start()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             lines, rounds = shard.decode_time_sharded(ctx, push, n_bytes, d)
         barrier()
         t = max_over_ranks(time.perf_counter() - t0)
         results[leg] = dict(t=t, lines=lines, rounds=rounds, launches=ctx.stats().kernel_launches - l0,
                             clocks=sampler.stop() if sampler else None, st=ctx.stats())
         ctx.close()
+    del host
     assert results["device"]["lines"] == results["host"]["lines"], "host-input and device-input legs disagree"
     totals = shard.reduce_counts(shard.count_lines(results["device"]["lines"]), device="cuda")
-    if rank == 0:
-        dv, hv = results["device"], results["host"]
-        k = shard.chunk_bounds(n_bytes, d, world)
-        out = {
-            "metric": METRIC, "value": round(n_iq * args.steps / dv["t"] / 1e6, 1), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dv["t"] / args.steps, 3),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "flags": wl["flags"], "capture_mib_total": args.mib,
-                       "sharding": "time chunks of ONE capture: halo warm start, boundary states compared over "
-                                   "all_gather (2 x 32 B per rank), NCCL all-reduce of packet counters",
-                       "chunk_bounds_iq": k, "halo_rounds": dv["rounds"],
-                       "l2": "input and intermediates are larger than L2; no flush needed"},
-            "clocks": dv["clocks"],
-            "e2e": {"value": round(n_iq * args.steps / hv["t"] / 1e6, 1), "unit": UNIT,
-                    "h2d_bytes_per_step": int((hv["st"].h2d_bytes) // (args.steps + max(1, args.warmup))),
-                    "d2h_bytes_per_step": int((hv["st"].d2h_bytes) // (args.steps + max(1, args.warmup))),
-                    "ms_per_step": round(1e3 * hv["t"] / args.steps, 3)},
-            "gpu_launches": int(dv["launches"]),
-            "packets": dict(totals, planted=len(plan)),
-        }
-        print(json.dumps(out))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    dv, hv = results["device"], results["host"]
+    k = shard.chunk_bounds(n_bytes, d, world)
+    return {
+        "metric": METRIC, "value": round(n_iq * steps / dv["t"] / 1e6, 1), "unit": UNIT, "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(1e3 * dv["t"] / steps, 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "flags": wl["flags"], "capture_mib_total": mib,
+                   "sharding": "time chunks of ONE capture: halo warm start, boundary states compared over "
+                               "all_gather (2 x 32 B per rank), NCCL all-reduce of packet counters",
+                   "chunk_bounds_iq": k, "halo_rounds": dv["rounds"],
+                   "l2": "input and intermediates are larger than L2; no flush needed"},
+        "clocks": dv["clocks"],
+        "e2e": {"value": round(n_iq * steps / hv["t"] / 1e6, 1), "unit": UNIT,
+                "h2d_bytes_per_step": int((hv["st"].h2d_bytes) // (steps + max(1, warmup))),
+                "d2h_bytes_per_step": int((hv["st"].d2h_bytes) // (steps + max(1, warmup))),
+                "ms_per_step": round(1e3 * hv["t"] / steps, 3)},
+        "gpu_launches": int(dv["launches"]),
+        "packets": dict(totals, planted=len(plan)),
+    }
 
 
 def main():
@@ -251,6 +319,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--warm", type=int, default=0, help="bit-sync warm-up samples (default: library)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (time chunks of one 2.4 MS/s -d 3 capture)")
+    ap.add_argument("--strong-mib", type=int, default=4096)
+    ap.add_argument("--strong-steps", type=int, default=3)
     ap.add_argument("--sharding", default="captures", choices=["captures", "time"],
                     help="N>1: one independent capture per GPU (weak scaling, default) or time chunks of ONE capture "
                          "(strong scaling, SURVEY 8e / BASELINE config 4)")
@@ -284,7 +355,13 @@ def main():
                                     device="cuda", center_shift_hz=wl.get("shift", 0.0))
     torch.cuda.synchronize()
     if time_sharded:
-        return run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local)
+        out = run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local)
+        if rank == 0:
+            print(json.dumps(out))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     tune = dict(max_batch_mib=args.batch_mib or min(args.mib, 1024))      # rings and candidate lists are sized for <= 1 GiB batches
     if args.chunk: tune["chunk_samples"] = args.chunk
     if args.warm: tune["warmup_samples"] = args.warm
@@ -350,47 +427,59 @@ def main():
     # ---------------- packet counters: the only collective on this path ----------------
     totals = shard.reduce_counts(shard.count_lines(lines), device="cuda")     # NCCL all-reduce over NVLink
 
+    del host, ctx_e
+
+    # ---------------- strong scaling over time chunks (BASELINE config 4), same run, reported under "strong" ----------------
+    strong = None
+    if not args.no_strong:
+        wl4 = workload_def("d3")
+        cap4, plan4 = synth.synth_capture(args.strong_mib << 20, fs=wl4["fs"], emitters=synth.default_emitters(wl4["emitters"]),
+                                          seed=shard.capture_seed(4, 0), device="cuda")
+        torch.cuda.synchronize()
+        strong = run_time_sharded(args, wl4, pkg, shard, lib, cap4, plan4, rank, world, local,
+                                  mib=args.strong_mib, steps=args.strong_steps, warmup=1)
+        del cap4
+
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         abytes = algorithmic_bytes_per_sample(wl["chains"], wl["d"]) * n_iq
         kern_s = (k1_ms + k2_ms) / args.steps / 1e3
         achieved = abytes / kern_s / 1e9 if kern_s > 0 else None
+        traffic, ncu_brief = ncu_step()
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1e3 * t_dev / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "flags": wl["flags"], "capture_mib_per_gpu": args.mib,
-                       "sharding": "one independent capture per GPU; NCCL all-reduce of packet counters only",
-                       "l2": "input (1 GiB) and intermediates are larger than L2; no flush needed",
-                       "device_batch_mib": tune["max_batch_mib"], "e2e_batch_mib": args.e2e_batch_mib},
+            "config": config_dict(args, wl),
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": n_bytes,
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": round(1e3 * t_e2e / args.steps, 3)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
-                         "traffic": ncu_traffic(), "peak_source": peak_src,
-                         "kernel": "k1_demod_kernel + k2a/k2t/k2p bit-sync kernels (the whole per-sample path; CUDA events on the launching stream)",
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "k1_demod_kernel + bit-sync kernels (the whole per-sample path; CUDA events on the launching stream)",
                          "algorithmic_bytes_per_step": int(abytes),
                          "k1_demod_ms": round(k1_ms / args.steps, 4), "k2_bitsync_ms": round(k2_ms / args.steps, 4),
                          "device_pass_ms": round(dev_ms / args.steps, 4),
-                         # the same algorithmic bytes over the demod kernel alone (the largest kernel), and what ncu
-                         # says bounds the two largest kernels instead of HBM (static: from the committed capture)
+                         # the same algorithmic bytes over the demod kernel alone (the largest kernel)
                          "k1_only": {"achieved": round(abytes / (k1_ms / args.steps / 1e3) / 1e9, 1) if k1_ms else None,
                                      "frac": round(abytes / (k1_ms / args.steps / 1e3) / 1e9 / peak, 4) if k1_ms else None},
-                         "issue_bound_ncu": {"k1_issue_active_pct": 76.0, "k2a_issue_active_pct_one_warp_per_scheduler": 64.5,
-                                             "k1_dram_pct": 10.6, "source": "profiles/r1z_ncu_full_summary.txt"}},
+                         "ncu": ncu_brief},
             "packets": dict(totals, planted_per_gpu=len(plan)),
             "lanes": {"run": int(st.lanes_run), "rerun": int(st.lanes_rerun), "rl_fallbacks": int(st.rl_fallbacks)},
             "host_ms_per_step": {"batch": round(st.host_batch_ms / (args.steps + args.warmup), 3),
                                  "gather": round(st.host_gather_ms / (args.steps + args.warmup), 3),
                                  "decode": round(st.host_decode_ms / (args.steps + args.warmup), 3)},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if strong:
+            out["strong"] = {k: strong[k] for k in ("value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "config",
+                                                   "e2e", "gpu_launches", "packets")}
+        if not args.no_cpu_baseline:
             sample = 64 << 20
             shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
             path = os.path.join(shm, f"wmbus_cpu_sample_{os.getpid()}.cu8")
-            host[:sample].numpy().tofile(path)
+            cap[:sample].cpu().numpy().tofile(path)
             try:
                 t_cpu = min(time_reference(path, wl["flags"], 1) for _ in range(2))
             finally:
@@ -398,9 +487,10 @@ def main():
             _, kind = ref_binary()
             out["cpu_baseline"] = {"value": round(sample / 2 / t_cpu / 1e6, 3), "unit": UNIT, "cores": 1, "kind": kind,
                                    "sample": f"first {sample >> 20} MiB of the same capture, one process, best of 2 "
-                                             f"({os.cpu_count()} host cores present)"}
+                                             f"({host_cpus()[0]} usable host CPUs)"}
         print(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
