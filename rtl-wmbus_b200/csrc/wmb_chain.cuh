@@ -32,6 +32,7 @@
 
 /* stream (ring) event: [63:24] global decimated sample, [23:16] rssi, [2] reset, [1] sync, [0] bit */
 #define EVG_M(e)     ((uint64_t)(e) >> 24)
+#define EVG_M_MASK   ((1ull << 40) - 1)
 #define EVG_RSSI(e)  ((uint32_t)((e) >> 16) & 0xFFu)
 #define EVG_RESET(e) ((uint32_t)((e) >> 2) & 1u)
 #define EVG_SYNC(e)  ((uint32_t)((e) >> 1) & 1u)

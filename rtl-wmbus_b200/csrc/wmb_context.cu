@@ -1033,9 +1033,12 @@ static int gather_frames(wmb_ctx *c, bool final)
 
     c->out_hdr.assign(c->h_hdr, c->h_hdr + nf);
     c->out_final = final;
+    /* the device keeps 40 bits of the sample index; widen to the 64-bit stream position: the newest value
+     * congruent to it that is not beyond the samples produced so far */
+    for (FrameHdr &h : c->out_hdr)
+        h.sync_sample = c->m_consumed - ((c->m_consumed - h.sync_sample) & EVG_M_MASK);
     /* frames point straight into the pinned copy; it stays valid until the next gather */
     for (const FrameHdr &h : c->out_hdr) {
-        if (h.overflow) return set_err(WMB_E_OVERFLOW, "bit spacing exceeds 2^23 samples inside a frame");
         if (!h.complete && !final) c->cb[h.chain].s[h.algo].pending.push_back(h.ordinal);
         if (h.nbits == 0 || dev_decode) continue;
         wmb_frame f;

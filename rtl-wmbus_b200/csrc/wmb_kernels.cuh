@@ -706,8 +706,11 @@ WMB_D void k3_copy(const K3Params &p, uint32_t i, int tid, int nthr)
     const uint64_t mask = p.ring_mask[h.chain][h.algo];
     for (uint32_t j = tid; j < h.nbits; j += nthr) {
         const uint64_t e = ring[(h.ordinal + j) & mask];
-        uint64_t off = EVG_M(e) - h.sync_sample;
-        if (off >= (1u << 23)) { off = (1u << 23) - 1; h.overflow = 1; }
+        /* the ring keeps 40 bits of the sample index (15.9 days at 800 kS/s): differences are taken modulo 2^40.
+         * The offset only orders the lines of one batch (end sample); a spacing beyond 2^23 samples inside one
+         * candidate (a carrier that keeps the slicer still for > 10 s) is clamped, not an error. */
+        uint64_t off = (EVG_M(e) - h.sync_sample) & EVG_M_MASK;
+        if (off >= (1u << 23)) off = (1u << 23) - 1;
         p.words[h.word_off + j] = ((uint32_t)off << 9) | (EVG_RSSI(e) << 1) | EVG_BIT(e);
     }
 }

@@ -158,3 +158,27 @@ def check_type2_fallback(pkg, lib):
     # forcing the monolithic lanes everywhere gives the same lines
     got, st = run_lines(pkg, lib, cu8, "-v", reserved=(C.c_uint32 * 2)(1, 0))
     assert got == want and st.rl_fallbacks == 0
+
+
+def check_sample_index_wrap(pkg, lib):
+    """The device keeps 40 bits of the decimated sample index in its bit events (15.9 days of streaming at 800 kS/s).
+    A stream positioned just below 2^40 must decode the telegrams that span the wrap exactly like a fresh stream:
+    same lines, same order, in small pushes (candidates stay pending across the wrap) and in one."""
+    cu8 = load_fixture("synth_mixed_1m6.cu8")
+    want = oracle_lines(cu8, "-v")
+    data = np.ascontiguousarray(cu8, np.uint8)
+    m_total = len(data) // 4                                  # decimated samples of the capture (d = 2)
+    for back in (2048 * 20, (m_total // 2) // 2048 * 2048):   # the wrap falls early in / in the middle of the capture
+        first_iq = ((1 << 40) - back) * 2
+        for step in (len(data), 1 << 17):
+            with pkg.WmbusB200("-v", lib=lib, max_batch_mib=1) as ctx:
+                ctx.seek(first_iq)
+                lines = []
+                for off in range(0, len(data), step):
+                    n = min(step, len(data) - off)
+                    lines += ctx.process(data.ctypes.data + off, n, flush=False, timestamp_mode=2)
+                lines += ctx.process(0, 0, flush=True, timestamp_mode=2)
+            shard = importlib.import_module("rtl-wmbus_b200.shard")
+            keys = [shard.line_key(l) for l in lines]
+            assert keys == sorted(keys) and keys[0][0] > (1 << 40) - back and keys[-1][0] > (1 << 40)
+            assert [shard.blank_position(l) for l in lines] == want, (back, step)

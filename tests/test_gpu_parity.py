@@ -75,6 +75,10 @@ def test_degenerate_inputs(pkg, gpu_lib):
     pc.check_degenerate(pkg, gpu_lib)
 
 
+def test_sample_index_wrap_at_2_pow_40(pkg, gpu_lib):
+    pc.check_sample_index_wrap(pkg, gpu_lib)
+
+
 def test_synthetic_64mib_vs_oracle_and_device_input(pkg, gpu_lib):
     """A 64 MiB synthetic capture (all telegram types), generated on the GPU, decoded (a) from host memory,
     (b) from device memory in one batch, (c) in 8 MiB batches: identical lines, equal to the oracle's."""

@@ -53,3 +53,7 @@ def test_error_paths(pkg, hostsim_lib):
     assert b"decimation" in hostsim_lib.wmb_last_error()
     o = pkg.opts_from_flags(hostsim_lib, "")
     assert hostsim_lib.wmb_create(C.byref(o), 7, C.byref(ctx)) == -2        # WMB_E_NODEVICE
+
+
+def test_sample_index_wrap_at_2_pow_40(pkg, hostsim_lib):
+    pc.check_sample_index_wrap(pkg, hostsim_lib)
