@@ -64,7 +64,8 @@ typedef struct wmb_opts {
     uint32_t manual_frames;   /* 1: wmb_push only gathers candidates; the caller drives the
                                  framers with wmb_poll + wmb_decode_frames.  0 (default):
                                  wmb_push feeds the context's framers itself.            */
-    uint32_t reserved[2];
+    uint32_t reserved[2];     /* test knobs, 0 in production: [0] = 1 forces the monolithic run-length lanes for
+                                 T1/C1; [1] bit 0 keeps the clock-sign words for wmb_debug_copy_bits(.., 2, ..)  */
 } wmb_opts;
 
 typedef struct wmb_ctx wmb_ctx;
@@ -188,6 +189,20 @@ int wmb_get_stats(wmb_ctx *c, wmb_stats *s);
  * (dphi: post-FIR, pre-DC-block discriminator output; rssi: (unsigned)rssi).
  * Returns the number of samples copied or a negative error. */
 long wmb_debug_copy_stage(wmb_ctx *c, int chain, float *dphi, uint8_t *rssi, size_t cap);
+
+/* Bit-sync stage taps of the LAST batch, packed: bit i of word w = decimated sample 32 w + i of the batch.
+ *   which 0: data bits   -- the slicer's output, behind the DC block with -o  (rtl_wmbus.c:1059, bits.bin tap :1060-1061)
+ *   which 1: time2 strobes -- the samples at which the clock lock delivers a bit (rtl_wmbus.c:1092-1111)
+ *   which 2: clock signs -- sign of the clock-recovery band-pass (rtl_wmbus.c:1089-1090, clock.bin tap); kept only by a
+ *            context created with opts.reserved[1] = 1
+ * Returns the number of words copied or a negative error. */
+long wmb_debug_copy_bits(wmb_ctx *c, int chain, int which, uint32_t *words, size_t cap_words);
+
+/* The bit events the LAST batch appended to one (chain, algo) bit stream, i.e. the calls of
+ * t1_c1_packet_decoder() / s1_packet_decoder() the reference makes (rtl_wmbus.c:773-781, :822-830, rawbits.bin tap
+ * :1107-1108): [63:24] decimated sample (40 bits), [23:16] (unsigned)rssi, [2] run-length reset since the previous
+ * event, [1] access code matched on this bit, [0] the bit.  Returns the number of events copied. */
+long wmb_debug_copy_events(wmb_ctx *c, int chain, int algo, uint64_t *ev, size_t cap);
 
 /* ---- time-chunk sharding of one capture (several contexts / GPUs on one stream) ----
  * The reference has no counterpart: it is one sequential loop (rtl_wmbus.c:1298-1357).  A worker that

@@ -68,6 +68,10 @@ def _bind(lib):
     lib.wmb_get_stats.argtypes = [C.c_void_p, C.POINTER(WmbStats)]
     lib.wmb_debug_copy_stage.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.wmb_debug_copy_stage.restype = C.c_long
+    lib.wmb_debug_copy_bits.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    lib.wmb_debug_copy_bits.restype = C.c_long
+    lib.wmb_debug_copy_events.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    lib.wmb_debug_copy_events.restype = C.c_long
     lib.wmb_seek.argtypes = [C.c_void_p, C.c_uint64]
     lib.wmb_set_line_window.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     lib.wmb_boundary_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -77,7 +81,7 @@ def _bind(lib):
 
 EXPORTS = ["wmb_reset", "wmb_host_alloc", "wmb_host_free", "wmb_default_opts", "wmb_abi_version", "wmb_last_error", "wmb_version_string", "wmb_create",
            "wmb_destroy", "wmb_push", "wmb_push_device", "wmb_poll", "wmb_decode_frames", "wmb_take_lines",
-           "wmb_process", "wmb_process_device", "wmb_get_stats", "wmb_debug_copy_stage",
+           "wmb_process", "wmb_process_device", "wmb_get_stats", "wmb_debug_copy_stage", "wmb_debug_copy_bits", "wmb_debug_copy_events",
            "wmb_seek", "wmb_set_line_window", "wmb_boundary_state"]
 
 
@@ -234,3 +238,19 @@ class WmbusB200:
         rssi = np.zeros(n, np.uint8)
         got = self._check(self.lib.wmb_debug_copy_stage(self._ctx, chain, dphi.ctypes.data, rssi.ctypes.data, n))
         return dphi[:got], rssi[:got]
+
+    def debug_bits(self, chain: int, which: int, n: int):
+        """Unpacked 0/1 array of the last batch's data bits (0), time2 strobes (1) or clock signs (2)."""
+        import numpy as np
+        words = np.zeros((n + 31) // 32, np.uint32)
+        got = self._check(self.lib.wmb_debug_copy_bits(self._ctx, chain, which, words.ctypes.data, len(words)))
+        return np.unpackbits(words[:got].view(np.uint8), bitorder="little")[:n]
+
+    def debug_events(self, chain: int, algo: int, cap: int = 1 << 22):
+        """The last batch's bit events of one stream as (sample, rssi, reset, sync, bit) arrays."""
+        import numpy as np
+        ev = np.zeros(cap, np.uint64)
+        got = self._check(self.lib.wmb_debug_copy_events(self._ctx, chain, algo, ev.ctypes.data, cap))
+        ev = ev[:got]
+        return dict(m=ev >> np.uint64(24), rssi=(ev >> np.uint64(16)) & np.uint64(0xFF), reset=(ev >> np.uint64(2)) & np.uint64(1),
+                    sync=(ev >> np.uint64(1)) & np.uint64(1), bit=ev & np.uint64(1))

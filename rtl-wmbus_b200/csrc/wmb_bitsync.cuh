@@ -31,6 +31,7 @@ struct K2aParams {
     int64_t  M, hist;
     uint32_t C, W, lanes;       /* all multiples of 32                                        */
     uint32_t *dbits, *sbits;    /* word w covers samples 32w..32w+31 (bit i = sample 32w+i)   */
+    uint32_t *cbits;            /* optional stage tap: the clock signs (null unless the context was made with taps) */
     IirState *st_start, *st_end;
     const IirState *carry;
     uint32_t *rerun;
@@ -221,6 +222,7 @@ WMB_D void k2a_lane_t(const K2aParams &p, uint32_t lane)
             const uint32_t keep = (n == 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
             p.dbits[m >> 5] = dword & keep;
             p.sbits[m >> 5] = sword & keep;
+            if (p.cbits) p.cbits[m >> 5] = cword & keep;
         }
         m += n;
 #pragma unroll

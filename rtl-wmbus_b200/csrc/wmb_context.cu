@@ -75,6 +75,7 @@ struct Stream {                     /* one (chain, algo) bit stream */
     uint64_t *cand = nullptr;       /* device candidate ordinals                  */
     uint64_t *agg = nullptr;        /* scan scratch [tiles]                       */
     uint64_t total = 0;             /* host mirror of sd->total                   */
+    uint64_t total_prev = 0;        /* ... before the last batch (stage tap)      */
     std::vector<uint64_t> pending;  /* candidates not yet complete                */
     /* host framer bookkeeping */
     int64_t busy_until = -1;        /* last ordinal consumed by an accepted packet */
@@ -85,6 +86,7 @@ struct ChainBuf {
     uint8_t *rssi = nullptr;        /* [W | M_max]                                 */
     uint32_t *dbits = nullptr;      /* [W/32 | M_max/32] data bits                 */
     uint32_t *sbits = nullptr;      /* [W/32 | M_max/32] time2 strobes             */
+    uint32_t *cbits = nullptr;      /* [W/32 | M_max/32] clock signs (stage tap, opts.reserved[1] & 1) */
     IirState *ia_start = nullptr, *ia_end = nullptr, *ia_carry = nullptr;
     RlState *rl_start = nullptr, *rl_end = nullptr, *rl_carry = nullptr;
     uint32_t *rerun = nullptr;
@@ -134,6 +136,7 @@ struct wmb_ctx {
     uint32_t p1_lanes_max = 0, p2_lanes_max = 0;
     size_t rec_max = 0;
     bool two_phase = true;
+    bool taps = false;              /* opts.reserved[1] & 1: keep the clock-sign words for wmb_debug_copy_bits */
     K2pDev *h_pd = nullptr;
     uint32_t cap_words_rl = 0;
     size_t ring_events = 0;
@@ -505,6 +508,7 @@ static int ctx_alloc(wmb_ctx *c)
         TRY(dev_alloc(c, &b.rssi, n));
         TRY(dev_alloc(c, &b.dbits, n / 32 + 64, true));      /* slack: lanes prefetch 16 words ahead */
         TRY(dev_alloc(c, &b.sbits, n / 32 + 64, true));
+        if (c->taps) TRY(dev_alloc(c, &b.cbits, n / 32 + 64, true));
         TRY(dev_alloc(c, &b.ia_start, c->lanes_max));
         TRY(dev_alloc(c, &b.ia_end, c->lanes_max));
         TRY(dev_alloc(c, &b.ia_carry, 1));
@@ -603,6 +607,7 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
         if (o->rla_enabled) c->W = std::max(c->W, c->W_m[ch]);
     }
     c->manual = o->manual_frames != 0;
+    c->taps = (o->reserved[1] & 1u) != 0;
     c->two_phase = o->reserved[0] == 0;                  /* reserved[0] = 1: force the monolithic run-length lanes (tests) */
     c->C_fixed = o->chunk_samples ? (o->chunk_samples + 255) / 256 * 256 : 0;
     if (c->C_fixed && (c->C_fixed < 1024 || c->C_fixed > K2_MAX_CHUNK)) { delete c; return set_err(WMB_E_INVAL, "chunk_samples out of range"); }
@@ -697,6 +702,8 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
     c->last_M = M;
     if (M <= 0) return WMB_OK;
     (void)src_is_ctx_buffer;
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++)
+        for (int a = 0; a < WMB_N_ALGOS; a++) c->cb[ch].s[a].total_prev = c->cb[ch].s[a].total;   /* stage tap: events of this batch */
 
     /* ---- K1: demod ---- */
     CUDA_TRY(cudaEventRecord(c->ev_t[0], c->cs));
@@ -747,6 +754,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             memset(&p, 0, sizeof(p));
             p.dphi = b.dphi + c->W; p.M = M; p.hist = c->hist_m; p.C = C; p.W = c->W_a[ch]; p.lanes = lanes;
             p.dbits = b.dbits + wofs; p.sbits = b.sbits + wofs;
+            p.cbits = b.cbits ? b.cbits + wofs : nullptr;
             p.st_start = b.ia_start; p.st_end = b.ia_end; p.carry = b.ia_carry; p.rerun = b.rerun;
             p.dc = c->o.remove_dc; p.t2 = c->o.t2_enabled;
             c->st.lanes_run += lanes;
@@ -1541,7 +1549,7 @@ extern "C" int wmb_reset(wmb_ctx *c)
             for (int a = 0; a < WMB_N_ALGOS; a++) {
                 Stream &s = b.s[a];
                 CUDA_TRY(cudaMemsetAsync(s.sd, 0, sizeof(StreamDev), c->cs));
-                s.total = 0; s.pending.clear(); s.busy_until = -1;
+                s.total = 0; s.total_prev = 0; s.pending.clear(); s.busy_until = -1;
             }
         }
         CUDA_TRY(cudaStreamSynchronize(c->cs));
@@ -1644,5 +1652,37 @@ extern "C" long wmb_debug_copy_stage(wmb_ctx *c, int chain, float *dphi, uint8_t
     const size_t n = std::min<size_t>((size_t)c->last_M, cap);
     if (dphi) CUDA_TRY(cudaMemcpy(dphi, c->cb[chain].dphi + c->W, n * 4, cudaMemcpyDeviceToHost));
     if (rssi) CUDA_TRY(cudaMemcpy(rssi, c->cb[chain].rssi + c->W, n, cudaMemcpyDeviceToHost));
+    return (long)n;
+}
+
+extern "C" long wmb_debug_copy_bits(wmb_ctx *c, int chain, int which, uint32_t *words, size_t cap_words)
+{
+    if (!c || chain < 0 || chain >= WMB_N_CHAINS || !words || !c->allocated || !c->cb[chain].dbits)
+        return set_err(WMB_E_INVAL, "stage not available");
+    const ChainBuf &b = c->cb[chain];
+    const uint32_t *src = which == 0 ? b.dbits : which == 1 ? b.sbits : which == 2 ? b.cbits : nullptr;
+    if (!src) return set_err(WMB_E_INVAL, which == 2 ? "clock signs are kept only by a context created with opts.reserved[1] = 1" : "no such tap");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->cs));
+    const size_t n = std::min<size_t>(((size_t)c->last_M + 31) / 32, cap_words);
+    CUDA_TRY(cudaMemcpy(words, src + c->W / 32, n * 4, cudaMemcpyDeviceToHost));
+    return (long)n;
+}
+
+extern "C" long wmb_debug_copy_events(wmb_ctx *c, int chain, int algo, uint64_t *ev, size_t cap)
+{
+    if (!c || chain < 0 || chain >= WMB_N_CHAINS || algo < 0 || algo >= WMB_N_ALGOS || !ev || !c->allocated || !c->cb[chain].s[algo].ring)
+        return set_err(WMB_E_INVAL, "stream not available");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->cs));
+    const Stream &s = c->cb[chain].s[algo];
+    const uint64_t n = std::min<uint64_t>(s.total - s.total_prev, cap);
+    if (s.total - s.total_prev > s.ring_cap) return set_err(WMB_E_OVERFLOW, "the batch wrote more events than the ring holds");
+    for (uint64_t i = 0; i < n;) {                                   /* the ring wraps */
+        const uint64_t at = (s.total_prev + i) & (s.ring_cap - 1);
+        const uint64_t run = std::min<uint64_t>(n - i, s.ring_cap - at);
+        CUDA_TRY(cudaMemcpy(ev + i, s.ring + at, (size_t)run * 8, cudaMemcpyDeviceToHost));
+        i += run;
+    }
     return (long)n;
 }

@@ -182,3 +182,39 @@ def check_sample_index_wrap(pkg, lib):
             keys = [shard.line_key(l) for l in lines]
             assert keys == sorted(keys) and keys[0][0] > (1 << 40) - back and keys[-1][0] > (1 << 40)
             assert [shard.blank_position(l) for l in lines] == want, (back, step)
+
+
+def check_bitsync_stages(pkg, lib, cu8, flags):
+    """Every intermediate of the bit-sync stage, one by one, against the oracle (which is pinned stage by stage to
+    the reference's own functions, tests/test_oracle.py): slicer bits behind the optional DC block (a6/a7), clock signs
+    of the band-pass (a9), lock-stencil strobes (a10), and per (chain, algorithm) the exact sequence of decoder calls
+    -- sample, bit, access-code flag, run-length reset, (unsigned)rssi (a11, a12, a13)."""
+    o = orc.opts_from_flags(flags)
+    gran = 4096 * max(1, o.decimation)
+    data = np.ascontiguousarray(cu8[:len(cu8) // gran * gran], np.uint8)
+    counts = {}
+    with pkg.WmbusB200(flags, lib=lib, reserved=(C.c_uint32 * 2)(0, 1)) as ctx:
+        ctx.process(data.ctypes.data, len(data), flush=True)
+        assert ctx.stats().batches == 1
+        for chain in (0, 1):
+            if (chain == 0 and not o.t1c1_enabled) or (chain == 1 and not o.s1_enabled):
+                continue
+            st = orc.stages(data, o, chain)
+            M = st["M"]
+            for which, name in ((0, "bit"), (2, "clk"), (1, "strobe")):
+                if which != 0 and not o.t2_enabled:
+                    continue
+                got = ctx.debug_bits(chain, which, M)
+                bad = np.nonzero(got != st[name])[0]
+                assert len(bad) == 0, (flags, chain, name, len(bad), bad[:5])
+            for algo in (0, 1):
+                if (algo == 0 and not o.rla_enabled) or (algo == 1 and not o.t2_enabled):
+                    continue
+                want = orc.events(st, chain, algo)
+                got = ctx.debug_events(chain, algo)
+                assert len(got["m"]) == len(want), (flags, chain, algo, len(got["m"]), len(want))
+                for f in ("m", "bit", "sync", "rssi") + (("reset",) if algo == 0 else ()):
+                    bad = np.nonzero(got[f] != want[f].astype(np.uint64))[0]
+                    assert len(bad) == 0, (flags, chain, algo, f, len(bad), bad[:5], got[f][bad[:5]], want[f][bad[:5]])
+                counts[(chain, algo)] = (len(want), int(want["sync"].sum()), int(want["reset"].sum()))
+    return counts

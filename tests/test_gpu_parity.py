@@ -34,6 +34,22 @@ def test_stage_outputs_bit_exact(pkg, gpu_lib):
     pc.check_stages(pkg, gpu_lib, load_fixture("synth_mixed_1m6.cu8"), "-d 4 -s")
 
 
+def test_bitsync_stage_taps(pkg, gpu_lib):
+    """Each bit-sync stage on its own: a6/a7 slicer (+DC block), a9 clock signs, a10 lock strobes, a11 deglitch +
+    a12 run-length events, a13 time2 shift register / access code -- every sample and every event vs the oracle."""
+    cu8 = load_fixture("synth_mixed_1m6.cu8")
+    counts = pc.check_bitsync_stages(pkg, gpu_lib, cu8, "")
+    assert all(n > 1000 and syncs >= 1 for n, syncs, _ in counts.values()) and counts[(0, 0)][2] > 100
+    pc.check_bitsync_stages(pkg, gpu_lib, cu8, "-o")
+    pc.check_bitsync_stages(pkg, gpu_lib, cu8, "-r 0")
+    pc.check_bitsync_stages(pkg, gpu_lib, cu8, "-t 0 -a")
+    pc.check_bitsync_stages(pkg, gpu_lib, load_fixture("excerpt_samples2_a.cu8"), "-p S")
+    pc.check_bitsync_stages(pkg, gpu_lib, load_fixture("excerpt_issue48_2m4.cu8"), "-d 3 -s -o")
+    pc.check_bitsync_stages(pkg, gpu_lib, load_fixture("excerpt_issue47_c1.cu8"), "")
+    rng = np.random.default_rng(11)
+    pc.check_bitsync_stages(pkg, gpu_lib, rng.integers(0, 256, 1 << 22).astype(np.uint8), "")      # full-scale noise
+
+
 def test_golden_lines_all_flags(pkg, gpu_lib, golden_lines):
     assert pc.check_golden(pkg, gpu_lib, golden_lines) > 200
 

@@ -57,3 +57,12 @@ def test_error_paths(pkg, hostsim_lib):
 
 def test_sample_index_wrap_at_2_pow_40(pkg, hostsim_lib):
     pc.check_sample_index_wrap(pkg, hostsim_lib)
+
+
+def test_bitsync_stage_taps(pkg, hostsim_lib):
+    """a6/a7 slicer (+DC block), a9 clock signs, a10 lock strobes, a11-a13 bit events of all four streams"""
+    cu8 = load_fixture("synth_mixed_1m6.cu8")
+    counts = pc.check_bitsync_stages(pkg, hostsim_lib, cu8, "")
+    assert all(n > 1000 and syncs >= 1 for n, syncs, _ in counts.values()) and counts[(0, 0)][2] > 100
+    pc.check_bitsync_stages(pkg, hostsim_lib, cu8, "-o")
+    pc.check_bitsync_stages(pkg, hostsim_lib, load_fixture("excerpt_issue48_2m4.cu8"), "-d 3 -s -o")
