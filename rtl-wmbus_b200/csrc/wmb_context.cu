@@ -1125,11 +1125,18 @@ extern "C" int wmb_push_device(wmb_ctx *c, const void *dev_cu8, size_t nbytes)
     if (!c || (!dev_cu8 && nbytes)) return set_err(WMB_E_INVAL, "null argument");
     if (nbytes % 4096) return set_err(WMB_E_INVAL, "wmb_push_device needs a multiple of 4096 bytes");
     if (((uintptr_t)dev_cu8) & 15u) return set_err(WMB_E_INVAL, "device buffer must be 16-byte aligned");
-    if (!c->remainder.empty()) return set_err(WMB_E_STATE, "wmb_push_device after a partial host push");
+    if (!c->remainder.empty()) return set_err(WMB_E_STATE, "wmb_push_device after a partial push");
     CUDA_TRY(cudaSetDevice(c->device));
     int rc = ctx_alloc(c);
     if (rc) return rc;
-    return process_device_batches(c, (const uint8_t *)dev_cu8, nbytes, false);
+    /* whole decimation granules (4096 * d bytes) go to the device as they are; a trailing partial granule (a capture
+     * whose length is a multiple of 4096 but not of 4096 * d) waits on the host side like the remainder of a host push */
+    const size_t tail = nbytes % batch_granule(c);
+    rc = process_device_batches(c, (const uint8_t *)dev_cu8, nbytes - tail, false);
+    if (rc || !tail) return rc;
+    c->remainder.resize(tail);
+    CUDA_TRY(cudaMemcpy(c->remainder.data(), (const uint8_t *)dev_cu8 + (nbytes - tail), tail, cudaMemcpyDeviceToHost));
+    return WMB_OK;
 }
 
 /* dev points to device memory that stays valid during the call */

@@ -218,3 +218,21 @@ def check_bitsync_stages(pkg, lib, cu8, flags):
                     assert len(bad) == 0, (flags, chain, algo, f, len(bad), bad[:5], got[f][bad[:5]], want[f][bad[:5]])
                 counts[(chain, algo)] = (len(want), int(want["sync"].sum()), int(want["reset"].sum()))
     return counts
+
+
+def check_device_push_ragged(pkg, lib, to_device=None):
+    """wmb_push_device with a capture whose length is a multiple of 4096 but not of 4096 * d: the trailing partial
+    granule waits for the flush, exactly like the reference's last whole 4096-byte items (rtl_wmbus.c:1301-1308)."""
+    cu8 = load_fixture("synth_mixed_2m4_shift.cu8")
+    n = len(cu8) // 4096 * 4096
+    if n % (4096 * 3) == 0:
+        n -= 4096
+    data = np.ascontiguousarray(cu8[:n])
+    want = oracle_lines(data, "-v -d 3 -s")
+    keep = to_device(data) if to_device else data           # GPU: a device copy; CPU simulation: the host array
+    ptr = keep.data_ptr() if to_device else data.ctypes.data
+    with pkg.WmbusB200("-v -d 3 -s", lib=lib) as ctx:
+        ctx.push_device(ptr, n)
+        ctx.poll_flush()
+        got = ctx.take_lines()
+    assert got == want and len(want) > 3

@@ -91,6 +91,11 @@ def test_degenerate_inputs(pkg, gpu_lib):
     pc.check_degenerate(pkg, gpu_lib)
 
 
+def test_device_push_with_ragged_tail(pkg, gpu_lib):
+    import torch
+    pc.check_device_push_ragged(pkg, gpu_lib, to_device=lambda a: torch.from_numpy(a).cuda())
+
+
 def test_sample_index_wrap_at_2_pow_40(pkg, gpu_lib):
     pc.check_sample_index_wrap(pkg, gpu_lib)
 

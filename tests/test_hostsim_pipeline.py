@@ -66,3 +66,7 @@ def test_bitsync_stage_taps(pkg, hostsim_lib):
     assert all(n > 1000 and syncs >= 1 for n, syncs, _ in counts.values()) and counts[(0, 0)][2] > 100
     pc.check_bitsync_stages(pkg, hostsim_lib, cu8, "-o")
     pc.check_bitsync_stages(pkg, hostsim_lib, load_fixture("excerpt_issue48_2m4.cu8"), "-d 3 -s -o")
+
+
+def test_device_push_with_ragged_tail(pkg, hostsim_lib):
+    pc.check_device_push_ragged(pkg, hostsim_lib)
