@@ -346,6 +346,7 @@ struct CountScan {
     uint64_t *agg;                  /* [tiles] */
     uint64_t *total;                /* in: ordinal of the first item; out: += sum of cnt */
     const uint32_t *skip;           /* optional: nonzero -> leave everything untouched */
+    uint32_t skip_invert;           /* ... zero -> leave everything untouched instead */
     uint32_t *clear;                /* optional: word zeroed by phase B */
     uint32_t from_zero;             /* ignore *total on input */
 };
@@ -364,9 +365,11 @@ WMB_D void cscan_a_finish(const CountScan &p, uint32_t tile, const uint64_t *par
     for (uint32_t t = 0; t < SCAN_BLOCK; t++) s += part[t];
     p.agg[tile] = s;
 }
+WMB_D bool cscan_skipped(const CountScan &p) { return p.skip && ((*p.skip != 0) != (p.skip_invert != 0)); }
+
 WMB_D void cscan_b(const CountScan &p)
 {
-    if (p.skip && *p.skip) return;
+    if (cscan_skipped(p)) return;
     uint64_t acc = p.from_zero ? 0 : *p.total;
     const uint32_t nt = scan_tiles(p.n);
     for (uint32_t t = 0; t < nt; t++) { const uint64_t c = p.agg[t]; p.agg[t] = acc; acc += c; }
@@ -380,7 +383,7 @@ WMB_D void cscan_c_block(const CountScan &p, uint32_t tile, uint64_t *part)
 }
 WMB_D void cscan_c_write(const CountScan &p, uint32_t tile, uint32_t tid, const uint64_t *part)
 {
-    if (p.skip && *p.skip) return;
+    if (cscan_skipped(p)) return;
     const uint32_t l0 = tile * SCAN_TILE + tid * SCAN_ITEMS;
     uint64_t acc = part[tid];
 #pragma unroll
@@ -533,6 +536,8 @@ struct K2mParams {
     uint32_t *rerun;
     uint32_t *errors;           /* bit0 event overflow, bit1 run-length tracker out of range  */
     uint32_t mode;
+    const uint32_t *run_if;     /* optional: the whole pass happens only if this word is nonzero (T1/C1 fallback
+                                   from the two-phase path, decided on the device)                */
 };
 
 struct K2Out { uint32_t *ev; uint32_t cap; uint32_t n; uint32_t overflow; };
@@ -655,6 +660,7 @@ template <class CH>
 WMB_D void k2m_lane(const K2mParams &p, uint32_t lane)
 {
     if (lane >= p.lanes) return;
+    if (p.run_if && !*p.run_if) return;
     constexpr int K = (CH::ID == 0) ? 5 : 3;
     const int64_t s0 = (int64_t)lane * p.C;
     const int64_t e0 = (s0 + p.C < p.M) ? s0 + p.C : p.M;
@@ -739,6 +745,7 @@ WMB_D void k2m_lane(const K2mParams &p, uint32_t lane)
 WMB_D void k2m_verify_lane(const K2mParams &p, uint32_t lane, uint32_t *n_fail)
 {
     if (lane >= p.lanes) return;
+    if (p.run_if && !*p.run_if) return;
     uint32_t bad = 0;
     if (lane > 0) {
         const RlState &a = p.st_start[lane], &b = p.st_end[lane - 1];
@@ -1130,9 +1137,15 @@ WMB_D void k2p2w_c(const K2p2Params &p, uint32_t lane, uint32_t tid, const uint3
 
 /* end of batch: compose the carried RlState from phase 1's end state (raw bits, level, run,
  * "reset since the last record") and phase 2's state after the last record */
-WMB_D void k2p_fold(const P1State *p1_end, RlState *p2_out, RlState *carry, const K2pDev *pd)
+WMB_D void k2p_fold(const P1State *p1_end, RlState *p2_out, RlState *carry, const K2pDev *pd, const RlState *mono_end,
+                    uint32_t *stat_fallbacks)
 {
-    if (pd->fallback) return;
+    if (pd->fallback) {                 /* the batch was redone with the monolithic lanes: their end state carries */
+        *carry = *mono_end;
+        p2_out->run = 0;
+        (*stat_fallbacks)++;
+        return;
+    }
     RlState c = *carry;
     if (p2_out->run) { c.a = p2_out->a; c.b = p2_out->b; c.sr = p2_out->sr; }
     c.raw = p1_end->raw; c.run = p1_end->run;

@@ -72,11 +72,11 @@ struct Stream {                     /* one (chain, algo) bit stream */
     uint64_t *ring = nullptr;       /* global event ring                          */
     uint64_t ring_cap = 0;          /* power of two                               */
     StreamDev *sd = nullptr;        /* device bookkeeping                         */
-    uint64_t *cand = nullptr;       /* device candidate ordinals                  */
+    uint64_t *cand = nullptr;       /* device: new access-code matches (ordinals, unordered) */
+    uint64_t *pend = nullptr;       /* device: candidates waiting for more bits   */
     uint64_t *agg = nullptr;        /* scan scratch [tiles]                       */
-    uint64_t total = 0;             /* host mirror of sd->total                   */
+    uint64_t total = 0;             /* host mirror of sd->total at the last read  */
     uint64_t total_prev = 0;        /* ... before the last batch (stage tap)      */
-    std::vector<uint64_t> pending;  /* candidates not yet complete                */
     /* host framer bookkeeping */
     int64_t busy_until = -1;        /* last ordinal consumed by an accepted packet */
 };
@@ -150,22 +150,29 @@ struct wmb_ctx {
     uint8_t *d_hist = nullptr;
     float *d_lut = nullptr;
     ChainBuf cb[WMB_N_CHAINS];
-    uint32_t *d_errors = nullptr, *d_nfail = nullptr, *d_nwords = nullptr;
-    FrameHdr *d_hdr = nullptr;
+    uint32_t *d_errors = nullptr, *d_nfail = nullptr;      /* [0] error bits; d_nfail[0..7]: refuted lanes per verified pass */
+    GatherDev *d_gd = nullptr;      /* gather bookkeeping + statistics                 */
+    BatchRec *d_rec = nullptr;      /* one record per batch since the last read        */
+    FrameHdr *d_hdr = nullptr;      /* result log: candidates ...                      */
+    DecHdr *d_dec = nullptr;        /* ... and K4's verdicts                           */
+    uint32_t log_cap = 0, rec_cap = 0, pend_cap = 0;
     uint32_t *d_words = nullptr;
     uint32_t *d_cut_n = nullptr;
     uint64_t *d_k3_agg = nullptr;
-
-    /* pinned host mirrors */
-    uint32_t *h_small = nullptr;    /* [0] errors [1] nfail [2] nwords */
-    StreamDev *h_sd = nullptr;      /* 4 entries */
-    uint64_t *h_cand = nullptr;
-    FrameHdr *h_hdr = nullptr;
-    DecHdr *d_dec = nullptr, *h_dec = nullptr;       /* K4 results, one per candidate */
-    uint8_t *d_pool = nullptr, *h_pool = nullptr;    /* CRC-stripped datagrams */
+    uint8_t *d_pool = nullptr;      /* CRC-stripped datagrams */
     uint32_t pool_cap = 0;
-    uint32_t *d_pool_n = nullptr;
+
+    /* pinned host mirrors, filled by one copy + one synchronisation per push */
+    struct HostRead { uint32_t errors; uint32_t pad; GatherDev gd; };
+    HostRead *h_read = nullptr;
+    BatchRec *h_rec = nullptr;
+    FrameHdr *h_hdr = nullptr;
+    DecHdr *h_dec = nullptr;
+    uint8_t *h_pool = nullptr;
     uint32_t *h_words = nullptr;
+    uint32_t spec_n = 0, spec_pool = 0;              /* entries / bytes copied before their counts are known */
+    std::vector<uint8_t> batch_final;                /* host side of the batch records: end of input?       */
+    uint64_t stat_rerun_seen = 0, stat_fallback_seen = 0;
 
     /* stream position */
     uint64_t iq_consumed = 0;       /* input IQ samples handed to the device    */
@@ -178,10 +185,6 @@ struct wmb_ctx {
     int64_t last_M = 0;
 
     /* results */
-    std::vector<FrameHdr> out_hdr;
-    std::vector<uint32_t> out_words;
-    std::vector<wmb_frame> out_frames;
-    bool out_final = false;
     uint64_t win_lo = 0, win_hi = ~0ull;             /* line window (access-code match sample) */
     /* manual mode (opts.manual_frames): frames wait here for wmb_poll */
     struct Held { wmb_frame f; std::vector<uint32_t> words; };
@@ -195,6 +198,9 @@ struct wmb_ctx {
 /* --------------------------------------------------------------------------- */
 /* launches                                                                    */
 /* --------------------------------------------------------------------------- */
+
+static uint32_t *gd_field(wmb_ctx *c, size_t off) { return (uint32_t *)((uint8_t *)c->d_gd + off); }
+#define GD_FIELD(c, f) gd_field(c, offsetof(GatherDev, f))
 
 #ifdef WMB_HOSTSIM
 #include "hostsim_launch.inl"
@@ -220,43 +226,62 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     return WMB_OK;
 }
 
+/* speculative pass + verification + on-device fix-up of refuted lanes: no host round trip */
 static int launch_k2a(wmb_ctx *c, int chain, const K2aParams &p, cudaStream_t st)
 {
     const unsigned grid = (p.lanes + K2_THREADS - 1) / K2_THREADS;
-    if (chain == 0) k2a_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, st>>>(p);
-    else            k2a_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, st>>>(p);
-    k2a_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, c->d_nfail);
+    uint32_t *nf = c->d_nfail + chain;
+    if (chain == 0) {
+        k2a_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, st>>>(p);
+        k2a_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, nf);
+        k2a_fixup_kernel<ChainT1C1><<<1, FIX_THREADS, 0, st>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
+    } else {
+        k2a_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, st>>>(p);
+        k2a_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, nf);
+        k2a_fixup_kernel<ChainS1><<<1, FIX_THREADS, 0, st>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
+    }
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 2;
+    c->st.kernel_launches += 3;
     return WMB_OK;
 }
 
 static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p, cudaStream_t st)
 {
     const unsigned grid = (p.lanes + K2_THREADS - 1) / K2_THREADS;
-    if (chain == 0) k2m_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, st>>>(p);
-    else            k2m_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, st>>>(p);
-    k2m_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, c->d_nfail);
+    uint32_t *nf = c->d_nfail + 2 + chain;
+    if (chain == 0) {
+        k2m_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, st>>>(p);
+        k2m_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, nf);
+        k2m_fixup_kernel<ChainT1C1><<<1, FIX_THREADS, 0, st>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
+    } else {
+        k2m_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, st>>>(p);
+        k2m_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, nf);
+        k2m_fixup_kernel<ChainS1><<<1, FIX_THREADS, 0, st>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
+    }
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 2;
+    c->st.kernel_launches += 3;
     return WMB_OK;
 }
 
 static int launch_k2p1(wmb_ctx *c, const K2p1Params &p)
 {
+    uint32_t *nf = c->d_nfail + 4;
     k2p1_lanes_kernel<<<(p.lanes + 127) / 128, 128, 0, c->cs>>>(p);
-    k2p1_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, c->cs>>>(p, c->d_nfail);
+    k2p1_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, c->cs>>>(p, nf);
+    k2p1_fixup_kernel<<<1, FIX_THREADS, 0, c->cs>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 2;
+    c->st.kernel_launches += 3;
     return WMB_OK;
 }
 
 static void launch_cscan(wmb_ctx *c, const uint32_t *cnt, uint64_t *base, uint32_t n, uint64_t *agg, uint64_t *total,
-                         const uint32_t *skip = nullptr, uint32_t *clear = nullptr, uint32_t from_zero = 0, cudaStream_t st = nullptr)
+                         const uint32_t *skip = nullptr, uint32_t *clear = nullptr, uint32_t from_zero = 0, cudaStream_t st = nullptr,
+                         uint32_t skip_invert = 0)
 {
     if (!st) st = c->cs;
     CountScan s;
     s.cnt = cnt; s.base = base; s.n = n; s.agg = agg; s.total = total; s.skip = skip; s.clear = clear; s.from_zero = from_zero;
+    s.skip_invert = skip_invert;
     const unsigned tiles = scan_tiles(n);
     cscan_a_kernel<<<tiles, SCAN_BLOCK, 0, st>>>(s);
     cscan_b_kernel<<<1, 32, 0, st>>>(s);
@@ -264,7 +289,8 @@ static void launch_cscan(wmb_ctx *c, const uint32_t *cnt, uint64_t *base, uint32
     c->st.kernel_launches += 3;
 }
 
-static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, const P1State *p1_end_last, RlState *carry)
+/* two-phase run-length path after phase 1: records -> phase 2 -> ring (the carried state is folded later) */
+static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2)
 {
     launch_cscan(c, pc.cnt, pc.base, pc.lanes, pc.agg, &pc.pd->n_rec, nullptr, &pc.pd->fallback, 1);
     k2pc_compact_kernel<<<pc.lanes, 128, 0, c->cs>>>(pc);
@@ -272,9 +298,25 @@ static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, cons
     k2p2_sum_kernel<<<p2.lanes, K2P2W_THREADS, 0, c->cs>>>(p2);
     launch_cscan(c, p2.cnt, p2.base, p2.lanes, p2.agg, &p2.sd->total, &p2.pd->fallback);
     k2p2_write_kernel<<<p2.lanes, K2P2W_THREADS, 0, c->cs>>>(p2);
-    k2p_fold_kernel<<<1, 32, 0, c->cs>>>(p1_end_last, p2.p2_out, carry, p2.pd);
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 5;
+    c->st.kernel_launches += 4;
+    return WMB_OK;
+}
+
+static int launch_k2p_fold(wmb_ctx *c, const P1State *p1_end_last, RlState *p2_out, RlState *carry, const K2pDev *pd,
+                           const RlState *mono_end)
+{
+    k2p_fold_kernel<<<1, 32, 0, c->cs>>>(p1_end_last, p2_out, carry, pd, mono_end, GD_FIELD(c, rl_fallbacks));
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches += 1;
+    return WMB_OK;
+}
+
+static int launch_k2m_carry(wmb_ctx *c, const RlState *end, RlState *carry, const uint32_t *run_if, cudaStream_t st)
+{
+    k2m_carry_kernel<<<1, 32, 0, st>>>(end, carry, run_if);
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches += 1;
     return WMB_OK;
 }
 
@@ -301,27 +343,37 @@ static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
 
 static int launch_k2c(wmb_ctx *c, const K2cParams &p, cudaStream_t st)
 {
-    launch_cscan(c, p.cnt, p.base, p.lanes, p.agg, &p.sd->total, nullptr, nullptr, 0, st);
+    launch_cscan(c, p.cnt, p.base, p.lanes, p.agg, &p.sd->total, p.run_if, nullptr, 0, st, p.run_if ? 1u : 0u);
     k2c_compact_kernel<<<p.lanes, 128, 0, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches += 1;
     return WMB_OK;
 }
 
-static int launch_k3(wmb_ctx *c, const K3Params &p)
+/* the whole gather + device framer; grids are fixed (the kernels loop over however many candidates there are) */
+static int launch_k3_k4(wmb_ctx *c, const K3Params &p, const K4Params *q)
 {
-    k3_size_kernel<<<(p.n + 127) / 128, 128, 0, c->cs>>>(p);
-    k3_cut_kernel<<<p.n, 64, 0, c->cs>>>(p);
+    static int sms = 0;
+    if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    k3_plan_kernel<<<1, 32, 0, c->cs>>>(p);
+    k3_fill_kernel<<<sms * 2, 256, 0, c->cs>>>(p);
+    k3_size_kernel<<<sms, 128, 0, c->cs>>>(p);
+    k3_cut_kernel<<<sms * 8, 64, 0, c->cs>>>(p);
     k3_offsets_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(p);
-    k3_copy_kernel<<<p.n, 128, 0, c->cs>>>(p);
+    k3_copy_kernel<<<sms * 8, 128, 0, c->cs>>>(p);
+    k3_carry_kernel<<<sms, 128, 0, c->cs>>>(p);
+    c->st.kernel_launches += 7;
+    if (q) {
+        k4_decode_kernel<<<sms * 16, K4_THREADS, 0, c->cs>>>(*q);
+        c->st.kernel_launches += 1;
+    }
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 4;
     return WMB_OK;
 }
 
 static int launch_k4(wmb_ctx *c, const K4Params &p)
 {
-    k4_decode_kernel<<<p.n, K4_THREADS, 0, c->cs>>>(p);
+    k4_decode_kernel<<<p.n ? p.n : 1, K4_THREADS, 0, c->cs>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches += 1;
     return WMB_OK;
@@ -466,24 +518,27 @@ static int ctx_alloc(wmb_ctx *c)
     TRY(dev_alloc(c, &c->d_tmp, std::max<size_t>((size_t)c->W * 4, (size_t)k1_hist_bytes(d))));
     TRY(dev_alloc(c, &c->d_lut, 2 * 4096));
     TRY(dev_alloc(c, &c->d_errors, 16, true));
-    c->d_nfail = c->d_errors + 1;
-    c->d_nwords = c->d_errors + 2;
-    c->d_pool_n = c->d_errors + 3;
-    TRY(dev_alloc(c, &c->d_hdr, c->cand_cap));
+    c->d_nfail = c->d_errors + 4;
+    TRY(dev_alloc(c, &c->d_gd, 1, true));
+    c->rec_cap = 1024;
+    TRY(dev_alloc(c, &c->d_rec, c->rec_cap, true));
+    c->log_cap = c->cand_cap;
+    c->pend_cap = 1u << 16;                      /* candidates younger than one telegram at a batch end */
+    TRY(dev_alloc(c, &c->d_hdr, c->log_cap));
+    TRY(dev_alloc(c, &c->d_dec, c->log_cap));
     TRY(dev_alloc(c, &c->d_words, c->frame_words_cap));
     TRY(dev_alloc(c, &c->d_cut_n, c->cand_cap));
     TRY(dev_alloc(c, &c->d_k3_agg, SCAN_THREADS));
-    TRY(host_alloc(c, &c->h_small, 16));
-    TRY(host_alloc(c, &c->h_sd, 4));
-    TRY(host_alloc(c, &c->h_pd, 1));
-    TRY(host_alloc(c, &c->h_cand, c->cand_cap));
-    TRY(host_alloc(c, &c->h_hdr, c->cand_cap));
     c->pool_cap = c->frame_words_cap / 8 + 4 * c->cand_cap;    /* a datagram byte takes >= 8 shipped bit words */
-    TRY(dev_alloc(c, &c->d_dec, c->cand_cap));
-    TRY(host_alloc(c, &c->h_dec, c->cand_cap));
     TRY(dev_alloc(c, &c->d_pool, c->pool_cap));
+    TRY(host_alloc(c, &c->h_read, 1));
+    TRY(host_alloc(c, &c->h_rec, c->rec_cap));
+    TRY(host_alloc(c, &c->h_hdr, c->log_cap));
+    TRY(host_alloc(c, &c->h_dec, c->log_cap));
     TRY(host_alloc(c, &c->h_pool, c->pool_cap));
     TRY(host_alloc(c, &c->h_words, c->frame_words_cap));
+    c->spec_n = std::min<uint32_t>(8192, c->log_cap);
+    c->spec_pool = std::min<uint32_t>(1u << 20, c->pool_cap);
 
     /* mixer look-up tables, built with the host libm exactly like the reference
      * (setup_lookup_tables_for_frequency_translation, rtl_wmbus.c:974-993) */
@@ -556,6 +611,7 @@ static int ctx_alloc(wmb_ctx *c)
             TRY(dev_alloc(c, &s.ring, s.ring_cap));
             TRY(dev_alloc(c, &s.sd, 1, true));
             TRY(dev_alloc(c, &s.cand, c->cand_cap));
+            TRY(dev_alloc(c, &s.pend, c->pend_cap));
             TRY(dev_alloc(c, &s.agg, n_agg));
         }
     }
@@ -672,27 +728,10 @@ static int slide_history(wmb_ctx *c, void *buf, size_t es, int64_t hist, int64_t
     return WMB_OK;
 }
 
-/* run `launch(mode)` for all chains, then re-run refuted lanes until every lane's start state
- * equals its predecessor's end state */
-template <typename F>
-static int verified_pass(wmb_ctx *c, uint32_t lanes, F launch)
-{
-    CUDA_TRY(cudaMemsetAsync(c->d_nfail, 0, 4, c->cs));
-    TRY(launch(0u));
-    for (int round = 0;; round++) {
-        CUDA_TRY(cudaMemcpyAsync(&c->h_small[1], c->d_nfail, 4, cudaMemcpyDeviceToHost, c->cs));
-        CUDA_TRY(cudaStreamSynchronize(c->cs));
-        const uint32_t nfail = c->h_small[1];
-        if (!nfail) return WMB_OK;
-        if (round > (int)lanes + 2) return set_err(WMB_E_STATE, "internal: lane verification does not converge");
-        c->st.lanes_rerun += nfail;
-        c->st.lanes_run += nfail;
-        CUDA_TRY(cudaMemsetAsync(c->d_nfail, 0, 4, c->cs));
-        TRY(launch(1u));
-    }
-}
-
-/* Enqueue the whole device pass for one batch whose bytes are at `src` (device memory). */
+/* Enqueue the per-sample device pass for one batch whose bytes are at `src` (device memory): demod and bit sync.
+ * Nothing here waits for the device: refuted speculative lanes are re-run by on-device fix-up kernels, and the
+ * fallback from the two-phase run-length path to the monolithic lanes is a set of kernels that do nothing unless the
+ * device flag asks for them. */
 static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_ctx_buffer)
 {
     tr("batch-start");
@@ -745,22 +784,27 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
     const int64_t wofs = c->W / 32;                       /* word offset of batch sample 0 */
 
     if (any_sync) {
-        /* ---- K2a: clock-recovery lanes (both chains), verified ---- */
-        K2aParams ka[WMB_N_CHAINS];
+        /* ---- K2a: clock-recovery lanes (both chains), verified ----
+         * (measured: the two chains' clock lanes side by side are SLOWER, 8.3 vs 7.2 ms of bit sync per GiB --
+         * each already fills the fp32 pipe of its scheduler; only the run-length lanes below share the GPU) */
         for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
             if (!(c->chains & (1u << ch))) continue;
             ChainBuf &b = c->cb[ch];
-            K2aParams &p = ka[ch];
+            K2aParams p;
             memset(&p, 0, sizeof(p));
             p.dphi = b.dphi + c->W; p.M = M; p.hist = c->hist_m; p.C = C; p.W = c->W_a[ch]; p.lanes = lanes;
             p.dbits = b.dbits + wofs; p.sbits = b.sbits + wofs;
             p.cbits = b.cbits ? b.cbits + wofs : nullptr;
             p.st_start = b.ia_start; p.st_end = b.ia_end; p.carry = b.ia_carry; p.rerun = b.rerun;
             p.dc = c->o.remove_dc; p.t2 = c->o.t2_enabled;
+            p.mode = 0;
             c->st.lanes_run += lanes;
+            TRY(launch_k2a(c, ch, p, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(b.ia_carry, b.ia_end + (lanes - 1), sizeof(IirState), cudaMemcpyDeviceToDevice, c->cs));
         }
-        /* chain 1's run-length lanes can run on their own stream (forked after whatever cs holds, joined before
-         * the verdict is read) */
+        tr("k1+k2a");
+
+        /* chain 1's run-length lanes run on their own stream (forked after whatever cs holds, joined at the end) */
         auto fork2 = [&]() -> int {
             CUDA_TRY(cudaEventRecord(c->ev_fork2, c->cs));
             CUDA_TRY(cudaStreamWaitEvent(c->s2, c->ev_fork2, 0));
@@ -771,24 +815,6 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_join2, 0));
             return WMB_OK;
         };
-        /* (measured: the two chains' clock lanes side by side are SLOWER, 8.3 vs 7.2 ms of bit sync per GiB --
-         * each already fills the fp32 pipe of its scheduler; only the run-length lanes below share the GPU) */
-        const bool both = false;
-        TRY(verified_pass(c, lanes, [&](uint32_t mode) {
-            if (both) TRY(fork2());
-            for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-                if (!(c->chains & (1u << ch))) continue;
-                ka[ch].mode = mode;
-                TRY(launch_k2a(c, ch, ka[ch], (both && ch == 1) ? c->s2 : c->cs));
-            }
-            if (both) TRY(join2());
-            return (int)WMB_OK;
-        }));
-        tr("k1+k2a");
-        for (int ch = 0; ch < WMB_N_CHAINS; ch++)
-            if (c->chains & (1u << ch))
-                CUDA_TRY(cudaMemcpyAsync(c->cb[ch].ia_carry, c->cb[ch].ia_end + (lanes - 1), sizeof(IirState),
-                                         cudaMemcpyDeviceToDevice, c->cs));
 
         /* ---- K2t: time2 bit streams straight into the rings (own stream: independent of the
          *      run-length kernels below, and both leave most of the GPU idle on their own) ---- */
@@ -818,12 +844,10 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
         /* ---- run-length bit sync ---- */
         if (c->o.rla_enabled) {
             const bool two = (c->chains & 1u) && c->two_phase;
-            /* chains that take the monolithic lanes: S1 always, T1/C1 when forced (tests) */
-            uint32_t mono = (c->chains & 2u) | (((c->chains & 1u) && !two) ? 1u : 0u);
-            K2p1Params p1;
+            /* chains that take the monolithic lanes unconditionally: S1 always, T1/C1 when forced (tests) */
+            const uint32_t mono = (c->chains & 2u) | (((c->chains & 1u) && !two) ? 1u : 0u);
             K2mParams km[WMB_N_CHAINS];
-            memset(&p1, 0, sizeof(p1));
-            auto setup_mono = [&](int ch) -> int {
+            auto setup_mono = [&](int ch, const uint32_t *run_if) -> int {
                 ChainBuf &b = c->cb[ch];
                 K2mParams &p = km[ch];
                 memset(&p, 0, sizeof(p));
@@ -834,53 +858,46 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
                 p.ev = b.s[WMB_ALGO_RLA].ev; p.cnt = b.s[WMB_ALGO_RLA].cnt;
                 p.st_start = b.rl_start; p.st_end = b.rl_end; p.carry = b.rl_carry; p.rerun = b.rerun;
                 p.errors = c->d_errors;
-                c->st.lanes_run += lanes;
+                p.mode = 0; p.run_if = run_if;
+                if (!run_if) c->st.lanes_run += lanes;
                 return WMB_OK;
             };
-            auto finish_mono = [&](int ch, cudaStream_t st) -> int {          /* carry + compaction into the ring */
+            auto compact_mono = [&](int ch, cudaStream_t st, const uint32_t *run_if) -> int {       /* lane events -> ring */
                 ChainBuf &b = c->cb[ch];
                 Stream &s = b.s[WMB_ALGO_RLA];
-                CUDA_TRY(cudaMemcpyAsync(b.rl_carry, b.rl_end + (lanes - 1), sizeof(RlState), cudaMemcpyDeviceToDevice, st));
                 K2cParams q;
                 memset(&q, 0, sizeof(q));
                 q.ev = s.ev; q.cnt = s.cnt; q.base = s.base; q.lanes = lanes; q.cap = km[ch].cap; q.C = C;
                 q.m_base = (int64_t)c->m_consumed;
                 q.ring = s.ring; q.ring_mask = s.ring_cap - 1; q.sd = s.sd; q.cand = s.cand; q.cand_cap = c->cand_cap;
-                q.agg = s.agg; q.rssi = b.rssi + c->W;
+                q.agg = s.agg; q.rssi = b.rssi + c->W; q.run_if = run_if;
                 return launch_k2c(c, q, st);
             };
+            /* S1 (and a forced T1/C1) beside the two-phase path of T1/C1 */
+            const bool s1_beside = two && (mono & 2u);
+            if (s1_beside) TRY(fork2());
+            for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+                if (!(mono & (1u << ch))) continue;
+                cudaStream_t st = (s1_beside && ch == 1) ? c->s2 : c->cs;
+                TRY(setup_mono(ch, nullptr));
+                TRY(launch_k2m(c, ch, km[ch], st));
+                TRY(launch_k2m_carry(c, c->cb[ch].rl_end + (lanes - 1), c->cb[ch].rl_carry, nullptr, st));
+                TRY(compact_mono(ch, st, nullptr));
+            }
             if (two) {
                 /* T1/C1: phase 1 (per-sample, verified) -> records -> phase 2 (per-run) */
                 ChainBuf &b = c->cb[0];
+                Stream &s = b.s[WMB_ALGO_RLA];
+                K2p1Params p1;
+                memset(&p1, 0, sizeof(p1));
                 p1.dbits = b.dbits + wofs; p1.M = M; p1.hist = c->hist_m;
                 p1.C = K2P1_CHUNK; p1.W = K2P1_WARM; p1.lanes = (uint32_t)((M + K2P1_CHUNK - 1) / K2P1_CHUNK);
                 p1.cap = K2P1_CAP; p1.rec = b.p1_rec; p1.cnt = b.p1_cnt;
                 p1.st_start = b.p1_start; p1.st_end = b.p1_end; p1.carry = b.rl_carry; p1.rerun = b.p1_rerun;
+                p1.mode = 0;
                 if (p1.lanes > c->p1_lanes_max) return set_err(WMB_E_INVAL, "internal: phase-1 lanes");
                 c->st.lanes_run += p1.lanes;
-            }
-            for (int ch = 0; ch < WMB_N_CHAINS; ch++) if (mono & (1u << ch)) TRY(setup_mono(ch));
-            /* one verified pass for everything that speculates: phase 1 of T1/C1 on cs, the S1 lanes beside it */
-            const bool s1_beside = two && (mono & 2u);
-            if (two || mono) {
-                TRY(verified_pass(c, std::max(lanes, p1.lanes), [&](uint32_t mode) {
-                    if (s1_beside) TRY(fork2());
-                    if (two) { p1.mode = mode; TRY(launch_k2p1(c, p1)); }
-                    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-                        if (!(mono & (1u << ch))) continue;
-                        km[ch].mode = mode;
-                        TRY(launch_k2m(c, ch, km[ch], (s1_beside && ch == 1) ? c->s2 : c->cs));
-                    }
-                    if (s1_beside) TRY(join2());
-                    return (int)WMB_OK;
-                }));
-            }
-            if (s1_beside) TRY(fork2());
-            for (int ch = 0; ch < WMB_N_CHAINS; ch++)
-                if (mono & (1u << ch)) TRY(finish_mono(ch, (s1_beside && ch == 1) ? c->s2 : c->cs));
-            if (two) {
-                ChainBuf &b = c->cb[0];
-                Stream &s = b.s[WMB_ALGO_RLA];
+                TRY(launch_k2p1(c, p1));
                 K2pcParams pc;
                 memset(&pc, 0, sizeof(pc));
                 pc.rec = b.p1_rec; pc.cnt = b.p1_cnt; pc.base = b.p1_base; pc.lanes = p1.lanes; pc.cap = p1.cap; pc.C = p1.C;
@@ -893,25 +910,23 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
                 p2.cnt = b.p2_cnt; p2.base = b.p2_base; p2.rssi = b.rssi + c->W; p2.m_base = (int64_t)c->m_consumed;
                 p2.ring = s.ring; p2.ring_mask = s.ring_cap - 1; p2.sd = s.sd; p2.cand = s.cand; p2.cand_cap = c->cand_cap;
                 p2.carry = b.rl_carry; p2.p2_out = b.p2_out; p2.agg = s.agg;
-                TRY(launch_k2p_rest(c, pc, p2, b.p1_end + (p1.lanes - 1), b.rl_carry));
-                CUDA_TRY(cudaMemcpyAsync(c->h_pd, b.pd, sizeof(K2pDev), cudaMemcpyDeviceToHost, c->cs));
-                if (s1_beside) TRY(join2());
-                CUDA_TRY(cudaStreamSynchronize(c->cs));
-                tr("k2t+p1+p2");
-                if (c->h_pd->fallback) {
-                    /* the second reset rule fired in this batch: redo T1/C1 with the exact monolithic lanes */
-                    c->st.rl_fallbacks++;
-                    TRY(setup_mono(0));
-                    TRY(verified_pass(c, lanes, [&](uint32_t mode) { km[0].mode = mode; return launch_k2m(c, 0, km[0], c->cs); }));
-                    TRY(finish_mono(0, c->cs));
-                }
-            } else if (s1_beside) TRY(join2());
+                TRY(launch_k2p_rest(c, pc, p2));
+                /* the second reset rule (rtl_wmbus.c:756-762) fired somewhere in this batch (pd->fallback, set by phase
+                 * 2, which then wrote nothing): redo T1/C1 with the exact monolithic lanes.  The kernels are always
+                 * enqueued; without the flag every thread returns at once. */
+                const uint32_t *flag = &b.pd->fallback;
+                TRY(setup_mono(0, flag));
+                TRY(launch_k2m(c, 0, km[0], c->cs));
+                TRY(compact_mono(0, c->cs, flag));
+                TRY(launch_k2p_fold(c, b.p1_end + (p1.lanes - 1), b.p2_out, b.rl_carry, b.pd, b.rl_end + (lanes - 1)));
+            }
+            if (s1_beside) TRY(join2());
+            tr("k2t+p1+p2");
         }
     }
     if (any_sync && c->o.t2_enabled) CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_join, 0));
     CUDA_TRY(cudaEventRecord(c->ev_t[2], c->cs));
 
-    tr("mono");
     /* slide the histories: the last W samples move in front of index 0 */
     for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
         if (!(c->chains & (1u << ch))) continue;
@@ -935,130 +950,139 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
     return WMB_OK;
 }
 
-/* Gather frames for all new + pending candidates.  final: end of input. */
-static int gather_frames(wmb_ctx *c, bool final)
+/* Enqueue the frame gather (K3) and the device framer (K4) for everything the streams hold: the candidates carried
+ * over plus the new access-code matches.  final: end of input, nothing is carried over. */
+static int enqueue_gather(wmb_ctx *c, bool final)
 {
     const bool any_sync = c->o.rla_enabled || c->o.t2_enabled;
     if (!any_sync || !c->allocated) return WMB_OK;
-    /* fetch per-stream bookkeeping */
-    int k = 0;
-    Stream *order[4];
-    int och[4], oal[4];
+    if (c->batch_final.size() >= c->rec_cap) return set_err(WMB_E_STATE, "internal: too many batches between two reads");
+    K3Params p;
+    memset(&p, 0, sizeof(p));
     for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
         if (!(c->chains & (1u << ch))) continue;
         for (int a = 0; a < WMB_N_ALGOS; a++) {
             if ((a == WMB_ALGO_RLA && !c->o.rla_enabled) || (a == WMB_ALGO_T2A && !c->o.t2_enabled)) continue;
-            CUDA_TRY(cudaMemcpyAsync(&c->h_sd[k], c->cb[ch].s[a].sd, sizeof(StreamDev), cudaMemcpyDeviceToHost, c->cs));
-            order[k] = &c->cb[ch].s[a]; och[k] = ch; oal[k] = a;
-            k++;
+            Stream &s = c->cb[ch].s[a];
+            const int k = ch * WMB_N_ALGOS + a;
+            p.ring[k] = s.ring; p.ring_mask[k] = s.ring_cap - 1; p.sd[k] = s.sd; p.cand[k] = s.cand; p.pend[k] = s.pend;
         }
     }
-    CUDA_TRY(cudaMemcpyAsync(&c->h_small[0], c->d_errors, 4, cudaMemcpyDeviceToHost, c->cs));
-    CUDA_TRY(cudaStreamSynchronize(c->cs));
-    tr("g-sd");
-    if (c->h_small[0] & 1u) return set_err(WMB_E_OVERFLOW, "bit event buffer overflow (pathological input)");
-    if (c->h_small[0] & 2u) return set_err(WMB_E_OVERFLOW, "run-length tracker left its defined range (the reference would spin here)");
+    p.pend_cap = c->pend_cap; p.cand_cap = c->cand_cap;
+    p.gd = c->d_gd; p.rec = c->d_rec; p.rec_cap = c->rec_cap;
+    p.hdr_log = c->d_hdr; p.dec_log = c->d_dec; p.log_cap = c->log_cap;
+    p.words = c->d_words; p.words_cap = c->frame_words_cap;
+    p.cut_n = c->d_cut_n; p.agg = c->d_k3_agg; p.errors = c->d_errors;
+    p.final = final ? 1u : 0u;
+    p.pool = c->d_pool; p.pool_cap = c->pool_cap;
+    K4Params q;
+    memset(&q, 0, sizeof(q));
+    q.hdr = c->d_hdr; q.words = c->d_words; q.dec = c->d_dec;
+    q.pool = c->d_pool; q.pool_cap = c->pool_cap; q.pool_n = GD_FIELD(c, pool_n); q.errors = c->d_errors; q.gd = c->d_gd;
+    TRY(launch_k3_k4(c, p, c->manual ? nullptr : &q));
+    c->batch_final.push_back(final ? 1 : 0);
+    return WMB_OK;
+}
 
-    std::vector<FrameHdr> hdr;
-    for (int i = 0; i < k; i++) {
-        Stream &s = *order[i];
-        const StreamDev sd = c->h_sd[i];
-        if (sd.cand_overflow) return set_err(WMB_E_OVERFLOW, "too many access-code matches in one batch");
-        if (sd.total - s.total > s.ring_cap - WMB_MAXBITS - 64) return set_err(WMB_E_OVERFLOW, "bit event ring overflow");
-        s.total = sd.total;
-        std::vector<uint64_t> cand(s.pending);
-        if (sd.n_cand) {
-            CUDA_TRY(cudaMemcpyAsync(c->h_cand, s.cand, (size_t)sd.n_cand * 8, cudaMemcpyDeviceToHost, c->cs));
-            CUDA_TRY(cudaStreamSynchronize(c->cs));
-            cand.insert(cand.end(), c->h_cand, c->h_cand + sd.n_cand);
-            c->st.candidates[och[i]][oal[i]] += sd.n_cand;
-            CUDA_TRY(cudaMemsetAsync(&s.sd->n_cand, 0, 4, c->cs));
-        }
-        std::sort(cand.begin(), cand.end());
-        for (uint64_t ord : cand) {
-            FrameHdr h;
-            memset(&h, 0, sizeof(h));
-            h.ordinal = ord; h.chain = (uint8_t)och[i]; h.algo = (uint8_t)oal[i];
-            hdr.push_back(h);
-        }
-        s.pending.clear();
-    }
-    tr("g-cand");
-    c->out_hdr.clear(); c->out_words.clear(); c->out_frames.clear();
-    if (hdr.empty()) return WMB_OK;
-    if (hdr.size() > c->cand_cap) return set_err(WMB_E_OVERFLOW, "too many pending candidates");
+static int book_device_frames(wmb_ctx *c, const FrameHdr *hdr, const DecHdr *dec, size_t n, bool final);
 
-    K3Params p;
-    memset(&p, 0, sizeof(p));
-    for (int i = 0; i < k; i++) {
-        p.ring[och[i]][oal[i]] = order[i]->ring;
-        p.ring_mask[och[i]][oal[i]] = order[i]->ring_cap - 1;
-        p.total[och[i]][oal[i]] = order[i]->total;
-    }
-    memcpy(c->h_hdr, hdr.data(), hdr.size() * sizeof(FrameHdr));
-    CUDA_TRY(cudaMemcpyAsync(c->d_hdr, c->h_hdr, hdr.size() * sizeof(FrameHdr), cudaMemcpyHostToDevice, c->cs));
-    p.hdr = c->d_hdr; p.n = (uint32_t)hdr.size();
-    p.words = c->d_words; p.words_cap = c->frame_words_cap; p.n_words = c->d_nwords; p.errors = c->d_errors;
-    p.cut_n = c->d_cut_n; p.agg = c->d_k3_agg;
-    int rc = launch_k3(c, p);
-    if (rc) return rc;
-    const size_t nf = hdr.size();
+/* Fetch what the gathers since the last read produced -- one set of copies and ONE synchronisation in the common
+ * case (the counts travel with a prefix of the arrays they describe; a second copy follows only when a push produced
+ * more than that prefix) -- and run the stream-order bookkeeping over it, batch by batch. */
+static int read_results(wmb_ctx *c)
+{
+    if (c->batch_final.empty()) return WMB_OK;
+    const size_t nrec = c->batch_final.size();
     const bool dev_decode = !c->manual;
+    CUDA_TRY(cudaMemcpyAsync(&c->h_read->errors, c->d_errors, 4, cudaMemcpyDeviceToHost, c->cs));
+    CUDA_TRY(cudaMemcpyAsync(&c->h_read->gd, c->d_gd, sizeof(GatherDev), cudaMemcpyDeviceToHost, c->cs));
+    CUDA_TRY(cudaMemcpyAsync(c->h_rec, c->d_rec, nrec * sizeof(BatchRec), cudaMemcpyDeviceToHost, c->cs));
+    CUDA_TRY(cudaMemcpyAsync(c->h_hdr, c->d_hdr, (size_t)c->spec_n * sizeof(FrameHdr), cudaMemcpyDeviceToHost, c->cs));
     if (dev_decode) {
-        /* K4: decode every candidate on the device; only the verdicts and the datagrams travel */
-        CUDA_TRY(cudaMemsetAsync(c->d_pool_n, 0, 4, c->cs));
-        K4Params q;
-        memset(&q, 0, sizeof(q));
-        q.hdr = c->d_hdr; q.n = (uint32_t)nf; q.words = c->d_words; q.dec = c->d_dec;
-        q.pool = c->d_pool; q.pool_cap = c->pool_cap; q.pool_n = c->d_pool_n; q.errors = c->d_errors;
-        rc = launch_k4(c, q);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(c->h_dec, c->d_dec, nf * sizeof(DecHdr), cudaMemcpyDeviceToHost, c->cs));
-        CUDA_TRY(cudaMemcpyAsync(&c->h_small[3], c->d_pool_n, 4, cudaMemcpyDeviceToHost, c->cs));
+        CUDA_TRY(cudaMemcpyAsync(c->h_dec, c->d_dec, (size_t)c->spec_n * sizeof(DecHdr), cudaMemcpyDeviceToHost, c->cs));
+        CUDA_TRY(cudaMemcpyAsync(c->h_pool, c->d_pool, c->spec_pool, cudaMemcpyDeviceToHost, c->cs));
     }
-    CUDA_TRY(cudaMemcpyAsync(c->h_hdr, c->d_hdr, nf * sizeof(FrameHdr), cudaMemcpyDeviceToHost, c->cs));
-    CUDA_TRY(cudaMemcpyAsync(&c->h_small[2], c->d_nwords, 4, cudaMemcpyDeviceToHost, c->cs));
-    CUDA_TRY(cudaMemcpyAsync(&c->h_small[0], c->d_errors, 4, cudaMemcpyDeviceToHost, c->cs));
     CUDA_TRY(cudaStreamSynchronize(c->cs));
-    tr("g-k3");
-    if (c->h_small[0] & 4u) return set_err(WMB_E_OVERFLOW, "frame buffer overflow");
-    if (c->h_small[0] & 8u) return set_err(WMB_E_OVERFLOW, "datagram pool overflow");
-    const uint32_t nwords = c->h_small[2];
-    c->st.d2h_bytes += nf * sizeof(FrameHdr);
-    if (dev_decode) {
-        const uint32_t npool = c->h_small[3];
-        if (npool) {
-            CUDA_TRY(cudaMemcpyAsync(c->h_pool, c->d_pool, npool, cudaMemcpyDeviceToHost, c->cs));
-            CUDA_TRY(cudaStreamSynchronize(c->cs));
-        }
-        c->st.d2h_bytes += npool + nf * sizeof(DecHdr);
-    } else if (nwords) {
-        CUDA_TRY(cudaMemcpyAsync(c->h_words, c->d_words, (size_t)nwords * 4, cudaMemcpyDeviceToHost, c->cs));
-        CUDA_TRY(cudaStreamSynchronize(c->cs));
-        c->st.d2h_bytes += (uint64_t)nwords * 4;
+    tr("read-1");
+    const uint32_t err = c->h_read->errors;
+    const GatherDev &g = c->h_read->gd;
+    if (err & 1u) return set_err(WMB_E_OVERFLOW, "bit event buffer overflow (pathological input)");
+    if (err & 2u) return set_err(WMB_E_OVERFLOW, "run-length tracker left its defined range (the reference would spin here)");
+    if (err & 4u) return set_err(WMB_E_OVERFLOW, "frame buffer overflow");
+    if (err & 8u) return set_err(WMB_E_OVERFLOW, "datagram pool overflow");
+    if (err & 16u) return set_err(WMB_E_OVERFLOW, "too many access-code matches in one batch");
+    if (err & 32u) return set_err(WMB_E_OVERFLOW, "bit event ring overflow");
+    if (err & 64u) return set_err(WMB_E_OVERFLOW, "too many pending candidates");
+    if (err & 128u) return set_err(WMB_E_STATE, "internal: batch records exhausted");
+    if (err & 256u) return set_err(WMB_E_STATE, "internal: lane verification does not converge");
+    if (g.n_rec != nrec) return set_err(WMB_E_STATE, "internal: %u batch records for %zu gathers", g.n_rec, nrec);
+    const uint32_t n = g.log_n, npool = g.pool_n;
+    bool more = false;
+    if (n > c->spec_n) {
+        CUDA_TRY(cudaMemcpyAsync(c->h_hdr + c->spec_n, c->d_hdr + c->spec_n, (size_t)(n - c->spec_n) * sizeof(FrameHdr), cudaMemcpyDeviceToHost, c->cs));
+        if (dev_decode) CUDA_TRY(cudaMemcpyAsync(c->h_dec + c->spec_n, c->d_dec + c->spec_n, (size_t)(n - c->spec_n) * sizeof(DecHdr), cudaMemcpyDeviceToHost, c->cs));
+        more = true;
     }
-    tr("g-d2h");
-
-    c->out_hdr.assign(c->h_hdr, c->h_hdr + nf);
-    c->out_final = final;
+    if (dev_decode && npool > c->spec_pool) {
+        CUDA_TRY(cudaMemcpyAsync(c->h_pool + c->spec_pool, c->d_pool + c->spec_pool, npool - c->spec_pool, cudaMemcpyDeviceToHost, c->cs));
+        more = true;
+    }
+    if (!dev_decode && g.n_words) {
+        CUDA_TRY(cudaMemcpyAsync(c->h_words, c->d_words, (size_t)g.n_words * 4, cudaMemcpyDeviceToHost, c->cs));
+        c->st.d2h_bytes += (uint64_t)g.n_words * 4;
+        more = true;
+    }
+    /* empty the log for the next push (log_n, pool_n, n_rec are adjacent) */
+    CUDA_TRY(cudaMemsetAsync(GD_FIELD(c, log_n), 0, 12, c->cs));
+    if (more) CUDA_TRY(cudaStreamSynchronize(c->cs));
+    tr("read-2");
+    c->st.d2h_bytes += sizeof(*c->h_read) + nrec * sizeof(BatchRec) + (size_t)n * sizeof(FrameHdr) +
+                       (dev_decode ? (size_t)n * sizeof(DecHdr) + npool : 0);
+    /* statistics kept on the device */
+    c->st.lanes_rerun += g.lanes_rerun - c->stat_rerun_seen; c->st.lanes_run += g.lanes_rerun - c->stat_rerun_seen;
+    c->stat_rerun_seen = g.lanes_rerun;
+    c->st.rl_fallbacks += g.rl_fallbacks - c->stat_fallback_seen;
+    c->stat_fallback_seen = g.rl_fallbacks;
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++)
+        for (int a = 0; a < WMB_N_ALGOS; a++) {
+            const int k = ch * WMB_N_ALGOS + a;
+            c->st.candidates[ch][a] = g.n_cand_total[k];
+            c->cb[ch].s[a].total = g.total_prev[k];
+        }
     /* the device keeps 40 bits of the sample index; widen to the 64-bit stream position: the newest value
      * congruent to it that is not beyond the samples produced so far */
-    for (FrameHdr &h : c->out_hdr)
-        h.sync_sample = c->m_consumed - ((c->m_consumed - h.sync_sample) & EVG_M_MASK);
-    /* frames point straight into the pinned copy; it stays valid until the next gather */
-    for (const FrameHdr &h : c->out_hdr) {
-        if (!h.complete && !final) c->cb[h.chain].s[h.algo].pending.push_back(h.ordinal);
-        if (h.nbits == 0 || dev_decode) continue;
-        wmb_frame f;
-        memset(&f, 0, sizeof(f));
-        f.sync_sample = h.sync_sample; f.ordinal = h.ordinal; f.chain = h.chain; f.algo = h.algo;
-        f.truncated = (uint8_t)((h.complete && !h.cut) ? 0 : 1);
-        f.reserved = (uint8_t)((!h.complete && !final) ? 1 : 0);      /* partial: will be re-delivered */
-        f.nbits = h.nbits;
-        f.bits = c->h_words + h.word_off;
-        c->out_frames.push_back(f);
+    for (uint32_t i = 0; i < n; i++)
+        c->h_hdr[i].sync_sample = c->m_consumed - ((c->m_consumed - c->h_hdr[i].sync_sample) & EVG_M_MASK);
+
+    int rc = WMB_OK;
+    for (size_t r = 0; r < nrec && rc == WMB_OK; r++) {
+        const BatchRec &br = c->h_rec[r];
+        const bool final = c->batch_final[r] != 0;
+        if ((uint64_t)br.base + br.n > n) { rc = set_err(WMB_E_STATE, "internal: batch record beyond the log"); break; }
+        if (dev_decode) {
+            rc = book_device_frames(c, c->h_hdr + br.base, c->h_dec + br.base, br.n, final);
+            continue;
+        }
+        /* manual mode (one batch per read): keep the frames (newest version of a re-delivered partial one wins) for wmb_poll */
+        for (uint32_t i = 0; i < br.n; i++) {
+            const FrameHdr &h = c->h_hdr[br.base + i];
+            if (h.nbits == 0) continue;
+            wmb_frame f;
+            memset(&f, 0, sizeof(f));
+            f.sync_sample = h.sync_sample; f.ordinal = h.ordinal; f.chain = h.chain; f.algo = h.algo;
+            f.truncated = (uint8_t)((h.complete && !h.cut) ? 0 : 1);
+            f.reserved = (uint8_t)((!h.complete && !final) ? 1 : 0);      /* partial: will be re-delivered */
+            f.nbits = h.nbits;
+            wmb_ctx::Held *slot = nullptr;
+            for (auto &hh : c->held)
+                if (hh.f.chain == f.chain && hh.f.algo == f.algo && hh.f.ordinal == f.ordinal) { slot = &hh; break; }
+            if (!slot) { c->held.emplace_back(); slot = &c->held.back(); }
+            slot->f = f;
+            slot->words.assign(c->h_words + h.word_off, c->h_words + h.word_off + h.nbits);
+        }
     }
-    return WMB_OK;
+    c->batch_final.clear();
+    return rc;
 }
 
 static void read_timers(wmb_ctx *c)
@@ -1073,12 +1097,6 @@ static void read_timers(wmb_ctx *c)
 /* push / poll                                                                 */
 /* --------------------------------------------------------------------------- */
 
-/* frames gathered after each batch are appended here until the caller polls */
-struct FrameStore {
-    std::vector<FrameHdr> hdr;
-    std::vector<uint32_t> words;
-};
-
 static int process_device_batches(wmb_ctx *c, const uint8_t *dev, size_t nbytes, bool final);
 
 static double wall_ms()
@@ -1088,34 +1106,20 @@ static double wall_ms()
     return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
 }
 
-static int book_device_frames(wmb_ctx *c);
-
+/* gather what the last batch produced and bring the results to the host */
 static int finish_batch(wmb_ctx *c, bool final)
 {
     const double t0 = wall_ms();
-    int rc = gather_frames(c, final);
+    int rc = enqueue_gather(c, final);
     if (rc) return rc;
-    read_timers(c);
     const double t1 = wall_ms();
     c->st.host_gather_ms += t1 - t0;
-    if (!c->manual) {
-        rc = book_device_frames(c);
-        c->st.host_decode_ms += wall_ms() - t1;
-        tr("decode");
-        tr_dump();
-        return rc;
-    }
-    if (c->out_frames.empty()) return WMB_OK;
-    /* manual mode: keep the frames (newest version of a re-delivered partial one wins) for wmb_poll */
-    for (const wmb_frame &f : c->out_frames) {
-        wmb_ctx::Held *slot = nullptr;
-        for (auto &h : c->held)
-            if (h.f.chain == f.chain && h.f.algo == f.algo && h.f.ordinal == f.ordinal) { slot = &h; break; }
-        if (!slot) { c->held.emplace_back(); slot = &c->held.back(); }
-        slot->f = f;
-        slot->words.assign(f.bits, f.bits + f.nbits);
-    }
-    return WMB_OK;
+    rc = read_results(c);
+    read_timers(c);
+    c->st.host_decode_ms += wall_ms() - t1;
+    tr("decode");
+    tr_dump();
+    return rc;
 }
 
 static size_t batch_granule(const wmb_ctx *c) { return (size_t)4096 * c->d; }
@@ -1342,14 +1346,10 @@ static int book_frames(wmb_ctx *c, size_t n, Meta meta, Lite lite, Fill fill)
     return WMB_OK;
 }
 
-/* candidates of the last gather, decoded by K4 (already in stream order) */
-static int book_device_frames(wmb_ctx *c)
+/* candidates of one gathered batch, decoded by K4 (already in stream order) */
+static int book_device_frames(wmb_ctx *c, const FrameHdr *hdr, const DecHdr *dec, size_t n, bool final)
 {
     static const char modes[3][3] = { "T1", "C1", "S1" };
-    const size_t n = c->out_hdr.size();
-    const FrameHdr *hdr = c->out_hdr.data();
-    const DecHdr *dec = c->h_dec;
-    const bool final = c->out_final;
     /* frames without any bit (candidate at the very end of the stream) are not decoded at all */
     std::vector<uint32_t> idx;
     idx.reserve(n);
@@ -1400,14 +1400,16 @@ extern "C" int wmb_frame_decode_device(wmb_ctx *c, const wmb_frame *frames, size
     }
     CUDA_TRY(cudaMemcpyAsync(c->d_hdr, c->h_hdr, n * sizeof(FrameHdr), cudaMemcpyHostToDevice, c->cs));
     CUDA_TRY(cudaMemcpyAsync(c->d_words, c->h_words, words * 4, cudaMemcpyHostToDevice, c->cs));
-    CUDA_TRY(cudaMemsetAsync(c->d_pool_n, 0, 4, c->cs));
+    if (!c->batch_final.empty()) return set_err(WMB_E_STATE, "unread results");
+    CUDA_TRY(cudaMemsetAsync(GD_FIELD(c, pool_n), 0, 4, c->cs));
     K4Params q;
     memset(&q, 0, sizeof(q));
     q.hdr = c->d_hdr; q.n = (uint32_t)n; q.words = c->d_words; q.dec = c->d_dec;
-    q.pool = c->d_pool; q.pool_cap = c->pool_cap; q.pool_n = c->d_pool_n; q.errors = c->d_errors;
+    q.pool = c->d_pool; q.pool_cap = c->pool_cap; q.pool_n = GD_FIELD(c, pool_n); q.errors = c->d_errors;
     TRY(launch_k4(c, q));
     CUDA_TRY(cudaMemcpyAsync(c->h_dec, c->d_dec, n * sizeof(DecHdr), cudaMemcpyDeviceToHost, c->cs));
     CUDA_TRY(cudaMemcpyAsync(c->h_pool, c->d_pool, c->pool_cap < (1u << 24) ? c->pool_cap : (1u << 24), cudaMemcpyDeviceToHost, c->cs));
+    CUDA_TRY(cudaMemsetAsync(GD_FIELD(c, pool_n), 0, 4, c->cs));
     CUDA_TRY(cudaStreamSynchronize(c->cs));
     static const char modes[3][3] = { "T1", "C1", "S1" };
     for (size_t i = 0; i < n; i++) {
@@ -1541,9 +1543,11 @@ extern "C" int wmb_reset(wmb_ctx *c)
     if (c->xs) CUDA_TRY(cudaStreamSynchronize(c->xs));
     c->iq_consumed = 0; c->m_consumed = 0; c->hist_m = 0; c->hist_iq = 0;
     c->remainder.clear(); c->lines.clear(); c->held.clear(); c->held_prev.clear();
-    c->out_frames.clear(); c->batch_no = 0; c->last_M = 0;
+    c->batch_no = 0; c->last_M = 0; c->batch_final.clear();
     if (c->allocated) {
         CUDA_TRY(cudaMemsetAsync(c->d_errors, 0, 64, c->cs));
+        CUDA_TRY(cudaMemsetAsync(c->d_gd, 0, sizeof(GatherDev), c->cs));
+        c->stat_rerun_seen = 0; c->stat_fallback_seen = 0;
         for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
             if (!(c->chains & (1u << ch))) continue;
             ChainBuf &b = c->cb[ch];
@@ -1556,7 +1560,7 @@ extern "C" int wmb_reset(wmb_ctx *c)
             for (int a = 0; a < WMB_N_ALGOS; a++) {
                 Stream &s = b.s[a];
                 CUDA_TRY(cudaMemsetAsync(s.sd, 0, sizeof(StreamDev), c->cs));
-                s.total = 0; s.total_prev = 0; s.pending.clear(); s.busy_until = -1;
+                s.total = 0; s.total_prev = 0; s.busy_until = -1;
             }
         }
         CUDA_TRY(cudaStreamSynchronize(c->cs));
@@ -1589,7 +1593,11 @@ extern "C" long wmb_boundary_state(wmb_ctx *c, uint8_t *buf, size_t cap)
     CUDA_TRY(cudaSetDevice(c->device));
     int rc = ctx_alloc(c);
     if (rc) return rc;
+    rc = read_results(c);                               /* every enqueued batch is gathered and booked first */
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->cs));
+    GatherDev gd;
+    CUDA_TRY(cudaMemcpy(&gd, c->d_gd, sizeof(gd), cudaMemcpyDeviceToHost));
     std::vector<uint8_t> out;
     auto put = [&](const void *p, size_t n) { const uint8_t *b = (const uint8_t *)p; out.insert(out.end(), b, b + n); };
     const uint64_t pos[2] = { c->iq_consumed, c->m_consumed };
@@ -1615,7 +1623,8 @@ extern "C" long wmb_boundary_state(wmb_ctx *c, uint8_t *buf, size_t cap)
             const uint32_t sr = (a == WMB_ALGO_T2A) ? sd.t2_sr : 0u;
             put(&sr, 4);
             /* telegrams in flight: their bit events so far (sample, rssi, flags, bit are all in the word) */
-            std::vector<uint64_t> pend(s.pending);
+            std::vector<uint64_t> pend(gd.n_pend[ch * WMB_N_ALGOS + a]);
+            if (!pend.empty()) CUDA_TRY(cudaMemcpy(pend.data(), s.pend, pend.size() * 8, cudaMemcpyDeviceToHost));
             std::sort(pend.begin(), pend.end());
             const uint32_t np = (uint32_t)pend.size();
             put(&np, 4);

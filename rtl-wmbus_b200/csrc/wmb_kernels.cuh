@@ -518,11 +518,13 @@ struct K2cParams {
     uint64_t *cand; uint32_t cand_cap;      /* out: ordinals of access-code matches        */
     uint64_t *agg;                  /* [SCAN_THREADS] scan scratch                         */
     const uint8_t *rssi;            /* (unsigned)rssi, index 0 = batch sample 0            */
+    const uint32_t *run_if;         /* optional: only if this word is nonzero              */
 };
 
 WMB_D void k2c_compact(const K2cParams &p, uint32_t lane, int tid, int nthr)
 {
     if (lane >= p.lanes) return;
+    if (p.run_if && !*p.run_if) return;
     const uint32_t n = p.cnt[lane];
     const uint64_t base = p.base[lane];
     const uint32_t *src = p.ev + (size_t)lane * p.cap;
@@ -547,8 +549,16 @@ WMB_D void k2c_compact(const K2cParams &p, uint32_t lane, int tid, int nthr)
 }
 
 /* =========================================================================== */
-/* K3: frame gather                                                            */
+/* K3: frame gather -- driven entirely from the device                         */
 /* =========================================================================== */
+/* After the bit-sync kernels of a batch every (chain, algorithm) stream holds its new access-code matches as an
+ * unordered list of ordinals (appended with atomics) next to the candidates the previous batch could not complete.
+ * The gather orders them, looks at each candidate's header to see how many bits a framer can ask for, cuts
+ * run-length lists at resets, copies the bits, keeps the still incomplete candidates for the next batch and hands
+ * the complete list to K4.  Nothing here needs the host: counts live in GatherDev, kernels are grid-stride loops
+ * over however many candidates there are, results are appended to a log the host reads once per push. */
+
+#define WMB_N_STREAMS (WMB_N_CHAINS * WMB_N_ALGOS)          /* stream k = chain * WMB_N_ALGOS + algo */
 
 struct FrameHdr {                   /* one per candidate, device -> host                   */
     uint64_t ordinal;
@@ -557,23 +567,104 @@ struct FrameHdr {                   /* one per candidate, device -> host        
     uint32_t word_off;              /* offset into the frame word buffer                   */
     uint8_t  chain, algo;
     uint8_t  complete;              /* 1: all bits the header can ask for (or cut by a reset) */
-    uint8_t  overflow;              /* sample offset did not fit 23 bits                   */
+    uint8_t  overflow;              /* (unused)                                            */
     uint8_t  cut;                   /* 1: list ends at a run-length reset                  */
     uint8_t  pad[3];
 };
 
-struct K3Params {
-    const uint64_t *ring[WMB_N_CHAINS][WMB_N_ALGOS];
-    uint64_t ring_mask[WMB_N_CHAINS][WMB_N_ALGOS];
-    uint64_t total[WMB_N_CHAINS][WMB_N_ALGOS];
-    FrameHdr *hdr;                  /* in: ordinal/chain/algo filled by host; out: the rest */
-    uint32_t n;
-    uint32_t *words; uint32_t words_cap;
-    uint32_t *n_words;              /* out: total words used                               */
-    uint32_t *cut_n;                /* [n] scratch: list length before the reset cut       */
-    uint64_t *agg;                  /* [SCAN_THREADS] scan scratch                         */
-    uint32_t *errors;
+struct GatherDev {                  /* device-resident state of the gather, one per context */
+    uint32_t n;                     /* candidates of the current batch                      */
+    uint32_t base;                  /* where they start in the result log                   */
+    uint32_t n_words;               /* frame words of the current batch                     */
+    uint32_t log_n;                 /* log entries since the host last emptied the log      */
+    uint32_t pool_n;                /* datagram bytes since then                            */
+    uint32_t n_rec;                 /* batch records since then                             */
+    uint32_t off[WMB_N_STREAMS + 1];/* this batch: first candidate of every stream          */
+    uint32_t n_pend[WMB_N_STREAMS]; /* candidates waiting for more bits                     */
+    uint64_t total_prev[WMB_N_STREAMS];   /* stream totals at the previous gather           */
+    uint64_t n_cand_total[WMB_N_STREAMS]; /* access-code matches since the context was made (statistics) */
+    uint32_t lanes_rerun;           /* statistics: refuted speculative lanes                */
+    uint32_t rl_fallbacks;          /* statistics: batches redone with the monolithic run-length lanes */
 };
+
+struct BatchRec { uint32_t base, n, n_words, final; };      /* one per gathered batch, for the host */
+
+struct DecHdr;
+
+struct K3Params {
+    const uint64_t *ring[WMB_N_STREAMS];
+    uint64_t ring_mask[WMB_N_STREAMS];
+    StreamDev *sd[WMB_N_STREAMS];   /* null: stream not enabled                             */
+    const uint64_t *cand[WMB_N_STREAMS];   /* new matches, unordered                        */
+    uint64_t *pend[WMB_N_STREAMS];  /* carried candidates, ordered                          */
+    uint32_t pend_cap, cand_cap;
+    GatherDev *gd;
+    BatchRec *rec; uint32_t rec_cap;
+    FrameHdr *hdr_log; DecHdr *dec_log; uint32_t log_cap;
+    uint32_t *words; uint32_t words_cap;
+    uint32_t *cut_n;                /* [cand_cap] scratch: list length before the reset cut */
+    uint64_t *agg;                  /* [SCAN_THREADS] scan scratch                          */
+    uint32_t *errors;
+    uint32_t final;                 /* end of input: nothing is carried over                */
+    uint8_t *pool; uint32_t pool_cap;      /* K4: CRC-stripped datagrams                    */
+};
+
+WMB_D void k3_flag(uint32_t *errors, uint32_t bit)
+{
+#ifdef WMB_HOSTSIM
+    *errors |= bit;
+#else
+    atomicOr(errors, bit);
+#endif
+}
+
+/* step 1 (one thread): per-stream counts -> offsets, a place in the log, the batch record */
+WMB_D void k3_plan(const K3Params &p)
+{
+    GatherDev &g = *p.gd;
+    uint32_t n = 0;
+    for (int k = 0; k < WMB_N_STREAMS; k++) {
+        g.off[k] = n;
+        if (!p.sd[k]) continue;
+        StreamDev &sd = *p.sd[k];
+        if (sd.cand_overflow) { k3_flag(p.errors, 16u); sd.cand_overflow = 0; sd.n_cand = p.cand_cap; }
+        if (sd.total - g.total_prev[k] > p.ring_mask[k] + 1 - WMB_MAXBITS - 64) k3_flag(p.errors, 32u);   /* ring overrun */
+        g.total_prev[k] = sd.total;
+        g.n_cand_total[k] += sd.n_cand;
+        n += g.n_pend[k] + sd.n_cand;
+    }
+    g.off[WMB_N_STREAMS] = n;
+    if (n > p.cand_cap || g.log_n + n > p.log_cap) { k3_flag(p.errors, 64u); n = 0; for (int k = 0; k <= WMB_N_STREAMS; k++) g.off[k] = 0; }
+    g.n = n;
+    g.base = g.log_n;
+    g.log_n += n;
+    g.n_words = 0;
+    if (g.n_rec < p.rec_cap) { BatchRec r = { g.base, n, 0u, p.final }; p.rec[g.n_rec] = r; }
+    else k3_flag(p.errors, 128u);
+}
+
+/* step 2 (thread per candidate, any grid): the ordered candidate list of every stream = the candidates carried
+ * over from the previous batch plus the new matches, by rank -- ordinals of one stream are distinct, so the number
+ * of smaller ones is the position.  Matches are a few thousand per GiB (false ones at 2^-16 per bit plus the
+ * telegrams), so the quadratic count is microseconds; the inner loops read one address per warp. */
+WMB_D void k3_fill(const K3Params &p, uint32_t i)
+{
+    const GatherDev &g = *p.gd;
+    if (i >= g.n) return;
+    int k = 0;
+    while (k + 1 < WMB_N_STREAMS && i >= g.off[k + 1]) k++;
+    const uint32_t j = i - g.off[k];
+    const uint32_t np = g.n_pend[k], nn = g.off[k + 1] - g.off[k] - np;
+    const uint64_t key = j < np ? p.pend[k][j] : p.cand[k][j - np];
+    uint32_t rank = 0;
+    for (uint32_t q = 0; q < np; q++) rank += (p.pend[k][q] < key) ? 1u : 0u;
+    for (uint32_t q = 0; q < nn; q++) rank += (p.cand[k][q] < key) ? 1u : 0u;
+    FrameHdr h;
+    h.ordinal = key; h.sync_sample = 0; h.nbits = 0; h.word_off = 0; h.complete = 0; h.overflow = 0; h.cut = 0;
+    h.pad[0] = h.pad[1] = h.pad[2] = 0;
+    h.chain = (uint8_t)(k / WMB_N_ALGOS); h.algo = (uint8_t)(k % WMB_N_ALGOS);
+    p.hdr_log[g.base + g.off[k] + rank] = h;
+}
 
 /* EN 13757-4 3-out-of-6 decode (t1_c1_packet_decoder.h:50-65), 0xFF = invalid */
 WMB_HD uint32_t wmb_dec3of6(uint32_t c)
@@ -628,10 +719,12 @@ WMB_D uint32_t k3_bits_needed(const uint64_t *ring, uint64_t mask, uint64_t ord,
 /* pass 1 (thread per candidate): how many events to ship */
 WMB_D void k3_size(const K3Params &p, uint32_t i)
 {
-    if (i >= p.n) return;
-    FrameHdr &h = p.hdr[i];
-    const uint64_t *ring = p.ring[h.chain][h.algo];
-    const uint64_t mask = p.ring_mask[h.chain][h.algo], total = p.total[h.chain][h.algo];
+    const GatherDev &g = *p.gd;
+    if (i >= g.n) return;
+    FrameHdr &h = p.hdr_log[g.base + i];
+    const int k = h.chain * WMB_N_ALGOS + h.algo;
+    const uint64_t *ring = p.ring[k];
+    const uint64_t mask = p.ring_mask[k], total = p.sd[k]->total;
     const uint64_t avail = total - h.ordinal;
     uint32_t need = k3_bits_needed(ring, mask, h.ordinal, total, h.chain);
     uint32_t n = (need == 0 || need > avail) ? (uint32_t)avail : need;
@@ -646,11 +739,13 @@ WMB_D void k3_size(const K3Params &p, uint32_t i)
  * follows a reset.  Threads stride over the list; the earliest hit wins through an atomic min. */
 WMB_D void k3_cut(const K3Params &p, uint32_t i, int tid, int nthr)
 {
-    if (i >= p.n) return;
-    FrameHdr &h = p.hdr[i];
+    const GatherDev &g = *p.gd;
+    if (i >= g.n) return;
+    FrameHdr &h = p.hdr_log[g.base + i];
     if (h.algo != 0) return;                                  /* time2 never resets */
-    const uint64_t *ring = p.ring[h.chain][h.algo];
-    const uint64_t mask = p.ring_mask[h.chain][h.algo];
+    const int k = h.chain * WMB_N_ALGOS + h.algo;
+    const uint64_t *ring = p.ring[k];
+    const uint64_t mask = p.ring_mask[k];
     const uint32_t n = p.cut_n[i];                            /* list length before cutting (k3_size) */
     for (uint32_t j = 1 + tid; j < n; j += nthr) {
         if (EVG_RESET(ring[(h.ordinal + j) & mask])) {
@@ -667,11 +762,12 @@ WMB_D void k3_cut(const K3Params &p, uint32_t i, int tid, int nthr)
 /* pass 2: exclusive scan of nbits -> word offsets (three-phase block scan) */
 WMB_D void k3_offsets_a(const K3Params &p, uint32_t t)
 {
-    const uint32_t per = scan_per_thread(p.n);
-    const uint32_t i0 = t * per, i1 = (i0 + per < p.n) ? i0 + per : p.n;
+    const GatherDev &g = *p.gd;
+    const uint32_t per = scan_per_thread(g.n);
+    const uint32_t i0 = t * per, i1 = (i0 + per < g.n) ? i0 + per : g.n;
     uint64_t acc = 0;
-    for (uint32_t i = i0; i < i1 && i0 < p.n; i++) {
-        FrameHdr &h = p.hdr[i];
+    for (uint32_t i = i0; i < i1 && i0 < g.n; i++) {
+        FrameHdr &h = p.hdr_log[g.base + i];
         if (h.nbits < p.cut_n[i]) { h.complete = 1; h.cut = 1; }     /* k3_cut found a reset */
         acc += h.nbits;
     }
@@ -679,31 +775,39 @@ WMB_D void k3_offsets_a(const K3Params &p, uint32_t t)
 }
 WMB_D void k3_offsets_b(const K3Params &p)
 {
+    GatherDev &g = *p.gd;
     uint64_t acc = 0;
     for (uint32_t t = 0; t < SCAN_THREADS; t++) { const uint64_t c = p.agg[t]; p.agg[t] = acc; acc += c; }
-    if (acc > p.words_cap) { *p.errors |= 4u; acc = 0; }
-    *p.n_words = (uint32_t)acc;
+    if (acc > p.words_cap) { k3_flag(p.errors, 4u); acc = 0; }
+    g.n_words = (uint32_t)acc;
+    if (g.n_rec < p.rec_cap) p.rec[g.n_rec].n_words = (uint32_t)acc;
+    g.n_rec++;                                                       /* the record is complete */
+    for (int k = 0; k < WMB_N_STREAMS; k++) g.n_pend[k] = 0;         /* k3_carry collects the next batch's */
 }
 WMB_D void k3_offsets_c(const K3Params &p, uint32_t t)
 {
-    const uint32_t per = scan_per_thread(p.n);
-    const uint32_t i0 = t * per, i1 = (i0 + per < p.n) ? i0 + per : p.n;
+    const GatherDev &g = *p.gd;
+    const uint32_t per = scan_per_thread(g.n);
+    const uint32_t i0 = t * per, i1 = (i0 + per < g.n) ? i0 + per : g.n;
     uint64_t acc = p.agg[t];
-    const bool overflow = (*p.n_words == 0);
-    for (uint32_t i = i0; i < i1 && i0 < p.n; i++) {
-        if (overflow) { p.hdr[i].nbits = 0; p.hdr[i].complete = 0; }
-        p.hdr[i].word_off = (uint32_t)acc;
-        acc += p.hdr[i].nbits;
+    const bool overflow = (g.n_words == 0);
+    for (uint32_t i = i0; i < i1 && i0 < g.n; i++) {
+        FrameHdr &h = p.hdr_log[g.base + i];
+        if (overflow) { h.nbits = 0; h.complete = 0; }
+        h.word_off = (uint32_t)acc;
+        acc += h.nbits;
     }
 }
 
 /* pass 3 (block per candidate): copy events as wmb_bit words */
 WMB_D void k3_copy(const K3Params &p, uint32_t i, int tid, int nthr)
 {
-    if (i >= p.n) return;
-    FrameHdr &h = p.hdr[i];
-    const uint64_t *ring = p.ring[h.chain][h.algo];
-    const uint64_t mask = p.ring_mask[h.chain][h.algo];
+    const GatherDev &g = *p.gd;
+    if (i >= g.n) return;
+    const FrameHdr &h = p.hdr_log[g.base + i];
+    const int k = h.chain * WMB_N_ALGOS + h.algo;
+    const uint64_t *ring = p.ring[k];
+    const uint64_t mask = p.ring_mask[k];
     for (uint32_t j = tid; j < h.nbits; j += nthr) {
         const uint64_t e = ring[(h.ordinal + j) & mask];
         /* the ring keeps 40 bits of the sample index (15.9 days at 800 kS/s): differences are taken modulo 2^40.
@@ -713,6 +817,25 @@ WMB_D void k3_copy(const K3Params &p, uint32_t i, int tid, int nthr)
         if (off >= (1u << 23)) off = (1u << 23) - 1;
         p.words[h.word_off + j] = ((uint32_t)off << 9) | (EVG_RSSI(e) << 1) | EVG_BIT(e);
     }
+}
+
+/* pass 4 (thread per candidate, any grid): candidates that are still waiting for bits go to the next batch (any
+ * order: k3_fill ranks them again); the streams' match lists are emptied.  n_pend was zeroed by k3_offsets_b. */
+WMB_D void k3_carry(const K3Params &p, uint32_t i)
+{
+    GatherDev &g = *p.gd;
+    if (i < WMB_N_STREAMS && p.sd[i]) p.sd[i]->n_cand = 0;
+    if (i >= g.n || p.final) return;
+    const FrameHdr &h = p.hdr_log[g.base + i];
+    if (h.complete) return;
+    const int k = h.chain * WMB_N_ALGOS + h.algo;
+#ifdef WMB_HOSTSIM
+    const uint32_t slot = g.n_pend[k]++;
+#else
+    const uint32_t slot = atomicAdd(&g.n_pend[k], 1u);
+#endif
+    if (slot < p.pend_cap) p.pend[k][slot] = h.ordinal;
+    else k3_flag(p.errors, 64u);
 }
 
 
@@ -742,12 +865,15 @@ struct DecHdr {                     /* one per candidate, device -> host        
 };
 
 struct K4Params {
-    const FrameHdr *hdr; uint32_t n;
+    const FrameHdr *hdr; uint32_t n;    /* gd == null: n candidates at hdr / dec (test hook)                       */
     const uint32_t *words;
     DecHdr *dec;
     uint8_t *pool; uint32_t pool_cap; uint32_t *pool_n;
     uint32_t *errors;
+    const GatherDev *gd;                /* else: the current batch's candidates, gd->n of them from gd->base on    */
 };
+
+WMB_D uint32_t k4_count(const K4Params &p) { return p.gd ? p.gd->n : p.n; }
 
 struct K4Smem {
     uint8_t pkt[296];
@@ -817,14 +943,16 @@ WMB_D bool k4_block_ok(const uint8_t *q, uint32_t n)                       /* n 
 
 WMB_D void k4_decode(const K4Params &p, uint32_t f, int tid, int nthr, K4Smem &sm)
 {
-    if (f >= p.n) return;
-    const FrameHdr h = p.hdr[f];
+    if (f >= k4_count(p)) return;
+    const uint32_t lb = p.gd ? p.gd->base : 0u;
+    DecHdr *const dec_out = p.dec + lb;
+    const FrameHdr h = p.hdr[lb + f];
     const uint32_t *b = p.words + h.word_off;
     const uint32_t nbits = h.nbits;
     DecHdr d;
     d.consumed = 0; d.end_off = 0; d.serial = 0; d.data_off = 0; d.len = 0; d.status = K4_SKIP; d.mode = 0;
     d.crc_ok = 0; d.ok_3of6 = 0; d.packet_rssi = 0; d.current_rssi = 0;
-    if (nbits == 0) { if (tid == 0) p.dec[f] = d; return; }
+    if (nbits == 0) { if (tid == 0) dec_out[f] = d; return; }
 
     for (int i = tid; i < 296; i += nthr) sm.pkt[i] = 0;
     if (tid == 0) sm.flags = 0;
@@ -898,7 +1026,7 @@ WMB_D void k4_decode(const K4Params &p, uint32_t f, int tid, int nthr, K4Smem &s
     d.status = (uint8_t)status;
     d.consumed = pos + 1;
     d.end_off = WMB_BIT_OFFSET(b[pos]);
-    if (status != K4_LINE) { if (tid == 0) p.dec[f] = d; return; }
+    if (status != K4_LINE) { if (tid == 0) dec_out[f] = d; return; }
 
     /* block CRCs, one block per thread */
     const uint32_t n = len;
@@ -969,7 +1097,7 @@ WMB_D void k4_decode(const K4Params &p, uint32_t f, int tid, int nthr, K4Smem &s
         d.serial = (uint32_t)sm.pkt[4] | ((uint32_t)sm.pkt[5] << 8) | ((uint32_t)sm.pkt[6] << 16) | ((uint32_t)sm.pkt[7] << 24);
         d.len = (uint16_t)out_len;
         d.data_off = data_off == 0xFFFFFFFFu ? 0 : data_off;
-        p.dec[f] = d;
+        dec_out[f] = d;
     }
 }
 
@@ -1059,13 +1187,83 @@ __global__ void __launch_bounds__(K2P2W_THREADS) k2p2_write_kernel(const K2p2Par
     __syncthreads();
     k2p2w_c(p, blockIdx.x, threadIdx.x, part);
 }
-__global__ void k2p_fold_kernel(const P1State *p1_end, RlState *p2_out, RlState *carry, const K2pDev *pd)
+__global__ void k2p_fold_kernel(const P1State *p1_end, RlState *p2_out, RlState *carry, const K2pDev *pd, const RlState *mono_end,
+                                uint32_t *stat_fallbacks)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) k2p_fold(p1_end, p2_out, carry, pd);
+    if (threadIdx.x == 0 && blockIdx.x == 0) k2p_fold(p1_end, p2_out, carry, pd, mono_end, stat_fallbacks);
+}
+__global__ void k2m_carry_kernel(const RlState *end, RlState *carry, const uint32_t *run_if)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0 && (!run_if || *run_if)) *carry = *end;
+}
+
+/* ---- lane verification without the host ------------------------------------------------------------------------
+ * A speculative pass is followed by its verify kernel (every lane: start state == predecessor's end state?  count
+ * the refuted ones) and by ONE block of the matching fix-up kernel: nothing to do in the common case (n_fail == 0,
+ * a few microseconds); otherwise it re-runs the refuted lanes from their predecessors' exact end states and verifies
+ * again until no lane is refuted -- what the host used to drive with a stream synchronisation per round. */
+#define FIX_THREADS 128
+template <class RERUN, class VERIFY>
+__device__ __forceinline__ void fixup_loop(uint32_t lanes, uint32_t *n_fail, uint32_t *stat_rerun, uint32_t *errors,
+                                           RERUN rerun, VERIFY verify)
+{
+    __shared__ uint32_t s_fail;
+    for (uint32_t round = 0;; round++) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_fail = *(volatile uint32_t *)n_fail;
+        __syncthreads();
+        const uint32_t nf = s_fail;
+        if (nf == 0) return;
+        if (round > lanes + 2) {                                  /* cannot happen: lane 0 is exact, so every round fixes at least one lane */
+            if (threadIdx.x == 0) { atomicOr(errors, 256u); *n_fail = 0; }
+            return;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { atomicAdd(stat_rerun, nf); *n_fail = 0; }
+        __threadfence();
+        __syncthreads();
+        for (uint32_t lane = threadIdx.x; lane < lanes; lane += blockDim.x) rerun(lane);      /* returns at once unless flagged */
+        __threadfence();
+        __syncthreads();
+        for (uint32_t lane = threadIdx.x; lane < lanes; lane += blockDim.x) verify(lane);
+        __threadfence();
+    }
+}
+template <class CH>
+__global__ void __launch_bounds__(FIX_THREADS) k2a_fixup_kernel(K2aParams p, uint32_t *n_fail, uint32_t *stat_rerun, uint32_t *errors)
+{
+    p.mode = 1;
+    fixup_loop(p.lanes, n_fail, stat_rerun, errors, [&](uint32_t lane) { k2a_lane<CH>(p, lane); },
+               [&](uint32_t lane) { k2a_verify_lane(p, lane, n_fail); });
+}
+template <class CH>
+__global__ void __launch_bounds__(FIX_THREADS) k2m_fixup_kernel(K2mParams p, uint32_t *n_fail, uint32_t *stat_rerun, uint32_t *errors)
+{
+    p.mode = 1;
+    fixup_loop(p.lanes, n_fail, stat_rerun, errors, [&](uint32_t lane) { k2m_lane<CH>(p, lane); },
+               [&](uint32_t lane) { k2m_verify_lane(p, lane, n_fail); });
+}
+__global__ void __launch_bounds__(FIX_THREADS) k2p1_fixup_kernel(K2p1Params p, uint32_t *n_fail, uint32_t *stat_rerun, uint32_t *errors)
+{
+    p.mode = 1;
+    fixup_loop(p.lanes, n_fail, stat_rerun, errors, [&](uint32_t lane) { k2p1_lane(p, lane); },
+               [&](uint32_t lane) { k2p1_verify_lane(p, lane, n_fail); });
 }
 __global__ void k2c_compact_kernel(const K2cParams p) { k2c_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
-__global__ void k3_size_kernel(const K3Params p) { k3_size(p, blockIdx.x * blockDim.x + threadIdx.x); }
-__global__ void k3_cut_kernel(const K3Params p) { k3_cut(p, blockIdx.x, threadIdx.x, blockDim.x); }
+__global__ void k3_plan_kernel(const K3Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) k3_plan(p); }
+/* the kernels below do not know on the host how many candidates there are: grid-stride loops over gd->n */
+__global__ void k3_fill_kernel(const K3Params p)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.gd->n; i += gridDim.x * blockDim.x) k3_fill(p, i);
+}
+__global__ void k3_size_kernel(const K3Params p)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.gd->n; i += gridDim.x * blockDim.x) k3_size(p, i);
+}
+__global__ void k3_cut_kernel(const K3Params p)
+{
+    for (uint32_t i = blockIdx.x; i < p.gd->n; i += gridDim.x) k3_cut(p, i, threadIdx.x, blockDim.x);
+}
 __global__ void __launch_bounds__(SCAN_THREADS) k3_offsets_kernel(const K3Params p)
 {
     k3_offsets_a(p, threadIdx.x);
@@ -1074,10 +1272,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) k3_offsets_kernel(const K3Params
     __syncthreads();
     k3_offsets_c(p, threadIdx.x);
 }
-__global__ void k3_copy_kernel(const K3Params p) { k3_copy(p, blockIdx.x, threadIdx.x, blockDim.x); }
+__global__ void k3_copy_kernel(const K3Params p)
+{
+    for (uint32_t i = blockIdx.x; i < p.gd->n; i += gridDim.x) k3_copy(p, i, threadIdx.x, blockDim.x);
+}
+__global__ void k3_carry_kernel(const K3Params p)
+{
+    const uint32_t n = p.gd->n > WMB_N_STREAMS ? p.gd->n : WMB_N_STREAMS;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) k3_carry(p, i);
+}
 __global__ void __launch_bounds__(K4_THREADS) k4_decode_kernel(const K4Params p)
 {
     __shared__ K4Smem sm;
-    k4_decode(p, blockIdx.x, threadIdx.x, blockDim.x, sm);
+    const uint32_t n = k4_count(p);
+    for (uint32_t f = blockIdx.x; f < n; f += gridDim.x) {
+        k4_decode(p, f, threadIdx.x, blockDim.x, sm);
+        __syncthreads();
+    }
 }
 #endif

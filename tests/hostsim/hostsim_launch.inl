@@ -42,41 +42,72 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     return WMB_OK;
 }
 
-static int launch_k2a(wmb_ctx *c, int chain, const K2aParams &p, cudaStream_t)
+/* speculative pass, verification, and the fix-up loop of k2*_fixup_kernel (re-run refuted lanes from their
+ * predecessors' exact end states until none is left) */
+template <class RERUN, class VERIFY>
+static int hostsim_fixup(wmb_ctx *c, uint32_t lanes, uint32_t *n_fail, RERUN rerun, VERIFY verify)
 {
+    for (uint32_t round = 0; *n_fail; round++) {
+        if (round > lanes + 2) { *c->d_errors |= 256u; *n_fail = 0; break; }
+        c->d_gd->lanes_rerun += *n_fail;
+        *n_fail = 0;
+        for (uint32_t lane = 0; lane < lanes; lane++) rerun(lane);
+        for (uint32_t lane = 0; lane < lanes; lane++) verify(lane);
+    }
+    return WMB_OK;
+}
+
+static int launch_k2a(wmb_ctx *c, int chain, const K2aParams &p0, cudaStream_t)
+{
+    K2aParams p = p0;
+    uint32_t *nf = c->d_nfail + chain;
     for (uint32_t lane = 0; lane < p.lanes; lane++) {
         if (chain == 0) k2a_lane<ChainT1C1>(p, lane);
         else            k2a_lane<ChainS1>(p, lane);
     }
-    for (uint32_t lane = 0; lane < p.lanes; lane++) k2a_verify_lane(p, lane, c->d_nfail);
-    c->st.kernel_launches += 2;
-    return WMB_OK;
+    for (uint32_t lane = 0; lane < p.lanes; lane++) k2a_verify_lane(p, lane, nf);
+    p.mode = 1;
+    c->st.kernel_launches += 3;
+    return hostsim_fixup(c, p.lanes, nf,
+                         [&](uint32_t lane) { if (chain == 0) k2a_lane<ChainT1C1>(p, lane); else k2a_lane<ChainS1>(p, lane); },
+                         [&](uint32_t lane) { k2a_verify_lane(p, lane, nf); });
 }
 
-static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p, cudaStream_t)
+static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p0, cudaStream_t)
 {
+    K2mParams p = p0;
+    uint32_t *nf = c->d_nfail + 2 + chain;
     for (uint32_t lane = 0; lane < p.lanes; lane++) {
         if (chain == 0) k2m_lane<ChainT1C1>(p, lane);
         else            k2m_lane<ChainS1>(p, lane);
     }
-    for (uint32_t lane = 0; lane < p.lanes; lane++) k2m_verify_lane(p, lane, c->d_nfail);
-    c->st.kernel_launches += 2;
-    return WMB_OK;
+    for (uint32_t lane = 0; lane < p.lanes; lane++) k2m_verify_lane(p, lane, nf);
+    p.mode = 1;
+    c->st.kernel_launches += 3;
+    return hostsim_fixup(c, p.lanes, nf,
+                         [&](uint32_t lane) { if (chain == 0) k2m_lane<ChainT1C1>(p, lane); else k2m_lane<ChainS1>(p, lane); },
+                         [&](uint32_t lane) { k2m_verify_lane(p, lane, nf); });
 }
 
-static int launch_k2p1(wmb_ctx *c, const K2p1Params &p)
+static int launch_k2p1(wmb_ctx *c, const K2p1Params &p0)
 {
+    K2p1Params p = p0;
+    uint32_t *nf = c->d_nfail + 4;
     for (uint32_t lane = 0; lane < p.lanes; lane++) k2p1_lane(p, lane);
-    for (uint32_t lane = 0; lane < p.lanes; lane++) k2p1_verify_lane(p, lane, c->d_nfail);
-    c->st.kernel_launches += 2;
-    return WMB_OK;
+    for (uint32_t lane = 0; lane < p.lanes; lane++) k2p1_verify_lane(p, lane, nf);
+    p.mode = 1;
+    c->st.kernel_launches += 3;
+    return hostsim_fixup(c, p.lanes, nf, [&](uint32_t lane) { k2p1_lane(p, lane); },
+                         [&](uint32_t lane) { k2p1_verify_lane(p, lane, nf); });
 }
 
 static void launch_cscan(wmb_ctx *c, const uint32_t *cnt, uint64_t *base, uint32_t n, uint64_t *agg, uint64_t *total,
-                         const uint32_t *skip = nullptr, uint32_t *clear = nullptr, uint32_t from_zero = 0, cudaStream_t = nullptr)
+                         const uint32_t *skip = nullptr, uint32_t *clear = nullptr, uint32_t from_zero = 0, cudaStream_t = nullptr,
+                         uint32_t skip_invert = 0)
 {
     CountScan s;
     s.cnt = cnt; s.base = base; s.n = n; s.agg = agg; s.total = total; s.skip = skip; s.clear = clear; s.from_zero = from_zero;
+    s.skip_invert = skip_invert;
     static uint64_t part[SCAN_BLOCK];
     const uint32_t tiles = scan_tiles(n);
     for (uint32_t b = 0; b < tiles; b++) {
@@ -92,7 +123,7 @@ static void launch_cscan(wmb_ctx *c, const uint32_t *cnt, uint64_t *base, uint32
     c->st.kernel_launches += 3;
 }
 
-static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, const P1State *p1_end_last, RlState *carry)
+static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2)
 {
     launch_cscan(c, pc.cnt, pc.base, pc.lanes, pc.agg, &pc.pd->n_rec, nullptr, &pc.pd->fallback, 1);
     for (uint32_t lane = 0; lane < pc.lanes; lane++)
@@ -114,8 +145,22 @@ static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2, cons
             for (uint32_t t = 0; t < K2P2W_THREADS; t++) k2p2w_c(p2, lane, t, part);
         }
     }
-    k2p_fold(p1_end_last, p2.p2_out, carry, p2.pd);
-    c->st.kernel_launches += 5;
+    c->st.kernel_launches += 4;
+    return WMB_OK;
+}
+
+static int launch_k2p_fold(wmb_ctx *c, const P1State *p1_end_last, RlState *p2_out, RlState *carry, const K2pDev *pd,
+                           const RlState *mono_end)
+{
+    k2p_fold(p1_end_last, p2_out, carry, pd, mono_end, GD_FIELD(c, rl_fallbacks));
+    c->st.kernel_launches += 1;
+    return WMB_OK;
+}
+
+static int launch_k2m_carry(wmb_ctx *c, const RlState *end, RlState *carry, const uint32_t *run_if, cudaStream_t)
+{
+    if (!run_if || *run_if) *carry = *end;
+    c->st.kernel_launches += 1;
     return WMB_OK;
 }
 
@@ -147,24 +192,33 @@ static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
 
 static int launch_k2c(wmb_ctx *c, const K2cParams &p, cudaStream_t)
 {
-    launch_cscan(c, p.cnt, p.base, p.lanes, p.agg, &p.sd->total);
+    launch_cscan(c, p.cnt, p.base, p.lanes, p.agg, &p.sd->total, p.run_if, nullptr, 0, nullptr, p.run_if ? 1u : 0u);
     for (uint32_t lane = 0; lane < p.lanes; lane++)
         for (int t = 0; t < 4; t++) k2c_compact(p, lane, t, 4);
     c->st.kernel_launches += 1;
     return WMB_OK;
 }
 
-static int launch_k3(wmb_ctx *c, const K3Params &p)
+static int launch_k3_k4(wmb_ctx *c, const K3Params &p, const K4Params *q)
 {
-    for (uint32_t i = 0; i < p.n; i++) k3_size(p, i);
-    for (uint32_t i = 0; i < p.n; i++)
+    k3_plan(p);
+    const uint32_t n = p.gd->n;
+    for (uint32_t i = 0; i < n; i++) k3_fill(p, i);
+    for (uint32_t i = 0; i < n; i++) k3_size(p, i);
+    for (uint32_t i = 0; i < n; i++)
         for (int t = 0; t < 4; t++) k3_cut(p, i, t, 4);
     for (uint32_t t = 0; t < SCAN_THREADS; t++) k3_offsets_a(p, t);
     k3_offsets_b(p);
     for (uint32_t t = 0; t < SCAN_THREADS; t++) k3_offsets_c(p, t);
-    for (uint32_t i = 0; i < p.n; i++)
+    for (uint32_t i = 0; i < n; i++)
         for (int t = 0; t < 4; t++) k3_copy(p, i, t, 4);
-    c->st.kernel_launches += 4;
+    for (uint32_t i = 0; i < (n > WMB_N_STREAMS ? n : WMB_N_STREAMS); i++) k3_carry(p, i);
+    c->st.kernel_launches += 7;
+    if (q) {
+        static K4Smem sm;                   /* the block's phases need real barriers: one simulated thread */
+        for (uint32_t i = 0; i < n; i++) k4_decode(*q, i, 0, 1, sm);
+        c->st.kernel_launches += 1;
+    }
     return WMB_OK;
 }
 
