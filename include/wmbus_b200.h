@@ -173,9 +173,10 @@ typedef struct wmb_stats {
     uint64_t lines[2][2];         /* datagram lines       [chain][algo]               */
     uint64_t lines_crc_ok[2][2];
     uint64_t h2d_bytes, d2h_bytes;
-    double   demod_kernel_ms;     /* CUDA-event time of the demod kernel(s), last batch */
-    double   bitsync_kernel_ms;   /* CUDA-event time of the bit-sync kernel(s), last batch */
-    double   batch_device_ms;     /* CUDA-event time of the whole device pass, last batch */
+    double   demod_kernel_ms;     /* CUDA-event time of the demod kernels of the last push (sum over its batches) */
+    double   bitsync_kernel_ms;   /* ... of the bit-sync kernels (clock-recovery lanes + bit streams; they overlap the
+                                     next batch's demod kernel, so the two sums can exceed the wall time)      */
+    double   batch_device_ms;     /* first demod kernel -> last bit-sync kernel of the last push (device clock) */
     uint64_t rl_fallbacks;        /* T1/C1 batches redone with the monolithic run-length lanes */
     double   host_batch_ms;       /* cumulative wall time in the enqueue+verify part of batches */
     double   host_gather_ms;      /* cumulative wall time gathering candidate frames          */

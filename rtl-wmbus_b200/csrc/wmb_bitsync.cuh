@@ -37,6 +37,8 @@ struct K2aParams {
     uint32_t *rerun;
     uint32_t mode;              /* 0 speculative pass, 1 re-run flagged lanes                 */
     uint32_t dc, t2;            /* -o ; time2 enabled (else only the data bits are produced)  */
+    uint32_t spec0;             /* lane 0 starts cold from the history too (its predecessor -- the previous batch's last
+                                   lane -- may still be running); verified against the carried state like any lane  */
 };
 
 /* registers of one clock-recovery lane */
@@ -172,15 +174,15 @@ WMB_D void k2a_lane_t(const K2aParams &p, uint32_t lane)
     IirState st;
     int64_t m;
     if (p.mode == 0) {
-        if (lane == 0) { st = *p.carry; m = 0; }
+        if (lane == 0 && !p.spec0) { st = *p.carry; m = 0; }
         else {
             iir_state_init(st);
             m = s0 - (int64_t)p.W;
             if (m < -p.hist) m = -p.hist;
         }
     } else {
-        if (lane == 0 || !p.rerun[lane]) return;
-        st = p.st_end[lane - 1];
+        if (!p.rerun[lane]) return;
+        st = lane ? p.st_end[lane - 1] : *p.carry;
         m = s0;
     }
     K2aRegs r;
@@ -255,7 +257,8 @@ WMB_D void k2a_verify_lane(const K2aParams &p, uint32_t lane, uint32_t *n_fail)
 {
     if (lane >= p.lanes) return;
     uint32_t bad = 0;
-    if (lane > 0 && !iir_state_equal(p.st_start[lane], p.st_end[lane - 1], p.dc, p.t2)) bad = 1;
+    if (lane > 0) { if (!iir_state_equal(p.st_start[lane], p.st_end[lane - 1], p.dc, p.t2)) bad = 1; }
+    else if (p.spec0 && !iir_state_equal(p.st_start[0], *p.carry, p.dc, p.t2)) bad = 1;
     p.rerun[lane] = bad;
     if (bad) {
 #ifdef WMB_HOSTSIM

@@ -81,13 +81,21 @@ struct Stream {                     /* one (chain, algo) bit stream */
     int64_t busy_until = -1;        /* last ordinal consumed by an accepted packet */
 };
 
-struct ChainBuf {
+/* Buffers that the demod / clock-recovery stage of batch i+1 writes while the bit-stream stage of batch i still
+ * reads them: two sets, alternating from batch to batch.  Layout of the sample arrays: [W history | batch]. */
+struct SetBuf {
     float *dphi = nullptr;          /* [W | M_max]  post-FIR discriminator output  */
     uint8_t *rssi = nullptr;        /* [W | M_max]                                 */
     uint32_t *dbits = nullptr;      /* [W/32 | M_max/32] data bits                 */
     uint32_t *sbits = nullptr;      /* [W/32 | M_max/32] time2 strobes             */
     uint32_t *cbits = nullptr;      /* [W/32 | M_max/32] clock signs (stage tap, opts.reserved[1] & 1) */
-    IirState *ia_start = nullptr, *ia_end = nullptr, *ia_carry = nullptr;
+    IirState *ia_start = nullptr, *ia_end = nullptr;
+    uint32_t *rerun_a = nullptr;
+};
+
+struct ChainBuf {
+    SetBuf set[2];
+    IirState *ia_carry = nullptr;
     RlState *rl_start = nullptr, *rl_end = nullptr, *rl_carry = nullptr;
     uint32_t *rerun = nullptr;
     /* two-phase run-length path (T1/C1) */
@@ -100,6 +108,8 @@ struct ChainBuf {
     uint32_t *t2_tail = nullptr, *t2_len = nullptr, *t2_sr = nullptr, *t2_agg_tail = nullptr, *t2_agg_len = nullptr;
     Stream s[WMB_N_ALGOS];
 };
+
+#define WMB_NSLOT 4                      /* batches whose results may be waiting for the host */
 
 static uint32_t g_p2_block = 128u;       /* threads per block of the phase-2 count pass (WMBUS_B200_P2BLK, experiments) */
 
@@ -115,13 +125,22 @@ struct wmb_ctx {
     int device = 0;
     uint32_t d = 2;                 /* effective decimation (>= 1) */
     uint32_t chains = 3;
-    cudaStream_t cs = nullptr, xs = nullptr;       /* compute, copy */
-    cudaStream_t ts = nullptr;                     /* time2 bit streams, beside the run-length chain on cs */
+    /* Streams: k1s runs the demod kernels of consecutive batches back to back; as[set] the clock-recovery lanes of
+     * a batch (they only need its demod output, so they overlap the next batch's demod and each other); cs everything
+     * that is sequential from batch to batch (lane verification, bit streams, gather, framer, result copies), with ts
+     * (time2) and s2 (S1 run-length lanes) forked from and joined to it; xs the H2D copies. */
+    cudaStream_t cs = nullptr, xs = nullptr, k1s = nullptr, as[2] = {nullptr, nullptr};
+    cudaStream_t ts = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaStream_t s2 = nullptr;                     /* the S1 chain's lanes, beside the T1/C1 chain's on cs */
+    cudaStream_t s2 = nullptr;
     cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k1done[2] = {nullptr, nullptr};
-    cudaEvent_t ev_t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_k1[2] = {nullptr, nullptr}, ev_k2a[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};
+    bool chain_recorded[2] = {false, false};
+    cudaEvent_t ev_res[WMB_NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_push_start = nullptr;           /* first demod kernel of the current push (timers) */
+    bool push_started = false;
+    cudaEvent_t ev_t[WMB_NSLOT][6];                /* per result slot: demod start/end, bit sync start/end (timers) */
     bool allocated = false;
 
     /* geometry */
@@ -152,27 +171,21 @@ struct wmb_ctx {
     ChainBuf cb[WMB_N_CHAINS];
     uint32_t *d_errors = nullptr, *d_nfail = nullptr;      /* [0] error bits; d_nfail[0..7]: refuted lanes per verified pass */
     GatherDev *d_gd = nullptr;      /* gather bookkeeping + statistics                 */
-    BatchRec *d_rec = nullptr;      /* one record per batch since the last read        */
-    FrameHdr *d_hdr = nullptr;      /* result log: candidates ...                      */
-    DecHdr *d_dec = nullptr;        /* ... and K4's verdicts                           */
-    uint32_t log_cap = 0, rec_cap = 0, pend_cap = 0;
-    uint32_t *d_words = nullptr;
+    /* results: WMB_NSLOT slots, one per batch in flight, each with its part of the candidate / verdict arrays and of
+     * the datagram pool; the host mirrors are pinned and filled by copies enqueued right behind the device framer */
+    BatchRec *d_rec = nullptr, *h_rec = nullptr;
+    FrameHdr *d_hdr = nullptr, *h_hdr = nullptr;
+    DecHdr *d_dec = nullptr, *h_dec = nullptr;
+    uint8_t *d_pool = nullptr, *h_pool = nullptr;
+    uint32_t slot_cap = 0, slot_pool = 0, pend_cap = 0;
+    uint32_t *d_words = nullptr, *h_words = nullptr;
     uint32_t *d_cut_n = nullptr;
     uint64_t *d_k3_agg = nullptr;
-    uint8_t *d_pool = nullptr;      /* CRC-stripped datagrams */
-    uint32_t pool_cap = 0;
-
-    /* pinned host mirrors, filled by one copy + one synchronisation per push */
-    struct HostRead { uint32_t errors; uint32_t pad; GatherDev gd; };
-    HostRead *h_read = nullptr;
-    BatchRec *h_rec = nullptr;
-    FrameHdr *h_hdr = nullptr;
-    DecHdr *h_dec = nullptr;
-    uint8_t *h_pool = nullptr;
-    uint32_t *h_words = nullptr;
     uint32_t spec_n = 0, spec_pool = 0;              /* entries / bytes copied before their counts are known */
-    std::vector<uint8_t> batch_final;                /* host side of the batch records: end of input?       */
+    struct InFlight { int slot; bool final; bool has_timers; uint64_t m_end; };
+    std::vector<InFlight> inflight;                  /* gathered batches whose results the host has not read yet */
     uint64_t stat_rerun_seen = 0, stat_fallback_seen = 0;
+    double acc_demod_ms = 0, acc_bitsync_ms = 0, acc_pass_ms = 0;    /* timers of the current push */
 
     /* stream position */
     uint64_t iq_consumed = 0;       /* input IQ samples handed to the device    */
@@ -181,8 +194,10 @@ struct wmb_ctx {
     int64_t hist_iq = 0;            /* input history retained (samples)         */
     std::vector<uint8_t> remainder; /* bytes not yet forming a whole batch granule */
     int buf_idx = 0;
-    uint64_t batch_no = 0;
-    int64_t last_M = 0;
+    uint64_t batch_no = 0;          /* batches enqueued since create / reset: set = batch_no & 1 */
+    uint64_t gather_no = 0;         /* gathers enqueued: result slot = gather_no % WMB_NSLOT    */
+    int64_t last_M = 0, prev_M = 0;
+    int last_set = 0;
 
     /* results */
     uint64_t win_lo = 0, win_hi = ~0ull;             /* line window (access-code match sample) */
@@ -220,28 +235,32 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     if (blocks_per_sm < 1) return set_err(WMB_E_INVAL, "decimation %u needs %zu B shared memory per CTA", p.d, smem);
     int64_t grid = (int64_t)sm_count * blocks_per_sm;      /* persistent: whole waves of resident CTAs */
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, K1_THREADS, smem, c->cs>>>(p);
+    kern<<<(unsigned)grid, K1_THREADS, smem, c->k1s>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches++;
     return WMB_OK;
 }
 
-/* speculative pass + verification + on-device fix-up of refuted lanes: no host round trip */
-static int launch_k2a(wmb_ctx *c, int chain, const K2aParams &p, cudaStream_t st)
+/* speculative pass (st: the batch's lane stream), then -- on cs, where batches follow each other in order --
+ * verification + on-device fix-up of refuted lanes: no host round trip */
+static int launch_k2a_lanes(wmb_ctx *c, int chain, const K2aParams &p, cudaStream_t st)
 {
     const unsigned grid = (p.lanes + K2_THREADS - 1) / K2_THREADS;
-    uint32_t *nf = c->d_nfail + chain;
-    if (chain == 0) {
-        k2a_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, st>>>(p);
-        k2a_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, nf);
-        k2a_fixup_kernel<ChainT1C1><<<1, FIX_THREADS, 0, st>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
-    } else {
-        k2a_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, st>>>(p);
-        k2a_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, nf);
-        k2a_fixup_kernel<ChainS1><<<1, FIX_THREADS, 0, st>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
-    }
+    if (chain == 0) k2a_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, st>>>(p);
+    else            k2a_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, st>>>(p);
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 3;
+    c->st.kernel_launches += 1;
+    return WMB_OK;
+}
+
+static int launch_k2a_verify(wmb_ctx *c, int chain, const K2aParams &p)
+{
+    uint32_t *nf = c->d_nfail + chain;
+    k2a_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, c->cs>>>(p, nf);
+    if (chain == 0) k2a_fixup_kernel<ChainT1C1><<<1, FIX_THREADS, 0, c->cs>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
+    else            k2a_fixup_kernel<ChainS1><<<1, FIX_THREADS, 0, c->cs>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
+    CUDA_TRY(cudaGetLastError());
+    c->st.kernel_launches += 2;
     return WMB_OK;
 }
 
@@ -362,11 +381,12 @@ static int launch_k3_k4(wmb_ctx *c, const K3Params &p, const K4Params *q)
     k3_offsets_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(p);
     k3_copy_kernel<<<sms * 8, 128, 0, c->cs>>>(p);
     k3_carry_kernel<<<sms, 128, 0, c->cs>>>(p);
-    c->st.kernel_launches += 7;
+    c->st.kernel_launches += 8;
     if (q) {
         k4_decode_kernel<<<sms * 16, K4_THREADS, 0, c->cs>>>(*q);
         c->st.kernel_launches += 1;
     }
+    k3_publish_kernel<<<1, 32, 0, c->cs>>>(p);
     CUDA_TRY(cudaGetLastError());
     return WMB_OK;
 }
@@ -418,19 +438,6 @@ static uint64_t next_pow2(uint64_t v)
     return p;
 }
 
-static uint32_t pick_chunk(const wmb_ctx *c, int64_t M)
-{
-    if (c->C_fixed) return c->C_fixed;
-    /* The clock-recovery lanes are bound by the fp32 pipe of the scheduler they sit on, so a
-     * big batch is cut into about one warp per scheduler (148 SMs x 4 x 32 lanes); never
-     * below 8192 samples per lane (the warm-up is 32768) */
-    int64_t C = (M + 18943) / 18944;
-    C = (C + 1023) / 1024 * 1024;
-    if (C < 8192) C = 8192;
-    if (C > 65536) C = 65536;
-    return (uint32_t)C;
-}
-
 template <typename T>
 static int dev_alloc(wmb_ctx *c, T **p, size_t count, bool zero = false)
 {
@@ -480,8 +487,11 @@ static void tr_dump()
     g_marks.clear();
 }
 
+static size_t g_pipe_bytes = (size_t)256 << 20;          /* WMBUS_B200_PIPE_MIB: batch size of a long device push */
+
 static void read_tuning()
 {
+    if (const char *b = getenv("WMBUS_B200_PIPE_MIB")) { const unsigned long v = strtoul(b, nullptr, 10); if (v >= 1 && v <= 4096) g_pipe_bytes = (size_t)v << 20; }
     if (const char *b = getenv("WMBUS_B200_P2BLK")) { const unsigned v = (unsigned)atoi(b); if (v == 32 || v == 64 || v == 128) g_p2_block = v; }
     const char *e = getenv("WMBUS_B200_TUNE");
     unsigned a = 0, b = 0, r = 0;
@@ -520,25 +530,23 @@ static int ctx_alloc(wmb_ctx *c)
     TRY(dev_alloc(c, &c->d_errors, 16, true));
     c->d_nfail = c->d_errors + 4;
     TRY(dev_alloc(c, &c->d_gd, 1, true));
-    c->rec_cap = 1024;
-    TRY(dev_alloc(c, &c->d_rec, c->rec_cap, true));
-    c->log_cap = c->cand_cap;
+    c->slot_cap = c->cand_cap;                   /* candidates of one batch */
     c->pend_cap = 1u << 16;                      /* candidates younger than one telegram at a batch end */
-    TRY(dev_alloc(c, &c->d_hdr, c->log_cap));
-    TRY(dev_alloc(c, &c->d_dec, c->log_cap));
+    c->slot_pool = c->frame_words_cap / 8 + 4 * c->cand_cap;    /* a datagram byte takes >= 8 shipped bit words */
+    TRY(dev_alloc(c, &c->d_rec, WMB_NSLOT, true));
+    TRY(dev_alloc(c, &c->d_hdr, (size_t)WMB_NSLOT * c->slot_cap));
+    TRY(dev_alloc(c, &c->d_dec, (size_t)WMB_NSLOT * c->slot_cap));
+    TRY(dev_alloc(c, &c->d_pool, (size_t)WMB_NSLOT * c->slot_pool));
     TRY(dev_alloc(c, &c->d_words, c->frame_words_cap));
     TRY(dev_alloc(c, &c->d_cut_n, c->cand_cap));
     TRY(dev_alloc(c, &c->d_k3_agg, SCAN_THREADS));
-    c->pool_cap = c->frame_words_cap / 8 + 4 * c->cand_cap;    /* a datagram byte takes >= 8 shipped bit words */
-    TRY(dev_alloc(c, &c->d_pool, c->pool_cap));
-    TRY(host_alloc(c, &c->h_read, 1));
-    TRY(host_alloc(c, &c->h_rec, c->rec_cap));
-    TRY(host_alloc(c, &c->h_hdr, c->log_cap));
-    TRY(host_alloc(c, &c->h_dec, c->log_cap));
-    TRY(host_alloc(c, &c->h_pool, c->pool_cap));
+    TRY(host_alloc(c, &c->h_rec, WMB_NSLOT));
+    TRY(host_alloc(c, &c->h_hdr, (size_t)WMB_NSLOT * c->slot_cap));
+    TRY(host_alloc(c, &c->h_dec, (size_t)WMB_NSLOT * c->slot_cap));
+    TRY(host_alloc(c, &c->h_pool, (size_t)WMB_NSLOT * c->slot_pool));
     TRY(host_alloc(c, &c->h_words, c->frame_words_cap));
-    c->spec_n = std::min<uint32_t>(8192, c->log_cap);
-    c->spec_pool = std::min<uint32_t>(1u << 20, c->pool_cap);
+    c->spec_n = std::min<uint32_t>(4096, c->slot_cap);
+    c->spec_pool = std::min<uint32_t>(1u << 18, c->slot_pool);
 
     /* mixer look-up tables, built with the host libm exactly like the reference
      * (setup_lookup_tables_for_frequency_translation, rtl_wmbus.c:974-993) */
@@ -559,13 +567,17 @@ static int ctx_alloc(wmb_ctx *c)
         if (!(c->chains & (1u << ch))) continue;
         ChainBuf &b = c->cb[ch];
         const size_t n = (size_t)c->W + (size_t)c->M_max + 512;    /* slack: block loads may run past M */
-        TRY(dev_alloc(c, &b.dphi, n));
-        TRY(dev_alloc(c, &b.rssi, n));
-        TRY(dev_alloc(c, &b.dbits, n / 32 + 64, true));      /* slack: lanes prefetch 16 words ahead */
-        TRY(dev_alloc(c, &b.sbits, n / 32 + 64, true));
-        if (c->taps) TRY(dev_alloc(c, &b.cbits, n / 32 + 64, true));
-        TRY(dev_alloc(c, &b.ia_start, c->lanes_max));
-        TRY(dev_alloc(c, &b.ia_end, c->lanes_max));
+        for (int k = 0; k < 2; k++) {
+            SetBuf &sb = b.set[k];
+            TRY(dev_alloc(c, &sb.dphi, n));
+            TRY(dev_alloc(c, &sb.rssi, n));
+            TRY(dev_alloc(c, &sb.dbits, n / 32 + 64, true));      /* slack: lanes prefetch 16 words ahead */
+            TRY(dev_alloc(c, &sb.sbits, n / 32 + 64, true));
+            if (c->taps) TRY(dev_alloc(c, &sb.cbits, n / 32 + 64, true));
+            TRY(dev_alloc(c, &sb.ia_start, c->lanes_max));
+            TRY(dev_alloc(c, &sb.ia_end, c->lanes_max));
+            TRY(dev_alloc(c, &sb.rerun_a, c->lanes_max, true));
+        }
         TRY(dev_alloc(c, &b.ia_carry, 1));
         TRY(dev_alloc(c, &b.rl_start, c->lanes_max));
         TRY(dev_alloc(c, &b.rl_end, c->lanes_max));
@@ -674,13 +686,24 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
     memset(&c->st, 0, sizeof(c->st));
     if (cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->xs, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->k1s, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->as[0], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->as[1], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->ts, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return set_err(WMB_E_CUDA, "cannot create CUDA streams");
     }
-    for (int i = 0; i < 2; i++) { cudaEventCreate(&c->ev_h2d[i]); cudaEventCreate(&c->ev_k1done[i]); }
-    for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev_t[i]);
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreate(&c->ev_h2d[i]); cudaEventCreate(&c->ev_k1done[i]);
+        cudaEventCreateWithFlags(&c->ev_k1[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_k2a[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_chain[i], cudaEventDisableTiming);
+    }
+    cudaEventCreate(&c->ev_push_start);
+    for (int i = 0; i < WMB_NSLOT; i++) {
+        cudaEventCreateWithFlags(&c->ev_res[i], cudaEventDisableTiming);
+        for (int k = 0; k < 6; k++) cudaEventCreate(&c->ev_t[i][k]);
+    }
     cudaEventCreate(&c->ev_fork);
     cudaEventCreate(&c->ev_join);
     cudaEventCreate(&c->ev_fork2);
@@ -697,8 +720,17 @@ extern "C" void wmb_destroy(wmb_ctx *c)
     if (c->xs) cudaStreamSynchronize(c->xs);
     for (void *p : c->dev_allocs) cudaFree(p);
     for (void *p : c->host_allocs) cudaFreeHost(p);
-    for (int i = 0; i < 2; i++) { if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]); if (c->ev_k1done[i]) cudaEventDestroy(c->ev_k1done[i]); }
-    for (int i = 0; i < 6; i++) if (c->ev_t[i]) cudaEventDestroy(c->ev_t[i]);
+    for (cudaStream_t st : { c->k1s, c->as[0], c->as[1], c->ts, c->s2 }) if (st) cudaStreamSynchronize(st);
+    for (int i = 0; i < 2; i++) {
+        for (cudaEvent_t e : { c->ev_h2d[i], c->ev_k1done[i], c->ev_k1[i], c->ev_k2a[i], c->ev_chain[i] }) if (e) cudaEventDestroy(e);
+        if (c->as[i]) cudaStreamDestroy(c->as[i]);
+    }
+    if (c->k1s) cudaStreamDestroy(c->k1s);
+    if (c->ev_push_start) cudaEventDestroy(c->ev_push_start);
+    for (int i = 0; i < WMB_NSLOT; i++) {
+        if (c->ev_res[i]) cudaEventDestroy(c->ev_res[i]);
+        for (int k = 0; k < 6; k++) if (c->ev_t[i][k]) cudaEventDestroy(c->ev_t[i][k]);
+    }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ts) cudaStreamDestroy(c->ts);
@@ -714,38 +746,62 @@ extern "C" void wmb_destroy(wmb_ctx *c)
 /* one batch on the device                                                     */
 /* --------------------------------------------------------------------------- */
 
-/* device-to-device slide of a [hist | batch] buffer: the last `hist` elements move in front
- * of index 0 (element size es); goes through scratch when source and destination overlap */
-static int slide_history(wmb_ctx *c, void *buf, size_t es, int64_t hist, int64_t M)
+/* The history prefix of a [W | batch] array of the set the next batch will use <- the last W elements the previous
+ * batch left in its set (element size es, prev_M elements in the previous batch).  Source and destination are different
+ * allocations, so one copy does. */
+static int copy_history(void *dst, const void *src_set, size_t es, int64_t W, int64_t prev_M, cudaStream_t st)
 {
-    uint8_t *p = (uint8_t *)buf;
-    if (M >= hist) {
-        CUDA_TRY(cudaMemcpyAsync(p, p + (size_t)M * es, (size_t)hist * es, cudaMemcpyDeviceToDevice, c->cs));
-    } else {
-        CUDA_TRY(cudaMemcpyAsync(c->d_tmp, p + (size_t)M * es, (size_t)hist * es, cudaMemcpyDeviceToDevice, c->cs));
-        CUDA_TRY(cudaMemcpyAsync(p, c->d_tmp, (size_t)hist * es, cudaMemcpyDeviceToDevice, c->cs));
-    }
+    if (W <= 0) return WMB_OK;
+    CUDA_TRY(cudaMemcpyAsync(dst, (const uint8_t *)src_set + (size_t)prev_M * es, (size_t)W * es, cudaMemcpyDeviceToDevice, st));
     return WMB_OK;
 }
 
-/* Enqueue the per-sample device pass for one batch whose bytes are at `src` (device memory): demod and bit sync.
- * Nothing here waits for the device: refuted speculative lanes are re-run by on-device fix-up kernels, and the
- * fallback from the two-phase run-length path to the monolithic lanes is a set of kernels that do nothing unless the
- * device flag asks for them. */
-static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_ctx_buffer)
+static uint32_t pick_chunk(const wmb_ctx *c, int64_t M, bool alone)
+{
+    if (c->C_fixed) return c->C_fixed;
+    /* The clock-recovery lanes are bound by the fp32 pipe of the scheduler they sit on, so a batch that has the GPU to
+     * itself is cut into about one warp per scheduler (148 SMs x 4 x 32 lanes).  A batch that is followed by another
+     * one overlaps its lanes with that batch's demod kernel: their latency is hidden, what counts is the redundant
+     * warm-up arithmetic, so the lanes are made longer. */
+    int64_t C = (M + 18943) / 18944;
+    C = (C + 1023) / 1024 * 1024;
+    const int64_t lo = alone ? 8192 : 16384;
+    if (C < lo) C = lo;
+    if (C > 65536) C = 65536;
+    return (uint32_t)C;
+}
+
+/* Enqueue the per-sample device pass for one batch whose bytes are at `src` (device memory): demod on k1s, clock
+ * recovery lanes on as[set], everything that is sequential from batch to batch on cs.  Nothing here waits for the
+ * device: refuted speculative lanes are re-run by on-device fix-up kernels, and the fallback from the two-phase
+ * run-length path to the monolithic lanes is a set of kernels that do nothing unless the device flag asks for them.
+ * input_ready: event after which `src` holds the bytes (H2D copy), or null.  alone: no batch follows in this push. */
+static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t input_ready, bool alone)
 {
     tr("batch-start");
     const uint32_t d = c->d;
     const int64_t n_iq = (int64_t)(nbytes / 2);
     const int64_t M = n_iq / d;
-    c->last_M = M;
     if (M <= 0) return WMB_OK;
-    (void)src_is_ctx_buffer;
+    const int set = (int)(c->batch_no & 1u), pset = set ^ 1;
+    const int slot = (int)(c->gather_no % WMB_NSLOT);           /* the gather that follows this batch */
+    cudaEvent_t *evt = c->ev_t[slot];
+    const bool first = c->batch_no == 0;
     for (int ch = 0; ch < WMB_N_CHAINS; ch++)
         for (int a = 0; a < WMB_N_ALGOS; a++) c->cb[ch].s[a].total_prev = c->cb[ch].s[a].total;   /* stage tap: events of this batch */
 
-    /* ---- K1: demod ---- */
-    CUDA_TRY(cudaEventRecord(c->ev_t[0], c->cs));
+    /* ================= stage 1 (k1s): history prefix of this set, demod ================= */
+    if (c->chain_recorded[set]) CUDA_TRY(cudaStreamWaitEvent(c->k1s, c->ev_chain[set], 0));    /* batch i-2 is done with the set */
+    if (input_ready) CUDA_TRY(cudaStreamWaitEvent(c->k1s, input_ready, 0));
+    if (!first)
+        for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+            if (!(c->chains & (1u << ch))) continue;
+            ChainBuf &b = c->cb[ch];
+            TRY(copy_history(b.set[set].dphi, b.set[pset].dphi, 4, c->W, c->prev_M, c->k1s));
+            TRY(copy_history(b.set[set].rssi, b.set[pset].rssi, 1, c->W, c->prev_M, c->k1s));
+        }
+    CUDA_TRY(cudaEventRecord(evt[0], c->k1s));
+    if (!c->push_started) { CUDA_TRY(cudaEventRecord(c->ev_push_start, c->k1s)); c->push_started = true; }
     K1Params k1;
     memset(&k1, 0, sizeof(k1));
     k1.in = src; k1.hist = c->d_hist; k1.in_bytes = (int64_t)nbytes;
@@ -756,53 +812,74 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
     k1.lut_phase0 = (uint32_t)((13ull * (c->iq_consumed % k1.lut_n)) % k1.lut_n);
     k1.lut_cos = c->d_lut; k1.lut_msin = c->d_lut + 4096;
     for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-        k1.dphi[ch] = c->cb[ch].dphi ? c->cb[ch].dphi + c->W : nullptr;
-        k1.rssi[ch] = c->cb[ch].rssi ? c->cb[ch].rssi + c->W : nullptr;
+        k1.dphi[ch] = c->cb[ch].set[set].dphi ? c->cb[ch].set[set].dphi + c->W : nullptr;
+        k1.rssi[ch] = c->cb[ch].set[set].rssi ? c->cb[ch].set[set].rssi + c->W : nullptr;
     }
     TRY(launch_k1(c, k1));
-    CUDA_TRY(cudaEventRecord(c->ev_t[1], c->cs));
-
+    CUDA_TRY(cudaEventRecord(evt[1], c->k1s));
+    CUDA_TRY(cudaEventRecord(c->ev_k1[set], c->k1s));
     /* keep the last k1_hist_bytes() of the stream for the next batch's tile 0 */
     {
         const size_t hb = (size_t)k1_hist_bytes(d);
         if (nbytes >= hb) {
-            CUDA_TRY(cudaMemcpyAsync(c->d_hist, src + nbytes - hb, hb, cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(c->d_hist, src + nbytes - hb, hb, cudaMemcpyDeviceToDevice, c->k1s));
         } else {
-            CUDA_TRY(cudaMemcpyAsync(c->d_tmp, c->d_hist + nbytes, hb - nbytes, cudaMemcpyDeviceToDevice, c->cs));
-            CUDA_TRY(cudaMemcpyAsync(c->d_tmp + (hb - nbytes), src, nbytes, cudaMemcpyDeviceToDevice, c->cs));
-            CUDA_TRY(cudaMemcpyAsync(c->d_hist, c->d_tmp, hb, cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(c->d_tmp, c->d_hist + nbytes, hb - nbytes, cudaMemcpyDeviceToDevice, c->k1s));
+            CUDA_TRY(cudaMemcpyAsync(c->d_tmp + (hb - nbytes), src, nbytes, cudaMemcpyDeviceToDevice, c->k1s));
+            CUDA_TRY(cudaMemcpyAsync(c->d_hist, c->d_tmp, hb, cudaMemcpyDeviceToDevice, c->k1s));
         }
         c->hist_iq = std::min<int64_t>(c->hist_iq + n_iq, (int64_t)hb / 2);
     }
     /* the input buffer may be overwritten by the next H2D from here on */
-    CUDA_TRY(cudaEventRecord(c->ev_k1done[c->buf_idx], c->cs));
+    CUDA_TRY(cudaEventRecord(c->ev_k1done[c->buf_idx], c->k1s));
 
-    const uint32_t C = pick_chunk(c, M);
+    const uint32_t C = pick_chunk(c, M, alone);
     const uint32_t lanes = (uint32_t)((M + C - 1) / C);
     if (lanes > c->lanes_max) return set_err(WMB_E_INVAL, "internal: %u lanes > %u", lanes, c->lanes_max);
     const bool any_sync = c->o.rla_enabled || c->o.t2_enabled;
     const int64_t wofs = c->W / 32;                       /* word offset of batch sample 0 */
 
     if (any_sync) {
-        /* ---- K2a: clock-recovery lanes (both chains), verified ----
+        /* ================= stage 2 (as[set]): clock-recovery lanes, every lane speculative =================
          * (measured: the two chains' clock lanes side by side are SLOWER, 8.3 vs 7.2 ms of bit sync per GiB --
-         * each already fills the fp32 pipe of its scheduler; only the run-length lanes below share the GPU) */
+         * each already fills the fp32 pipe of its scheduler) */
+        K2aParams ka[WMB_N_CHAINS];
+        CUDA_TRY(cudaStreamWaitEvent(c->as[set], c->ev_k1[set], 0));
+        CUDA_TRY(cudaEventRecord(evt[4], c->as[set]));
         for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
             if (!(c->chains & (1u << ch))) continue;
             ChainBuf &b = c->cb[ch];
-            K2aParams p;
+            SetBuf &sb = b.set[set];
+            K2aParams &p = ka[ch];
             memset(&p, 0, sizeof(p));
-            p.dphi = b.dphi + c->W; p.M = M; p.hist = c->hist_m; p.C = C; p.W = c->W_a[ch]; p.lanes = lanes;
-            p.dbits = b.dbits + wofs; p.sbits = b.sbits + wofs;
-            p.cbits = b.cbits ? b.cbits + wofs : nullptr;
-            p.st_start = b.ia_start; p.st_end = b.ia_end; p.carry = b.ia_carry; p.rerun = b.rerun;
+            p.dphi = sb.dphi + c->W; p.M = M; p.hist = c->hist_m; p.C = C; p.W = c->W_a[ch]; p.lanes = lanes;
+            p.dbits = sb.dbits + wofs; p.sbits = sb.sbits + wofs;
+            p.cbits = sb.cbits ? sb.cbits + wofs : nullptr;
+            p.st_start = sb.ia_start; p.st_end = sb.ia_end; p.carry = b.ia_carry; p.rerun = sb.rerun_a;
             p.dc = c->o.remove_dc; p.t2 = c->o.t2_enabled;
             p.mode = 0;
+            p.spec0 = first ? 0u : 1u;                   /* the previous batch's lanes may still be running */
             c->st.lanes_run += lanes;
-            TRY(launch_k2a(c, ch, p, c->cs));
-            CUDA_TRY(cudaMemcpyAsync(b.ia_carry, b.ia_end + (lanes - 1), sizeof(IirState), cudaMemcpyDeviceToDevice, c->cs));
+            TRY(launch_k2a_lanes(c, ch, p, c->as[set]));
         }
+        CUDA_TRY(cudaEventRecord(evt[5], c->as[set]));
+        CUDA_TRY(cudaEventRecord(c->ev_k2a[set], c->as[set]));
         tr("k1+k2a");
+
+        /* ================= stage 3 (cs): in order from batch to batch ================= */
+        CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_k2a[set], 0));
+        CUDA_TRY(cudaEventRecord(evt[2], c->cs));
+        for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+            if (!(c->chains & (1u << ch))) continue;
+            ChainBuf &b = c->cb[ch];
+            TRY(launch_k2a_verify(c, ch, ka[ch]));
+            CUDA_TRY(cudaMemcpyAsync(b.ia_carry, b.set[set].ia_end + (lanes - 1), sizeof(IirState), cudaMemcpyDeviceToDevice, c->cs));
+            /* bit history for the run-length warm-ups: the previous batch's last W samples (exact since its fix-up) */
+            if (!first && c->prev_M % 32 == 0) {         /* only a final (flush) batch can be ragged */
+                TRY(copy_history(b.set[set].dbits, b.set[pset].dbits, 4, c->W / 32, c->prev_M / 32, c->cs));
+                TRY(copy_history(b.set[set].sbits, b.set[pset].sbits, 4, c->W / 32, c->prev_M / 32, c->cs));
+            }
+        }
 
         /* chain 1's run-length lanes run on their own stream (forked after whatever cs holds, joined at the end) */
         auto fork2 = [&]() -> int {
@@ -824,10 +901,11 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
                 if (!(c->chains & (1u << ch))) continue;
                 ChainBuf &b = c->cb[ch];
+                SetBuf &sb = b.set[set];
                 Stream &s = b.s[WMB_ALGO_T2A];
                 K2tParams p;
                 memset(&p, 0, sizeof(p));
-                p.dbits = b.dbits + wofs; p.sbits = b.sbits + wofs; p.rssi = b.rssi + c->W;
+                p.dbits = sb.dbits + wofs; p.sbits = sb.sbits + wofs; p.rssi = sb.rssi + c->W;
                 p.M = M; p.Cw = K2T_WORDS_PER_LANE;
                 const uint32_t nw = (uint32_t)((M + 31) / 32);
                 p.lanes = (nw + p.Cw - 1) / p.Cw;
@@ -849,9 +927,10 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             K2mParams km[WMB_N_CHAINS];
             auto setup_mono = [&](int ch, const uint32_t *run_if) -> int {
                 ChainBuf &b = c->cb[ch];
+                SetBuf &sb = b.set[set];
                 K2mParams &p = km[ch];
                 memset(&p, 0, sizeof(p));
-                p.dbits = b.dbits + wofs; p.rssi = b.rssi + c->W; p.M = M; p.hist = c->hist_m;
+                p.dbits = sb.dbits + wofs; p.rssi = sb.rssi + c->W; p.M = M; p.hist = c->hist_m;
                 p.C = C; p.W = c->W_m[ch]; p.lanes = lanes;
                 p.cap = C / 4 + K2_EDGE_EMIT_CAP + 8;
                 if ((uint64_t)lanes * p.cap > c->cap_words_rl) return set_err(WMB_E_INVAL, "internal: event buffers too small for C=%u", C);
@@ -870,7 +949,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
                 q.ev = s.ev; q.cnt = s.cnt; q.base = s.base; q.lanes = lanes; q.cap = km[ch].cap; q.C = C;
                 q.m_base = (int64_t)c->m_consumed;
                 q.ring = s.ring; q.ring_mask = s.ring_cap - 1; q.sd = s.sd; q.cand = s.cand; q.cand_cap = c->cand_cap;
-                q.agg = s.agg; q.rssi = b.rssi + c->W; q.run_if = run_if;
+                q.agg = s.agg; q.rssi = b.set[set].rssi + c->W; q.run_if = run_if;
                 return launch_k2c(c, q, st);
             };
             /* S1 (and a forced T1/C1) beside the two-phase path of T1/C1 */
@@ -890,7 +969,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
                 Stream &s = b.s[WMB_ALGO_RLA];
                 K2p1Params p1;
                 memset(&p1, 0, sizeof(p1));
-                p1.dbits = b.dbits + wofs; p1.M = M; p1.hist = c->hist_m;
+                p1.dbits = b.set[set].dbits + wofs; p1.M = M; p1.hist = c->hist_m;
                 p1.C = K2P1_CHUNK; p1.W = K2P1_WARM; p1.lanes = (uint32_t)((M + K2P1_CHUNK - 1) / K2P1_CHUNK);
                 p1.cap = K2P1_CAP; p1.rec = b.p1_rec; p1.cnt = b.p1_cnt;
                 p1.st_start = b.p1_start; p1.st_end = b.p1_end; p1.carry = b.rl_carry; p1.rerun = b.p1_rerun;
@@ -907,7 +986,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
                 p2.rec_m = b.rec_m; p2.rec_v = b.rec_v; p2.rec_n = b.rec_n; p2.pd = b.pd; p2.R = K2P2_RECORDS;
                 p2.lanes = (uint32_t)(((uint64_t)M / 5 + 2 * (uint64_t)p1.lanes) / K2P2_RECORDS + 2);
                 if (p2.lanes > c->p2_lanes_max) return set_err(WMB_E_INVAL, "internal: phase-2 lanes");
-                p2.cnt = b.p2_cnt; p2.base = b.p2_base; p2.rssi = b.rssi + c->W; p2.m_base = (int64_t)c->m_consumed;
+                p2.cnt = b.p2_cnt; p2.base = b.p2_base; p2.rssi = b.set[set].rssi + c->W; p2.m_base = (int64_t)c->m_consumed;
                 p2.ring = s.ring; p2.ring_mask = s.ring_cap - 1; p2.sd = s.sd; p2.cand = s.cand; p2.cand_cap = c->cand_cap;
                 p2.carry = b.rl_carry; p2.p2_out = b.p2_out; p2.agg = s.agg;
                 TRY(launch_k2p_rest(c, pc, p2));
@@ -923,22 +1002,13 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
             if (s1_beside) TRY(join2());
             tr("k2t+p1+p2");
         }
+        if (c->o.t2_enabled) CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_join, 0));
+        CUDA_TRY(cudaEventRecord(evt[3], c->cs));
+    } else {
+        CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_k1[set], 0));
+        CUDA_TRY(cudaEventRecord(evt[2], c->cs));
+        CUDA_TRY(cudaEventRecord(evt[3], c->cs));
     }
-    if (any_sync && c->o.t2_enabled) CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_join, 0));
-    CUDA_TRY(cudaEventRecord(c->ev_t[2], c->cs));
-
-    /* slide the histories: the last W samples move in front of index 0 */
-    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-        if (!(c->chains & (1u << ch))) continue;
-        ChainBuf &b = c->cb[ch];
-        TRY(slide_history(c, b.dphi, 4, c->W, M));
-        TRY(slide_history(c, b.rssi, 1, c->W, M));
-        if (any_sync && M % 32 == 0) {                  /* only a final (flush) batch can be ragged */
-            TRY(slide_history(c, b.dbits, 4, c->W / 32, M / 32));
-            TRY(slide_history(c, b.sbits, 4, c->W / 32, M / 32));
-        }
-    }
-    CUDA_TRY(cudaEventRecord(c->ev_t[3], c->cs));
 
     c->hist_m = std::min<int64_t>(c->hist_m + M, c->W);
     c->iq_consumed += (uint64_t)n_iq;
@@ -947,65 +1017,96 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, bool src_is_
     c->st.decimated_samples += (uint64_t)M;
     c->st.batches++;
     c->batch_no++;
+    c->prev_M = M; c->last_M = M; c->last_set = set;
     return WMB_OK;
 }
 
-/* Enqueue the frame gather (K3) and the device framer (K4) for everything the streams hold: the candidates carried
- * over plus the new access-code matches.  final: end of input, nothing is carried over. */
-static int enqueue_gather(wmb_ctx *c, bool final)
+static int consume_oldest(wmb_ctx *c);
+
+/* Enqueue the frame gather (K3), the device framer (K4) and the copies of their results into the host mirror of the
+ * next result slot, for everything the streams hold: the candidates carried over plus the new access-code matches.
+ * after_batch: this gather closes the batch just enqueued (its set may be reused once it is done).  final: end of
+ * input, nothing is carried over. */
+static int enqueue_gather(wmb_ctx *c, bool final, bool after_batch)
 {
+    if (!c->allocated) return WMB_OK;
     const bool any_sync = c->o.rla_enabled || c->o.t2_enabled;
-    if (!any_sync || !c->allocated) return WMB_OK;
-    if (c->batch_final.size() >= c->rec_cap) return set_err(WMB_E_STATE, "internal: too many batches between two reads");
-    K3Params p;
-    memset(&p, 0, sizeof(p));
-    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
-        if (!(c->chains & (1u << ch))) continue;
-        for (int a = 0; a < WMB_N_ALGOS; a++) {
-            if ((a == WMB_ALGO_RLA && !c->o.rla_enabled) || (a == WMB_ALGO_T2A && !c->o.t2_enabled)) continue;
-            Stream &s = c->cb[ch].s[a];
-            const int k = ch * WMB_N_ALGOS + a;
-            p.ring[k] = s.ring; p.ring_mask[k] = s.ring_cap - 1; p.sd[k] = s.sd; p.cand[k] = s.cand; p.pend[k] = s.pend;
+    if (c->inflight.size() >= WMB_NSLOT) TRY(consume_oldest(c));          /* the slot's host mirror must be free */
+    const int slot = (int)(c->gather_no % WMB_NSLOT);
+    const size_t lb = (size_t)slot * c->slot_cap, pb = (size_t)slot * c->slot_pool;
+    if (any_sync) {
+        K3Params p;
+        memset(&p, 0, sizeof(p));
+        for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+            if (!(c->chains & (1u << ch))) continue;
+            for (int a = 0; a < WMB_N_ALGOS; a++) {
+                if ((a == WMB_ALGO_RLA && !c->o.rla_enabled) || (a == WMB_ALGO_T2A && !c->o.t2_enabled)) continue;
+                Stream &s = c->cb[ch].s[a];
+                const int k = ch * WMB_N_ALGOS + a;
+                p.ring[k] = s.ring; p.ring_mask[k] = s.ring_cap - 1; p.sd[k] = s.sd; p.cand[k] = s.cand; p.pend[k] = s.pend;
+            }
+        }
+        p.pend_cap = c->pend_cap; p.cand_cap = c->cand_cap;
+        p.gd = c->d_gd; p.rec = c->d_rec + slot;
+        p.hdr_log = c->d_hdr; p.dec_log = c->d_dec; p.log_base = (uint32_t)lb; p.log_cap = c->slot_cap;
+        p.words = c->d_words; p.words_cap = c->frame_words_cap;
+        p.cut_n = c->d_cut_n; p.agg = c->d_k3_agg; p.errors = c->d_errors;
+        p.final = final ? 1u : 0u;
+        K4Params q;
+        memset(&q, 0, sizeof(q));
+        q.hdr = c->d_hdr; q.words = c->d_words; q.dec = c->d_dec;
+        q.pool = c->d_pool + pb; q.pool_cap = c->slot_pool; q.pool_n = GD_FIELD(c, pool_n); q.errors = c->d_errors; q.gd = c->d_gd;
+        TRY(launch_k3_k4(c, p, c->manual ? nullptr : &q));
+        /* results -> pinned host mirror: the record and a prefix of the arrays it describes (the rest, if a batch ever
+         * produces more, is fetched when the record has been read) */
+        CUDA_TRY(cudaMemcpyAsync(c->h_rec + slot, c->d_rec + slot, sizeof(BatchRec), cudaMemcpyDeviceToHost, c->cs));
+        CUDA_TRY(cudaMemcpyAsync(c->h_hdr + lb, c->d_hdr + lb, (size_t)c->spec_n * sizeof(FrameHdr), cudaMemcpyDeviceToHost, c->cs));
+        if (!c->manual) {
+            CUDA_TRY(cudaMemcpyAsync(c->h_dec + lb, c->d_dec + lb, (size_t)c->spec_n * sizeof(DecHdr), cudaMemcpyDeviceToHost, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(c->h_pool + pb, c->d_pool + pb, c->spec_pool, cudaMemcpyDeviceToHost, c->cs));
         }
     }
-    p.pend_cap = c->pend_cap; p.cand_cap = c->cand_cap;
-    p.gd = c->d_gd; p.rec = c->d_rec; p.rec_cap = c->rec_cap;
-    p.hdr_log = c->d_hdr; p.dec_log = c->d_dec; p.log_cap = c->log_cap;
-    p.words = c->d_words; p.words_cap = c->frame_words_cap;
-    p.cut_n = c->d_cut_n; p.agg = c->d_k3_agg; p.errors = c->d_errors;
-    p.final = final ? 1u : 0u;
-    p.pool = c->d_pool; p.pool_cap = c->pool_cap;
-    K4Params q;
-    memset(&q, 0, sizeof(q));
-    q.hdr = c->d_hdr; q.words = c->d_words; q.dec = c->d_dec;
-    q.pool = c->d_pool; q.pool_cap = c->pool_cap; q.pool_n = GD_FIELD(c, pool_n); q.errors = c->d_errors; q.gd = c->d_gd;
-    TRY(launch_k3_k4(c, p, c->manual ? nullptr : &q));
-    c->batch_final.push_back(final ? 1 : 0);
+    CUDA_TRY(cudaEventRecord(c->ev_res[slot], c->cs));
+    if (after_batch) {
+        CUDA_TRY(cudaEventRecord(c->ev_chain[c->last_set], c->cs));
+        c->chain_recorded[c->last_set] = true;
+    }
+    wmb_ctx::InFlight f;
+    f.slot = slot; f.final = final; f.has_timers = after_batch; f.m_end = c->m_consumed;
+    c->inflight.push_back(f);
+    c->gather_no++;
     return WMB_OK;
 }
 
-static int book_device_frames(wmb_ctx *c, const FrameHdr *hdr, const DecHdr *dec, size_t n, bool final);
+static int book_device_frames(wmb_ctx *c, const FrameHdr *hdr, const DecHdr *dec, const uint8_t *pool, size_t n, bool final);
 
-/* Fetch what the gathers since the last read produced -- one set of copies and ONE synchronisation in the common
- * case (the counts travel with a prefix of the arrays they describe; a second copy follows only when a push produced
- * more than that prefix) -- and run the stream-order bookkeeping over it, batch by batch. */
-static int read_results(wmb_ctx *c)
+/* Wait for the oldest gathered batch's results (an event, not a stream: later batches keep running), fetch what the
+ * prefix copy did not cover, and run the stream-order bookkeeping over it. */
+static int consume_oldest(wmb_ctx *c)
 {
-    if (c->batch_final.empty()) return WMB_OK;
-    const size_t nrec = c->batch_final.size();
-    const bool dev_decode = !c->manual;
-    CUDA_TRY(cudaMemcpyAsync(&c->h_read->errors, c->d_errors, 4, cudaMemcpyDeviceToHost, c->cs));
-    CUDA_TRY(cudaMemcpyAsync(&c->h_read->gd, c->d_gd, sizeof(GatherDev), cudaMemcpyDeviceToHost, c->cs));
-    CUDA_TRY(cudaMemcpyAsync(c->h_rec, c->d_rec, nrec * sizeof(BatchRec), cudaMemcpyDeviceToHost, c->cs));
-    CUDA_TRY(cudaMemcpyAsync(c->h_hdr, c->d_hdr, (size_t)c->spec_n * sizeof(FrameHdr), cudaMemcpyDeviceToHost, c->cs));
-    if (dev_decode) {
-        CUDA_TRY(cudaMemcpyAsync(c->h_dec, c->d_dec, (size_t)c->spec_n * sizeof(DecHdr), cudaMemcpyDeviceToHost, c->cs));
-        CUDA_TRY(cudaMemcpyAsync(c->h_pool, c->d_pool, c->spec_pool, cudaMemcpyDeviceToHost, c->cs));
+    if (c->inflight.empty()) return WMB_OK;
+    const wmb_ctx::InFlight f = c->inflight.front();
+    c->inflight.erase(c->inflight.begin());
+    const bool any_sync = c->o.rla_enabled || c->o.t2_enabled;
+    const double t0 = wall_ms();
+    CUDA_TRY(cudaEventSynchronize(c->ev_res[f.slot]));
+    const double t1 = wall_ms();
+    c->st.host_gather_ms += t1 - t0;
+    if (f.has_timers) {
+        float ms = 0.f;
+        cudaEvent_t *evt = c->ev_t[f.slot];
+        const bool any = c->o.rla_enabled || c->o.t2_enabled;
+        if (cudaEventElapsedTime(&ms, evt[0], evt[1]) == cudaSuccess) c->acc_demod_ms += ms;
+        if (any && cudaEventElapsedTime(&ms, evt[4], evt[5]) == cudaSuccess) c->acc_bitsync_ms += ms;     /* clock-recovery lanes */
+        if (cudaEventElapsedTime(&ms, evt[2], evt[3]) == cudaSuccess) c->acc_bitsync_ms += ms;            /* bit streams */
+        /* the whole per-sample pass of the push so far: first demod kernel -> this batch's last bit-sync kernel */
+        if (cudaEventElapsedTime(&ms, c->ev_push_start, evt[3]) == cudaSuccess) c->acc_pass_ms = ms;
     }
-    CUDA_TRY(cudaStreamSynchronize(c->cs));
-    tr("read-1");
-    const uint32_t err = c->h_read->errors;
-    const GatherDev &g = c->h_read->gd;
+    if (!any_sync) return WMB_OK;
+    const bool dev_decode = !c->manual;
+    const size_t lb = (size_t)f.slot * c->slot_cap, pb = (size_t)f.slot * c->slot_pool;
+    const BatchRec r = c->h_rec[f.slot];
+    const uint32_t err = r.errors;
     if (err & 1u) return set_err(WMB_E_OVERFLOW, "bit event buffer overflow (pathological input)");
     if (err & 2u) return set_err(WMB_E_OVERFLOW, "run-length tracker left its defined range (the reference would spin here)");
     if (err & 4u) return set_err(WMB_E_OVERFLOW, "frame buffer overflow");
@@ -1013,84 +1114,72 @@ static int read_results(wmb_ctx *c)
     if (err & 16u) return set_err(WMB_E_OVERFLOW, "too many access-code matches in one batch");
     if (err & 32u) return set_err(WMB_E_OVERFLOW, "bit event ring overflow");
     if (err & 64u) return set_err(WMB_E_OVERFLOW, "too many pending candidates");
-    if (err & 128u) return set_err(WMB_E_STATE, "internal: batch records exhausted");
     if (err & 256u) return set_err(WMB_E_STATE, "internal: lane verification does not converge");
-    if (g.n_rec != nrec) return set_err(WMB_E_STATE, "internal: %u batch records for %zu gathers", g.n_rec, nrec);
-    const uint32_t n = g.log_n, npool = g.pool_n;
     bool more = false;
-    if (n > c->spec_n) {
-        CUDA_TRY(cudaMemcpyAsync(c->h_hdr + c->spec_n, c->d_hdr + c->spec_n, (size_t)(n - c->spec_n) * sizeof(FrameHdr), cudaMemcpyDeviceToHost, c->cs));
-        if (dev_decode) CUDA_TRY(cudaMemcpyAsync(c->h_dec + c->spec_n, c->d_dec + c->spec_n, (size_t)(n - c->spec_n) * sizeof(DecHdr), cudaMemcpyDeviceToHost, c->cs));
+    if (r.n > c->spec_n) {
+        CUDA_TRY(cudaMemcpyAsync(c->h_hdr + lb + c->spec_n, c->d_hdr + lb + c->spec_n, (size_t)(r.n - c->spec_n) * sizeof(FrameHdr), cudaMemcpyDeviceToHost, c->xs));
+        if (dev_decode) CUDA_TRY(cudaMemcpyAsync(c->h_dec + lb + c->spec_n, c->d_dec + lb + c->spec_n, (size_t)(r.n - c->spec_n) * sizeof(DecHdr), cudaMemcpyDeviceToHost, c->xs));
         more = true;
     }
-    if (dev_decode && npool > c->spec_pool) {
-        CUDA_TRY(cudaMemcpyAsync(c->h_pool + c->spec_pool, c->d_pool + c->spec_pool, npool - c->spec_pool, cudaMemcpyDeviceToHost, c->cs));
+    if (dev_decode && r.pool_n > c->spec_pool) {
+        CUDA_TRY(cudaMemcpyAsync(c->h_pool + pb + c->spec_pool, c->d_pool + pb + c->spec_pool, r.pool_n - c->spec_pool, cudaMemcpyDeviceToHost, c->xs));
         more = true;
     }
-    if (!dev_decode && g.n_words) {
-        CUDA_TRY(cudaMemcpyAsync(c->h_words, c->d_words, (size_t)g.n_words * 4, cudaMemcpyDeviceToHost, c->cs));
-        c->st.d2h_bytes += (uint64_t)g.n_words * 4;
+    if (!dev_decode && r.n_words) {          /* manual mode reads after every batch: the frame words are this batch's */
+        CUDA_TRY(cudaMemcpyAsync(c->h_words, c->d_words, (size_t)r.n_words * 4, cudaMemcpyDeviceToHost, c->xs));
+        c->st.d2h_bytes += (uint64_t)r.n_words * 4;
         more = true;
     }
-    /* empty the log for the next push (log_n, pool_n, n_rec are adjacent) */
-    CUDA_TRY(cudaMemsetAsync(GD_FIELD(c, log_n), 0, 12, c->cs));
-    if (more) CUDA_TRY(cudaStreamSynchronize(c->cs));
-    tr("read-2");
-    c->st.d2h_bytes += sizeof(*c->h_read) + nrec * sizeof(BatchRec) + (size_t)n * sizeof(FrameHdr) +
-                       (dev_decode ? (size_t)n * sizeof(DecHdr) + npool : 0);
+    if (more) CUDA_TRY(cudaStreamSynchronize(c->xs));       /* the slot is not written again before it is consumed */
+    c->st.d2h_bytes += sizeof(BatchRec) + (size_t)r.n * sizeof(FrameHdr) + (dev_decode ? (size_t)r.n * sizeof(DecHdr) + r.pool_n : 0);
     /* statistics kept on the device */
-    c->st.lanes_rerun += g.lanes_rerun - c->stat_rerun_seen; c->st.lanes_run += g.lanes_rerun - c->stat_rerun_seen;
-    c->stat_rerun_seen = g.lanes_rerun;
-    c->st.rl_fallbacks += g.rl_fallbacks - c->stat_fallback_seen;
-    c->stat_fallback_seen = g.rl_fallbacks;
+    c->st.lanes_rerun += r.lanes_rerun - c->stat_rerun_seen; c->st.lanes_run += r.lanes_rerun - c->stat_rerun_seen;
+    c->stat_rerun_seen = r.lanes_rerun;
+    c->st.rl_fallbacks += r.rl_fallbacks - c->stat_fallback_seen;
+    c->stat_fallback_seen = r.rl_fallbacks;
     for (int ch = 0; ch < WMB_N_CHAINS; ch++)
         for (int a = 0; a < WMB_N_ALGOS; a++) {
             const int k = ch * WMB_N_ALGOS + a;
-            c->st.candidates[ch][a] = g.n_cand_total[k];
-            c->cb[ch].s[a].total = g.total_prev[k];
+            c->st.candidates[ch][a] = r.n_cand_total[k];
+            c->cb[ch].s[a].total = r.total[k];
         }
+    if (r.n > c->slot_cap) return set_err(WMB_E_STATE, "internal: batch record beyond its slot");
+    FrameHdr *hdr = c->h_hdr + lb;
     /* the device keeps 40 bits of the sample index; widen to the 64-bit stream position: the newest value
-     * congruent to it that is not beyond the samples produced so far */
-    for (uint32_t i = 0; i < n; i++)
-        c->h_hdr[i].sync_sample = c->m_consumed - ((c->m_consumed - c->h_hdr[i].sync_sample) & EVG_M_MASK);
-
+     * congruent to it that is not beyond the samples produced when the batch was gathered */
+    for (uint32_t i = 0; i < r.n; i++) hdr[i].sync_sample = f.m_end - ((f.m_end - hdr[i].sync_sample) & EVG_M_MASK);
     int rc = WMB_OK;
-    for (size_t r = 0; r < nrec && rc == WMB_OK; r++) {
-        const BatchRec &br = c->h_rec[r];
-        const bool final = c->batch_final[r] != 0;
-        if ((uint64_t)br.base + br.n > n) { rc = set_err(WMB_E_STATE, "internal: batch record beyond the log"); break; }
-        if (dev_decode) {
-            rc = book_device_frames(c, c->h_hdr + br.base, c->h_dec + br.base, br.n, final);
-            continue;
-        }
-        /* manual mode (one batch per read): keep the frames (newest version of a re-delivered partial one wins) for wmb_poll */
-        for (uint32_t i = 0; i < br.n; i++) {
-            const FrameHdr &h = c->h_hdr[br.base + i];
+    if (dev_decode) rc = book_device_frames(c, hdr, c->h_dec + lb, c->h_pool + pb, r.n, f.final);
+    else {
+        /* manual mode: keep the frames (newest version of a re-delivered partial one wins) for wmb_poll */
+        for (uint32_t i = 0; i < r.n; i++) {
+            const FrameHdr &h = hdr[i];
             if (h.nbits == 0) continue;
-            wmb_frame f;
-            memset(&f, 0, sizeof(f));
-            f.sync_sample = h.sync_sample; f.ordinal = h.ordinal; f.chain = h.chain; f.algo = h.algo;
-            f.truncated = (uint8_t)((h.complete && !h.cut) ? 0 : 1);
-            f.reserved = (uint8_t)((!h.complete && !final) ? 1 : 0);      /* partial: will be re-delivered */
-            f.nbits = h.nbits;
+            wmb_frame fr;
+            memset(&fr, 0, sizeof(fr));
+            fr.sync_sample = h.sync_sample; fr.ordinal = h.ordinal; fr.chain = h.chain; fr.algo = h.algo;
+            fr.truncated = (uint8_t)((h.complete && !h.cut) ? 0 : 1);
+            fr.reserved = (uint8_t)((!h.complete && !f.final) ? 1 : 0);      /* partial: will be re-delivered */
+            fr.nbits = h.nbits;
             wmb_ctx::Held *slot = nullptr;
             for (auto &hh : c->held)
-                if (hh.f.chain == f.chain && hh.f.algo == f.algo && hh.f.ordinal == f.ordinal) { slot = &hh; break; }
+                if (hh.f.chain == fr.chain && hh.f.algo == fr.algo && hh.f.ordinal == fr.ordinal) { slot = &hh; break; }
             if (!slot) { c->held.emplace_back(); slot = &c->held.back(); }
-            slot->f = f;
+            slot->f = fr;
             slot->words.assign(c->h_words + h.word_off, c->h_words + h.word_off + h.nbits);
         }
     }
-    c->batch_final.clear();
+    c->st.host_decode_ms += wall_ms() - t1;
     return rc;
 }
 
-static void read_timers(wmb_ctx *c)
+static int consume_all(wmb_ctx *c)
 {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, c->ev_t[0], c->ev_t[1]) == cudaSuccess) c->st.demod_kernel_ms = ms;
-    if (cudaEventElapsedTime(&ms, c->ev_t[1], c->ev_t[2]) == cudaSuccess) c->st.bitsync_kernel_ms = ms;
-    if (cudaEventElapsedTime(&ms, c->ev_t[0], c->ev_t[3]) == cudaSuccess) c->st.batch_device_ms = ms;
+    while (!c->inflight.empty()) TRY(consume_oldest(c));
+    c->st.demod_kernel_ms = c->acc_demod_ms; c->st.bitsync_kernel_ms = c->acc_bitsync_ms; c->st.batch_device_ms = c->acc_pass_ms;
+    tr("consumed");
+    tr_dump();
+    return WMB_OK;
 }
 
 /* --------------------------------------------------------------------------- */
@@ -1106,20 +1195,12 @@ static double wall_ms()
     return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
 }
 
-/* gather what the last batch produced and bring the results to the host */
-static int finish_batch(wmb_ctx *c, bool final)
+/* gather what the batch just enqueued produced; manual mode reads it at once (the frame words are per batch) */
+static int finish_batch(wmb_ctx *c, bool final, bool after_batch)
 {
-    const double t0 = wall_ms();
-    int rc = enqueue_gather(c, final);
-    if (rc) return rc;
-    const double t1 = wall_ms();
-    c->st.host_gather_ms += t1 - t0;
-    rc = read_results(c);
-    read_timers(c);
-    c->st.host_decode_ms += wall_ms() - t1;
-    tr("decode");
-    tr_dump();
-    return rc;
+    TRY(enqueue_gather(c, final, after_batch));
+    if (c->manual) TRY(consume_all(c));
+    return WMB_OK;
 }
 
 static size_t batch_granule(const wmb_ctx *c) { return (size_t)4096 * c->d; }
@@ -1137,29 +1218,40 @@ extern "C" int wmb_push_device(wmb_ctx *c, const void *dev_cu8, size_t nbytes)
      * whose length is a multiple of 4096 but not of 4096 * d) waits on the host side like the remainder of a host push */
     const size_t tail = nbytes % batch_granule(c);
     rc = process_device_batches(c, (const uint8_t *)dev_cu8, nbytes - tail, false);
+    if (rc) return rc;
+    rc = consume_all(c);                                  /* also: the caller's buffer is no longer in use */
     if (rc || !tail) return rc;
     c->remainder.resize(tail);
     CUDA_TRY(cudaMemcpy(c->remainder.data(), (const uint8_t *)dev_cu8 + (nbytes - tail), tail, cudaMemcpyDeviceToHost));
     return WMB_OK;
 }
 
-/* dev points to device memory that stays valid during the call */
+/* dev points to device memory that stays valid until the results have been consumed.  A long push is cut into
+ * batches that follow each other through the device like through a pipeline: the demod kernel of batch i+1 runs
+ * beside the latency-bound bit-stream kernels of batch i (run_batch), and the host books batch i's results while
+ * later batches are still running. */
 static int process_device_batches(wmb_ctx *c, const uint8_t *dev, size_t nbytes, bool final)
 {
     const size_t gran = batch_granule(c);
+    size_t cap = std::min(c->max_batch_bytes, g_pipe_bytes);
+    cap -= cap % gran;
+    if (!cap) cap = gran;
     size_t off = 0;
+    c->acc_demod_ms = c->acc_bitsync_ms = c->acc_pass_ms = 0; c->push_started = false;
     while (off < nbytes) {
-        size_t n = std::min(nbytes - off, c->max_batch_bytes);
+        size_t n = std::min(nbytes - off, cap);
+        if (nbytes - off - n < cap / 4) n = nbytes - off;                /* no dwarf batch at the end */
+        if (n > c->max_batch_bytes) n = c->max_batch_bytes;
         if (n < nbytes - off || !final) {
             /* keep batch boundaries on whole decimation periods */
             if (n % gran) n -= n % gran;
             if (n == 0) break;
         }
         const double tb = wall_ms();
-        int rc = run_batch(c, dev + off, n, false);
+        int rc = run_batch(c, dev + off, n, nullptr, off + n >= nbytes);
         if (rc) return rc;
         c->st.host_batch_ms += wall_ms() - tb;
-        rc = finish_batch(c, false);
+        rc = finish_batch(c, false, true);
         if (rc) return rc;
         off += n;
     }
@@ -1195,6 +1287,7 @@ static int push_host_bytes(wmb_ctx *c, const uint8_t *p, size_t nbytes, bool fin
         c->remainder.assign(p, p + nbytes);             /* less than one granule: keep for later */
         return WMB_OK;
     }
+    c->acc_demod_ms = c->acc_bitsync_ms = c->acc_pass_ms = 0; c->push_started = false;
     int idx = c->buf_idx;
     CUDA_TRY(cudaStreamWaitEvent(c->xs, c->ev_k1done[idx], 0));
     CUDA_TRY(cudaMemcpyAsync(c->d_in[idx], p, cur_n, cudaMemcpyHostToDevice, c->xs));
@@ -1208,21 +1301,20 @@ static int push_host_bytes(wmb_ctx *c, const uint8_t *p, size_t nbytes, bool fin
             CUDA_TRY(cudaMemcpyAsync(c->d_in[nidx], p + nxt_off, nxt_n, cudaMemcpyHostToDevice, c->xs));
             CUDA_TRY(cudaEventRecord(c->ev_h2d[nidx], c->xs));
         }
-        CUDA_TRY(cudaStreamWaitEvent(c->cs, c->ev_h2d[idx], 0));
         c->buf_idx = idx;
         const double tb = wall_ms();
-        int rc = run_batch(c, c->d_in[idx], cur_n, true);
+        int rc = run_batch(c, c->d_in[idx], cur_n, c->ev_h2d[idx], nxt_n == 0);
         if (rc) return rc;
         c->st.host_batch_ms += wall_ms() - tb;
         c->st.h2d_bytes += cur_n;
-        rc = finish_batch(c, false);
+        rc = finish_batch(c, false, true);
         if (rc) return rc;
         off = nxt_off; cur_n = nxt_n; idx ^= 1;
     }
     c->buf_idx = idx;
     CUDA_TRY(cudaStreamSynchronize(c->xs));             /* the caller may reuse its buffer now */
     if (off < nbytes) c->remainder.assign(p + off, p + nbytes);
-    return WMB_OK;
+    return consume_all(c);
 }
 
 extern "C" int wmb_push(wmb_ctx *c, const uint8_t *cu8, size_t nbytes)
@@ -1262,7 +1354,9 @@ static int flush_input(wmb_ctx *c)
             c->remainder.clear();
         }
     }
-    return finish_batch(c, true);
+    rc = finish_batch(c, true, false);
+    if (rc) return rc;
+    return consume_all(c);
 }
 
 extern "C" int wmb_poll(wmb_ctx *c, wmb_frame *out, size_t cap, size_t *n, int flush)
@@ -1347,7 +1441,7 @@ static int book_frames(wmb_ctx *c, size_t n, Meta meta, Lite lite, Fill fill)
 }
 
 /* candidates of one gathered batch, decoded by K4 (already in stream order) */
-static int book_device_frames(wmb_ctx *c, const FrameHdr *hdr, const DecHdr *dec, size_t n, bool final)
+static int book_device_frames(wmb_ctx *c, const FrameHdr *hdr, const DecHdr *dec, const uint8_t *pool, size_t n, bool final)
 {
     static const char modes[3][3] = { "T1", "C1", "S1" };
     /* frames without any bit (candidate at the very end of the stream) are not decoded at all */
@@ -1376,7 +1470,7 @@ static int book_device_frames(wmb_ctx *c, const FrameHdr *hdr, const DecHdr *dec
             memcpy(o.mode, modes[d.mode < 3 ? d.mode : 0], 3);
             o.crc_ok = d.crc_ok; o.ok_3of6 = d.ok_3of6; o.packet_rssi = d.packet_rssi; o.current_rssi = d.current_rssi;
             o.serial = d.serial; o.len = d.len;
-            memcpy(o.datagram, c->h_pool + d.data_off, d.len);
+            memcpy(o.datagram, pool + d.data_off, d.len);
         });
 }
 
@@ -1400,15 +1494,15 @@ extern "C" int wmb_frame_decode_device(wmb_ctx *c, const wmb_frame *frames, size
     }
     CUDA_TRY(cudaMemcpyAsync(c->d_hdr, c->h_hdr, n * sizeof(FrameHdr), cudaMemcpyHostToDevice, c->cs));
     CUDA_TRY(cudaMemcpyAsync(c->d_words, c->h_words, words * 4, cudaMemcpyHostToDevice, c->cs));
-    if (!c->batch_final.empty()) return set_err(WMB_E_STATE, "unread results");
+    if (!c->inflight.empty()) return set_err(WMB_E_STATE, "unread results");
     CUDA_TRY(cudaMemsetAsync(GD_FIELD(c, pool_n), 0, 4, c->cs));
     K4Params q;
     memset(&q, 0, sizeof(q));
     q.hdr = c->d_hdr; q.n = (uint32_t)n; q.words = c->d_words; q.dec = c->d_dec;
-    q.pool = c->d_pool; q.pool_cap = c->pool_cap; q.pool_n = GD_FIELD(c, pool_n); q.errors = c->d_errors;
+    q.pool = c->d_pool; q.pool_cap = c->slot_pool; q.pool_n = GD_FIELD(c, pool_n); q.errors = c->d_errors;
     TRY(launch_k4(c, q));
     CUDA_TRY(cudaMemcpyAsync(c->h_dec, c->d_dec, n * sizeof(DecHdr), cudaMemcpyDeviceToHost, c->cs));
-    CUDA_TRY(cudaMemcpyAsync(c->h_pool, c->d_pool, c->pool_cap < (1u << 24) ? c->pool_cap : (1u << 24), cudaMemcpyDeviceToHost, c->cs));
+    CUDA_TRY(cudaMemcpyAsync(c->h_pool, c->d_pool, c->slot_pool < (1u << 24) ? c->slot_pool : (1u << 24), cudaMemcpyDeviceToHost, c->cs));
     CUDA_TRY(cudaMemsetAsync(GD_FIELD(c, pool_n), 0, 4, c->cs));
     CUDA_TRY(cudaStreamSynchronize(c->cs));
     static const char modes[3][3] = { "T1", "C1", "S1" };
@@ -1522,10 +1616,9 @@ extern "C" long wmb_process_device(wmb_ctx *c, const void *dev_cu8, size_t nbyte
     rc = process_device_batches(c, (const uint8_t *)dev_cu8, nbytes, flush != 0);
     if (rc) return rc;
     tr("batches");
-    if (flush) {
-        rc = flush_input(c);
-        if (rc) return rc;
-    }
+    if (flush) rc = flush_input(c);
+    else rc = consume_all(c);
+    if (rc) return rc;
     tr("flush");
     const long len = (long)wmb_take_lines(c, out, outcap, n_lines, timestamp_mode);
     tr("lines");
@@ -1543,7 +1636,8 @@ extern "C" int wmb_reset(wmb_ctx *c)
     if (c->xs) CUDA_TRY(cudaStreamSynchronize(c->xs));
     c->iq_consumed = 0; c->m_consumed = 0; c->hist_m = 0; c->hist_iq = 0;
     c->remainder.clear(); c->lines.clear(); c->held.clear(); c->held_prev.clear();
-    c->batch_no = 0; c->last_M = 0; c->batch_final.clear();
+    for (cudaStream_t st : { c->k1s, c->as[0], c->as[1], c->ts, c->s2 }) if (st) CUDA_TRY(cudaStreamSynchronize(st));
+    c->batch_no = 0; c->last_M = 0; c->prev_M = 0; c->last_set = 0; c->inflight.clear();
     if (c->allocated) {
         CUDA_TRY(cudaMemsetAsync(c->d_errors, 0, 64, c->cs));
         CUDA_TRY(cudaMemsetAsync(c->d_gd, 0, sizeof(GatherDev), c->cs));
@@ -1593,7 +1687,7 @@ extern "C" long wmb_boundary_state(wmb_ctx *c, uint8_t *buf, size_t cap)
     CUDA_TRY(cudaSetDevice(c->device));
     int rc = ctx_alloc(c);
     if (rc) return rc;
-    rc = read_results(c);                               /* every enqueued batch is gathered and booked first */
+    rc = consume_all(c);                                /* every enqueued batch is gathered and booked first */
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->cs));
     GatherDev gd;
@@ -1660,22 +1754,23 @@ extern "C" int wmb_get_stats(wmb_ctx *c, wmb_stats *s)
 
 extern "C" long wmb_debug_copy_stage(wmb_ctx *c, int chain, float *dphi, uint8_t *rssi, size_t cap)
 {
-    if (!c || chain < 0 || chain >= WMB_N_CHAINS || !c->allocated || !c->cb[chain].dphi)
+    if (!c || chain < 0 || chain >= WMB_N_CHAINS || !c->allocated || !c->cb[chain].set[0].dphi)
         return set_err(WMB_E_INVAL, "stage not available");
+    const SetBuf &sb = c->cb[chain].set[c->last_set];
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->cs));
     /* the last batch's outputs still sit at [W, W + last_M) until the next batch overwrites them */
     const size_t n = std::min<size_t>((size_t)c->last_M, cap);
-    if (dphi) CUDA_TRY(cudaMemcpy(dphi, c->cb[chain].dphi + c->W, n * 4, cudaMemcpyDeviceToHost));
-    if (rssi) CUDA_TRY(cudaMemcpy(rssi, c->cb[chain].rssi + c->W, n, cudaMemcpyDeviceToHost));
+    if (dphi) CUDA_TRY(cudaMemcpy(dphi, sb.dphi + c->W, n * 4, cudaMemcpyDeviceToHost));
+    if (rssi) CUDA_TRY(cudaMemcpy(rssi, sb.rssi + c->W, n, cudaMemcpyDeviceToHost));
     return (long)n;
 }
 
 extern "C" long wmb_debug_copy_bits(wmb_ctx *c, int chain, int which, uint32_t *words, size_t cap_words)
 {
-    if (!c || chain < 0 || chain >= WMB_N_CHAINS || !words || !c->allocated || !c->cb[chain].dbits)
+    if (!c || chain < 0 || chain >= WMB_N_CHAINS || !words || !c->allocated || !c->cb[chain].set[0].dbits)
         return set_err(WMB_E_INVAL, "stage not available");
-    const ChainBuf &b = c->cb[chain];
+    const SetBuf &b = c->cb[chain].set[c->last_set];
     const uint32_t *src = which == 0 ? b.dbits : which == 1 ? b.sbits : which == 2 ? b.cbits : nullptr;
     if (!src) return set_err(WMB_E_INVAL, which == 2 ? "clock signs are kept only by a context created with opts.reserved[1] = 1" : "no such tap");
     CUDA_TRY(cudaSetDevice(c->device));

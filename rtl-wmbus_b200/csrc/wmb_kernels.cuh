@@ -574,11 +574,9 @@ struct FrameHdr {                   /* one per candidate, device -> host        
 
 struct GatherDev {                  /* device-resident state of the gather, one per context */
     uint32_t n;                     /* candidates of the current batch                      */
-    uint32_t base;                  /* where they start in the result log                   */
+    uint32_t base;                  /* where they start in the result log (the batch's slot) */
     uint32_t n_words;               /* frame words of the current batch                     */
-    uint32_t log_n;                 /* log entries since the host last emptied the log      */
-    uint32_t pool_n;                /* datagram bytes since then                            */
-    uint32_t n_rec;                 /* batch records since then                             */
+    uint32_t pool_n;                /* datagram bytes of the current batch (relative to the slot's pool region) */
     uint32_t off[WMB_N_STREAMS + 1];/* this batch: first candidate of every stream          */
     uint32_t n_pend[WMB_N_STREAMS]; /* candidates waiting for more bits                     */
     uint64_t total_prev[WMB_N_STREAMS];   /* stream totals at the previous gather           */
@@ -587,7 +585,12 @@ struct GatherDev {                  /* device-resident state of the gather, one 
     uint32_t rl_fallbacks;          /* statistics: batches redone with the monolithic run-length lanes */
 };
 
-struct BatchRec { uint32_t base, n, n_words, final; };      /* one per gathered batch, for the host */
+struct BatchRec {                   /* what the host needs to know about one gathered batch; written last (k3_publish) */
+    uint32_t n, n_words, pool_n, errors;
+    uint32_t lanes_rerun, rl_fallbacks;
+    uint64_t total[WMB_N_STREAMS];
+    uint64_t n_cand_total[WMB_N_STREAMS];
+};
 
 struct DecHdr;
 
@@ -599,14 +602,14 @@ struct K3Params {
     uint64_t *pend[WMB_N_STREAMS];  /* carried candidates, ordered                          */
     uint32_t pend_cap, cand_cap;
     GatherDev *gd;
-    BatchRec *rec; uint32_t rec_cap;
-    FrameHdr *hdr_log; DecHdr *dec_log; uint32_t log_cap;
+    BatchRec *rec;                  /* this batch's record (its result slot)                */
+    FrameHdr *hdr_log; DecHdr *dec_log;
+    uint32_t log_base, log_cap;     /* the slot's part of the log                           */
     uint32_t *words; uint32_t words_cap;
     uint32_t *cut_n;                /* [cand_cap] scratch: list length before the reset cut */
     uint64_t *agg;                  /* [SCAN_THREADS] scan scratch                          */
     uint32_t *errors;
     uint32_t final;                 /* end of input: nothing is carried over                */
-    uint8_t *pool; uint32_t pool_cap;      /* K4: CRC-stripped datagrams                    */
 };
 
 WMB_D void k3_flag(uint32_t *errors, uint32_t bit)
@@ -634,13 +637,22 @@ WMB_D void k3_plan(const K3Params &p)
         n += g.n_pend[k] + sd.n_cand;
     }
     g.off[WMB_N_STREAMS] = n;
-    if (n > p.cand_cap || g.log_n + n > p.log_cap) { k3_flag(p.errors, 64u); n = 0; for (int k = 0; k <= WMB_N_STREAMS; k++) g.off[k] = 0; }
+    if (n > p.cand_cap || n > p.log_cap) { k3_flag(p.errors, 64u); n = 0; for (int k = 0; k <= WMB_N_STREAMS; k++) g.off[k] = 0; }
     g.n = n;
-    g.base = g.log_n;
-    g.log_n += n;
+    g.base = p.log_base;
     g.n_words = 0;
-    if (g.n_rec < p.rec_cap) { BatchRec r = { g.base, n, 0u, p.final }; p.rec[g.n_rec] = r; }
-    else k3_flag(p.errors, 128u);
+    g.pool_n = 0;
+}
+
+/* last step of a batch (one thread, after K4): the record the host reads */
+WMB_D void k3_publish(const K3Params &p)
+{
+    const GatherDev &g = *p.gd;
+    BatchRec r;
+    r.n = g.n; r.n_words = g.n_words; r.pool_n = g.pool_n; r.errors = *p.errors;
+    r.lanes_rerun = g.lanes_rerun; r.rl_fallbacks = g.rl_fallbacks;
+    for (int k = 0; k < WMB_N_STREAMS; k++) { r.total[k] = g.total_prev[k]; r.n_cand_total[k] = g.n_cand_total[k]; }
+    *p.rec = r;
 }
 
 /* step 2 (thread per candidate, any grid): the ordered candidate list of every stream = the candidates carried
@@ -780,8 +792,6 @@ WMB_D void k3_offsets_b(const K3Params &p)
     for (uint32_t t = 0; t < SCAN_THREADS; t++) { const uint64_t c = p.agg[t]; p.agg[t] = acc; acc += c; }
     if (acc > p.words_cap) { k3_flag(p.errors, 4u); acc = 0; }
     g.n_words = (uint32_t)acc;
-    if (g.n_rec < p.rec_cap) p.rec[g.n_rec].n_words = (uint32_t)acc;
-    g.n_rec++;                                                       /* the record is complete */
     for (int k = 0; k < WMB_N_STREAMS; k++) g.n_pend[k] = 0;         /* k3_carry collects the next batch's */
 }
 WMB_D void k3_offsets_c(const K3Params &p, uint32_t t)
@@ -1251,6 +1261,7 @@ __global__ void __launch_bounds__(FIX_THREADS) k2p1_fixup_kernel(K2p1Params p, u
 }
 __global__ void k2c_compact_kernel(const K2cParams p) { k2c_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
 __global__ void k3_plan_kernel(const K3Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) k3_plan(p); }
+__global__ void k3_publish_kernel(const K3Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) k3_publish(p); }
 /* the kernels below do not know on the host how many candidates there are: grid-stride loops over gd->n */
 __global__ void k3_fill_kernel(const K3Params p)
 {
