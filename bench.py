@@ -314,8 +314,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="t1x2")
     ap.add_argument("--mib", type=int, default=1024)
-    ap.add_argument("--batch-mib", type=int, default=256, help="device batch size: a step is cut into batches of this size that "
-                    "follow each other through the device like through a pipeline")
+    ap.add_argument("--batch-mib", type=int, default=0, help="device batch size (default: the whole capture, at most 1 GiB)")
     ap.add_argument("--e2e-batch-mib", type=int, default=256)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--warm", type=int, default=0, help="bit-sync warm-up samples (default: library)")

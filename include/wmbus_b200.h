@@ -205,6 +205,12 @@ long wmb_debug_copy_bits(wmb_ctx *c, int chain, int which, uint32_t *words, size
  * event, [1] access code matched on this bit, [0] the bit.  Returns the number of events copied. */
 long wmb_debug_copy_events(wmb_ctx *c, int chain, int algo, uint64_t *ev, size_t cap);
 
+/* Test hook: the device's exact-arithmetic building blocks (csrc/wmb_exact.cuh) on caller-made operands, host arrays of
+ * n floats.  mode 0: atan2f(y, x) as the discriminator uses it (operands zero or in [2^-8, 2^23))   1: general
+ * atan2f(y, x) (glibc 2.39 fdlibm restated)   2: IEEE division y / x for such operands   3: IEEE sqrt(y) for y zero or an
+ * integer below 2^23   4: the polar discriminator of (I, Q) = (y[i], x[i]) against (y[i-1], x[i-1]) (atan2.h:7-10) */
+int wmb_debug_arith(wmb_ctx *c, int mode, const float *y, const float *x, float *out, size_t n);
+
 /* ---- time-chunk sharding of one capture (several contexts / GPUs on one stream) ----
  * The reference has no counterpart: it is one sequential loop (rtl_wmbus.c:1298-1357).  A worker that
  * owns the decimated samples [lo, hi) of a capture (1) seeks its context to a position a warm-up halo

@@ -72,6 +72,7 @@ def _bind(lib):
     lib.wmb_debug_copy_bits.restype = C.c_long
     lib.wmb_debug_copy_events.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     lib.wmb_debug_copy_events.restype = C.c_long
+    lib.wmb_debug_arith.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.wmb_seek.argtypes = [C.c_void_p, C.c_uint64]
     lib.wmb_set_line_window.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     lib.wmb_boundary_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -81,7 +82,7 @@ def _bind(lib):
 
 EXPORTS = ["wmb_reset", "wmb_host_alloc", "wmb_host_free", "wmb_default_opts", "wmb_abi_version", "wmb_last_error", "wmb_version_string", "wmb_create",
            "wmb_destroy", "wmb_push", "wmb_push_device", "wmb_poll", "wmb_decode_frames", "wmb_take_lines",
-           "wmb_process", "wmb_process_device", "wmb_get_stats", "wmb_debug_copy_stage", "wmb_debug_copy_bits", "wmb_debug_copy_events",
+           "wmb_process", "wmb_process_device", "wmb_get_stats", "wmb_debug_copy_stage", "wmb_debug_copy_bits", "wmb_debug_copy_events", "wmb_debug_arith",
            "wmb_seek", "wmb_set_line_window", "wmb_boundary_state"]
 
 
@@ -254,3 +255,11 @@ class WmbusB200:
         ev = ev[:got]
         return dict(m=ev >> np.uint64(24), rssi=(ev >> np.uint64(16)) & np.uint64(0xFF), reset=(ev >> np.uint64(2)) & np.uint64(1),
                     sync=(ev >> np.uint64(1)) & np.uint64(1), bit=ev & np.uint64(1))
+
+    def debug_arith(self, mode: int, y, x):
+        """device arithmetic test hook: see wmb_debug_arith() in include/wmbus_b200.h"""
+        import numpy as np
+        y = np.ascontiguousarray(y, np.float32); x = np.ascontiguousarray(x, np.float32)
+        out = np.zeros(len(y), np.float32)
+        self._check(self.lib.wmb_debug_arith(self._ctx, mode, y.ctypes.data, x.ctypes.data, out.ctypes.data, len(y)))
+        return out

@@ -487,7 +487,13 @@ static void tr_dump()
     g_marks.clear();
 }
 
-static size_t g_pipe_bytes = (size_t)256 << 20;          /* WMBUS_B200_PIPE_MIB: batch size of a long device push */
+/* WMBUS_B200_PIPE_MIB: cut a long device push into batches of this size that follow each other through the device
+ * like through a pipeline (run_batch).  Off by default: measured on the 1 GiB benchmark step, 4 x 256 MiB took 7.7 ms
+ * of device time against 5.7 ms for one batch -- the demod kernel is a persistent grid that owns every SM's register
+ * file, so the clock-recovery lanes of the batch before (128 registers x 64 threads per block, one serial chain per
+ * thread) only get on an SM when demod blocks retire, and whatever issue slots they win stretch their critical path.
+ * Host pushes are batched by the H2D copies anyway and go through the same machinery. */
+static size_t g_pipe_bytes = ~(size_t)0;
 
 static void read_tuning()
 {
@@ -1796,4 +1802,31 @@ extern "C" long wmb_debug_copy_events(wmb_ctx *c, int chain, int algo, uint64_t 
         i += run;
     }
     return (long)n;
+}
+
+/* Test hook: run the device's exact-arithmetic building blocks on caller-made operands (host arrays of n floats).
+ * mode 0: bounded atan2f(y, x)   1: general atan2f(y, x)   2: bounded division y / x   3: bounded sqrt(y)
+ *      4: discriminator of (y[i], x[i]) against (y[i-1], x[i-1]) taken as (I, Q) */
+extern "C" int wmb_debug_arith(wmb_ctx *c, int mode, const float *y, const float *x, float *out, size_t n)
+{
+    if (!c || !y || !x || !out || mode < 0 || mode > 4) return set_err(WMB_E_INVAL, "bad argument");
+#ifdef WMB_HOSTSIM
+    for (size_t i = 0; i < n; i++)
+        out[i] = mode == 0 ? wmb_atan2f_t<true>(y[i], x[i]) : mode == 1 ? wmb_atan2f_t<false>(y[i], x[i])
+               : mode == 2 ? wmb_fdiv_bounded(y[i], x[i]) : mode == 3 ? wmb_fsqrt_pos(y[i])
+               : wmb_discriminator(y[i], x[i], y[i ? i - 1 : 0], x[i ? i - 1 : 0]);
+    return WMB_OK;
+#else
+    CUDA_TRY(cudaSetDevice(c->device));
+    float *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 3 * n * sizeof(float) + 16));
+    cudaError_t e = cudaMemcpy(d, y, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + n, x, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { dbg_arith_kernel<<<1024, 256, 0, c->cs>>>(d, d + n, d + 2 * n, n, mode); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->cs);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d + 2 * n, n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return set_err(WMB_E_CUDA, "wmb_debug_arith: %s", cudaGetErrorString(e));
+    return WMB_OK;
+#endif
 }

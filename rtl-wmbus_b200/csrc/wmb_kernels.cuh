@@ -267,8 +267,11 @@ WMB_D void k1_box_disc(const K1Params &p, K1Smem &sm, int tid)
 #pragma unroll
                 for (int i = 0; i < DW; i++) acc = acc - w[(k - 1) * DW + i] + w[(k - 1) * DW + i + NWIN];   /* both halves stay non-negative */
             }
-            si[k] = wmb_fmul((float)((int)(acc & 0xFFFFu) - NWIN * BIASW), inv);
-            sq[k] = wmb_fmul((float)((int)(acc >> 16) - NWIN * BIASW), inv);
+            /* the box sums themselves, not sum/len: the discriminator only sees the quotient and the signs of
+             * s * conj(s_prev), which a common factor len^2 leaves untouched (zeros and their signs included), and
+             * sqrt(len^2 x) = len sqrt(x) exactly, so the division by len moves into the constant behind the sqrt */
+            si[k] = (float)((int)(acc & 0xFFFFu) - NWIN * BIASW);
+            sq[k] = (float)((int)(acc >> 16) - NWIN * BIASW);
         }
         float dr[4];
 #pragma unroll
@@ -276,8 +279,11 @@ WMB_D void k1_box_disc(const K1Params &p, K1Smem &sm, int tid)
             const int r = r0 + k;
             dr[k] = 0.f;
             if (r > 0) dr[k] = p.accurate ? wmb_discriminator(si[k + 1], sq[k + 1], si[k], sq[k])
-                                          : wmb_discriminator_fast(si[k + 1], sq[k + 1], si[k], sq[k]);
-            sm.mag[k1_pad(r)] = wmb_fmul(0.6789f, wmb_fsqrt(wmb_fadd(wmb_fmul(si[k + 1], si[k + 1]), wmb_fmul(sq[k + 1], sq[k + 1]))));
+                                          : wmb_discriminator_fast(wmb_fmul(si[k + 1], inv), wmb_fmul(sq[k + 1], inv),
+                                                                   wmb_fmul(si[k], inv), wmb_fmul(sq[k], inv));
+            /* 0.6789f * sqrt(i^2 + q^2) with i = S_i / len (rtl_wmbus.c:480, :1066): the scaling by the power of two
+             * 1 / len commutes with the correctly rounded sqrt and with the product */
+            sm.mag[k1_pad(r)] = wmb_fmul(0.6789f * inv, wmb_fsqrt_pos(wmb_fadd(wmb_fmul(si[k + 1], si[k + 1]), wmb_fmul(sq[k + 1], sq[k + 1]))));
         }
         float4 o; o.x = dr[0]; o.y = dr[1]; o.z = dr[2]; o.w = dr[3];
         *(float4 *)(sm.draw + r0) = o;
@@ -433,12 +439,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+/* (the buffer index never indexes the pointer struct: a dynamically indexed member would push the whole struct into
+ * local memory, and every shared-memory access of the kernel would become a generic LD/ST with 64-bit addressing) */
 __device__ __forceinline__ void k1_issue_load(const K1Params &p, K1Smem &sm, int buf, int64_t tile)
 {
     const K1Load L = k1_plan_load(p, tile);
-    mbar_expect_tx(&sm.bar[buf], (uint32_t)(L.n0 + L.n1));
-    if (L.n0) bulk_g2s(sm.bytes[buf], L.src0, (uint32_t)L.n0, &sm.bar[buf]);
-    if (L.n1) bulk_g2s(sm.bytes[buf] + L.off1, L.src1, (uint32_t)L.n1, &sm.bar[buf]);
+    uint8_t *dst = buf ? sm.bytes[1] : sm.bytes[0];
+    uint64_t *bar = sm.bar + buf;
+    mbar_expect_tx(bar, (uint32_t)(L.n0 + L.n1));
+    if (L.n0) bulk_g2s(dst, L.src0, (uint32_t)L.n0, bar);
+    if (L.n1) bulk_g2s(dst + L.off1, L.src1, (uint32_t)L.n1, bar);
 }
 
 template <class CH>
@@ -482,14 +492,14 @@ WMB_D void k1_demod_body(const K1Params &p)
     __syncthreads();
     int64_t tile = blockIdx.x;
     if (tid == 0 && tile < ntiles) k1_issue_load(p, sm, 0, tile);
-    uint32_t phase[2] = {0, 0};
+    uint32_t phase = 0;                                       /* bit b: parity to wait for on barrier b */
     int buf = 0;
     for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         const int64_t next = tile + gridDim.x;
         if (tid == 0 && next < ntiles) k1_issue_load(p, sm, buf ^ 1, next);   /* prefetch */
-        mbar_wait(&sm.bar[buf], phase[buf]);
-        phase[buf] ^= 1;
-        const uint8_t *raw = sm.bytes[buf];
+        mbar_wait(sm.bar + buf, (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        const uint8_t *raw = buf ? sm.bytes[1] : sm.bytes[0];
         if (CHAINS & 1u) k1_chain<ChainT1C1>(p, sm, raw, tile, tid, true);
         if (CHAINS & 2u) k1_chain<ChainS1>(p, sm, raw, tile, tid, p.mix || !(CHAINS & 1u));
     }
@@ -1260,6 +1270,19 @@ __global__ void __launch_bounds__(FIX_THREADS) k2p1_fixup_kernel(K2p1Params p, u
                [&](uint32_t lane) { k2p1_verify_lane(p, lane, n_fail); });
 }
 __global__ void k2c_compact_kernel(const K2cParams p) { k2c_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
+/* test hook (wmb_debug_arith): the device arithmetic on caller-made operands */
+__global__ void dbg_arith_kernel(const float *y, const float *x, float *out, size_t n, int mode)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float r;
+        if (mode == 0) r = wmb_atan2f_t<true>(y[i], x[i]);
+        else if (mode == 1) r = wmb_atan2f_t<false>(y[i], x[i]);
+        else if (mode == 2) r = wmb_fdiv_bounded(y[i], x[i]);
+        else if (mode == 3) r = wmb_fsqrt_pos(y[i]);
+        else r = wmb_discriminator(y[i], x[i], y[i ? i - 1 : 0], x[i ? i - 1 : 0]);
+        out[i] = r;
+    }
+}
 __global__ void k3_plan_kernel(const K3Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) k3_plan(p); }
 __global__ void k3_publish_kernel(const K3Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) k3_publish(p); }
 /* the kernels below do not know on the host how many candidates there are: grid-stride loops over gd->n */

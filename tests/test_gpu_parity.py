@@ -26,6 +26,12 @@ def test_device_atan2f_and_discriminator_bit_exact(pkg, gpu_lib, orc_mod):
     pc.check_stages(pkg, gpu_lib, np.ascontiguousarray(edge), "")
 
 
+def test_device_arith_operand_by_operand(pkg, gpu_lib, orc_mod):
+    """device atan2f (bounded / general), slow-path-free IEEE division and sqrt, discriminator scaling invariance"""
+    import test_device_arith
+    test_device_arith.check_device_arith(pkg, gpu_lib, orc_mod, 400000)
+
+
 def test_stage_outputs_bit_exact(pkg, gpu_lib):
     pc.check_stages(pkg, gpu_lib, load_fixture("excerpt_samples2_a.cu8"), "")
     pc.check_stages(pkg, gpu_lib, load_fixture("excerpt_samples2_a.cu8"), "-a")
