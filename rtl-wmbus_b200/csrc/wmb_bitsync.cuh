@@ -242,6 +242,157 @@ WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
     else      { if (p.t2) k2a_lane_t<CH, false, true>(p, lane); else k2a_lane_t<CH, false, false>(p, lane); }
 }
 
+#ifndef WMB_HOSTSIM
+/* ------------------------------------------------------------------------------------- */
+/* K2a, warp-cooperative: three threads per lane, one per biquad section                 */
+/*                                                                                       */
+/* k2a_lane_t above runs one lane per thread: ~38 instructions per sample on a single     */
+/* dependent stream, 59 cycles per sample for a lone warp -- the lane's LENGTH in time is  */
+/* what every small batch and every tail waits for, and it forces short lanes (many of    */
+/* them, each with its own 24576-sample warm-up: 2.7 x redundant arithmetic at 1 GiB).    */
+/* Here the three sections of a lane sit in three neighbouring threads and work on        */
+/* different samples at the same moment: in step s thread r handles sample s - 2r, takes   */
+/* its input from its left neighbour's output of two steps ago (a shuffle issued one step  */
+/* ahead, so its latency is off the recurrence), and the warp issues ONE biquad per step   */
+/* for ten lanes.  Every sample still sees exactly the operations of k2a_block in the     */
+/* same order -- only the interleaving changes -- so states and bits are bit-identical to  */
+/* the per-thread version (which stays: -o, re-runs, ragged final batches, CPU tests).    */
+/* A step costs ~15 issue slots instead of 38 and its critical path is the biquad         */
+/* recurrence itself (multiply, add, subtract: 12 cycles).                                */
+/*                                                                                       */
+/* All lanes of a warp run the same number of steps: W warm-up samples (lanes whose        */
+/* warm-up is cut short by the start of the stream are fed zeros before it, which keeps a  */
+/* zero state zero), C live samples, and one more block in which the two lagging sections */
+/* reach the lane's end.  A lane's state "at sample q" is picked up section by section as  */
+/* each thread arrives there (steps q, q+2, q+4).  Output bits are collected at the step's */
+/* position in the block and re-aligned by 2r with a funnel shift when the next block is   */
+/* complete.                                                                              */
+/* ------------------------------------------------------------------------------------- */
+#define K2A2_LPW 10                  /* lanes per warp: 30 threads, two idle */
+#define K2A2_THREADS 64
+
+struct K2a2Thread {
+    float h1, h2;                   /* this section's memories                                  */
+    float o, sh;                    /* last output (to be passed on), input for the next step   */
+    float a1, a2, b1, b2;
+    uint32_t R, Rprev;              /* bits of this block / the block before, at step positions */
+    bool r0, r2;
+};
+
+template <bool OUT>
+__device__ __forceinline__ void k2a2_step(K2a2Thread &t, const float xs, const int i)
+{
+    constexpr float gain = 1.874981046e-06;                       /* rtl_wmbus.c:338 */
+    const float xx = wmb_fmul(xs, xs);                            /* rtl_wmbus.c:1089 */
+    const float in = t.r0 ? xx : t.sh;
+    t.sh = __shfl_up_sync(0xFFFFFFFFu, t.o, 1);                   /* the neighbour's output of the step before: next step's input */
+    const float h0 = wmb_fsub(in, wmb_fadd(wmb_fmul(t.a1, t.h1), wmb_fmul(t.a2, t.h2)));
+    const float out = wmb_fadd(wmb_fadd(h0, wmb_fmul(t.b1, t.h1)), wmb_fmul(t.b2, t.h2));
+    t.h2 = t.h1; t.h1 = h0; t.o = out;
+    if (OUT) {
+        const float z = t.r0 ? xs : wmb_fmul(out, gain);          /* data bit (rtl_wmbus.c:1059) / clock sign */
+        if (z >= 0.0f) t.R |= 1u << i;
+    }
+}
+
+template <class CH>
+__global__ void __launch_bounds__(K2A2_THREADS) k2a2_lanes_kernel(const K2aParams p)
+{
+    const int lid = threadIdx.x & 31;
+    const int role = lid % 3;
+    const uint32_t lane = (blockIdx.x * (K2A2_THREADS / 32) + (threadIdx.x >> 5)) * K2A2_LPW + lid / 3;
+    const bool valid = lid < 3 * K2A2_LPW && lane < p.lanes;
+    K2a2Thread t;
+    t.h1 = t.h2 = t.o = t.sh = 0.0f;
+    t.R = t.Rprev = 0;
+    t.r0 = role == 0; t.r2 = role == 2;
+    t.a1 = role == 0 ? CH::A10 : role == 1 ? CH::A11 : CH::A12;
+    t.a2 = role == 0 ? CH::A20 : role == 1 ? CH::A21 : CH::A22;
+    t.b1 = role == 0 ? CH::B10 : role == 1 ? CH::B11 : CH::B12;
+    t.b2 = role == 0 ? CH::B20 : role == 1 ? CH::B21 : CH::B22;
+
+    const int64_t s0 = (int64_t)lane * p.C;
+    const int64_t e0 = (s0 + p.C < p.M) ? s0 + p.C : p.M;
+    const int64_t m0 = s0 - (int64_t)p.W;                           /* nominal start of the run; real samples begin at -hist */
+    const int jw = (int)(p.W / 32);                                 /* first live block                                      */
+    const int je = valid ? jw + (int)((e0 - s0) / 32) : -1;         /* block in which the sections reach the lane's end       */
+    const int nb = jw + (int)(p.C / 32) + 1;                        /* blocks run by every lane of the grid                   */
+    const int64_t m_last = p.M + 256;                               /* reads stay inside the buffer's slack                   */
+    const bool loader = valid && t.r0;
+
+    float4 cur[8], nxt[8];
+    auto load = [&](float4 (&b)[8], int j) {
+        const int64_t m = m0 + 32 * (int64_t)j;
+        if (loader && m >= -p.hist) {
+            const float4 *s4 = (const float4 *)(p.dphi + (m < m_last ? m : m_last));
+#pragma unroll
+            for (int q = 0; q < 8; q++) b[q] = s4[q];
+            if (m + 32 * K2A_L2_AHEAD < p.M) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.dphi + m + 32 * K2A_L2_AHEAD));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) b[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+#define K2A2_X(i) ((i & 3) == 0 ? cur[i >> 2].x : (i & 3) == 1 ? cur[i >> 2].y : (i & 3) == 2 ? cur[i >> 2].z : cur[i >> 2].w)
+
+    load(cur, 0);
+    int j = 0;
+    /* warm-up blocks but the last: state only */
+    for (; j < jw - 1; j++) {
+        load(nxt, j + 1);
+#pragma unroll
+        for (int i = 0; i < 32; i++) k2a2_step<false>(t, K2A2_X(i), i);
+#pragma unroll
+        for (int q = 0; q < 8; q++) cur[q] = nxt[q];
+    }
+    /* last warm-up block, live blocks, one block past the end: bits, states at the chunk borders, stores */
+    uint32_t clk3 = 0;
+    const int sh2r = 2 * role;
+    for (; j < nb; j++) {
+        load(nxt, j + 1);
+        const bool at_start = valid && j == jw, at_end = j == je;
+        float c1 = 0.f, c2 = 0.f;
+        t.R = 0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            if (i == 0 || i == 2 || i == 4) {                           /* section i/2 arrives at the block's first sample */
+                if ((at_start || at_end) && role == i / 2) { c1 = t.h1; c2 = t.h2; }
+            }
+            k2a2_step<true>(t, K2A2_X(i), i);
+        }
+        /* the block before this one is complete now: its samples sit 2r positions up */
+        const uint32_t A = __funnelshift_r(t.Rprev, t.R, sh2r);
+        t.Rprev = t.R;
+        const int jb = j - 1;
+        uint32_t sword = 0;
+        if (t.r2) {
+            /* lock stencil on the whole word: sample the data bit where the clock reads low, high, high, high at
+             * m-3..m (rtl_wmbus.c:1092-1111) */
+            const uint64_t hist3 = ((clk3 & 1u) << 2) | (clk3 & 2u) | ((clk3 >> 2) & 1u);
+            const uint64_t H = ((uint64_t)A << 3) | hist3;
+            sword = (uint32_t)((H >> 3) & (H >> 2) & (H >> 1) & ~H);
+            clk3 = ((A >> 31) & 1u) | (((A >> 30) & 1u) << 1) | (((A >> 29) & 1u) << 2);
+            if (j == jw && m0 + 32 * (int64_t)jw <= -p.hist) clk3 = 0;     /* the lane starts at the stream's first sample: no clock history */
+        }
+        if (valid && jb >= jw && jb < je) {
+            const int64_t w = (m0 >> 5) + jb;                               /* word of the batch (m0 is a multiple of 32) */
+            if (t.r0) p.dbits[w] = A;
+            if (t.r2) { p.sbits[w] = sword; if (p.cbits) p.cbits[w] = A; }
+        }
+        if (at_start || at_end) {
+            IirState *st = at_end ? p.st_end + lane : p.st_start + lane;
+            st->h[2 * role] = c1; st->h[2 * role + 1] = c2;
+            if (t.r0) { st->dc_x = 0.f; st->dc_y = 0.f; }
+            if (t.r2) { st->clk3 = clk3; st->pad = 0; }
+            /* a lane without live samples (e0 == s0 cannot happen: lanes = ceil(M / C)) would need both at once */
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) cur[q] = nxt[q];
+    }
+#undef K2A2_X
+}
+#endif /* !WMB_HOSTSIM */
+
 WMB_D bool iir_state_equal(const IirState &a, const IirState &b, uint32_t dc, uint32_t t2)
 {
     bool eq = true;

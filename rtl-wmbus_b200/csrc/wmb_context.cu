@@ -243,8 +243,21 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
 
 /* speculative pass (st: the batch's lane stream), then -- on cs, where batches follow each other in order --
  * verification + on-device fix-up of refuted lanes: no host round trip */
+static bool g_k2a_coop = true;           /* WMBUS_B200_K2A=scalar: one lane per thread everywhere (experiments) */
+
 static int launch_k2a_lanes(wmb_ctx *c, int chain, const K2aParams &p, cudaStream_t st)
 {
+    /* three threads per lane where the lane is the plain case (time2 on, no DC block, whole words); the per-thread
+     * kernel otherwise */
+    if (g_k2a_coop && p.t2 && !p.dc && p.M % 32 == 0 && p.W % 32 == 0 && p.C % 32 == 0 && p.hist % 32 == 0) {
+        const unsigned per = (K2A2_THREADS / 32) * K2A2_LPW;
+        const unsigned grid = (p.lanes + per - 1) / per;
+        if (chain == 0) k2a2_lanes_kernel<ChainT1C1><<<grid, K2A2_THREADS, 0, st>>>(p);
+        else            k2a2_lanes_kernel<ChainS1><<<grid, K2A2_THREADS, 0, st>>>(p);
+        CUDA_TRY(cudaGetLastError());
+        c->st.kernel_launches += 1;
+        return WMB_OK;
+    }
     const unsigned grid = (p.lanes + K2_THREADS - 1) / K2_THREADS;
     if (chain == 0) k2a_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, st>>>(p);
     else            k2a_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, st>>>(p);
@@ -497,6 +510,9 @@ static size_t g_pipe_bytes = ~(size_t)0;
 
 static void read_tuning()
 {
+#ifndef WMB_HOSTSIM
+    if (const char *k = getenv("WMBUS_B200_K2A")) g_k2a_coop = strcmp(k, "scalar") != 0;
+#endif
     if (const char *b = getenv("WMBUS_B200_PIPE_MIB")) { const unsigned long v = strtoul(b, nullptr, 10); if (v >= 1 && v <= 4096) g_pipe_bytes = (size_t)v << 20; }
     if (const char *b = getenv("WMBUS_B200_P2BLK")) { const unsigned v = (unsigned)atoi(b); if (v == 32 || v == 64 || v == 128) g_p2_block = v; }
     const char *e = getenv("WMBUS_B200_TUNE");
@@ -777,6 +793,19 @@ static uint32_t pick_chunk(const wmb_ctx *c, int64_t M, bool alone)
     return (uint32_t)C;
 }
 
+/* Lane length of the clock-recovery kernel when three threads share a lane (k2a2_lanes_kernel): a step costs a lone
+ * warp ~17 cycles instead of 59, so lanes can be long -- about 1.5 warps (15 lanes) per scheduler -- and the warm-up is
+ * paid less often. */
+static uint32_t pick_chunk_coop(const wmb_ctx *c, int64_t M)
+{
+    if (c->C_fixed) return c->C_fixed;
+    int64_t C = (M + 8879) / 8880;
+    C = (C + 1023) / 1024 * 1024;
+    if (C < 8192) C = 8192;
+    if (C > 131072) C = 131072;
+    return (uint32_t)C;
+}
+
 /* Enqueue the per-sample device pass for one batch whose bytes are at `src` (device memory): demod on k1s, clock
  * recovery lanes on as[set], everything that is sequential from batch to batch on cs.  Nothing here waits for the
  * device: refuted speculative lanes are re-run by on-device fix-up kernels, and the fallback from the two-phase
@@ -850,6 +879,9 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
          * (measured: the two chains' clock lanes side by side are SLOWER, 8.3 vs 7.2 ms of bit sync per GiB --
          * each already fills the fp32 pipe of its scheduler) */
         K2aParams ka[WMB_N_CHAINS];
+        const bool coop = c->o.t2_enabled && !c->o.remove_dc && M % 32 == 0;
+        const uint32_t Ca = coop ? pick_chunk_coop(c, M) : C;
+        const uint32_t lanes_a = (uint32_t)((M + Ca - 1) / Ca);
         CUDA_TRY(cudaStreamWaitEvent(c->as[set], c->ev_k1[set], 0));
         CUDA_TRY(cudaEventRecord(evt[4], c->as[set]));
         for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
@@ -858,14 +890,14 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
             SetBuf &sb = b.set[set];
             K2aParams &p = ka[ch];
             memset(&p, 0, sizeof(p));
-            p.dphi = sb.dphi + c->W; p.M = M; p.hist = c->hist_m; p.C = C; p.W = c->W_a[ch]; p.lanes = lanes;
+            p.dphi = sb.dphi + c->W; p.M = M; p.hist = c->hist_m; p.C = Ca; p.W = c->W_a[ch]; p.lanes = lanes_a;
             p.dbits = sb.dbits + wofs; p.sbits = sb.sbits + wofs;
             p.cbits = sb.cbits ? sb.cbits + wofs : nullptr;
             p.st_start = sb.ia_start; p.st_end = sb.ia_end; p.carry = b.ia_carry; p.rerun = sb.rerun_a;
             p.dc = c->o.remove_dc; p.t2 = c->o.t2_enabled;
             p.mode = 0;
             p.spec0 = first ? 0u : 1u;                   /* the previous batch's lanes may still be running */
-            c->st.lanes_run += lanes;
+            c->st.lanes_run += lanes_a;
             TRY(launch_k2a_lanes(c, ch, p, c->as[set]));
         }
         CUDA_TRY(cudaEventRecord(evt[5], c->as[set]));
@@ -879,7 +911,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
             if (!(c->chains & (1u << ch))) continue;
             ChainBuf &b = c->cb[ch];
             TRY(launch_k2a_verify(c, ch, ka[ch]));
-            CUDA_TRY(cudaMemcpyAsync(b.ia_carry, b.set[set].ia_end + (lanes - 1), sizeof(IirState), cudaMemcpyDeviceToDevice, c->cs));
+            CUDA_TRY(cudaMemcpyAsync(b.ia_carry, b.set[set].ia_end + (ka[ch].lanes - 1), sizeof(IirState), cudaMemcpyDeviceToDevice, c->cs));
             /* bit history for the run-length warm-ups: the previous batch's last W samples (exact since its fix-up) */
             if (!first && c->prev_M % 32 == 0) {         /* only a final (flush) batch can be ragged */
                 TRY(copy_history(b.set[set].dbits, b.set[pset].dbits, 4, c->W / 32, c->prev_M / 32, c->cs));
