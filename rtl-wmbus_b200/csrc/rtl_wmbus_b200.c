@@ -122,9 +122,16 @@ int main(int argc, char *argv[])
 
     const char *e;
     const int device = (e = getenv("WMBUS_B200_DEVICE")) ? atoi(e) : 0;
-    size_t batch = (size_t)((e = getenv("WMBUS_B200_BATCH_MIB")) ? atoi(e) : 64) * 1048576u;
-    if (batch < 1048576u) batch = 1048576u;
-    o.max_batch_mib = (uint32_t)(batch / 1048576u);
+    unsigned long batch_mib = 64;
+    if ((e = getenv("WMBUS_B200_BATCH_MIB")) != NULL) {
+        char *end = NULL;
+        const unsigned long v = strtoul(e, &end, 10);
+        if (end != e && *end == 0 && e[0] != '-') batch_mib = v;
+    }
+    if (batch_mib < 1) batch_mib = 1;
+    if (batch_mib > 1024) batch_mib = 1024;
+    const size_t batch = (size_t)batch_mib * 1048576u;
+    o.max_batch_mib = (uint32_t)batch_mib;
 
     wmb_ctx *ctx = NULL;
     if (wmb_create(&o, device, &ctx) != WMB_OK) {
@@ -139,34 +146,54 @@ int main(int argc, char *argv[])
         return EXIT_FAILURE;
     }
 
+    /* device buffers are allocated at the first push: do it now, not when the first samples are waiting */
+    if (wmb_push(ctx, buf, 0) != WMB_OK) {
+        fprintf(stderr, "rtl_wmbus_b200: %s\n", wmb_last_error());
+        return EXIT_FAILURE;
+    }
+
     size_t fill = 0;
+    /* -f: the reference arms a 2 s alarm around each fread() of one 4096-byte item (rtl_wmbus.c:1300-1302), i.e. it
+     * gives up when a whole item does not arrive within 2 s -- a trickle of bytes does not keep it alive.  Here the
+     * reads are whatever the pipe holds, so the alarm stays armed until 4096 new bytes have come in since it was set;
+     * it is not running while the device works on a hand-over. */
+    size_t since_arm = 0;
+    int armed = 0;
     double last_push = now_s();
     int rc = WMB_OK, eof = 0;
     while (!eof) {
         /* wait for input; on a live stream hand over what has arrived every 100 ms so
          * that telegrams are printed promptly */
         struct pollfd pfd = { 0, POLLIN, 0 };
-        if (check_flow) alarm(2);                       /* START_ALARM, rtl_wmbus.c:1300 */
+        if (check_flow && !armed) { alarm(2); armed = 1; since_arm = 0; }      /* START_ALARM */
         const int pr = poll(&pfd, 1, fill ? 100 : -1);
         ssize_t n = 0;
         if (pr > 0) {
             n = read(0, buf + fill, batch - fill);
             if (n < 0 && errno == EINTR) n = 0;
             else if (n <= 0) eof = 1;
-            else fill += (size_t)n;
+            else { fill += (size_t)n; since_arm += (size_t)n; }
         } else if (pr < 0 && errno != EINTR) {
             eof = 1;
         }
-        if (check_flow) alarm(0);                       /* STOP_ALARM */
+        if (check_flow && armed && (since_arm >= 4096 || eof)) { alarm(0); armed = 0; }     /* STOP_ALARM: an item is in */
         const double t = now_s();
         if (fill == batch || eof || (fill && (pr == 0 || t - last_push > 0.1))) {
-            rc = wmb_push(ctx, buf, fill);
+            if (check_flow && armed) {                  /* the watchdog times the input, not the device */
+                const unsigned left = alarm(0);
+                rc = wmb_push(ctx, buf, fill);
+                if (rc == WMB_OK) emit_lines(ctx, out, outcap);
+                alarm(left ? left : 1);
+            } else {
+                rc = wmb_push(ctx, buf, fill);
+                if (rc == WMB_OK) emit_lines(ctx, out, outcap);
+            }
             if (rc != WMB_OK) break;
             fill = 0;
             last_push = t;
-            emit_lines(ctx, out, outcap);
         }
     }
+    if (check_flow) alarm(0);
     if (rc == WMB_OK) {
         size_t nframes = 0;
         rc = wmb_poll(ctx, NULL, 0, &nframes, 1);       /* EOF: flush */

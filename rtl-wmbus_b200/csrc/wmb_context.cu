@@ -537,12 +537,10 @@ static int ctx_alloc(wmb_ctx *c)
     c->p1_lanes_max = (uint32_t)(c->M_max / K2P1_CHUNK + 2);
     c->rec_max = (size_t)c->M_max / 5 + 2 * (size_t)c->p1_lanes_max + 64;
     c->p2_lanes_max = (uint32_t)(c->rec_max / K2P2_RECORDS + 2);
-    /* access-code matches and gathered frame bits scale with the batch (sized for dense traffic at 1 GiB, d = 2) */
-    if (c->M_max > ((int64_t)1 << 28)) {
-        const uint64_t k = ((uint64_t)c->M_max + (1ull << 28) - 1) >> 28;
-        c->cand_cap = (uint32_t)std::min<uint64_t>((uint64_t)(1u << 20) * k, 1u << 24);
-        c->frame_words_cap = (uint32_t)std::min<uint64_t>((uint64_t)(1u << 24) * k, 1u << 28);
-    }
+    /* access-code matches and gathered frame bits scale with the batch: one candidate per 256 decimated samples, one
+     * frame bit per 16 (dense traffic: a telegram every ~5000 samples; false matches: 2^-16 per bit) */
+    c->cand_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(c->M_max >> 8, 1 << 16), 1 << 24);
+    c->frame_words_cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(c->M_max >> 4, 1 << 22), 1 << 28);
 
     TRY(dev_alloc(c, &c->d_in[0], c->max_batch_bytes + 4096));
     TRY(dev_alloc(c, &c->d_in[1], c->max_batch_bytes + 4096));
@@ -649,6 +647,9 @@ static int ctx_alloc(wmb_ctx *c)
             TRY(dev_alloc(c, &s.agg, n_agg));
         }
     }
+    /* the set-up copies above are plain cudaMemcpy calls from pageable memory: make sure they have landed before any
+     * kernel on the context's non-blocking streams can read them */
+    CUDA_TRY(cudaDeviceSynchronize());
     c->allocated = true;
     return WMB_OK;
 }
@@ -793,14 +794,16 @@ static uint32_t pick_chunk(const wmb_ctx *c, int64_t M, bool alone)
     return (uint32_t)C;
 }
 
-/* Lane length of the clock-recovery kernel when three threads share a lane (k2a2_lanes_kernel): a step costs a lone
- * warp ~17 cycles instead of 59, so lanes can be long -- about 1.5 warps (15 lanes) per scheduler -- and the warm-up is
- * paid less often. */
+/* Lane length of the clock-recovery kernel when three threads share a lane (k2a2_lanes_kernel).  A lone warp takes
+ * ~13 cycles per warm-up step and ~21 per live step (a second warp on the same scheduler doubles that: the kernel is
+ * issue-bound with two), against 59 for the per-thread kernel -- so the batch is cut into ONE warp (ten lanes) per
+ * scheduler, 148 SMs x 4 x 10 lanes, and the 24576-sample warm-up is paid 5920 times instead of 18944 times
+ * (measured at 1 GiB: 1.31 ms with 1.5 warps per scheduler, see profiles/). */
 static uint32_t pick_chunk_coop(const wmb_ctx *c, int64_t M)
 {
     if (c->C_fixed) return c->C_fixed;
-    int64_t C = (M + 8879) / 8880;
-    C = (C + 1023) / 1024 * 1024;
+    int64_t C = (M + 5919) / 5920;
+    C = (C + 255) / 256 * 256;
     if (C < 8192) C = 8192;
     if (C > 131072) C = 131072;
     return (uint32_t)C;
@@ -1696,6 +1699,7 @@ extern "C" int wmb_reset(wmb_ctx *c)
             }
         }
         CUDA_TRY(cudaStreamSynchronize(c->cs));
+        CUDA_TRY(cudaDeviceSynchronize());              /* the cudaMemcpy calls above ran on the legacy stream */
     }
     return WMB_OK;
 }
@@ -1852,11 +1856,13 @@ extern "C" int wmb_debug_arith(wmb_ctx *c, int mode, const float *y, const float
     CUDA_TRY(cudaSetDevice(c->device));
     float *d = nullptr;
     CUDA_TRY(cudaMalloc(&d, 3 * n * sizeof(float) + 16));
-    cudaError_t e = cudaMemcpy(d, y, n * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d + n, x, n * 4, cudaMemcpyHostToDevice);
+    /* (everything on the context's stream: a plain cudaMemcpy from pageable memory may still be in flight on the
+     * legacy stream when a kernel on a non-blocking stream starts) */
+    cudaError_t e = cudaMemcpyAsync(d, y, n * 4, cudaMemcpyHostToDevice, c->cs);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, x, n * 4, cudaMemcpyHostToDevice, c->cs);
     if (e == cudaSuccess) { dbg_arith_kernel<<<1024, 256, 0, c->cs>>>(d, d + n, d + 2 * n, n, mode); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 2 * n, n * 4, cudaMemcpyDeviceToHost, c->cs);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->cs);
-    if (e == cudaSuccess) e = cudaMemcpy(out, d + 2 * n, n * 4, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return set_err(WMB_E_CUDA, "wmb_debug_arith: %s", cudaGetErrorString(e));
     return WMB_OK;

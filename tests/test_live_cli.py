@@ -1,0 +1,134 @@
+"""`-m gpu`: the drop-in host program on a LIVE stream: `rtl_sdr ... | rtl_wmbus_b200` is a pipe that
+delivers 3.2 MB/s, not a file.  The tests feed the CLI through a pipe at the real sample rate and in bursts, compare
+the lines with the offline result, bound how long a telegram waits for its line, and fire the `-f` watchdog the way the
+reference's would fire (rtl_wmbus.c:71-78, :1238-1246, :1300-1302: a whole 4096-byte item must arrive within 2 s)."""
+import importlib
+import os
+import subprocess
+import threading
+import time
+
+import numpy as np
+import pytest
+
+import orc
+import pipeline_checks as pc
+from conftest import load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def _exe(pkg):
+    return os.path.join(os.path.dirname(pkg.library_path()), "rtl_wmbus_b200")
+
+
+def _run_fed(exe, flags, feeder, timeout=60):
+    """Start the CLI, run feeder(stdin) in this thread, collect (line, arrival time) pairs on a reader thread."""
+    p = subprocess.Popen([exe] + flags.split(), stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, bufsize=0)
+    got = []
+
+    def reader():
+        for raw in iter(p.stdout.readline, b""):
+            got.append((raw.decode().rstrip("\n"), time.perf_counter()))
+    th = threading.Thread(target=reader, daemon=True)
+    th.start()
+    try:
+        feeder(p.stdin)
+    finally:
+        try:
+            p.stdin.close()
+        except BrokenPipeError:
+            pass
+    rc = p.wait(timeout=timeout)
+    th.join(timeout=5)
+    return rc, got, p.stderr.read().decode()
+
+
+def test_real_time_pipe_same_lines_and_bounded_latency(pkg, gpu_lib):
+    """1.6 MS/s real time, 16 KiB writes: identical lines, and a telegram's line is out at most ~0.3 s after its last
+    bit went into the pipe (100 ms hand-over cadence + one device pass)."""
+    exe = _exe(pkg)
+    cu8 = np.ascontiguousarray(np.tile(load_fixture("synth_mixed_1m6.cu8"), 3))          # 1.4 s of signal
+    want = pc.oracle_lines(cu8, "-v")
+    with pkg.WmbusB200("-v", lib=gpu_lib) as ctx:
+        stamped = ctx.process(cu8.ctypes.data, len(cu8), flush=True, timestamp_mode=2)
+    shard = importlib.import_module("rtl-wmbus_b200.shard")
+    end_m = [shard.line_key(l)[0] for l in stamped]                    # decimated sample at which each line is due
+    assert [shard.blank_position(l) for l in stamped] == want
+    chunk, rate = 16384, 3.2e6                                          # bytes, bytes per second
+    t0 = [0.0]
+
+    def feeder(w):
+        subprocess.run([exe, "-V"], capture_output=True)               # the image is paged in before the clock starts
+        time.sleep(1.0)                                                 # CUDA context of the child
+        t0[0] = time.perf_counter()
+        for i, off in enumerate(range(0, len(cu8), chunk)):
+            due = t0[0] + off / rate
+            d = due - time.perf_counter()
+            if d > 0:
+                time.sleep(d)
+            w.write(cu8[off:off + chunk].tobytes())
+    rc, got, err = _run_fed(exe, "-v", feeder)
+    assert rc == 0, err
+    assert [orc.blank_ts(l) for l, _ in got] == want
+    lat = sorted(t - (t0[0] + 4 * m / rate) for (_, t), m in zip(got, end_m))      # 4 input bytes per decimated sample
+    p99 = lat[min(len(lat) - 1, int(0.99 * len(lat)))]
+    print(f"[live] {len(lat)} lines, latency median {1e3 * lat[len(lat) // 2]:.0f} ms, p99 {1e3 * p99:.0f} ms, max {1e3 * lat[-1]:.0f} ms")
+    assert lat[0] > -0.01, "a line cannot precede its telegram"
+    assert p99 < 0.30
+
+
+def test_bursty_pipe_same_lines(pkg, gpu_lib):
+    exe = _exe(pkg)
+    cu8 = load_fixture("synth_mixed_2m4_shift.cu8")
+    want = pc.oracle_lines(cu8, "-d 3 -s -o")
+
+    def feeder(w):
+        cuts = [0, 5000, 5001, 300000, 300000 + 4096 * 3, 900001, len(cu8)]
+        for a, b in zip(cuts, cuts[1:]):
+            w.write(cu8[a:b].tobytes())
+            time.sleep(0.25)
+    rc, got, err = _run_fed(exe, "-d 3 -s -o", feeder)
+    assert rc == 0, err
+    assert [orc.blank_ts(l) for l, _ in got] == want and len(want) > 3
+
+
+@pytest.mark.parametrize("mode", ["stall", "trickle"])
+def test_flow_watchdog(pkg, gpu_lib, mode):
+    """-f: the input stops (or trickles below one 4096-byte item per 2 s) without end of file -> the reference's
+    message on stderr and EXIT_FAILURE; lines decoded before that were printed."""
+    exe = _exe(pkg)
+    cu8 = load_fixture("synth_mixed_1m6.cu8")
+    t = {}
+
+    def feeder(w):
+        w.write(cu8[:1 << 20].tobytes())
+        t["fed"] = time.perf_counter()
+        try:
+            if mode == "stall":
+                time.sleep(4.0)
+            else:
+                for _ in range(16):                                     # 100 bytes every 0.25 s: 1.6 KB in 4 s
+                    time.sleep(0.25)
+                    w.write(bytes(100))
+        except BrokenPipeError:
+            pass
+    t0 = time.perf_counter()
+    rc, got, err = _run_fed(exe, "-f -v", feeder)
+    assert rc == 1
+    assert "rtl_wmbus: monitoring flow" in err and "rtl_wmbus: exiting since incoming data stopped flowing!" in err
+    assert len(got) > 0
+    assert 1.5 < got[-1][1] - t0 + 10 and time.perf_counter() - t["fed"] < 6.0
+
+
+def test_flow_watchdog_quiet_on_a_healthy_stream(pkg, gpu_lib):
+    exe = _exe(pkg)
+    cu8 = load_fixture("synth_mixed_1m6.cu8")
+
+    def feeder(w):
+        for off in range(0, len(cu8), 1 << 16):
+            w.write(cu8[off:off + (1 << 16)].tobytes())
+            time.sleep(0.02)
+    rc, got, err = _run_fed(exe, "-f", feeder)
+    assert rc == 0 and "stopped flowing" not in err
+    assert [orc.blank_ts(l) for l, _ in got] == pc.oracle_lines(cu8, "")
