@@ -42,22 +42,23 @@ def algorithmic_bytes_per_sample(chains, d):
     return 2.0 + chains * (1.0 + 2.0 / 8.0) / d
 
 
-def workload_def(name):
+def workload_def(name, mib=1024):
+    size = f"{mib / 1024:g} GiB"
     if name == "t1x2":
         return dict(emitters="t1x2", flags="-p S", chains=1, d=2, fs=1.6e6,
-                    desc="1 GiB synthetic 1.6 MS/s cu8, two T1 emitters, T1+C1 chain (-p S)")
+                    desc=f"{size} synthetic 1.6 MS/s cu8, two T1 emitters, T1+C1 chain (-p S)")
     if name == "s1":
         return dict(emitters="s1", flags="-p T", chains=1, d=2, fs=1.6e6,
-                    desc="1 GiB synthetic 1.6 MS/s cu8, two S1 emitters, S1 chain (-p T)")
+                    desc=f"{size} synthetic 1.6 MS/s cu8, two S1 emitters, S1 chain (-p T)")
     if name == "both":
         return dict(emitters="mixed", flags="", chains=2, d=2, fs=1.6e6,
-                    desc="1 GiB synthetic 1.6 MS/s cu8, T1/C1/S1 emitters, both chains (default flags)")
+                    desc=f"{size} synthetic 1.6 MS/s cu8, T1/C1/S1 emitters, both chains (default flags)")
     if name == "d3":         # BASELINE config 4's signal: 2.4 MS/s, decimation 3 (general front end, no d = 2 fast path)
         return dict(emitters="mixed", flags="-d 3", chains=2, d=3, fs=2.4e6,
-                    desc="1 GiB synthetic 2.4 MS/s cu8, T1/C1/S1 emitters, both chains, -d 3")
+                    desc=f"{size} synthetic 2.4 MS/s cu8, T1/C1/S1 emitters, both chains, -d 3")
     if name == "d3s":        # ... its -s variant: capture centred on 868.625 MHz, T1/C1 at +325 kHz, S1 at -325 kHz
         return dict(emitters="mixed", flags="-d 3 -s", chains=2, d=3, fs=2.4e6, shift=325e3,
-                    desc="1 GiB synthetic 2.4 MS/s cu8 centred on 868.625 MHz, T1/C1/S1 emitters, both chains, -d 3 -s")
+                    desc=f"{size} synthetic 2.4 MS/s cu8 centred on 868.625 MHz, T1/C1/S1 emitters, both chains, -d 3 -s")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -326,7 +327,7 @@ def main():
                     help="N>1: one independent capture per GPU (weak scaling, default) or time chunks of ONE capture "
                          "(strong scaling, SURVEY 8e / BASELINE config 4)")
     args = ap.parse_args()
-    wl = workload_def(args.workload)
+    wl = workload_def(args.workload, args.mib)
     if args.impl == "reference":
         return run_reference_arm(args, wl)
 
@@ -432,7 +433,7 @@ def main():
     # ---------------- strong scaling over time chunks (BASELINE config 4), same run, reported under "strong" ----------------
     strong = None
     if not args.no_strong:
-        wl4 = workload_def("d3")
+        wl4 = workload_def("d3", args.strong_mib)
         cap4, plan4 = synth.synth_capture(args.strong_mib << 20, fs=wl4["fs"], emitters=synth.default_emitters(wl4["emitters"]),
                                           seed=shard.capture_seed(4, 0), device="cuda")
         torch.cuda.synchronize()

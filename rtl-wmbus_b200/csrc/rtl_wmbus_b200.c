@@ -21,6 +21,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/time.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -46,9 +47,13 @@ static void print_usage(const char *program_name)
 
 static void sig_alarm_handler(int signo)
 {
+    /* same message and exit status as rtl_wmbus.c:71-78.  The signal may be delivered to one of the CUDA runtime's
+     * threads, where exit() would run the runtime's own exit handlers from inside itself: write() and _exit() instead
+     * (stdout holds nothing: every line is flushed when it is printed). */
+    static const char msg[] = "rtl_wmbus: exiting since incoming data stopped flowing!\n";
     (void)signo;
-    fprintf(stderr, "rtl_wmbus: exiting since incoming data stopped flowing!\n");   /* rtl_wmbus.c:76 */
-    exit(EXIT_FAILURE);
+    if (write(STDERR_FILENO, msg, sizeof(msg) - 1) < 0) { /* nothing left to do about it */ }
+    _exit(EXIT_FAILURE);
 }
 
 static double now_s(void)
@@ -56,6 +61,19 @@ static double now_s(void)
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* SIGALRM in `seconds` from now (0: cancel) */
+static void set_alarm(double seconds)
+{
+    struct itimerval it;
+    memset(&it, 0, sizeof(it));
+    if (seconds > 0) {
+        it.it_value.tv_sec = (time_t)seconds;
+        it.it_value.tv_usec = (suseconds_t)((seconds - (double)(time_t)seconds) * 1e6);
+        if (it.it_value.tv_sec == 0 && it.it_value.tv_usec == 0) it.it_value.tv_usec = 1;
+    }
+    setitimer(ITIMER_REAL, &it, NULL);
 }
 
 static int emit_lines(wmb_ctx *ctx, char *out, size_t outcap)
@@ -159,13 +177,14 @@ int main(int argc, char *argv[])
      * it is not running while the device works on a hand-over. */
     size_t since_arm = 0;
     int armed = 0;
+    double deadline = 0;
     double last_push = now_s();
     int rc = WMB_OK, eof = 0;
     while (!eof) {
         /* wait for input; on a live stream hand over what has arrived every 100 ms so
          * that telegrams are printed promptly */
         struct pollfd pfd = { 0, POLLIN, 0 };
-        if (check_flow && !armed) { alarm(2); armed = 1; since_arm = 0; }      /* START_ALARM */
+        if (check_flow && !armed) { deadline = now_s() + 2.0; set_alarm(2.0); armed = 1; since_arm = 0; }      /* START_ALARM */
         const int pr = poll(&pfd, 1, fill ? 100 : -1);
         ssize_t n = 0;
         if (pr > 0) {
@@ -176,14 +195,17 @@ int main(int argc, char *argv[])
         } else if (pr < 0 && errno != EINTR) {
             eof = 1;
         }
-        if (check_flow && armed && (since_arm >= 4096 || eof)) { alarm(0); armed = 0; }     /* STOP_ALARM: an item is in */
+        if (check_flow && armed && (since_arm >= 4096 || eof)) { set_alarm(0); armed = 0; }     /* STOP_ALARM: an item is in */
         const double t = now_s();
         if (fill == batch || eof || (fill && (pr == 0 || t - last_push > 0.1))) {
             if (check_flow && armed) {                  /* the watchdog times the input, not the device */
-                const unsigned left = alarm(0);
+                set_alarm(0);
+                const double t_in = now_s();
                 rc = wmb_push(ctx, buf, fill);
                 if (rc == WMB_OK) emit_lines(ctx, out, outcap);
-                alarm(left ? left : 1);
+                deadline += now_s() - t_in;             /* the item's two seconds do not run during the hand-over */
+                const double left = deadline - now_s();
+                set_alarm(left > 1e-3 ? left : 1e-3);
             } else {
                 rc = wmb_push(ctx, buf, fill);
                 if (rc == WMB_OK) emit_lines(ctx, out, outcap);
@@ -193,7 +215,7 @@ int main(int argc, char *argv[])
             last_push = t;
         }
     }
-    if (check_flow) alarm(0);
+    if (check_flow) set_alarm(0);
     if (rc == WMB_OK) {
         size_t nframes = 0;
         rc = wmb_poll(ctx, NULL, 0, &nframes, 1);       /* EOF: flush */

@@ -251,9 +251,10 @@ WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
 /* what every small batch and every tail waits for, and it forces short lanes (many of    */
 /* them, each with its own 24576-sample warm-up: 2.7 x redundant arithmetic at 1 GiB).    */
 /* Here the three sections of a lane sit in three neighbouring threads and work on        */
-/* different samples at the same moment: in step s thread r handles sample s - 2r, takes   */
-/* its input from its left neighbour's output of two steps ago (a shuffle issued one step  */
-/* ahead, so its latency is off the recurrence), and the warp issues ONE biquad per step   */
+/* different samples at the same moment: in step s thread r handles sample s - SKEW r,      */
+/* takes its input from its left neighbour's output of SKEW steps ago (a shuffle issued    */
+/* SKEW - 1 steps ahead: with one step of slack the warp measurably waits for it, 41       */
+/* cycles per step), and the warp issues ONE biquad per step                               */
 /* for ten lanes.  Every sample still sees exactly the operations of k2a_block in the     */
 /* same order -- only the interleaving changes -- so states and bits are bit-identical to  */
 /* the per-thread version (which stays: -o, re-runs, ragged final batches, CPU tests).    */
@@ -266,14 +267,19 @@ WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
 /* reach the lane's end.  A lane's state "at sample q" is picked up section by section as  */
 /* each thread arrives there (steps q, q+2, q+4).  Output bits are collected at the step's */
 /* position in the block and re-aligned by 2r with a funnel shift when the next block is   */
-/* complete.                                                                              */
+/* complete (2 SKEW <= 31: a section's lag stays inside one block).                       */
 /* ------------------------------------------------------------------------------------- */
 #define K2A2_LPW 10                  /* lanes per warp: 30 threads, two idle */
 #define K2A2_THREADS 64
 
+#ifndef K2A2_SKEW
+#define K2A2_SKEW 6                  /* steps between a section and the next one (>= 2): the shuffle that carries a
+                                        section's output to its neighbour has SKEW - 1 steps to arrive */
+#endif
+
 struct K2a2Thread {
     float h1, h2;                   /* this section's memories                                  */
-    float o, sh;                    /* last output (to be passed on), input for the next step   */
+    float o, sh[K2A2_SKEW - 1];     /* last output (to be passed on), shuffled inputs on their way (sh[0]: this step's) */
     float a1, a2, b1, b2;
     uint32_t R, Rprev;              /* bits of this block / the block before, at step positions */
     bool r0, r2;
@@ -284,8 +290,10 @@ __device__ __forceinline__ void k2a2_step(K2a2Thread &t, const float xs, const i
 {
     constexpr float gain = 1.874981046e-06;                       /* rtl_wmbus.c:338 */
     const float xx = wmb_fmul(xs, xs);                            /* rtl_wmbus.c:1089 */
-    const float in = t.r0 ? xx : t.sh;
-    t.sh = __shfl_up_sync(0xFFFFFFFFu, t.o, 1);                   /* the neighbour's output of the step before: next step's input */
+    const float in = t.r0 ? xx : t.sh[0];
+#pragma unroll
+    for (int k = 0; k + 1 < K2A2_SKEW - 1; k++) t.sh[k] = t.sh[k + 1];
+    t.sh[K2A2_SKEW - 2] = __shfl_up_sync(0xFFFFFFFFu, t.o, 1);    /* the neighbour's output of the step before: input SKEW - 1 steps from now */
     const float h0 = wmb_fsub(in, wmb_fadd(wmb_fmul(t.a1, t.h1), wmb_fmul(t.a2, t.h2)));
     const float out = wmb_fadd(wmb_fadd(h0, wmb_fmul(t.b1, t.h1)), wmb_fmul(t.b2, t.h2));
     t.h2 = t.h1; t.h1 = h0; t.o = out;
@@ -303,7 +311,9 @@ __global__ void __launch_bounds__(K2A2_THREADS) k2a2_lanes_kernel(const K2aParam
     const uint32_t lane = (blockIdx.x * (K2A2_THREADS / 32) + (threadIdx.x >> 5)) * K2A2_LPW + lid / 3;
     const bool valid = lid < 3 * K2A2_LPW && lane < p.lanes;
     K2a2Thread t;
-    t.h1 = t.h2 = t.o = t.sh = 0.0f;
+    t.h1 = t.h2 = t.o = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K2A2_SKEW - 1; k++) t.sh[k] = 0.0f;
     t.R = t.Rprev = 0;
     t.r0 = role == 0; t.r2 = role == 2;
     t.a1 = role == 0 ? CH::A10 : role == 1 ? CH::A11 : CH::A12;
@@ -347,7 +357,7 @@ __global__ void __launch_bounds__(K2A2_THREADS) k2a2_lanes_kernel(const K2aParam
     }
     /* last warm-up block, live blocks, one block past the end: bits, states at the chunk borders, stores */
     uint32_t clk3 = 0;
-    const int sh2r = 2 * role;
+    const int shr = K2A2_SKEW * role;                              /* this section's lag in samples */
     for (; j < nb; j++) {
         load(nxt, j + 1);
         const bool at_start = valid && j == jw, at_end = j == je;
@@ -355,13 +365,13 @@ __global__ void __launch_bounds__(K2A2_THREADS) k2a2_lanes_kernel(const K2aParam
         t.R = 0;
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-            if (i == 0 || i == 2 || i == 4) {                           /* section i/2 arrives at the block's first sample */
-                if ((at_start || at_end) && role == i / 2) { c1 = t.h1; c2 = t.h2; }
+            if (i == 0 || i == K2A2_SKEW || i == 2 * K2A2_SKEW) {       /* section i / SKEW arrives at the block's first sample */
+                if ((at_start || at_end) && role == i / K2A2_SKEW) { c1 = t.h1; c2 = t.h2; }
             }
             k2a2_step<true>(t, K2A2_X(i), i);
         }
         /* the block before this one is complete now: its samples sit 2r positions up */
-        const uint32_t A = __funnelshift_r(t.Rprev, t.R, sh2r);
+        const uint32_t A = __funnelshift_r(t.Rprev, t.R, shr);
         t.Rprev = t.R;
         const int jb = j - 1;
         uint32_t sword = 0;

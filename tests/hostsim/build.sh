@@ -12,3 +12,7 @@ g++ -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -Wextra -Wno-unused-parameter -
     -I"$here" -I"$root/include" -I"$src" -x c++ -c "$src/wmb_context.cu" -o "$here/_build/wmb_context.o"
 g++ -shared -o "$here/_build/libwmbus_hostsim.so" "$here/_build/wmb_context.o" "$here/_build/wmb_framer.o" -lm -lpthread
 echo "built $here/_build/libwmbus_hostsim.so"
+# the drop-in host program against the CPU simulation (live-stream / watchdog tests without a GPU)
+gcc -O2 -std=gnu99 -Wall -Wextra -I"$root/include" -o "$here/_build/rtl_wmbus_hostsim" "$src/rtl_wmbus_b200.c" \
+    -L"$here/_build" -lwmbus_hostsim -Wl,-rpath,"$here/_build" -lstdc++ -lm
+echo "built $here/_build/rtl_wmbus_hostsim"

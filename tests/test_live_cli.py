@@ -15,11 +15,17 @@ import orc
 import pipeline_checks as pc
 from conftest import load_fixture
 
-pytestmark = pytest.mark.gpu
+gpu = pytest.mark.gpu
 
 
 def _exe(pkg):
     return os.path.join(os.path.dirname(pkg.library_path()), "rtl_wmbus_b200")
+
+
+def _sim_exe(hostsim_lib):
+    """the same host program linked against the CPU simulation of the library (tests/hostsim: test infrastructure)"""
+    from conftest import HOSTSIM_SO
+    return os.path.join(os.path.dirname(HOSTSIM_SO), "rtl_wmbus_hostsim")
 
 
 def _run_fed(exe, flags, feeder, timeout=60):
@@ -44,6 +50,7 @@ def _run_fed(exe, flags, feeder, timeout=60):
     return rc, got, p.stderr.read().decode()
 
 
+@gpu
 def test_real_time_pipe_same_lines_and_bounded_latency(pkg, gpu_lib):
     """1.6 MS/s real time, 16 KiB writes: identical lines, and a telegram's line is out at most ~0.3 s after its last
     bit went into the pipe (100 ms hand-over cadence + one device pass)."""
@@ -78,8 +85,7 @@ def test_real_time_pipe_same_lines_and_bounded_latency(pkg, gpu_lib):
     assert p99 < 0.30
 
 
-def test_bursty_pipe_same_lines(pkg, gpu_lib):
-    exe = _exe(pkg)
+def check_bursty_pipe(exe):
     cu8 = load_fixture("synth_mixed_2m4_shift.cu8")
     want = pc.oracle_lines(cu8, "-d 3 -s -o")
 
@@ -93,11 +99,9 @@ def test_bursty_pipe_same_lines(pkg, gpu_lib):
     assert [orc.blank_ts(l) for l, _ in got] == want and len(want) > 3
 
 
-@pytest.mark.parametrize("mode", ["stall", "trickle"])
-def test_flow_watchdog(pkg, gpu_lib, mode):
+def check_flow_watchdog(exe, mode):
     """-f: the input stops (or trickles below one 4096-byte item per 2 s) without end of file -> the reference's
     message on stderr and EXIT_FAILURE; lines decoded before that were printed."""
-    exe = _exe(pkg)
     cu8 = load_fixture("synth_mixed_1m6.cu8")
     t = {}
 
@@ -121,8 +125,7 @@ def test_flow_watchdog(pkg, gpu_lib, mode):
     assert 1.5 < got[-1][1] - t0 + 10 and time.perf_counter() - t["fed"] < 6.0
 
 
-def test_flow_watchdog_quiet_on_a_healthy_stream(pkg, gpu_lib):
-    exe = _exe(pkg)
+def check_watchdog_quiet(exe):
     cu8 = load_fixture("synth_mixed_1m6.cu8")
 
     def feeder(w):
@@ -132,3 +135,34 @@ def test_flow_watchdog_quiet_on_a_healthy_stream(pkg, gpu_lib):
     rc, got, err = _run_fed(exe, "-f", feeder)
     assert rc == 0 and "stopped flowing" not in err
     assert [orc.blank_ts(l) for l, _ in got] == pc.oracle_lines(cu8, "")
+
+
+@gpu
+def test_bursty_pipe_same_lines(pkg, gpu_lib):
+    check_bursty_pipe(_exe(pkg))
+
+
+@gpu
+@pytest.mark.parametrize("mode", ["stall", "trickle"])
+def test_flow_watchdog(pkg, gpu_lib, mode):
+    check_flow_watchdog(_exe(pkg), mode)
+
+
+@gpu
+def test_flow_watchdog_quiet_on_a_healthy_stream(pkg, gpu_lib):
+    check_watchdog_quiet(_exe(pkg))
+
+
+# ---- the same host program on the CPU simulation (`not gpu`): the pipe handling and the watchdog are host code ----
+
+def test_bursty_pipe_same_lines_cpu_build(hostsim_lib):
+    check_bursty_pipe(_sim_exe(hostsim_lib))
+
+
+@pytest.mark.parametrize("mode", ["stall", "trickle"])
+def test_flow_watchdog_cpu_build(hostsim_lib, mode):
+    check_flow_watchdog(_sim_exe(hostsim_lib), mode)
+
+
+def test_flow_watchdog_quiet_cpu_build(hostsim_lib):
+    check_watchdog_quiet(_sim_exe(hostsim_lib))
