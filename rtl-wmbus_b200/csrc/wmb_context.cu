@@ -220,6 +220,8 @@ static uint32_t *gd_field(wmb_ctx *c, size_t off) { return (uint32_t *)((uint8_t
 #ifdef WMB_HOSTSIM
 #include "hostsim_launch.inl"
 #else
+static int g_k1_ctas = 0;                /* WMBUS_B200_K1_CTAS: resident demod blocks per SM (0: as many as fit) */
+
 static int launch_k1(wmb_ctx *c, const K1Params &p)
 {
     const int64_t ntiles = (p.M + K1_TILE - 1) / K1_TILE;
@@ -233,8 +235,10 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, K1_THREADS, smem));
     if (blocks_per_sm < 1) return set_err(WMB_E_INVAL, "decimation %u needs %zu B shared memory per CTA", p.d, smem);
+    if (g_k1_ctas > 0 && blocks_per_sm > g_k1_ctas) blocks_per_sm = g_k1_ctas;
     int64_t grid = (int64_t)sm_count * blocks_per_sm;      /* persistent: whole waves of resident CTAs */
     if (grid > ntiles) grid = ntiles;
+    CUDA_TRY(cudaMemsetAsync(p.tile_ctr, 0, 4, c->k1s));
     kern<<<(unsigned)grid, K1_THREADS, smem, c->k1s>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches++;
@@ -512,6 +516,7 @@ static void read_tuning()
 {
 #ifndef WMB_HOSTSIM
     if (const char *k = getenv("WMBUS_B200_K2A")) g_k2a_coop = strcmp(k, "scalar") != 0;
+    if (const char *k = getenv("WMBUS_B200_K1_CTAS")) g_k1_ctas = atoi(k);
 #endif
     if (const char *b = getenv("WMBUS_B200_PIPE_MIB")) { const unsigned long v = strtoul(b, nullptr, 10); if (v >= 1 && v <= 4096) g_pipe_bytes = (size_t)v << 20; }
     if (const char *b = getenv("WMBUS_B200_P2BLK")) { const unsigned v = (unsigned)atoi(b); if (v == 32 || v == 64 || v == 128) g_p2_block = v; }
@@ -849,6 +854,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
     k1.lut_n = c->o.simultaneous ? (c->o.decimation * 800u) / 25u : 1u;
     k1.lut_phase0 = (uint32_t)((13ull * (c->iq_consumed % k1.lut_n)) % k1.lut_n);
     k1.lut_cos = c->d_lut; k1.lut_msin = c->d_lut + 4096;
+    k1.tile_ctr = c->d_errors + 12;
     for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
         k1.dphi[ch] = c->cb[ch].set[set].dphi ? c->cb[ch].set[set].dphi + c->W : nullptr;
         k1.rssi[ch] = c->cb[ch].set[set].rssi ? c->cb[ch].set[set].rssi + c->W : nullptr;

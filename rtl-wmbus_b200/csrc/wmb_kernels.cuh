@@ -44,6 +44,7 @@ struct K1Params {
     const float *lut_cos, *lut_msin;
     float   *dphi[WMB_N_CHAINS];   /* out: post-FIR discriminator, index 0 = batch sample 0 */
     uint8_t *rssi[WMB_N_CHAINS];   /* out: (unsigned)rssi                                    */
+    uint32_t *tile_ctr;            /* next tile to hand out (zeroed before the launch)       */
 };
 
 /* shared-memory layout of one CTA */
@@ -490,13 +491,26 @@ WMB_D void k1_demod_body(const K1Params &p)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    int64_t tile = blockIdx.x;
-    if (tid == 0 && tile < ntiles) k1_issue_load(p, sm, 0, tile);
+    /* Tiles are handed out by a counter, not by block index: a block that gets on its SM late (the clock-recovery
+     * lanes of the batch before may still hold registers there) simply takes fewer tiles.  Thread 0 draws the next
+     * tile and starts its bulk copy before the block works on the current one. */
+    __shared__ uint32_t s_tile[2];
+    if (tid == 0) {
+        const uint32_t t0 = atomicAdd(p.tile_ctr, 1u);
+        s_tile[0] = t0;
+        if ((int64_t)t0 < ntiles) k1_issue_load(p, sm, 0, t0);
+    }
+    __syncthreads();
     uint32_t phase = 0;                                       /* bit b: parity to wait for on barrier b */
     int buf = 0;
-    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-        const int64_t next = tile + gridDim.x;
-        if (tid == 0 && next < ntiles) k1_issue_load(p, sm, buf ^ 1, next);   /* prefetch */
+    for (;; buf ^= 1) {
+        const int64_t tile = s_tile[buf];
+        if (tile >= ntiles) break;
+        if (tid == 0) {                                       /* prefetch (s_tile[buf ^ 1] was last read before the barriers of the previous tile) */
+            const uint32_t nx = atomicAdd(p.tile_ctr, 1u);
+            s_tile[buf ^ 1] = nx;
+            if ((int64_t)nx < ntiles) k1_issue_load(p, sm, buf ^ 1, nx);
+        }
         mbar_wait(sm.bar + buf, (phase >> buf) & 1u);
         phase ^= 1u << buf;
         const uint8_t *raw = buf ? sm.bytes[1] : sm.bytes[0];
