@@ -13,10 +13,11 @@
 #define WMB_N_ALGOS  2
 
 /* ---- geometry of the demod kernel (K1) ---- */
-#define K1_THREADS   256
+#define K1_THREADS   256       /* threads that convert, filter and demodulate a tile                            */
+#define K1_BLOCK     (K1_THREADS + 32)   /* ... plus one warp that only runs the RSSI recurrences, one tile behind */
 #define K1_TILE      960       /* decimated samples produced per tile: TILE + HALO = 4 rows per thread exactly */
 #define K1_HALO      64        /* decimated samples recomputed left of each tile */
-#define K1_RSSI_SEG  16        /* outputs per RSSI recurrence segment            */
+#define K1_RSSI_SEG  32        /* outputs per RSSI recurrence segment (one thread of the RSSI warp)  */
 #define K1_RSSI_WARM 48        /* warm-up steps before each segment (contraction 0.32 per step) */
 #define K1_BOX_MAX   16
 

@@ -233,13 +233,13 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     }
     auto kern = p.chains == 1u ? k1_demod_kernel<1u> : p.chains == 2u ? k1_demod_kernel<2u> : k1_demod_kernel<3u>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, K1_THREADS, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, K1_BLOCK, smem));
     if (blocks_per_sm < 1) return set_err(WMB_E_INVAL, "decimation %u needs %zu B shared memory per CTA", p.d, smem);
     if (g_k1_ctas > 0 && blocks_per_sm > g_k1_ctas) blocks_per_sm = g_k1_ctas;
     int64_t grid = (int64_t)sm_count * blocks_per_sm;      /* persistent: whole waves of resident CTAs */
     if (grid > ntiles) grid = ntiles;
     CUDA_TRY(cudaMemsetAsync(p.tile_ctr, 0, 4, c->k1s));
-    kern<<<(unsigned)grid, K1_THREADS, smem, c->k1s>>>(p);
+    kern<<<(unsigned)grid, K1_BLOCK, smem, c->k1s>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches++;
     return WMB_OK;

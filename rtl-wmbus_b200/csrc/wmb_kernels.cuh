@@ -53,8 +53,10 @@ struct K1Smem {
     int32_t *v;             /* per input sample: truncated I (low 16), Q (high 16) */
     float   *si, *sq;       /* decimated box-filter outputs, TILE+HALO           */
     float   *draw;          /* discriminator output, TILE+HALO                   */
-    float   *mag;           /* |s|, padded                                       */
+    float   *mag;           /* 0.6789 |s|, padded; the buffer the current pass writes (one of mag2[])  */
+    float   *mag2[2];       /* two passes are in flight: the RSSI warp works one pass behind           */
     uint64_t *bar;          /* two mbarriers                                     */
+    int64_t *pass_tile;     /* [2] tile of the pass whose |s| is in mag2[b] (-1: no more passes)       */
 };
 
 static inline
@@ -78,7 +80,7 @@ size_t k1_smem_bytes(uint32_t d)
 {
     const size_t nb = (size_t)2 * k1_tile_iq(d);
     const size_t n = K1_TILE + K1_HALO;
-    return 2 * nb + 4 * (size_t)k1_tile_iq(d) + 3 * 4 * n + 4 * (n + n / 32 + 1) + 64 + 16;
+    return 2 * nb + 4 * (size_t)k1_tile_iq(d) + 3 * 4 * n + 2 * 4 * (n + n / 32 + 4) + 64 + 16 + 16;
 }
 
 WMB_HD void k1_carve(K1Smem &sm, uint8_t *base, uint32_t d)
@@ -89,11 +91,14 @@ WMB_HD void k1_carve(K1Smem &sm, uint8_t *base, uint32_t d)
     sm.bytes[0] = base + off; off += nb;
     sm.bytes[1] = base + off; off += nb;
     sm.bar = (uint64_t *)(base + off); off += 16;
+    sm.pass_tile = (int64_t *)(base + off); off += 16;
     sm.v = (int32_t *)(base + off); off += 4 * (size_t)k1_tile_iq(d);
     sm.si = (float *)(base + off); off += 4 * n;
     sm.sq = (float *)(base + off); off += 4 * n;
     sm.draw = (float *)(base + off); off += 4 * n;
-    sm.mag = (float *)(base + off); off += 4 * (n + n / 32 + 1);
+    sm.mag2[0] = (float *)(base + off); off += 4 * (n + n / 32 + 4);
+    sm.mag2[1] = (float *)(base + off); off += 4 * (n + n / 32 + 4);
+    sm.mag = sm.mag2[0];
 }
 
 /* first IQ sample (batch-relative, may be negative) held by tile `t` */
@@ -291,10 +296,9 @@ WMB_D void k1_box_disc(const K1Params &p, K1Smem &sm, int tid)
     }
 }
 
-/* phase D: FIR (fir.h:56-67: newest sample first, accumulate from 0) and RSSI one-pole
- * (rtl_wmbus.c:475-484) */
+/* phase D: FIR (fir.h:56-67: newest sample first, accumulate from 0) */
 template <class CH>
-WMB_D void k1_fir_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
+WMB_D void k1_fir(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
 {
     const float *b = (CH::ID == 0) ? c_fir_t1c1 : c_fir_s1;
     const int64_t m0 = tile * K1_TILE;
@@ -362,31 +366,42 @@ WMB_D void k1_fir_rssi(const K1Params &p, K1Smem &sm, int64_t tile, int tid)
             }
         }
     }
-    if (tid >= K1_THREADS - K1_TILE / K1_RSSI_SEG) {
-        /* one segment per thread (the upper warps, so that the FIR loop above and the recurrence
-         * below overlap across warps), started K1_RSSI_WARM samples early from r = 0 */
-        const int seg = tid - (K1_THREADS - K1_TILE / K1_RSSI_SEG);
-        const int o0 = seg * K1_RSSI_SEG;
-        const int r0 = K1_HALO + o0 - K1_RSSI_WARM;
-        float rr = 0.0f;
-        const float B = 1.0f - 0.6789f;
+}
+
+/* RSSI one-pole (rtl_wmbus.c:475-484) for one segment of K1_RSSI_SEG outputs, started K1_RSSI_WARM samples early from
+ * r = 0; seg = 0 .. K1_TILE / K1_RSSI_SEG - 1.  Runs in the block's extra warp while the other threads are already at
+ * the tile's FIR and the next tile's front end: the 80-step chain is nobody's barrier. */
+template <class CH>
+WMB_D void k1_rssi(const K1Params &p, const float *mag, int64_t tile, int seg)
+{
+    if (seg >= K1_TILE / K1_RSSI_SEG) return;
+    const int64_t m0 = tile * K1_TILE;
+    const int o0 = seg * K1_RSSI_SEG;
+    if (m0 + o0 >= p.M) return;
+    const int r0 = K1_HALO + o0 - K1_RSSI_WARM;
+    float rr = 0.0f;
+    const float B = 1.0f - 0.6789f;
 #pragma unroll 8
-        for (int j = 0; j < K1_RSSI_WARM; j++)
-            rr = wmb_fadd(sm.mag[k1_pad(r0 + j)], wmb_fmul(B, rr));
-        /* the segment's 16 bytes leave as one 128-bit store (consecutive threads, consecutive segments) */
-        uint32_t pk[K1_RSSI_SEG / 4] = { 0, 0, 0, 0 };
+    for (int j = 0; j < K1_RSSI_WARM; j++)
+        rr = wmb_fadd(mag[k1_pad(r0 + j)], wmb_fmul(B, rr));
+    /* the segment's bytes leave as 128-bit stores */
+    uint32_t pk[K1_RSSI_SEG / 4];
 #pragma unroll
-        for (int j = 0; j < K1_RSSI_SEG; j++) {
-            rr = wmb_fadd(sm.mag[k1_pad(r0 + K1_RSSI_WARM + j)], wmb_fmul(B, rr));
-            pk[j >> 2] |= ((uint32_t)(unsigned)rr & 0xFFu) << (8 * (j & 3));
+    for (int j = 0; j < K1_RSSI_SEG / 4; j++) pk[j] = 0;
+#pragma unroll
+    for (int j = 0; j < K1_RSSI_SEG; j++) {
+        rr = wmb_fadd(mag[k1_pad(r0 + K1_RSSI_WARM + j)], wmb_fmul(B, rr));
+        pk[j >> 2] |= ((uint32_t)(unsigned)rr & 0xFFu) << (8 * (j & 3));
+    }
+    uint8_t *dst = p.rssi[CH::ID] + m0 + o0;
+    if (m0 + o0 + K1_RSSI_SEG <= p.M) {
+#pragma unroll
+        for (int q = 0; q < K1_RSSI_SEG / 16; q++) {
+            K1Word4 v; v.x = pk[4 * q]; v.y = pk[4 * q + 1]; v.z = pk[4 * q + 2]; v.w = pk[4 * q + 3];
+            ((K1Word4 *)dst)[q] = v;
         }
-        uint8_t *dst = p.rssi[CH::ID] + m0 + o0;
-        if (m0 + o0 + K1_RSSI_SEG <= p.M) {
-            K1Word4 v; v.x = pk[0]; v.y = pk[1]; v.z = pk[2]; v.w = pk[3];
-            *(K1Word4 *)dst = v;
-        } else {
-            for (int j = 0; j < K1_RSSI_SEG; j++) if (m0 + o0 + j < p.M) dst[j] = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
-        }
+    } else {
+        for (int j = 0; j < K1_RSSI_SEG; j++) if (m0 + o0 + j < p.M) dst[j] = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
     }
 }
 
@@ -452,27 +467,44 @@ __device__ __forceinline__ void k1_issue_load(const K1Params &p, K1Smem &sm, int
     if (L.n1) bulk_g2s(dst + L.off1, L.src1, (uint32_t)L.n1, bar);
 }
 
+/* ---- named barriers of the demod block ------------------------------------------------------------------------
+ * 1: the K1_THREADS producer threads among themselves (phase boundaries of a pass)
+ * 2, 3 (by pass parity): "|s| of this pass is in shared memory" -- producers arrive, the RSSI warp waits
+ * 4, 5 (by pass parity): "the RSSI warp is done with this |s| buffer" -- it arrives, the producers wait before the
+ *       pass after next writes the buffer again
+ * A pass = one receiver chain of one tile.  The RSSI warp therefore has a whole pass of slack: its 80-step serial
+ * chains are nobody's barrier (round-1 profile: barrier stall 3.2-3.5 per issued instruction, most of it here). */
+__device__ __forceinline__ void k1_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void k1_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+#define K1_BAR_P 1
+#define K1_BAR_READY(pass) (2 + (int)((pass) & 1u))
+#define K1_BAR_FREE(pass)  (4 + (int)((pass) & 1u))
+
 template <class CH>
 __device__ __forceinline__ void k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile,
-                                         int tid, bool need_convert)
+                                         int tid, bool need_convert, uint32_t pass)
 {
     const bool fast = (p.d == 2 && !p.mix);
     if (need_convert) {
         if (fast) k1_convert_fast(p, sm, raw, tile, tid); else k1_convert<CH::ID>(p, sm, raw, tile, tid);
-        __syncthreads();
+        k1_bar_sync(K1_BAR_P, K1_THREADS);
     }
+    sm.mag = (pass & 1u) ? sm.mag2[1] : sm.mag2[0];
+    if (pass >= 2) k1_bar_sync(K1_BAR_FREE(pass), K1_BLOCK);         /* the RSSI warp has read what pass - 2 left there */
     if (fast) k1_box_disc<CH, 1, true>(p, sm, tid);
     else if (p.d == 3) k1_box_disc<CH, 3, false>(p, sm, tid);
     else if (p.d == 2) k1_box_disc<CH, 2, false>(p, sm, tid);
     else if (p.d == 1) k1_box_disc<CH, 1, false>(p, sm, tid);
     else {
         k1_box<CH>(p, sm, tid);
-        __syncthreads();
+        k1_bar_sync(K1_BAR_P, K1_THREADS);
         k1_disc_mag(p, sm, tid);
     }
-    __syncthreads();
-    k1_fir_rssi<CH>(p, sm, tile, tid);
-    __syncthreads();
+    if (tid == 0) sm.pass_tile[pass & 1u] = tile;
+    k1_bar_arrive(K1_BAR_READY(pass), K1_BLOCK);                      /* hand |s| to the RSSI warp ...            */
+    k1_bar_sync(K1_BAR_P, K1_THREADS);                                /* ... and go on with the FIR               */
+    k1_fir<CH>(p, sm, tile, tid);
+    k1_bar_sync(K1_BAR_P, K1_THREADS);
 }
 
 /* CHAINS (bit 0 T1/C1, bit 1 S1) is a template parameter so that a one-chain run does not carry the other
@@ -491,17 +523,35 @@ WMB_D void k1_demod_body(const K1Params &p)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    /* Tiles are handed out by a counter, not by block index: a block that gets on its SM late (the clock-recovery
-     * lanes of the batch before may still hold registers there) simply takes fewer tiles.  Thread 0 draws the next
-     * tile and starts its bulk copy before the block works on the current one. */
+    constexpr uint32_t NCH = (CHAINS & 1u) + ((CHAINS >> 1) & 1u);       /* passes per tile */
+
+    if (tid >= K1_THREADS) {
+        /* ---- the RSSI warp: pass after pass, one behind the producers ---- */
+        const int seg = tid - K1_THREADS;
+        for (uint32_t pass = 0;; pass++) {
+            k1_bar_sync(K1_BAR_READY(pass), K1_BLOCK);
+            const int64_t tile = sm.pass_tile[pass & 1u];
+            if (tile < 0) break;
+            const float *mag = (pass & 1u) ? sm.mag2[1] : sm.mag2[0];
+            const bool s1 = (CHAINS == 2u) || (CHAINS == 3u && (pass % NCH) == 1u);
+            if (s1) k1_rssi<ChainS1>(p, mag, tile, seg); else k1_rssi<ChainT1C1>(p, mag, tile, seg);
+            k1_bar_arrive(K1_BAR_FREE(pass), K1_BLOCK);
+        }
+        return;
+    }
+
+    /* ---- producers.  Tiles are handed out by a counter, not by block index: a block that gets on its SM late simply
+     * takes fewer tiles.  Thread 0 draws the next tile and starts its bulk copy before the block works on the
+     * current one. */
     __shared__ uint32_t s_tile[2];
     if (tid == 0) {
         const uint32_t t0 = atomicAdd(p.tile_ctr, 1u);
         s_tile[0] = t0;
         if ((int64_t)t0 < ntiles) k1_issue_load(p, sm, 0, t0);
     }
-    __syncthreads();
+    k1_bar_sync(K1_BAR_P, K1_THREADS);
     uint32_t phase = 0;                                       /* bit b: parity to wait for on barrier b */
+    uint32_t pass = 0;
     int buf = 0;
     for (;; buf ^= 1) {
         const int64_t tile = s_tile[buf];
@@ -514,13 +564,20 @@ WMB_D void k1_demod_body(const K1Params &p)
         mbar_wait(sm.bar + buf, (phase >> buf) & 1u);
         phase ^= 1u << buf;
         const uint8_t *raw = buf ? sm.bytes[1] : sm.bytes[0];
-        if (CHAINS & 1u) k1_chain<ChainT1C1>(p, sm, raw, tile, tid, true);
-        if (CHAINS & 2u) k1_chain<ChainS1>(p, sm, raw, tile, tid, p.mix || !(CHAINS & 1u));
+        if (CHAINS & 1u) k1_chain<ChainT1C1>(p, sm, raw, tile, tid, true, pass++);
+        if (CHAINS & 2u) k1_chain<ChainS1>(p, sm, raw, tile, tid, p.mix || !(CHAINS & 1u), pass++);
     }
+    /* tell the RSSI warp that there is no further pass (its buffer must be free first), then wait until it has read
+     * the last two */
+    if (pass >= 2) k1_bar_sync(K1_BAR_FREE(pass), K1_BLOCK);
+    if (tid == 0) sm.pass_tile[pass & 1u] = -1;
+    k1_bar_arrive(K1_BAR_READY(pass), K1_BLOCK);
+    if (pass >= 1) k1_bar_sync(K1_BAR_FREE(pass + 1), K1_BLOCK);
 }
 
+/* (resident blocks per SM pinned: the T1/C1-only kernel ran at 40 registers before the RSSI warp moved in) */
 template <uint32_t CHAINS>
-__global__ void __launch_bounds__(K1_THREADS) k1_demod_kernel(const K1Params p) { k1_demod_body<CHAINS>(p); }
+__global__ void __launch_bounds__(K1_BLOCK, CHAINS == 1u ? 5 : 4) k1_demod_kernel(const K1Params p) { k1_demod_body<CHAINS>(p); }
 
 #endif /* !WMB_HOSTSIM */
 

@@ -18,7 +18,8 @@ static void hostsim_k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, 
         for (int t = 0; t < K1_THREADS; t++) k1_box<CH>(p, sm, t);
         for (int t = 0; t < K1_THREADS; t++) k1_disc_mag(p, sm, t);
     }
-    for (int t = 0; t < K1_THREADS; t++) k1_fir_rssi<CH>(p, sm, tile, t);
+    for (int t = 0; t < K1_THREADS; t++) k1_fir<CH>(p, sm, tile, t);
+    for (int t = 0; t < 32; t++) k1_rssi<CH>(p, sm.mag, tile, t);            /* the block's RSSI warp */
 }
 
 static int launch_k1(wmb_ctx *c, const K1Params &p)
