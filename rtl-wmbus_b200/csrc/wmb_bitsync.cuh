@@ -1122,15 +1122,6 @@ WMB_D int wmb_div_small(int x, int n)
     return x < 0 ? -q : q;
 }
 
-/* the lane's first record: record 0 (carry state) or the first record in [r0, r1) that follows a reset */
-WMB_D bool k2p2_start(const K2p2Params &p, uint32_t lane, uint64_t r0, uint64_t r1, uint64_t &i)
-{
-    i = r0;
-    if (lane == 0) return true;
-    for (; i < r1; i++) if (p.rec_v[i] & 1u) return true;
-    return false;
-}
-
 /* pass A (serial in the PI recurrence, nothing else): bits per record -> rec_n.  A lane owns the
  * records from the first reset in its range up to the first reset of a later range, so a telegram
  * (which has no reset inside) is one dependent chain; the step is therefore written for latency:
@@ -1139,55 +1130,60 @@ WMB_D bool k2p2_start(const K2p2Params &p, uint32_t lane, uint64_t r0, uint64_t 
 WMB_D void k2p2_count(const K2p2Params &p, uint32_t lane)
 {
     if (lane >= p.lanes) return;
-    const uint64_t N = p.pd->n_rec;
-    const uint64_t r0 = (uint64_t)lane * p.R, r1 = (r0 + p.R < N) ? r0 + p.R : N;
-    uint64_t i;
-    if (!(r0 < N && k2p2_start(p, lane, r0, r1, i))) return;
+    const uint32_t N = (uint32_t)p.pd->n_rec;                        /* < 2^32: at most one record per five samples */
+    const uint64_t r0w = (uint64_t)lane * p.R;
+    if (r0w >= N) return;
+    const uint32_t r0 = (uint32_t)r0w, r1 = (N - r0 > p.R) ? r0 + p.R : N;
+    uint32_t i = r0;
+    if (lane != 0) {                                                 /* the lane's first record: the first one in its range that follows a reset */
+        while (i < r1 && !(p.rec_v[i] & 1u)) i++;
+        if (i >= r1) return;
+    }
     int32_t a = 8 * 256, b = 0;
     if (lane == 0) { const RlState c = *p.carry; a = c.a; b = c.b; }
     bool stop = false, ran_off_end = false;
     uint32_t v[K2P2_BLK], vn[K2P2_BLK];
 #pragma unroll
     for (int j = 0; j < K2P2_BLK; j++) v[j] = (i + j < N) ? p.rec_v[i + j] : 1u;
-    if (i >= N) ran_off_end = true;
-    while (!stop && i < N) {
+    while (!stop) {
 #pragma unroll
         for (int j = 0; j < K2P2_BLK; j++) vn[j] = (i + K2P2_BLK + j < N) ? p.rec_v[i + K2P2_BLK + j] : 1u;
 #pragma unroll
         for (int j = 0; j < K2P2_BLK; j++) {
             if (stop) continue;
-            if (i + j >= N) { stop = true; ran_off_end = true; continue; }
+            const uint32_t idx = i + j;
+            if (idx >= N) { stop = true; ran_off_end = true; continue; }
             const uint32_t vv = v[j];
             if (vv & 1u) {
-                if (i + j >= r1) { stop = true; continue; }          /* next lane's segment */
+                if (idx >= r1) { stop = true; continue; }            /* next lane's segment */
                 a = 8 * 256; b = 0;                                  /* runlength_algorithm_reset_t1_c1 */
             }
-            int rl = (int)((vv >> 2) * 256u);
-            const int half = a / 2;
-            if (rl <= half || a <= 0) {                              /* rtl_wmbus.c:756-762 (or a spin) */
+            const int32_t rl0 = (int32_t)((vv >> 2) << 8);
+            const int32_t half = a / 2;
+            if (rl0 <= half || a <= 0) {                             /* rtl_wmbus.c:756-762 (or a spin) */
                 p.pd->fallback = 1;
                 stop = true; continue;
             }
-            /* n = number of bit periods in the run (:765-779): the smallest n with rl - n*a <= half.
-             * Telegram runs are 1-4 bits long: compare against all of half + k*a at once and keep the
-             * integer division for the rare long run. */
-            int n;
-            if (rl - half <= 8 * a) {
-                n = 1;
-#pragma unroll
-                for (int k = 1; k < 8; k++) n += (rl > half + k * a) ? 1 : 0;
-                rl -= n * a;
-                b += rl;                                             /* :792 */
-                a += wmb_div_small(wmb_div_pow2(rl + wmb_div_pow2(b, 4), 5), n);   /* :796: x/(32 n) == (x/32)/n */
-            } else {
-                n = (rl - half + a - 1) / a; rl -= n * a;
-                b += rl;
-                a += wmb_div_pow2(rl + wmb_div_pow2(b, 4), 5) / n;
-            }
-            p.rec_n[i + j] = (uint16_t)(n < K2_EDGE_EMIT_CAP ? n : K2_EDGE_EMIT_CAP);
+            /* n = number of bit periods in the run (:765-779): the smallest n with rl0 - n*a <= half, i.e.
+             * floor((rl0 - half - 1) / a) + 1.  The quotient comes from a reciprocal estimate and is put right by
+             * the exact remainder (the estimate is off by at most one below 2^22); the remainder also is what is
+             * left of the run: rl = rl0 - n*a = half + 1 + rem - a. */
+            const int32_t x = rl0 - half - 1;
+            int32_t q, rem;
+            if (x < (1 << 22)) {
+                q = (int32_t)((float)x * wmb_rcp_approx((float)a));
+                rem = x - q * a;
+                if (rem < 0) { q--; rem += a; }
+                else if (rem >= a) { q++; rem -= a; }
+            } else { q = x / a; rem = x - q * a; }
+            const int32_t n = q + 1;
+            const int32_t rl = half + 1 + rem - a;
+            b += rl;                                                 /* :792 */
+            const int32_t t = wmb_div_pow2(rl + wmb_div_pow2(b, 4), 5);      /* :796: x/(32 n) == (x/32)/n */
+            a += (n <= 8) ? wmb_div_small(t, n) : t / n;
+            p.rec_n[idx] = (uint16_t)(n < K2_EDGE_EMIT_CAP ? n : K2_EDGE_EMIT_CAP);
         }
         i += K2P2_BLK;
-        if (!stop && i >= N) ran_off_end = true;
 #pragma unroll
         for (int j = 0; j < K2P2_BLK; j++) v[j] = vn[j];
     }
