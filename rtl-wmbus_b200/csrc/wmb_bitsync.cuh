@@ -330,16 +330,10 @@ __global__ void __launch_bounds__(K2A2_THREADS) k2a2_lanes_kernel(const K2aParam
     const int64_t m_last = p.M + 256;                               /* reads stay inside the buffer's slack                   */
     const bool loader = valid && t.r0;
 
-    /* two register buffers of one block (32 samples = one 128-byte line) each, used alternately: the block after the
-     * one being worked on is already in the other buffer, the one after that is requested as soon as a buffer is done.
-     * Only the lanes' first threads ever write them; everybody else's stay zero. */
-    float4 A[8], B[8];
-#pragma unroll
-    for (int q = 0; q < 8; q++) { A[q] = make_float4(0.f, 0.f, 0.f, 0.f); B[q] = A[q]; }
+    float4 cur[8], nxt[8];
     auto load = [&](float4 (&b)[8], int j) {
-        if (!loader) return;
         const int64_t m = m0 + 32 * (int64_t)j;
-        if (m >= -p.hist) {
+        if (loader && m >= -p.hist) {
             const float4 *s4 = (const float4 *)(p.dphi + (m < m_last ? m : m_last));
 #pragma unroll
             for (int q = 0; q < 8; q++) b[q] = s4[q];
@@ -349,17 +343,23 @@ __global__ void __launch_bounds__(K2A2_THREADS) k2a2_lanes_kernel(const K2aParam
             for (int q = 0; q < 8; q++) b[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-#define K2A2_X(b, i) ((i & 3) == 0 ? b[i >> 2].x : (i & 3) == 1 ? b[i >> 2].y : (i & 3) == 2 ? b[i >> 2].z : b[i >> 2].w)
+#define K2A2_X(i) ((i & 3) == 0 ? cur[i >> 2].x : (i & 3) == 1 ? cur[i >> 2].y : (i & 3) == 2 ? cur[i >> 2].z : cur[i >> 2].w)
 
+    load(cur, 0);
+    int j = 0;
+    /* warm-up blocks but the last: state only */
+    for (; j < jw - 1; j++) {
+        load(nxt, j + 1);
+#pragma unroll
+        for (int i = 0; i < 32; i++) k2a2_step<false>(t, K2A2_X(i), i);
+#pragma unroll
+        for (int q = 0; q < 8; q++) cur[q] = nxt[q];
+    }
+    /* last warm-up block, live blocks, one block past the end: bits, states at the chunk borders, stores */
     uint32_t clk3 = 0;
     const int shr = K2A2_SKEW * role;                              /* this section's lag in samples */
-    /* warm-up block: state only */
-    auto lite = [&](const float4 (&b)[8]) {
-#pragma unroll
-        for (int i = 0; i < 32; i++) k2a2_step<false>(t, K2A2_X(b, i), i);
-    };
-    /* last warm-up block, live blocks, one block past the end: bits, states at the chunk borders, stores */
-    auto full = [&](const float4 (&b)[8], int j) {
+    for (; j < nb; j++) {
+        load(nxt, j + 1);
         const bool at_start = valid && j == jw, at_end = j == je;
         float c1 = 0.f, c2 = 0.f;
         t.R = 0;
@@ -368,10 +368,10 @@ __global__ void __launch_bounds__(K2A2_THREADS) k2a2_lanes_kernel(const K2aParam
             if (i == 0 || i == K2A2_SKEW || i == 2 * K2A2_SKEW) {       /* section i / SKEW arrives at the block's first sample */
                 if ((at_start || at_end) && role == i / K2A2_SKEW) { c1 = t.h1; c2 = t.h2; }
             }
-            k2a2_step<true>(t, K2A2_X(b, i), i);
+            k2a2_step<true>(t, K2A2_X(i), i);
         }
-        /* the block before this one is complete now: its samples sit SKEW r positions up */
-        const uint32_t Aw = __funnelshift_r(t.Rprev, t.R, shr);
+        /* the block before this one is complete now: its samples sit 2r positions up */
+        const uint32_t A = __funnelshift_r(t.Rprev, t.R, shr);
         t.Rprev = t.R;
         const int jb = j - 1;
         uint32_t sword = 0;
@@ -379,35 +379,25 @@ __global__ void __launch_bounds__(K2A2_THREADS) k2a2_lanes_kernel(const K2aParam
             /* lock stencil on the whole word: sample the data bit where the clock reads low, high, high, high at
              * m-3..m (rtl_wmbus.c:1092-1111) */
             const uint64_t hist3 = ((clk3 & 1u) << 2) | (clk3 & 2u) | ((clk3 >> 2) & 1u);
-            const uint64_t H = ((uint64_t)Aw << 3) | hist3;
+            const uint64_t H = ((uint64_t)A << 3) | hist3;
             sword = (uint32_t)((H >> 3) & (H >> 2) & (H >> 1) & ~H);
-            clk3 = ((Aw >> 31) & 1u) | (((Aw >> 30) & 1u) << 1) | (((Aw >> 29) & 1u) << 2);
+            clk3 = ((A >> 31) & 1u) | (((A >> 30) & 1u) << 1) | (((A >> 29) & 1u) << 2);
             if (j == jw && m0 + 32 * (int64_t)jw <= -p.hist) clk3 = 0;     /* the lane starts at the stream's first sample: no clock history */
         }
         if (valid && jb >= jw && jb < je) {
             const int64_t w = (m0 >> 5) + jb;                               /* word of the batch (m0 is a multiple of 32) */
-            if (t.r0) p.dbits[w] = Aw;
-            if (t.r2) { p.sbits[w] = sword; if (p.cbits) p.cbits[w] = Aw; }
+            if (t.r0) p.dbits[w] = A;
+            if (t.r2) { p.sbits[w] = sword; if (p.cbits) p.cbits[w] = A; }
         }
         if (at_start || at_end) {
             IirState *st = at_end ? p.st_end + lane : p.st_start + lane;
             st->h[2 * role] = c1; st->h[2 * role + 1] = c2;
             if (t.r0) { st->dc_x = 0.f; st->dc_y = 0.f; }
             if (t.r2) { st->clk3 = clk3; st->pad = 0; }
+            /* a lane without live samples (e0 == s0 cannot happen: lanes = ceil(M / C)) would need both at once */
         }
-    };
-
-    /* W and C are multiples of 256, so both loops run an even number of blocks when the warm-up starts one (all-zero)
-     * block early: block -1 in B, block 0 in A */
-    load(A, 0);
-    int j = -1;
-    for (; j < jw - 1; j += 2) {
-        lite(B); load(B, j + 2);
-        lite(A); load(A, j + 3);
-    }
-    for (; j < nb; j += 2) {
-        full(B, j); load(B, j + 2);
-        full(A, j + 1); load(A, j + 3);
+#pragma unroll
+        for (int q = 0; q < 8; q++) cur[q] = nxt[q];
     }
 #undef K2A2_X
 }

@@ -253,7 +253,7 @@ static int launch_k2a_lanes(wmb_ctx *c, int chain, const K2aParams &p, cudaStrea
 {
     /* three threads per lane where the lane is the plain case (time2 on, no DC block, whole words); the per-thread
      * kernel otherwise */
-    if (g_k2a_coop && p.t2 && !p.dc && p.M % 32 == 0 && p.W % 256 == 0 && p.C % 256 == 0 && p.hist % 32 == 0) {
+    if (g_k2a_coop && p.t2 && !p.dc && p.M % 32 == 0 && p.W % 32 == 0 && p.C % 32 == 0 && p.hist % 32 == 0) {
         const unsigned per = (K2A2_THREADS / 32) * K2A2_LPW;
         const unsigned grid = (p.lanes + per - 1) / per;
         if (chain == 0) k2a2_lanes_kernel<ChainT1C1><<<grid, K2A2_THREADS, 0, st>>>(p);

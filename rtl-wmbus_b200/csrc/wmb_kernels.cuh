@@ -474,8 +474,20 @@ __device__ __forceinline__ void k1_issue_load(const K1Params &p, K1Smem &sm, int
  *       pass after next writes the buffer again
  * A pass = one receiver chain of one tile.  The RSSI warp therefore has a whole pass of slack: its 80-step serial
  * chains are nobody's barrier (round-1 profile: barrier stall 3.2-3.5 per issued instruction, most of it here). */
-__device__ __forceinline__ void k1_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void k1_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+/* (barrier numbers are immediates: with a register operand ptxas reserves all 16 barriers for the block, which caps
+ * the SM at 4 resident blocks) */
+template <int ID> __device__ __forceinline__ void k1_bar_sync_i(int count) { asm volatile("bar.sync %0, %1;" :: "n"(ID), "r"(count) : "memory"); }
+template <int ID> __device__ __forceinline__ void k1_bar_arrive_i(int count) { asm volatile("bar.arrive %0, %1;" :: "n"(ID), "r"(count) : "memory"); }
+__device__ __forceinline__ void k1_bar_sync(int id, int count)
+{
+    switch (id) { case 1: k1_bar_sync_i<1>(count); break; case 2: k1_bar_sync_i<2>(count); break; case 3: k1_bar_sync_i<3>(count); break;
+                  case 4: k1_bar_sync_i<4>(count); break; default: k1_bar_sync_i<5>(count); break; }
+}
+__device__ __forceinline__ void k1_bar_arrive(int id, int count)
+{
+    switch (id) { case 2: k1_bar_arrive_i<2>(count); break; case 3: k1_bar_arrive_i<3>(count); break;
+                  case 4: k1_bar_arrive_i<4>(count); break; default: k1_bar_arrive_i<5>(count); break; }
+}
 #define K1_BAR_P 1
 #define K1_BAR_READY(pass) (2 + (int)((pass) & 1u))
 #define K1_BAR_FREE(pass)  (4 + (int)((pass) & 1u))
