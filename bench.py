@@ -63,31 +63,64 @@ def workload_def(name, mib=1024):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons of one GPU during the timed region, through NVML inside this process (a query
+    costs microseconds; spawning nvidia-smi every 200 ms from every rank perturbed the other ranks' launches) with
+    nvidia-smi as the fallback."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        g = lambda name: getattr(n, name, 0)
+        flags = [bool(r & g("nvmlClocksThrottleReasonHwSlowdown")), bool(r & g("nvmlClocksThrottleReasonHwThermalSlowdown")),
+                 bool(r & g("nvmlClocksThrottleReasonSwThermalSlowdown")), bool(r & g("nvmlClocksThrottleReasonSwPowerCap"))]
+        return [str(mhz), str(self.max_mhz)] + ["Active" if f else "Not Active" for f in flags]
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                if self.nvml:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    if len(f) >= 6:
+                        self.samples.append(f)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02 if self.nvml else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=3)
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"]}
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
         reasons = set()
         for s in self.samples:
@@ -96,7 +129,7 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": sorted(reasons), "samples": len(self.samples), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def host_cpus():
@@ -396,9 +429,15 @@ def main():
         lines = ctx.process_device(cap.data_ptr(), n_bytes, flush=True, raw=True)     # the C ABI's text, as a user's C code gets it
         st = ctx.stats()
         k1_ms += st.demod_kernel_ms; k2_ms += st.bitsync_kernel_ms; dev_ms += st.batch_device_ms
+    t_mine = time.perf_counter() - t0
     barrier()
     t_dev = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop()
+    per_rank_ms = [round(1e3 * t_mine / args.steps, 3)]
+    if world > 1:
+        tt = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(tt, torch.tensor([1e3 * t_mine / args.steps], dtype=torch.float64, device="cuda"))
+        per_rank_ms = [round(float(x.item()), 3) for x in tt]
     st = ctx.stats()
     launches = st.kernel_launches - launches0
     value = world * n_iq * args.steps / t_dev / 1e6
@@ -459,6 +498,7 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": n_bytes,
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": round(1e3 * t_e2e / args.steps, 3)},
             "gpu_launches": int(launches),
+            "per_rank_ms_per_step": per_rank_ms,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
                          "traffic": traffic, "peak_source": peak_src,
