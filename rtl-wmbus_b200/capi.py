@@ -243,9 +243,10 @@ class WmbusB200:
         self._check(self.lib.wmb_set_line_window(self._ctx, sync_lo, sync_hi))
 
     def boundary_state(self) -> bytes:
-        buf = C.create_string_buffer(1 << 22)
-        n = self._check(self.lib.wmb_boundary_state(self._ctx, buf, len(buf)))
-        return buf.raw[:n]
+        if not hasattr(self, "_bbuf"):
+            self._bbuf = C.create_string_buffer(1 << 22)        # (allocating and copying 4 MiB per call cost 2 ms)
+        n = self._check(self.lib.wmb_boundary_state(self._ctx, self._bbuf, len(self._bbuf)))
+        return C.string_at(self._bbuf, n)
 
     def stats(self) -> WmbStats:
         s = WmbStats()
