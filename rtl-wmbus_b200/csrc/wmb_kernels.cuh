@@ -752,18 +752,24 @@ WMB_D void k3_publish(const K3Params &p)
  * over from the previous batch plus the new matches, by rank -- ordinals of one stream are distinct, so the number
  * of smaller ones is the position.  Matches are a few thousand per GiB (false ones at 2^-16 per bit plus the
  * telegrams), so the quadratic count is microseconds; the inner loops read one address per warp. */
-WMB_D void k3_fill(const K3Params &p, uint32_t i)
+WMB_D void k3_fill(const K3Params &p, uint32_t i, uint32_t part, uint32_t nparts)
 {
+    /* part / nparts: the threads that share candidate i (each counts a slice of the keys; the device wrapper adds the
+     * slices up with shuffles -- dense traffic has ~20 k candidates per GiB and stream, 4e8 comparisons) */
     const GatherDev &g = *p.gd;
-    if (i >= g.n) return;
+    const bool live = i < g.n;                                   /* (padding threads stay for the shuffles) */
     int k = 0;
-    while (k + 1 < WMB_N_STREAMS && i >= g.off[k + 1]) k++;
-    const uint32_t j = i - g.off[k];
-    const uint32_t np = g.n_pend[k], nn = g.off[k + 1] - g.off[k] - np;
-    const uint64_t key = j < np ? p.pend[k][j] : p.cand[k][j - np];
+    while (live && k + 1 < WMB_N_STREAMS && i >= g.off[k + 1]) k++;
+    const uint32_t j = live ? i - g.off[k] : 0u;
+    const uint32_t np = live ? g.n_pend[k] : 0u, nn = live ? g.off[k + 1] - g.off[k] - np : 0u;
+    const uint64_t key = !live ? 0ull : j < np ? p.pend[k][j] : p.cand[k][j - np];
     uint32_t rank = 0;
-    for (uint32_t q = 0; q < np; q++) rank += (p.pend[k][q] < key) ? 1u : 0u;
-    for (uint32_t q = 0; q < nn; q++) rank += (p.cand[k][q] < key) ? 1u : 0u;
+    for (uint32_t q = part; q < np; q += nparts) rank += (p.pend[k][q] < key) ? 1u : 0u;
+    for (uint32_t q = part; q < nn; q += nparts) rank += (p.cand[k][q] < key) ? 1u : 0u;
+#ifndef WMB_HOSTSIM
+    for (uint32_t d = nparts >> 1; d > 0; d >>= 1) rank += __shfl_xor_sync(0xFFFFFFFFu, rank, d);
+#endif
+    if (!live || part != 0) return;
     FrameHdr h;
     h.ordinal = key; h.sync_sample = 0; h.nbits = 0; h.word_off = 0; h.complete = 0; h.overflow = 0; h.cut = 0;
     h.pad[0] = h.pad[1] = h.pad[2] = 0;
@@ -1369,9 +1375,14 @@ __global__ void dbg_arith_kernel(const float *y, const float *x, float *out, siz
 __global__ void k3_plan_kernel(const K3Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) k3_plan(p); }
 __global__ void k3_publish_kernel(const K3Params p) { if (threadIdx.x == 0 && blockIdx.x == 0) k3_publish(p); }
 /* the kernels below do not know on the host how many candidates there are: grid-stride loops over gd->n */
+#define K3_FILL_PARTS 8
 __global__ void k3_fill_kernel(const K3Params p)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.gd->n; i += gridDim.x * blockDim.x) k3_fill(p, i);
+    /* all threads of a warp stay in the loop together (the shuffles inside k3_fill need them): whole groups of 8 */
+    const uint32_t n = p.gd->n, stride = gridDim.x * blockDim.x / K3_FILL_PARTS;
+    const uint32_t n_pad = (n + 3u) & ~3u;                       /* 4 candidates per warp */
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) / K3_FILL_PARTS; i < n_pad; i += stride)
+        k3_fill(p, i, threadIdx.x % K3_FILL_PARTS, K3_FILL_PARTS);
 }
 __global__ void k3_size_kernel(const K3Params p)
 {

@@ -210,7 +210,7 @@ static int launch_k3_k4(wmb_ctx *c, const K3Params &p, const K4Params *q)
 {
     k3_plan(p);
     const uint32_t n = p.gd->n;
-    for (uint32_t i = 0; i < n; i++) k3_fill(p, i);
+    for (uint32_t i = 0; i < n; i++) k3_fill(p, i, 0, 1);
     for (uint32_t i = 0; i < n; i++) k3_size(p, i);
     for (uint32_t i = 0; i < n; i++)
         for (int t = 0; t < 4; t++) k3_cut(p, i, t, 4);
