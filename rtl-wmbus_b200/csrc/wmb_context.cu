@@ -139,6 +139,8 @@ struct wmb_ctx {
     bool chain_recorded[2] = {false, false};
     cudaEvent_t ev_res[WMB_NSLOT] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_push_start = nullptr;           /* first demod kernel of the current push (timers) */
+    cudaEvent_t ev_reset = nullptr;                /* wmb_reset's device part (the first batch after it waits for it) */
+    bool reset_pending = false;
     bool push_started = false;
     cudaEvent_t ev_t[WMB_NSLOT][6];                /* per result slot: demod start/end, bit sync start/end (timers) */
     bool allocated = false;
@@ -394,13 +396,13 @@ static int launch_k3_k4(wmb_ctx *c, const K3Params &p, const K4Params *q)
     k3_plan_kernel<<<1, 32, 0, c->cs>>>(p);
     k3_fill_kernel<<<sms * 2, 256, 0, c->cs>>>(p);
     k3_size_kernel<<<sms, 128, 0, c->cs>>>(p);
-    k3_cut_kernel<<<sms * 8, 64, 0, c->cs>>>(p);
+    k3_cut_kernel<<<sms * 32, 64, 0, c->cs>>>(p);
     k3_offsets_kernel<<<1, SCAN_THREADS, 0, c->cs>>>(p);
-    k3_copy_kernel<<<sms * 8, 128, 0, c->cs>>>(p);
+    k3_copy_kernel<<<sms * 32, 128, 0, c->cs>>>(p);
     k3_carry_kernel<<<sms, 128, 0, c->cs>>>(p);
     c->st.kernel_launches += 8;
     if (q) {
-        k4_decode_kernel<<<sms * 16, K4_THREADS, 0, c->cs>>>(*q);
+        k4_decode_kernel<<<sms * 64, K4_THREADS, 0, c->cs>>>(*q);
         c->st.kernel_launches += 1;
     }
     k3_publish_kernel<<<1, 32, 0, c->cs>>>(p);
@@ -731,6 +733,7 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
         cudaEventCreateWithFlags(&c->ev_k2a2[i], cudaEventDisableTiming);
     }
     cudaEventCreate(&c->ev_push_start);
+    cudaEventCreateWithFlags(&c->ev_reset, cudaEventDisableTiming);
     for (int i = 0; i < WMB_NSLOT; i++) {
         cudaEventCreateWithFlags(&c->ev_res[i], cudaEventDisableTiming);
         for (int k = 0; k < 6; k++) cudaEventCreate(&c->ev_t[i][k]);
@@ -759,6 +762,7 @@ extern "C" void wmb_destroy(wmb_ctx *c)
     }
     if (c->k1s) cudaStreamDestroy(c->k1s);
     if (c->ev_push_start) cudaEventDestroy(c->ev_push_start);
+    if (c->ev_reset) cudaEventDestroy(c->ev_reset);
     for (int i = 0; i < WMB_NSLOT; i++) {
         if (c->ev_res[i]) cudaEventDestroy(c->ev_res[i]);
         for (int k = 0; k < 6; k++) if (c->ev_t[i][k]) cudaEventDestroy(c->ev_t[i][k]);
@@ -837,6 +841,10 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
     for (int ch = 0; ch < WMB_N_CHAINS; ch++)
         for (int a = 0; a < WMB_N_ALGOS; a++) c->cb[ch].s[a].total_prev = c->cb[ch].s[a].total;   /* stage tap: events of this batch */
 
+    if (c->reset_pending) {                            /* the streams that do not follow cs wait for wmb_reset's kernel */
+        for (cudaStream_t st : { c->k1s, c->as[0], c->as[1], c->as2[0], c->as2[1] }) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_reset, 0));
+        c->reset_pending = false;
+    }
     /* ================= stage 1 (k1s): history prefix of this set, demod ================= */
     if (c->chain_recorded[set]) CUDA_TRY(cudaStreamWaitEvent(c->k1s, c->ev_chain[set], 0));    /* batch i-2 is done with the set */
     if (input_ready) CUDA_TRY(cudaStreamWaitEvent(c->k1s, input_ready, 0));
@@ -1709,33 +1717,35 @@ extern "C" int wmb_reset(wmb_ctx *c)
 {
     if (!c) return set_err(WMB_E_INVAL, "null argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    if (c->cs) CUDA_TRY(cudaStreamSynchronize(c->cs));
-    if (c->xs) CUDA_TRY(cudaStreamSynchronize(c->xs));
+    /* whatever was enqueued is abandoned: let it finish (a completed push has left the streams idle) */
+    for (cudaStream_t st : { c->cs, c->xs, c->k1s, c->as[0], c->as[1], c->as2[0], c->as2[1], c->ts, c->s2 })
+        if (st && cudaStreamQuery(st) != cudaSuccess) CUDA_TRY(cudaStreamSynchronize(st));
     c->iq_consumed = 0; c->m_consumed = 0; c->hist_m = 0; c->hist_iq = 0;
     c->remainder.clear(); c->lines.clear(); c->held.clear(); c->held_prev.clear();
-    for (cudaStream_t st : { c->k1s, c->as[0], c->as[1], c->as2[0], c->as2[1], c->ts, c->s2 }) if (st) CUDA_TRY(cudaStreamSynchronize(st));
     c->batch_no = 0; c->last_M = 0; c->prev_M = 0; c->last_set = 0; c->inflight.clear();
+    c->chain_recorded[0] = c->chain_recorded[1] = false;
+    c->stat_rerun_seen = 0; c->stat_fallback_seen = 0;
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++)
+        for (int a = 0; a < WMB_N_ALGOS; a++) { Stream &s = c->cb[ch].s[a]; s.total = 0; s.total_prev = 0; s.busy_until = -1; }
     if (c->allocated) {
-        CUDA_TRY(cudaMemsetAsync(c->d_errors, 0, 64, c->cs));
-        CUDA_TRY(cudaMemsetAsync(c->d_gd, 0, sizeof(GatherDev), c->cs));
-        c->stat_rerun_seen = 0; c->stat_fallback_seen = 0;
+        /* device state back to the start of a stream, in stream order on cs: one small kernel, no host copy, no wait;
+         * the first batch's kernels on the other streams wait for it (ev_reset) */
+        ResetParams r;
+        memset(&r, 0, sizeof(r));
         for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
             if (!(c->chains & (1u << ch))) continue;
-            ChainBuf &b = c->cb[ch];
-            IirState ia;
-            iir_state_init(ia);
-            CUDA_TRY(cudaMemcpy(b.ia_carry, &ia, sizeof(ia), cudaMemcpyHostToDevice));
-            RlState rl;
-            rl_state_init(rl, ch);
-            CUDA_TRY(cudaMemcpy(b.rl_carry, &rl, sizeof(rl), cudaMemcpyHostToDevice));
-            for (int a = 0; a < WMB_N_ALGOS; a++) {
-                Stream &s = b.s[a];
-                CUDA_TRY(cudaMemsetAsync(s.sd, 0, sizeof(StreamDev), c->cs));
-                s.total = 0; s.total_prev = 0; s.busy_until = -1;
-            }
+            r.ia_carry[ch] = c->cb[ch].ia_carry; r.rl_carry[ch] = c->cb[ch].rl_carry;
+            for (int a = 0; a < WMB_N_ALGOS; a++) r.sd[ch * WMB_N_ALGOS + a] = c->cb[ch].s[a].sd;
         }
-        CUDA_TRY(cudaStreamSynchronize(c->cs));
-        CUDA_TRY(cudaDeviceSynchronize());              /* the cudaMemcpy calls above ran on the legacy stream */
+        r.gd = c->d_gd; r.errors = c->d_errors;
+#ifdef WMB_HOSTSIM
+        wmb_reset_device(r);
+#else
+        wmb_reset_kernel<<<1, 32, 0, c->cs>>>(r);
+        CUDA_TRY(cudaGetLastError());
+#endif
+        CUDA_TRY(cudaEventRecord(c->ev_reset, c->cs));
+        c->reset_pending = true;
     }
     return WMB_OK;
 }

@@ -1210,6 +1210,26 @@ WMB_D void k4_decode(const K4Params &p, uint32_t f, int tid, int nthr, K4Smem &s
     }
 }
 
+/* wmb_reset: a new capture starts -- carried states, stream bookkeeping, gather state and error flags back to their
+ * initial values, in stream order (no host copies, no synchronisation) */
+struct ResetParams {
+    IirState *ia_carry[WMB_N_CHAINS]; RlState *rl_carry[WMB_N_CHAINS];
+    StreamDev *sd[WMB_N_STREAMS];
+    GatherDev *gd; uint32_t *errors;                /* errors: 16 words (flags, per-pass fail counters, tile counter) */
+};
+WMB_D void wmb_reset_device(const ResetParams &p)
+{
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+        if (p.ia_carry[ch]) { IirState ia; iir_state_init(ia); *p.ia_carry[ch] = ia; }
+        if (p.rl_carry[ch]) { RlState rl; rl_state_init(rl, ch); *p.rl_carry[ch] = rl; }
+    }
+    for (int k = 0; k < WMB_N_STREAMS; k++)
+        if (p.sd[k]) { StreamDev z; z.total = 0; z.n_cand = 0; z.cand_overflow = 0; z.t2_sr = 0; z.pad = 0; *p.sd[k] = z; }
+    GatherDev g;
+    memset(&g, 0, sizeof(g));
+    *p.gd = g;
+    for (int i = 0; i < 16; i++) p.errors[i] = 0;
+}
 #ifndef WMB_HOSTSIM
 /* ---- __global__ wrappers ---- */
 __global__ void __launch_bounds__(SCAN_BLOCK) cscan_a_kernel(const CountScan p)
@@ -1359,6 +1379,8 @@ __global__ void __launch_bounds__(FIX_THREADS) k2p1_fixup_kernel(K2p1Params p, u
                [&](uint32_t lane) { k2p1_verify_lane(p, lane, n_fail); });
 }
 __global__ void k2c_compact_kernel(const K2cParams p) { k2c_compact(p, blockIdx.x, threadIdx.x, blockDim.x); }
+__global__ void wmb_reset_kernel(const ResetParams p) { if (threadIdx.x == 0 && blockIdx.x == 0) wmb_reset_device(p); }
+
 /* test hook (wmb_debug_arith): the device arithmetic on caller-made operands */
 __global__ void dbg_arith_kernel(const float *y, const float *x, float *out, size_t n, int mode)
 {
