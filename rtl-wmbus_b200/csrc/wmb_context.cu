@@ -224,7 +224,7 @@ static uint32_t *gd_field(wmb_ctx *c, size_t off) { return (uint32_t *)((uint8_t
 #else
 static int g_k1_ctas = 0;                /* WMBUS_B200_K1_CTAS: resident demod blocks per SM (0: as many as fit) */
 
-static int launch_k1(wmb_ctx *c, const K1Params &p)
+static int launch_k1(wmb_ctx *c, const K1Params &p, cudaStream_t st)
 {
     const int64_t ntiles = (p.M + K1_TILE - 1) / K1_TILE;
     if (ntiles <= 0) return WMB_OK;
@@ -240,8 +240,8 @@ static int launch_k1(wmb_ctx *c, const K1Params &p)
     if (g_k1_ctas > 0 && blocks_per_sm > g_k1_ctas) blocks_per_sm = g_k1_ctas;
     int64_t grid = (int64_t)sm_count * blocks_per_sm;      /* persistent: whole waves of resident CTAs */
     if (grid > ntiles) grid = ntiles;
-    CUDA_TRY(cudaMemsetAsync(p.tile_ctr, 0, 4, c->k1s));
-    kern<<<(unsigned)grid, K1_BLOCK, smem, c->k1s>>>(p);
+    CUDA_TRY(cudaMemsetAsync(p.tile_ctr, 0, 4, st));
+    kern<<<(unsigned)grid, K1_BLOCK, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     c->st.kernel_launches++;
     return WMB_OK;
@@ -838,6 +838,10 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
     const int slot = (int)(c->gather_no % WMB_NSLOT);           /* the gather that follows this batch */
     cudaEvent_t *evt = c->ev_t[slot];
     const bool first = c->batch_no == 0;
+    /* a batch with nothing before it in flight and nothing behind it has nobody to overlap with: its demod kernel and
+     * clock lanes go on cs too, which saves the cross-stream hand-overs (a few microseconds each) */
+    const bool solo = alone && c->inflight.empty();
+    cudaStream_t sk = solo ? c->cs : c->k1s, sa = solo ? c->cs : c->as[set];
     for (int ch = 0; ch < WMB_N_CHAINS; ch++)
         for (int a = 0; a < WMB_N_ALGOS; a++) c->cb[ch].s[a].total_prev = c->cb[ch].s[a].total;   /* stage tap: events of this batch */
 
@@ -846,17 +850,17 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
         c->reset_pending = false;
     }
     /* ================= stage 1 (k1s): history prefix of this set, demod ================= */
-    if (c->chain_recorded[set]) CUDA_TRY(cudaStreamWaitEvent(c->k1s, c->ev_chain[set], 0));    /* batch i-2 is done with the set */
-    if (input_ready) CUDA_TRY(cudaStreamWaitEvent(c->k1s, input_ready, 0));
+    if (c->chain_recorded[set]) CUDA_TRY(cudaStreamWaitEvent(sk, c->ev_chain[set], 0));    /* batch i-2 is done with the set */
+    if (input_ready) CUDA_TRY(cudaStreamWaitEvent(sk, input_ready, 0));
     if (!first)
         for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
             if (!(c->chains & (1u << ch))) continue;
             ChainBuf &b = c->cb[ch];
-            TRY(copy_history(b.set[set].dphi, b.set[pset].dphi, 4, c->W, c->prev_M, c->k1s));
-            TRY(copy_history(b.set[set].rssi, b.set[pset].rssi, 1, c->W, c->prev_M, c->k1s));
+            TRY(copy_history(b.set[set].dphi, b.set[pset].dphi, 4, c->W, c->prev_M, sk));
+            TRY(copy_history(b.set[set].rssi, b.set[pset].rssi, 1, c->W, c->prev_M, sk));
         }
-    CUDA_TRY(cudaEventRecord(evt[0], c->k1s));
-    if (!c->push_started) { CUDA_TRY(cudaEventRecord(c->ev_push_start, c->k1s)); c->push_started = true; }
+    CUDA_TRY(cudaEventRecord(evt[0], sk));
+    if (!c->push_started) { CUDA_TRY(cudaEventRecord(c->ev_push_start, sk)); c->push_started = true; }
     K1Params k1;
     memset(&k1, 0, sizeof(k1));
     k1.in = src; k1.hist = c->d_hist; k1.in_bytes = (int64_t)nbytes;
@@ -871,23 +875,23 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
         k1.dphi[ch] = c->cb[ch].set[set].dphi ? c->cb[ch].set[set].dphi + c->W : nullptr;
         k1.rssi[ch] = c->cb[ch].set[set].rssi ? c->cb[ch].set[set].rssi + c->W : nullptr;
     }
-    TRY(launch_k1(c, k1));
-    CUDA_TRY(cudaEventRecord(evt[1], c->k1s));
-    CUDA_TRY(cudaEventRecord(c->ev_k1[set], c->k1s));
+    TRY(launch_k1(c, k1, sk));
+    CUDA_TRY(cudaEventRecord(evt[1], sk));
+    CUDA_TRY(cudaEventRecord(c->ev_k1[set], sk));
     /* keep the last k1_hist_bytes() of the stream for the next batch's tile 0 */
     {
         const size_t hb = (size_t)k1_hist_bytes(d);
         if (nbytes >= hb) {
-            CUDA_TRY(cudaMemcpyAsync(c->d_hist, src + nbytes - hb, hb, cudaMemcpyDeviceToDevice, c->k1s));
+            CUDA_TRY(cudaMemcpyAsync(c->d_hist, src + nbytes - hb, hb, cudaMemcpyDeviceToDevice, sk));
         } else {
-            CUDA_TRY(cudaMemcpyAsync(c->d_tmp, c->d_hist + nbytes, hb - nbytes, cudaMemcpyDeviceToDevice, c->k1s));
-            CUDA_TRY(cudaMemcpyAsync(c->d_tmp + (hb - nbytes), src, nbytes, cudaMemcpyDeviceToDevice, c->k1s));
-            CUDA_TRY(cudaMemcpyAsync(c->d_hist, c->d_tmp, hb, cudaMemcpyDeviceToDevice, c->k1s));
+            CUDA_TRY(cudaMemcpyAsync(c->d_tmp, c->d_hist + nbytes, hb - nbytes, cudaMemcpyDeviceToDevice, sk));
+            CUDA_TRY(cudaMemcpyAsync(c->d_tmp + (hb - nbytes), src, nbytes, cudaMemcpyDeviceToDevice, sk));
+            CUDA_TRY(cudaMemcpyAsync(c->d_hist, c->d_tmp, hb, cudaMemcpyDeviceToDevice, sk));
         }
         c->hist_iq = std::min<int64_t>(c->hist_iq + n_iq, (int64_t)hb / 2);
     }
     /* the input buffer may be overwritten by the next H2D from here on */
-    CUDA_TRY(cudaEventRecord(c->ev_k1done[c->buf_idx], c->k1s));
+    CUDA_TRY(cudaEventRecord(c->ev_k1done[c->buf_idx], sk));
 
     const uint32_t C = pick_chunk(c, M, alone);
     const uint32_t lanes = (uint32_t)((M + C - 1) / C);
@@ -905,9 +909,9 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
          * idle (measured IPC 0.5), a second one from the other chain fills it.  (The per-thread kernel already runs at
          * 0.65: side by side it measured slower, 8.3 vs 7.2 ms of bit sync per GiB.) */
         const bool side = coop && c->chains == 3u;
-        CUDA_TRY(cudaStreamWaitEvent(c->as[set], c->ev_k1[set], 0));
+        CUDA_TRY(cudaStreamWaitEvent(sa, c->ev_k1[set], 0));
         if (side) CUDA_TRY(cudaStreamWaitEvent(c->as2[set], c->ev_k1[set], 0));
-        CUDA_TRY(cudaEventRecord(evt[4], c->as[set]));
+        CUDA_TRY(cudaEventRecord(evt[4], sa));
         for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
             if (!(c->chains & (1u << ch))) continue;
             ChainBuf &b = c->cb[ch];
@@ -922,14 +926,14 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
             p.mode = 0;
             p.spec0 = first ? 0u : 1u;                   /* the previous batch's lanes may still be running */
             c->st.lanes_run += lanes_a;
-            TRY(launch_k2a_lanes(c, ch, p, (side && ch == 0) ? c->as2[set] : c->as[set]));     /* S1's lanes are the longer ones: timers on theirs */
+            TRY(launch_k2a_lanes(c, ch, p, (side && ch == 0) ? c->as2[set] : sa));     /* S1's lanes are the longer ones: timers on theirs */
         }
         if (side) {
             CUDA_TRY(cudaEventRecord(c->ev_k2a2[set], c->as2[set]));
-            CUDA_TRY(cudaStreamWaitEvent(c->as[set], c->ev_k2a2[set], 0));
+            CUDA_TRY(cudaStreamWaitEvent(sa, c->ev_k2a2[set], 0));
         }
-        CUDA_TRY(cudaEventRecord(evt[5], c->as[set]));
-        CUDA_TRY(cudaEventRecord(c->ev_k2a[set], c->as[set]));
+        CUDA_TRY(cudaEventRecord(evt[5], sa));
+        CUDA_TRY(cudaEventRecord(c->ev_k2a[set], sa));
         tr("k1+k2a");
 
         /* ================= stage 3 (cs): in order from batch to batch ================= */

@@ -22,7 +22,7 @@ static void hostsim_k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, 
     for (int t = 0; t < 32; t++) k1_rssi<CH>(p, sm.mag, tile, t);            /* the block's RSSI warp */
 }
 
-static int launch_k1(wmb_ctx *c, const K1Params &p)
+static int launch_k1(wmb_ctx *c, const K1Params &p, cudaStream_t)
 {
     const int64_t ntiles = (p.M + K1_TILE - 1) / K1_TILE;
     std::vector<uint8_t> smem(k1_smem_bytes(p.d) + 256, 0xA5);   /* garbage-filled like real smem */
