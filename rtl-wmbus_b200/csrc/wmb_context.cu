@@ -1897,10 +1897,12 @@ extern "C" int wmb_debug_arith(wmb_ctx *c, int mode, const float *y, const float
 {
     if (!c || !y || !x || !out || mode < 0 || mode > 4) return set_err(WMB_E_INVAL, "bad argument");
 #ifdef WMB_HOSTSIM
+    WmbAtanTab tab;
+    for (int i = 0; i < WMB_ATAN_TAB_ELEMS; i++) wmb_atan_tab_fill(&tab, i);
     for (size_t i = 0; i < n; i++)
-        out[i] = mode == 0 ? wmb_atan2f_t<true>(y[i], x[i]) : mode == 1 ? wmb_atan2f_t<false>(y[i], x[i])
+        out[i] = mode == 0 ? wmb_atan2f_bounded(y[i], x[i], &tab) : mode == 1 ? wmb_atan2f(y[i], x[i])
                : mode == 2 ? wmb_fdiv_bounded(y[i], x[i]) : mode == 3 ? wmb_fsqrt_pos(y[i])
-               : wmb_discriminator(y[i], x[i], y[i ? i - 1 : 0], x[i ? i - 1 : 0]);
+               : wmb_discriminator(y[i], x[i], y[i ? i - 1 : 0], x[i ? i - 1 : 0], &tab);
     return WMB_OK;
 #else
     CUDA_TRY(cudaSetDevice(c->device));

@@ -57,7 +57,10 @@ struct K1Smem {
     float   *mag2[2];       /* two passes are in flight: the RSSI warp works one pass behind           */
     uint64_t *bar;          /* two mbarriers                                     */
     int64_t *pass_tile;     /* [2] tile of the pass whose |s| is in mag2[b] (-1: no more passes)       */
+    const WmbAtanTab *atab; /* constants of the discriminator's argument reduction (wmb_exact.cuh); first in the block */
 };
+#define K1_ATAB_BYTES 256   /* sizeof(WmbAtanTab) rounded up to the alignment of the IQ buffers */
+static_assert(sizeof(WmbAtanTab) <= K1_ATAB_BYTES, "table block");
 
 static inline
 #ifndef WMB_HOSTSIM
@@ -80,7 +83,7 @@ size_t k1_smem_bytes(uint32_t d)
 {
     const size_t nb = (size_t)2 * k1_tile_iq(d);
     const size_t n = K1_TILE + K1_HALO;
-    return 2 * nb + 4 * (size_t)k1_tile_iq(d) + 3 * 4 * n + 2 * 4 * (n + n / 32 + 4) + 64 + 16 + 16;
+    return 2 * nb + 4 * (size_t)k1_tile_iq(d) + 3 * 4 * n + 2 * 4 * (n + n / 32 + 4) + 64 + 16 + 16 + K1_ATAB_BYTES;
 }
 
 WMB_HD void k1_carve(K1Smem &sm, uint8_t *base, uint32_t d)
@@ -88,6 +91,7 @@ WMB_HD void k1_carve(K1Smem &sm, uint8_t *base, uint32_t d)
     const size_t nb = (size_t)2 * k1_tile_iq(d);
     const size_t n = K1_TILE + K1_HALO;
     size_t off = 0;
+    sm.atab = (const WmbAtanTab *)base; off += K1_ATAB_BYTES;
     sm.bytes[0] = base + off; off += nb;
     sm.bytes[1] = base + off; off += nb;
     sm.bar = (uint64_t *)(base + off); off += 16;
@@ -236,7 +240,7 @@ WMB_D void k1_disc_mag(const K1Params &p, K1Smem &sm, int tid)
         float dr = 0.f;
         if (r > 0) {
             const float ip = sm.si[r - 1], qp = sm.sq[r - 1];
-            dr = p.accurate ? wmb_discriminator(i, q, ip, qp) : wmb_discriminator_fast(i, q, ip, qp);
+            dr = p.accurate ? wmb_discriminator(i, q, ip, qp, sm.atab) : wmb_discriminator_fast(i, q, ip, qp);
         }
         sm.draw[r] = dr;
         /* the RSSI one-pole needs 0.6789f * |s| (rtl_wmbus.c:480); the product is formed here, in the
@@ -284,7 +288,7 @@ WMB_D void k1_box_disc(const K1Params &p, K1Smem &sm, int tid)
         for (int k = 0; k < 4; k++) {
             const int r = r0 + k;
             dr[k] = 0.f;
-            if (r > 0) dr[k] = p.accurate ? wmb_discriminator(si[k + 1], sq[k + 1], si[k], sq[k])
+            if (r > 0) dr[k] = p.accurate ? wmb_discriminator(si[k + 1], sq[k + 1], si[k], sq[k], sm.atab)
                                           : wmb_discriminator_fast(wmb_fmul(si[k + 1], inv), wmb_fmul(sq[k + 1], inv),
                                                                    wmb_fmul(si[k], inv), wmb_fmul(sq[k], inv));
             /* 0.6789f * sqrt(i^2 + q^2) with i = S_i / len (rtl_wmbus.c:480, :1066): the scaling by the power of two
@@ -534,6 +538,7 @@ WMB_D void k1_demod_body(const K1Params &p)
         mbar_init(&sm.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    wmb_atan_tab_fill((WmbAtanTab *)k1_smem_raw, tid);
     __syncthreads();
     constexpr uint32_t NCH = (CHAINS & 1u) + ((CHAINS >> 1) & 1u);       /* passes per tile */
 
@@ -1384,13 +1389,16 @@ __global__ void wmb_reset_kernel(const ResetParams p) { if (threadIdx.x == 0 && 
 /* test hook (wmb_debug_arith): the device arithmetic on caller-made operands */
 __global__ void dbg_arith_kernel(const float *y, const float *x, float *out, size_t n, int mode)
 {
+    __shared__ WmbAtanTab tab;
+    wmb_atan_tab_fill(&tab, (int)threadIdx.x);
+    __syncthreads();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float r;
-        if (mode == 0) r = wmb_atan2f_t<true>(y[i], x[i]);
-        else if (mode == 1) r = wmb_atan2f_t<false>(y[i], x[i]);
+        if (mode == 0) r = wmb_atan2f_bounded(y[i], x[i], &tab);
+        else if (mode == 1) r = wmb_atan2f(y[i], x[i]);
         else if (mode == 2) r = wmb_fdiv_bounded(y[i], x[i]);
         else if (mode == 3) r = wmb_fsqrt_pos(y[i]);
-        else r = wmb_discriminator(y[i], x[i], y[i ? i - 1 : 0], x[i ? i - 1 : 0]);
+        else r = wmb_discriminator(y[i], x[i], y[i ? i - 1 : 0], x[i ? i - 1 : 0], &tab);
         out[i] = r;
     }
 }

@@ -30,6 +30,7 @@ static int launch_k1(wmb_ctx *c, const K1Params &p, cudaStream_t)
     uint8_t *base = smem.data();
     base += (128 - ((uintptr_t)base & 127)) & 127;
     k1_carve(sm, base, p.d);
+    for (int i = 0; i < WMB_ATAN_TAB_ELEMS; i++) wmb_atan_tab_fill((WmbAtanTab *)base, i);
     for (int64_t tile = 0; tile < ntiles; tile++) {
         const K1Load L = k1_plan_load(p, tile);
         if (L.n0) memcpy(sm.bytes[0], L.src0, (size_t)L.n0);
@@ -239,7 +240,13 @@ static int launch_k4(wmb_ctx *c, const K4Params &p)
 }
 
 /* ---- test hooks into the device arithmetic (CPU build only) ---- */
-extern "C" float hostsim_atan2f_bounded(float y, float x) { return wmb_atan2f_t<true>(y, x); }
-extern "C" float hostsim_atan2f_general(float y, float x) { return wmb_atan2f_t<false>(y, x); }
+extern "C" float hostsim_atan2f_bounded(float y, float x)
+{
+    static WmbAtanTab tab;
+    static bool filled = false;
+    if (!filled) { for (int i = 0; i < WMB_ATAN_TAB_ELEMS; i++) wmb_atan_tab_fill(&tab, i); filled = true; }
+    return wmb_atan2f_bounded(y, x, &tab);
+}
+extern "C" float hostsim_atan2f_general(float y, float x) { return wmb_atan2f(y, x); }
 extern "C" int hostsim_div_small(int x, int n) { return wmb_div_small(x, n); }
 extern "C" int hostsim_div_pow2(int x, int s) { return wmb_div_pow2(x, s); }
