@@ -270,7 +270,9 @@ WMB_D void k2a_lane(const K2aParams &p, uint32_t lane)
 /* complete (2 SKEW <= 31: a section's lag stays inside one block).                       */
 /* ------------------------------------------------------------------------------------- */
 #define K2A2_LPW 10                  /* lanes per warp: 30 threads, two idle */
+#ifndef K2A2_THREADS
 #define K2A2_THREADS 64
+#endif
 
 #ifndef K2A2_SKEW
 #define K2A2_SKEW 6                  /* steps between a section and the next one (>= 2): the shuffle that carries a

@@ -187,13 +187,16 @@ WMB_D void k1_box(const K1Params &p, K1Smem &sm, int tid)
  * 32-bit adds without carries between the halves. */
 #define K1_PAIR_BIAS 512
 
-WMB_D int wmb_dp4a_u(uint32_t a, uint32_t b, int c)
+/* bytes of (a, b) picked by the four selector nibbles of sel (0-3: a, 4-7: b), lowest nibble -> lowest byte */
+WMB_D uint32_t wmb_prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
 #ifdef WMB_HOSTSIM
-    for (int i = 0; i < 4; i++) c += (int)((a >> (8 * i)) & 0xFFu) * (int)((b >> (8 * i)) & 0xFFu);
-    return c;
+    const uint64_t ab = (uint64_t)a | ((uint64_t)b << 32);
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((ab >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
 #else
-    return (int)__dp4a(a, b, (unsigned)c);
+    return __byte_perm(a, b, sel);
 #endif
 }
 
@@ -203,10 +206,11 @@ struct alignas(16) K1Word4 { uint32_t x, y, z, w; };
  * (int)(u - 127.5f) = u - 127 for u < 128 and u - 128 above (rtl_wmbus.c:1312-1313, moving_average_filter.h:47) */
 WMB_D uint32_t k1_pair_sums(uint32_t w)
 {
-    const uint32_t msb = (w >> 7) & 0x01010101u;
-    const int si = wmb_dp4a_u(w, 0x00010001u, 0) - wmb_dp4a_u(msb, 0x00010001u, 0) - 254 + K1_PAIR_BIAS;
-    const int sq = wmb_dp4a_u(w, 0x01000100u, 0) - wmb_dp4a_u(msb, 0x01000100u, 0) - 254 + K1_PAIR_BIAS;
-    return (uint32_t)si | ((uint32_t)sq << 16);
+    /* truncated sample + 127 = u - (u >> 7), byte by byte: no byte goes below zero, so one 32-bit subtraction does all
+     * four; then (I0 | Q0 << 16) + (I1 | Q1 << 16) + the constant is one three-input add */
+    const uint32_t t = w - ((w >> 7) & 0x01010101u);
+    const uint32_t k = (uint32_t)(K1_PAIR_BIAS - 254) * 0x00010001u;
+    return wmb_prmt(t, 0u, 0x4140u) + wmb_prmt(t, 0u, 0x4342u) + k;
 }
 
 WMB_D void k1_convert_fast(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile, int tid)
@@ -222,10 +226,13 @@ WMB_D void k1_convert_fast(const K1Params &p, K1Smem &sm, const uint8_t *raw, in
     for (int g = tid; g < nw / 4; g += K1_THREADS) {           /* four words per step: 128-bit shared accesses */
         const K1Word4 w = src[g];
         K1Word4 o;
-        o.x = 4 * g + 0 >= jmin ? k1_pair_sums(w.x) : zero;
-        o.y = 4 * g + 1 >= jmin ? k1_pair_sums(w.y) : zero;
-        o.z = 4 * g + 2 >= jmin ? k1_pair_sums(w.z) : zero;
-        o.w = 4 * g + 3 >= jmin ? k1_pair_sums(w.w) : zero;
+        o.x = k1_pair_sums(w.x); o.y = k1_pair_sums(w.y); o.z = k1_pair_sums(w.z); o.w = k1_pair_sums(w.w);
+        if (4 * g < jmin) {                                      /* first tile of the stream only */
+            if (4 * g + 0 < jmin) o.x = zero;
+            if (4 * g + 1 < jmin) o.y = zero;
+            if (4 * g + 2 < jmin) o.z = zero;
+            if (4 * g + 3 < jmin) o.w = zero;
+        }
         dst[g] = o;
     }
 }
@@ -280,8 +287,9 @@ WMB_D void k1_box_disc(const K1Params &p, K1Smem &sm, int tid)
             /* the box sums themselves, not sum/len: the discriminator only sees the quotient and the signs of
              * s * conj(s_prev), which a common factor len^2 leaves untouched (zeros and their signs included), and
              * sqrt(len^2 x) = len sqrt(x) exactly, so the division by len moves into the constant behind the sqrt */
-            si[k] = (float)((int)(acc & 0xFFFFu) - NWIN * BIASW);
-            sq[k] = (float)((int)(acc >> 16) - NWIN * BIASW);
+            /* (float)(half - bias) without a conversion: 2^23 + half as a bit pattern, minus (2^23 + bias), both exact */
+            si[k] = wmb_fsub(wmb_u2f((acc & 0xFFFFu) | 0x4B000000u), (float)(8388608 + NWIN * BIASW));
+            sq[k] = wmb_fsub(wmb_u2f(wmb_prmt(acc, 0x4B000000u, 0x7632u)), (float)(8388608 + NWIN * BIASW));
         }
         float dr[4];
 #pragma unroll
