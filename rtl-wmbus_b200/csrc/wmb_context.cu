@@ -801,7 +801,14 @@ static uint32_t pick_chunk(const wmb_ctx *c, int64_t M, bool alone)
      * warm-up arithmetic, so the lanes are made longer. */
     int64_t C = (M + 18943) / 18944;
     C = (C + 1023) / 1024 * 1024;
-    const int64_t lo = alone ? 8192 : 16384;
+    /* A small batch on its own (a live stream's 100 ms hand-over) is all latency: its lanes take warm-up + C steps
+     * however few they are, so they are made as short as the per-lane buffers allow (sized for lanes of 8192 samples at
+     * the largest batch). */
+    int64_t lo = alone ? 1024 : 16384;
+    if (alone && c->lanes_max > 2) {
+        const int64_t need = (M + c->lanes_max - 3) / (c->lanes_max - 2);
+        lo = std::max<int64_t>(lo, (need + 1023) / 1024 * 1024);
+    }
     if (C < lo) C = lo;
     if (C > 65536) C = 65536;
     return (uint32_t)C;
