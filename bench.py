@@ -488,7 +488,8 @@ def main():
         # kernel of one batch overlaps the bit-sync kernels of the batch before, so this is less than the sum of the two)
         kern_s = dev_ms / args.steps / 1e3
         achieved = abytes / kern_s / 1e9 if kern_s > 0 else None
-        traffic, ncu_brief = ncu_step()
+        # the committed ncu capture is of the default workload (1 GiB, -p S): other workloads carry no traffic figure
+        traffic, ncu_brief = ncu_step() if (args.workload == "t1x2" and args.mib == 1024) else (None, None)
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1e3 * t_dev / args.steps, 3), "higher_is_better": True,
