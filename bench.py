@@ -252,7 +252,7 @@ def run_reference_arm(args, wl):
     n_iq = slice_bytes // 2 * procs
     value = n_iq * args.steps / t / 1e6
     _, kind = ref_binary()
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -340,7 +340,23 @@ def run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local, m
     }
 
 
+_JSON_OUT = None
+
+
+def emit(obj):
+    """the one JSON line, on the process's real stdout"""
+    f = _JSON_OUT or sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
+
+
 def main():
+    # Libraries write to fd 1 behind Python's back (NCCL prints its version line there when the box sets NCCL_DEBUG):
+    # everything but the result line goes to stderr, so that stdout holds exactly one JSON line.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -391,7 +407,7 @@ def main():
     if time_sharded:
         out = run_time_sharded(args, wl, pkg, shard, lib, cap, plan, rank, world, local)
         if rank == 0:
-            print(json.dumps(out))
+            emit(out)
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -534,7 +550,7 @@ def main():
             out["cpu_baseline"] = {"value": round(sample / 2 / t_cpu / 1e6, 3), "unit": UNIT, "cores": 1, "kind": kind,
                                    "sample": f"first {sample >> 20} MiB of the same capture, one process, best of 2 "
                                              f"({host_cpus()[0]} usable host CPUs)"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
