@@ -65,7 +65,9 @@ typedef struct wmb_opts {
                                  framers with wmb_poll + wmb_decode_frames.  0 (default):
                                  wmb_push feeds the context's framers itself.            */
     uint32_t reserved[2];     /* test knobs, 0 in production: [0] = 1 forces the monolithic run-length lanes for
-                                 T1/C1; [1] bit 0 keeps the clock-sign words for wmb_debug_copy_bits(.., 2, ..)  */
+                                 T1/C1; [1] bit 0 keeps the clock-sign words for wmb_debug_copy_bits(.., 2, ..),
+                                 [1] >> 8 (if not 0) is the size of the per-batch candidate tables, to reach the
+                                 overflow path (wmb_stats.overflow_batches) with a small capture                  */
 } wmb_opts;
 
 typedef struct wmb_ctx wmb_ctx;
@@ -181,6 +183,10 @@ typedef struct wmb_stats {
     double   host_batch_ms;       /* cumulative wall time in the enqueue+verify part of batches */
     double   host_gather_ms;      /* cumulative wall time gathering candidate frames          */
     double   host_decode_ms;      /* cumulative wall time in the host framers                 */
+    uint64_t overflow_batches;    /* batches whose candidates did not fit a device table (frame words, datagram pool,
+                                     access-code matches, pending candidates) and lost some or all of their lines; the
+                                     stream goes on.  Takes an input no receiver produces: sized for one access-code
+                                     match per 256 decimated samples, sustained over a whole batch                 */
 } wmb_stats;
 
 int wmb_get_stats(wmb_ctx *c, wmb_stats *s);

@@ -30,7 +30,7 @@ class WmbStats(C.Structure):
                 ("lines_crc_ok", (C.c_uint64 * 2) * 2), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("demod_kernel_ms", C.c_double), ("bitsync_kernel_ms", C.c_double),
                 ("batch_device_ms", C.c_double), ("rl_fallbacks", C.c_uint64), ("host_batch_ms", C.c_double),
-                ("host_gather_ms", C.c_double), ("host_decode_ms", C.c_double)]
+                ("host_gather_ms", C.c_double), ("host_decode_ms", C.c_double), ("overflow_batches", C.c_uint64)]
 
 
 def library_path() -> str:

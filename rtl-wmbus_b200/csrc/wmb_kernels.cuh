@@ -718,6 +718,7 @@ struct K3Params {
     uint32_t final;                 /* end of input: nothing is carried over                */
 };
 
+#define K3_SOFT_ERRORS (4u | 8u | 16u | 64u)
 WMB_D void k3_flag(uint32_t *errors, uint32_t bit)
 {
 #ifdef WMB_HOSTSIM
@@ -756,6 +757,9 @@ WMB_D void k3_publish(const K3Params &p)
     const GatherDev &g = *p.gd;
     BatchRec r;
     r.n = g.n; r.n_words = g.n_words; r.pool_n = g.pool_n; r.errors = *p.errors;
+    /* the capacity overflows (frame words 4, datagram pool 8, matches 16, pending candidates 64) cost this batch's
+     * candidates, not the stream: the host counts them, the flags start the next batch clean */
+    *p.errors &= ~K3_SOFT_ERRORS;
     r.lanes_rerun = g.lanes_rerun; r.rl_fallbacks = g.rl_fallbacks;
     for (int k = 0; k < WMB_N_STREAMS; k++) { r.total[k] = g.total_prev[k]; r.n_cand_total[k] = g.n_cand_total[k]; }
     *p.rec = r;
@@ -1218,7 +1222,11 @@ WMB_D void k4_decode(const K4Params &p, uint32_t f, int tid, int nthr, K4Smem &s
         d.current_rssi = (uint8_t)WMB_BIT_RSSI(b[pos]);
         d.serial = (uint32_t)sm.pkt[4] | ((uint32_t)sm.pkt[5] << 8) | ((uint32_t)sm.pkt[6] << 16) | ((uint32_t)sm.pkt[7] << 24);
         d.len = (uint16_t)out_len;
-        d.data_off = data_off == 0xFFFFFFFFu ? 0 : data_off;
+        d.data_off = data_off;
+        if (data_off == 0xFFFFFFFFu) {                             /* no room in the pool: the line is dropped (counted by the host), */
+            d.data_off = 0; d.len = 0;                             /* the decoder's verdict on the bits consumed stays                */
+            if (d.status == K4_LINE) d.status = K4_ABORT;
+        }
         dec_out[f] = d;
     }
 }

@@ -160,6 +160,27 @@ def check_type2_fallback(pkg, lib):
     assert got == want and st.rl_fallbacks == 0
 
 
+def check_overflow_degrades(pkg, lib):
+    """More access-code matches in a batch than the device tables hold (a jammer repeating the sync
+    word, ...) costs lines, not the stream: no error, wmb_stats.overflow_batches counts the batches, what is printed is
+    a subsequence of the reference's lines, and the same context decodes everything again once the flood is over.
+    The tables are shrunk through the test knob opts.reserved[1] >> 8 so that an ordinary capture overflows them."""
+    cu8 = np.ascontiguousarray(np.tile(load_fixture("synth_mixed_1m6.cu8"), 3))
+    want = oracle_lines(cu8, "-v")
+    for cap in (4, 6):
+        with pkg.WmbusB200("-v", lib=lib, max_batch_mib=4, reserved=(C.c_uint32 * 2)(0, cap << 8)) as ctx:
+            got = [orc.blank_ts(l) for l in ctx.process(cu8.ctypes.data, len(cu8), flush=True)]
+            st = ctx.stats()
+            assert st.overflow_batches >= 1, "the capture is meant to overflow a %d-entry table" % cap
+            assert len(got) < len(want)
+            it = iter(want)
+            assert all(any(l == w for w in it) for l in got), "lines after an overflow must still be reference lines, in order"
+    # a table that is large enough again: nothing is lost, nothing is counted
+    with pkg.WmbusB200("-v", lib=lib, max_batch_mib=4, reserved=(C.c_uint32 * 2)(0, 4096 << 8)) as ctx:
+        got = [orc.blank_ts(l) for l in ctx.process(cu8.ctypes.data, len(cu8), flush=True)]
+        assert got == want and ctx.stats().overflow_batches == 0
+
+
 def check_sample_index_wrap(pkg, lib):
     """The device keeps 40 bits of the decimated sample index in its bit events (15.9 days of streaming at 800 kS/s).
     A stream positioned just below 2^40 must decode the telegrams that span the wrap exactly like a fresh stream:

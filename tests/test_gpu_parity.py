@@ -146,3 +146,8 @@ def test_cli_drop_in(pkg, gpu_lib, golden_lines):
             if l:
                 ts = l.split(";")[4 if flags.startswith("-v") else 3]
                 assert len(ts) == 26 and ts[4] == "-" and ts[19] == "."
+
+
+@gpu
+def test_table_overflow_costs_lines_not_the_stream(pkg, gpu_lib):
+    pc.check_overflow_degrades(pkg, gpu_lib)

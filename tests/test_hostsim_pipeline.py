@@ -70,3 +70,7 @@ def test_bitsync_stage_taps(pkg, hostsim_lib):
 
 def test_device_push_with_ragged_tail(pkg, hostsim_lib):
     pc.check_device_push_ragged(pkg, hostsim_lib)
+
+
+def test_table_overflow_costs_lines_not_the_stream(pkg, hostsim_lib):
+    pc.check_overflow_degrades(pkg, hostsim_lib)
