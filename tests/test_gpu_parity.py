@@ -148,6 +148,5 @@ def test_cli_drop_in(pkg, gpu_lib, golden_lines):
                 assert len(ts) == 26 and ts[4] == "-" and ts[19] == "."
 
 
-@gpu
 def test_table_overflow_costs_lines_not_the_stream(pkg, gpu_lib):
     pc.check_overflow_degrades(pkg, gpu_lib)
