@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WMB_ABI_VERSION 1
+#define WMB_ABI_VERSION 2
 
 /* error codes (negative) */
 #define WMB_OK             0
@@ -54,7 +54,8 @@ typedef struct wmb_opts {
     uint8_t  t2_enabled;      /* 0 with -t 0                                               */
     uint8_t  t1c1_enabled;    /* 0 with -p T                                               */
     uint8_t  s1_enabled;      /* 0 with -p S                                               */
-    uint8_t  simultaneous;    /* -s : +-325 kHz translation (:974-1031)                    */
+    uint8_t  simultaneous;    /* -s : +-325 kHz translation (:974-1031); 2: the same mixer with the carriers of
+                                 carrier_25khz[] below (not a switch of the reference)       */
     uint8_t  show_algorithm;  /* -v : prefix lines with rla; / t2a;                        */
     /* tuning knobs (0 = library default); they never change results, only how the
      * work is cut up on the device */
@@ -68,6 +69,11 @@ typedef struct wmb_opts {
                                  T1/C1; [1] bit 0 keeps the clock-sign words for wmb_debug_copy_bits(.., 2, ..),
                                  [1] >> 8 (if not 0) is the size of the per-batch candidate tables, to reach the
                                  overflow path (wmb_stats.overflow_batches) with a small capture                  */
+    /* simultaneous == 2 (many carriers per capture): offset of the carrier the T1/C1 chain [0] and the
+     * S1 chain [1] listen to from the capture's centre frequency, in units of 25 kHz (the grid of the reference's
+     * table, rtl_wmbus.c:974-993), |offset| <= fs / 2.  The reference's -s is {+13, -13}.  A capture with more than two
+     * carriers is decoded by several contexts over the same input (shard.decode_carriers in the Python mirror). */
+    int32_t  carrier_25khz[2];
 } wmb_opts;
 
 typedef struct wmb_ctx wmb_ctx;

@@ -164,6 +164,12 @@ void orc_frontend(const uint8_t *cu8, size_t n_iq, const orc_opts *o, int chain,
     const size_t n_max = (size_t)(o->decimation * 800u) / 25u;
     float *lut_c = NULL, *lut_s = NULL;
     size_t n = 0;
+    /* -s: both chains step 13 entries per sample, T1/C1 multiplies by the entry, S1 by its conjugate; simultaneous == 2
+     * takes both from the chain's carrier offset */
+    int32_t off = (chain == ORC_CHAIN_T1C1) ? 13 : -13;
+    if (o->simultaneous == 2) off = o->carrier_25khz[chain];
+    const int mix_conj = off < 0;
+    const size_t mix_step = n_max ? (size_t)(off < 0 ? -(int64_t)off : (int64_t)off) % n_max : 0;
     if (o->simultaneous && n_max) {
         lut_c = malloc(n_max * sizeof(float));
         lut_s = malloc(n_max * sizeof(float));
@@ -180,11 +186,11 @@ void orc_frontend(const uint8_t *cu8, size_t n_iq, const orc_opts *o, int chain,
         float xq = (float)cu8[2 * k + 1] - 127.5f;          /* :1313 */
         if (lut_c) {
             const float c = lut_c[n], z = lut_s[n];
-            n += 13;                                        /* 325/25, :1008 */
+            n += mix_step;                                  /* 325/25 = 13, :1008 */
             if (n >= n_max) n -= n_max;
             const float ix = xi * c, qx = xq * c, iz = xi * z, qz = xq * z;
-            if (chain == ORC_CHAIN_T1C1) { xi = ix - qz; xq = qx + iz; }   /* :1025-1026 */
-            else                         { xi = ix + qz; xq = qx - iz; }   /* :1029-1030 */
+            if (!mix_conj) { xi = ix - qz; xq = qx + iz; }  /* :1025-1026 (the T1/C1 chain) */
+            else           { xi = ix + qz; xq = qx - iz; }  /* :1029-1030 (the S1 chain)    */
         }
         const int vi = (int)xi, vq = (int)xq;               /* float -> int param of mavgi() */
         sum_i += vi - ring_i[pos]; ring_i[pos] = vi;

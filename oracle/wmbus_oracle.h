@@ -38,9 +38,13 @@ typedef struct orc_opts {
     uint8_t  t2_enabled;      /* -t 0 clears (default 1)                 */
     uint8_t  t1c1_enabled;    /* -p T clears (default 1)                 */
     uint8_t  s1_enabled;      /* -p S clears (default 1)                 */
-    uint8_t  simultaneous;    /* -s     (default 0)                      */
+    uint8_t  simultaneous;    /* -s     (default 0); 2: carriers below   */
     uint8_t  show_algorithm;  /* -v     (default 0)                      */
     uint8_t  real_timestamp;  /* 0: print the literal TS in the TIMESTAMP column */
+    /* simultaneous == 2: the -s mixer (rtl_wmbus.c:997-1031) with its two constants as parameters -- table entries per
+     * sample (the reference: 13 = 325 kHz / 25 kHz) and entry vs conjugate (the sign) -- per chain.  Pinned by the
+     * reference only at {+13, -13}; other carriers are this restatement's own generalisation. */
+    int32_t  carrier_25khz[2];
 } orc_opts;
 
 void   orc_default_opts(orc_opts *o);

@@ -14,7 +14,8 @@ class WmbOpts(C.Structure):
                 ("rla_enabled", C.c_uint8), ("t2_enabled", C.c_uint8), ("t1c1_enabled", C.c_uint8),
                 ("s1_enabled", C.c_uint8), ("simultaneous", C.c_uint8), ("show_algorithm", C.c_uint8),
                 ("chunk_samples", C.c_uint32), ("warmup_samples", C.c_uint32),
-                ("max_batch_mib", C.c_uint32), ("manual_frames", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+                ("max_batch_mib", C.c_uint32), ("manual_frames", C.c_uint32), ("reserved", C.c_uint32 * 2),
+                ("carrier_25khz", C.c_int32 * 2)]
 
 
 class WmbFrame(C.Structure):

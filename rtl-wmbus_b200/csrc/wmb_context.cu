@@ -674,6 +674,11 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
     if (cuda_device < 0 || cuda_device >= ndev) return set_err(WMB_E_NODEVICE, "CUDA device %d of %d", cuda_device, ndev);
     if (o->decimation > 64) return set_err(WMB_E_INVAL, "decimation %u not supported (max 64)", o->decimation);
     if (o->simultaneous && o->decimation == 0) return set_err(WMB_E_INVAL, "-s with -d 0 is undefined in the reference");
+    if (o->simultaneous > 2) return set_err(WMB_E_INVAL, "simultaneous: 0, 1 (-s) or 2 (explicit carriers)");
+    if (o->simultaneous == 2)
+        for (int ch = 0; ch < 2; ch++)
+            if (o->carrier_25khz[ch] == INT32_MIN || 2 * (o->carrier_25khz[ch] < 0 ? -o->carrier_25khz[ch] : o->carrier_25khz[ch]) > (int32_t)(o->decimation * 32u))
+                return set_err(WMB_E_INVAL, "carrier offset outside the sampled band (|offset| <= fs / 2)");
     CUDA_TRY(cudaSetDevice(cuda_device));
 
     wmb_ctx *c = new wmb_ctx();
@@ -874,9 +879,16 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
     k1.in = src; k1.hist = c->d_hist; k1.in_bytes = (int64_t)nbytes;
     k1.n_hist_iq = c->hist_iq;
     k1.M = M; k1.d = d; k1.chains = c->chains;
-    k1.accurate = c->o.accurate_atan; k1.mix = c->o.simultaneous;
+    k1.accurate = c->o.accurate_atan; k1.mix = c->o.simultaneous ? 1u : 0u;
     k1.lut_n = c->o.simultaneous ? (c->o.decimation * 800u) / 25u : 1u;
-    k1.lut_phase0 = (uint32_t)((13ull * (c->iq_consumed % k1.lut_n)) % k1.lut_n);
+    k1.mix_k0 = (uint32_t)(c->iq_consumed % k1.lut_n);
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+        /* the reference's -s: T1/C1 chain 325 kHz above the centre, S1 chain 325 kHz below (rtl_wmbus.c:1008, :1025-1030) */
+        const int32_t off = c->o.simultaneous == 2 ? c->o.carrier_25khz[ch] : (ch == 0 ? 13 : -13);
+        const uint32_t mag = (uint32_t)(off < 0 ? -(int64_t)off : (int64_t)off);
+        k1.mix_step[ch] = mag % k1.lut_n;
+        k1.mix_conj[ch] = off < 0 ? 1u : 0u;
+    }
     k1.lut_cos = c->d_lut; k1.lut_msin = c->d_lut + 4096;
     k1.tile_ctr = c->d_errors + 12;
     for (int ch = 0; ch < WMB_N_CHAINS; ch++) {

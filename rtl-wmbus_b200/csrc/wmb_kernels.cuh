@@ -38,9 +38,12 @@ struct K1Params {
     uint32_t d;                 /* decimation                                                */
     uint32_t chains;            /* bit0: T1/C1, bit1: S1                                     */
     uint32_t accurate;          /* 0 with -a                                                 */
-    uint32_t mix;               /* -s                                                        */
+    uint32_t mix;               /* -s (or explicit carriers)                                 */
     uint32_t lut_n;             /* mixer table length (fs_kHz/25)                            */
-    uint32_t lut_phase0;        /* table index of batch sample 0                             */
+    uint32_t mix_k0;            /* (index of batch sample 0 in the stream) mod lut_n          */
+    uint32_t mix_step[WMB_N_CHAINS];  /* table entries per sample = |carrier offset| / 25 kHz, mod lut_n (the reference: 13) */
+    uint32_t mix_conj[WMB_N_CHAINS];  /* 0: multiply by the table entry (carrier above the centre: the reference's T1/C1
+                                         chain), 1: by its conjugate (below: its S1 chain)         */
     const float *lut_cos, *lut_msin;
     float   *dphi[WMB_N_CHAINS];   /* out: post-FIR discriminator, index 0 = batch sample 0 */
     uint8_t *rssi[WMB_N_CHAINS];   /* out: (unsigned)rssi                                    */
@@ -136,12 +139,15 @@ WMB_D void k1_convert(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t
         return;
     }
     /* shift_freq_plus_minus325, rtl_wmbus.c:997-1031: LUT index (13 k) mod n_max, kept incrementally
-     * (the thread's samples are K1_THREADS apart) */
+     * (the thread's samples are K1_THREADS apart).  The 13 (325 kHz / 25 kHz) and the choice between the entry and
+     * its conjugate are per-chain parameters here: any carrier on the 25 kHz grid. */
     const uint32_t ln = p.lut_n;
     int64_t km = k0 % (int64_t)ln;
     if (km < 0) km += ln;
-    uint32_t idx = (uint32_t)(((uint64_t)p.lut_phase0 + 13ull * (uint64_t)km + 13ull * (uint64_t)tid) % ln);
-    const uint32_t step = (13u * K1_THREADS) % ln;
+    const uint32_t st = p.mix_step[CHAIN];
+    const bool cj = p.mix_conj[CHAIN] != 0;
+    uint32_t idx = (uint32_t)(((uint64_t)st * (((uint64_t)p.mix_k0 + (uint64_t)km + (uint64_t)tid) % ln)) % ln);
+    const uint32_t step = (uint32_t)(((uint64_t)st * K1_THREADS) % ln);
     for (int j = tid; j < n; j += K1_THREADS) {
         uint32_t packed = zero;
         if (j >= jmin) {
@@ -151,8 +157,8 @@ WMB_D void k1_convert(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t
             const float c = p.lut_cos[idx], z = p.lut_msin[idx];
             const float ix = wmb_fmul(xi, c), qx = wmb_fmul(xq, c);
             const float iz = wmb_fmul(xi, z), qz = wmb_fmul(xq, z);
-            if (CHAIN == 0) { xi = wmb_fsub(ix, qz); xq = wmb_fadd(qx, iz); }
-            else            { xi = wmb_fadd(ix, qz); xq = wmb_fsub(qx, iz); }
+            if (!cj) { xi = wmb_fsub(ix, qz); xq = wmb_fadd(qx, iz); }      /* :1025-1026 */
+            else     { xi = wmb_fadd(ix, qz); xq = wmb_fsub(qx, iz); }      /* :1029-1030 */
             const int vi = (int)xi, vq = (int)xq;                       /* float -> int parameter of mavgi() */
             packed = (uint32_t)(vi + K1_SAMPLE_BIAS) | ((uint32_t)(vq + K1_SAMPLE_BIAS) << 16);
         }

@@ -143,3 +143,45 @@ def decode_time_sharded(ctx, push, n_bytes: int, d: int, halo_m: int = 1 << 18):
         redo = rank in bad
         if redo:
             halo_m *= 4                                 # too short: the neighbour's state was not reached yet
+
+
+# ---- many carriers in one capture --------------------------------------------------
+
+def plan_carriers(carriers):
+    """carriers: [(offset_khz, "T" | "S"), ...] -- the carriers of one capture, as offsets from its centre frequency
+    (multiples of 25 kHz, the grid of the reference's mixer table, rtl_wmbus.c:974-993) and the chain that listens to
+    each: "T" = the T1/C1 chain, "S" = the S1 chain.  A context has one chain of each kind (the reference's -s is one
+    context with {+325 "T", -325 "S"}), so the carriers are dealt out two per context.
+    Returns [(t_offset_khz | None, s_offset_khz | None), ...]."""
+    for off, kind in carriers:
+        if kind not in ("T", "S"):
+            raise ValueError(f"carrier kind {kind!r}: 'T' (T1/C1 chain) or 'S' (S1 chain)")
+        if off % 25:
+            raise ValueError(f"carrier offset {off} kHz is not on the 25 kHz grid")
+    ts = [off for off, kind in carriers if kind == "T"]
+    ss = [off for off, kind in carriers if kind == "S"]
+    n = max(len(ts), len(ss))
+    return [(ts[i] if i < len(ts) else None, ss[i] if i < len(ss) else None) for i in range(n)]
+
+
+def decode_carriers(make_ctx, run, carriers, flags: str = ""):
+    """Decode every carrier of one capture: one context per (T, S) pair of plan_carriers(), all over the same input.
+    make_ctx(flags, **opts) -> a WmbusB200; run(ctx) -> its lines for the whole capture (e.g.
+    `lambda ctx: ctx.process_device(ptr, n, flush=True)` -- the capture stays where it is, every context reads it).
+    Returns {(offset_khz, kind): [lines in print order]}."""
+    import ctypes as C
+    out = {}
+    for t_off, s_off in plan_carriers(carriers):
+        carr = (C.c_int32 * 2)(0 if t_off is None else t_off // 25, 0 if s_off is None else s_off // 25)
+        opts = dict(simultaneous=2, carrier_25khz=carr, t1c1_enabled=int(t_off is not None), s1_enabled=int(s_off is not None))
+        with make_ctx(flags, **opts) as ctx:
+            lines = run(ctx)
+        if t_off is not None:
+            out[(t_off, "T")] = []
+        if s_off is not None:
+            out[(s_off, "S")] = []
+        for l in lines:
+            f = l.split(";")
+            mode = f[1] if f[0] in ("rla", "t2a") else f[0]
+            out[(s_off, "S") if mode == "S1" else (t_off, "T")].append(l)
+    return out

@@ -13,7 +13,7 @@ class OrcOpts(C.Structure):
     _fields_ = [("decimation", C.c_uint32), ("accurate_atan", C.c_uint8), ("remove_dc", C.c_uint8),
                 ("rla_enabled", C.c_uint8), ("t2_enabled", C.c_uint8), ("t1c1_enabled", C.c_uint8),
                 ("s1_enabled", C.c_uint8), ("simultaneous", C.c_uint8), ("show_algorithm", C.c_uint8),
-                ("real_timestamp", C.c_uint8)]
+                ("real_timestamp", C.c_uint8), ("carrier_25khz", C.c_int32 * 2)]
 
 
 class OrcEvent(C.Structure):

@@ -181,6 +181,57 @@ def check_overflow_degrades(pkg, lib):
         assert got == want and ctx.stats().overflow_batches == 0
 
 
+def carriers_capture(n_bytes=3 << 20, fs=1.6e6):
+    """Five emitters on five carriers of one 1.6 MS/s capture (offsets from the centre, kHz): T1 at +325 and -150,
+    C1 at +575, S1 at -325 and +100."""
+    import importlib
+    synth = importlib.import_module("rtl-wmbus_b200.synth")
+    E = synth.Emitter
+    em = [E("T1", 0x71200023, amp=60.0, offset_hz=325e3 + 6e3, l_field=0x29, period_s=0.11, start_s=0.004, seed=31),
+          E("T1", 0x64700082, amp=55.0, offset_hz=-150e3 - 4e3, l_field=0x19, period_s=0.13, start_s=0.021, seed=32),
+          E("C1A", 0x20338739, amp=55.0, offset_hz=575e3 + 3e3, l_field=0x19, period_s=0.12, start_s=0.040, seed=33),
+          E("S1", 0x19131290, amp=60.0, offset_hz=-325e3 + 2e3, l_field=0x19, period_s=0.17, start_s=0.010, seed=34),
+          E("S1", 0x02717473, amp=55.0, offset_hz=100e3 - 3e3, l_field=0x2E, period_s=0.19, start_s=0.060, seed=35)]
+    cap, plan = synth.synth_capture(n_bytes, fs=fs, emitters=em, seed=0xB2000061, noise_sigma=4.0)
+    return np.ascontiguousarray(cap.numpy()), [(325, "T"), (-150, "T"), (575, "T"), (-325, "S"), (100, "S")]
+
+
+def check_carriers(pkg, lib, to_device=None):
+    """the -s mixer with the carrier as a parameter.  (1) {+13, -13} through the parameter is the
+    reference's -s, bit for bit (the goldens of -s come from the reference binary); (2) every carrier of a five-carrier
+    capture decodes to the lines of the oracle's restatement with the same parameters, and each carrier yields its
+    emitter's telegrams."""
+    import importlib
+    shard = importlib.import_module("rtl-wmbus_b200.shard")
+    cu8s = load_fixture("synth_mixed_2m4_shift.cu8")
+    want = oracle_lines(cu8s, "-v -d 3 -s")
+    got, _ = run_lines(pkg, lib, cu8s, "-v -d 3", simultaneous=2, carrier_25khz=(C.c_int32 * 2)(13, -13))
+    assert got == want and len(want) > 3
+
+    cu8, carriers = carriers_capture()
+    dev = to_device(cu8) if to_device else None
+    if dev is not None:
+        run = lambda ctx: ctx.process_device(dev.data_ptr(), len(cu8), flush=True)
+    else:
+        run = lambda ctx: ctx.process(cu8.ctypes.data, len(cu8), flush=True)
+    got = shard.decode_carriers(lambda f, **kw: pkg.WmbusB200(f, lib=lib, **kw), run, carriers, "-v")
+    idents = {(325, "T"): "71200023", (-150, "T"): "64700082", (575, "T"): "20338739", (-325, "S"): "19131290", (100, "S"): "02717473"}
+    for (t_off, s_off) in shard.plan_carriers(carriers):
+        o = orc.opts_from_flags("-v")
+        o.simultaneous = 2
+        o.carrier_25khz[0] = 0 if t_off is None else t_off // 25
+        o.carrier_25khz[1] = 0 if s_off is None else s_off // 25
+        o.t1c1_enabled = int(t_off is not None); o.s1_enabled = int(s_off is not None)
+        ref = [orc.blank_ts(l) for l in orc.run_lines(cu8, o)]
+        mine = []
+        if t_off is not None: mine += got[(t_off, "T")]
+        if s_off is not None: mine += got[(s_off, "S")]
+        assert sorted(orc.blank_ts(l) for l in mine) == sorted(ref)
+    for key, ident in idents.items():
+        ok = [l for l in got[key] if l.split(";")[2] == "1" and ident in l]
+        assert len(ok) >= 4, (key, len(got[key]), len(ok))
+
+
 def check_sample_index_wrap(pkg, lib):
     """The device keeps 40 bits of the decimated sample index in its bit events (15.9 days of streaming at 800 kS/s).
     A stream positioned just below 2^40 must decode the telegrams that span the wrap exactly like a fresh stream:

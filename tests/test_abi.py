@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = C.CDLL(path)
     for n in declared_functions():
         assert hasattr(lib, n), f"{n} missing from {path}"
-    assert lib.wmb_abi_version() == 1
+    assert lib.wmb_abi_version() == 2
     # ... and nothing else: the dynamic symbol table is exactly the declared surface (csrc/wmb_exports.map)
     extra = [s for s in exported_symbols(path) if s not in declared_functions()]
     assert extra == [], f"exported but not declared in include/*.h: {extra}"

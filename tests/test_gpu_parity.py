@@ -150,3 +150,8 @@ def test_cli_drop_in(pkg, gpu_lib, golden_lines):
 
 def test_table_overflow_costs_lines_not_the_stream(pkg, gpu_lib):
     pc.check_overflow_degrades(pkg, gpu_lib)
+
+
+def test_many_carriers_per_capture(pkg, gpu_lib):
+    import torch
+    pc.check_carriers(pkg, gpu_lib, to_device=lambda a: torch.from_numpy(a).cuda())

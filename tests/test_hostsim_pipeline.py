@@ -74,3 +74,7 @@ def test_device_push_with_ragged_tail(pkg, hostsim_lib):
 
 def test_table_overflow_costs_lines_not_the_stream(pkg, hostsim_lib):
     pc.check_overflow_degrades(pkg, hostsim_lib)
+
+
+def test_many_carriers_per_capture(pkg, hostsim_lib):
+    pc.check_carriers(pkg, hostsim_lib)

@@ -1,0 +1,38 @@
+"""SURVEY 8f N3 on the GPU: a 1.6 MS/s capture with five carriers, device-resident, decoded by the three contexts
+shard.plan_carriers() deals them to.  python tools/carriers_bench.py [mib]   prints lines per carrier and the rate."""
+import importlib, sys, time
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import torch
+pkg = importlib.import_module("rtl-wmbus_b200"); synth = importlib.import_module("rtl-wmbus_b200.synth")
+shard = importlib.import_module("rtl-wmbus_b200.shard")
+lib = pkg.load_library()
+mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+n = mib << 20
+E = synth.Emitter
+em = [E("T1", 0x71200023, amp=60.0, offset_hz=325e3 + 6e3, l_field=0x29, period_s=0.11, start_s=0.004, seed=31),
+      E("T1", 0x64700082, amp=55.0, offset_hz=-150e3 - 4e3, l_field=0x19, period_s=0.13, start_s=0.021, seed=32),
+      E("C1A", 0x20338739, amp=55.0, offset_hz=575e3 + 3e3, l_field=0x19, period_s=0.12, start_s=0.040, seed=33),
+      E("S1", 0x19131290, amp=60.0, offset_hz=-325e3 + 2e3, l_field=0x19, period_s=0.17, start_s=0.010, seed=34),
+      E("S1", 0x02717473, amp=55.0, offset_hz=100e3 - 3e3, l_field=0x2E, period_s=0.19, start_s=0.060, seed=35)]
+carriers = [(325, "T"), (-150, "T"), (575, "T"), (-325, "S"), (100, "S")]
+cap, plan = synth.synth_capture(n, emitters=em, seed=0xB2000061, noise_sigma=4.0, device="cuda")
+torch.cuda.synchronize()
+ctxs = {}
+def make(flags, **kw):
+    key = tuple(kw["carrier_25khz"])
+    if key not in ctxs:
+        ctxs[key] = pkg.WmbusB200(flags, lib=lib, max_batch_mib=min(mib, 1024), **kw)
+    class Keep:                                   # contexts are kept across repetitions (allocation is not the path)
+        def __enter__(s): ctxs[key].reset(); return ctxs[key]
+        def __exit__(s, *a): return False
+    return Keep()
+run = lambda ctx: ctx.process_device(cap.data_ptr(), n, flush=True)
+best = None
+for rep in range(4):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    got = shard.decode_carriers(make, run, carriers, "")
+    dt = time.perf_counter() - t0
+    best = dt if best is None or dt < best else best
+print("planted", len(plan), {k: (len(v), sum(1 for l in v if l.split(';')[1] == '1')) for k, v in got.items()})
+print("%d MiB, %d carriers, %d contexts: %.2f ms -> %.1f k Msamples/s of capture, %.1f k carrier-Msamples/s" % (
+    mib, len(carriers), len(ctxs), best * 1e3, n / 2 / best / 1e9, len(carriers) * n / 2 / best / 1e9))
