@@ -249,6 +249,9 @@ static int launch_k1(wmb_ctx *c, const K1Params &p, cudaStream_t st)
 
 /* speculative pass (st: the batch's lane stream), then -- on cs, where batches follow each other in order --
  * verification + on-device fix-up of refuted lanes: no host round trip */
+static int g_fixseg = 3;             /* WMBUS_B200_FIXSEG: parallel segment pass in front of the fix-up block for 1: clock lanes, 2: monolithic
+                                            run-length lanes, 4: run-length phase 1 (off: its 2304-step lanes are cheap to re-run in one block, and the
+                                            4096 idle blocks of the pass cost 0.1 ms per GiB) */
 static bool g_k2a_coop = true;           /* WMBUS_B200_K2A=scalar: one lane per thread everywhere (experiments) */
 
 static int launch_k2a_lanes(wmb_ctx *c, int chain, const K2aParams &p, cudaStream_t st)
@@ -276,10 +279,16 @@ static int launch_k2a_verify(wmb_ctx *c, int chain, const K2aParams &p)
 {
     uint32_t *nf = c->d_nfail + chain;
     k2a_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, c->cs>>>(p, nf);
-    if (chain == 0) k2a_fixup_kernel<ChainT1C1><<<1, FIX_THREADS, 0, c->cs>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
-    else            k2a_fixup_kernel<ChainS1><<<1, FIX_THREADS, 0, c->cs>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
+    const unsigned segs = (p.lanes + FIX_SEG - 1) / FIX_SEG;
+    if (chain == 0) {
+        if (g_fixseg & 1) k2a_fixseg_kernel<ChainT1C1><<<segs, FIX_SEG, 0, c->cs>>>(p, nf, GD_FIELD(c, lanes_rerun));
+        k2a_fixup_kernel<ChainT1C1><<<1, FIX_THREADS, 0, c->cs>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
+    } else {
+        if (g_fixseg & 1) k2a_fixseg_kernel<ChainS1><<<segs, FIX_SEG, 0, c->cs>>>(p, nf, GD_FIELD(c, lanes_rerun));
+        k2a_fixup_kernel<ChainS1><<<1, FIX_THREADS, 0, c->cs>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
+    }
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 2;
+    c->st.kernel_launches += 3;
     return WMB_OK;
 }
 
@@ -290,14 +299,16 @@ static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p, cudaStream_t st
     if (chain == 0) {
         k2m_lanes_kernel<ChainT1C1><<<grid, K2_THREADS, 0, st>>>(p);
         k2m_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, nf);
+        if (g_fixseg & 2) k2m_fixseg_kernel<ChainT1C1><<<(p.lanes + FIX_SEG - 1) / FIX_SEG, FIX_SEG, 0, st>>>(p, nf, GD_FIELD(c, lanes_rerun));
         k2m_fixup_kernel<ChainT1C1><<<1, FIX_THREADS, 0, st>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
     } else {
         k2m_lanes_kernel<ChainS1><<<grid, K2_THREADS, 0, st>>>(p);
         k2m_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, st>>>(p, nf);
+        if (g_fixseg & 2) k2m_fixseg_kernel<ChainS1><<<(p.lanes + FIX_SEG - 1) / FIX_SEG, FIX_SEG, 0, st>>>(p, nf, GD_FIELD(c, lanes_rerun));
         k2m_fixup_kernel<ChainS1><<<1, FIX_THREADS, 0, st>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
     }
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 3;
+    c->st.kernel_launches += 4;
     return WMB_OK;
 }
 
@@ -306,9 +317,10 @@ static int launch_k2p1(wmb_ctx *c, const K2p1Params &p)
     uint32_t *nf = c->d_nfail + 4;
     k2p1_lanes_kernel<<<(p.lanes + 127) / 128, 128, 0, c->cs>>>(p);
     k2p1_verify_kernel<<<(p.lanes + 255) / 256, 256, 0, c->cs>>>(p, nf);
+    if (g_fixseg & 4) k2p1_fixseg_kernel<<<(p.lanes + FIX_SEG - 1) / FIX_SEG, FIX_SEG, 0, c->cs>>>(p, nf, GD_FIELD(c, lanes_rerun));
     k2p1_fixup_kernel<<<1, FIX_THREADS, 0, c->cs>>>(p, nf, GD_FIELD(c, lanes_rerun), c->d_errors);
     CUDA_TRY(cudaGetLastError());
-    c->st.kernel_launches += 3;
+    c->st.kernel_launches += 4;
     return WMB_OK;
 }
 
@@ -519,6 +531,7 @@ static void read_tuning()
 #ifndef WMB_HOSTSIM
     if (const char *k = getenv("WMBUS_B200_K2A")) g_k2a_coop = strcmp(k, "scalar") != 0;
     if (const char *k = getenv("WMBUS_B200_K1_CTAS")) g_k1_ctas = atoi(k);
+    if (const char *k = getenv("WMBUS_B200_FIXSEG")) g_fixseg = atoi(k);
 #endif
     if (const char *b = getenv("WMBUS_B200_PIPE_MIB")) { const unsigned long v = strtoul(b, nullptr, 10); if (v >= 1 && v <= 4096) g_pipe_bytes = (size_t)v << 20; }
     if (const char *b = getenv("WMBUS_B200_P2BLK")) { const unsigned v = (unsigned)atoi(b); if (v == 32 || v == 64 || v == 128) g_p2_block = v; }

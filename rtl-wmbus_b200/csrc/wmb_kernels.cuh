@@ -1359,11 +1359,56 @@ __global__ void k2m_carry_kernel(const RlState *end, RlState *carry, const uint3
  * a few microseconds); otherwise it re-runs the refuted lanes from their predecessors' exact end states and verifies
  * again until no lane is refuted -- what the host used to drive with a stream synchronisation per round. */
 #define FIX_THREADS 128
+/* Before that block: the same thing in parallel over segments of FIX_SEG lanes, one warp per segment (skipped when no
+ * lane is refuted).  A clean out-of-channel carrier or a very quiet band leaves the clock filter near a fixed point,
+ * where two trajectories can stay an ulp apart for good: then whole runs of lanes are refuted (measured: every lane of
+ * a five-carrier capture at noise sigma 4) and one block of 128 threads takes lanes / 128 lane times per round.  A
+ * segment's warp iterates re-run + verify over its lanes until they are consistent with the segment's FIRST lane,
+ * which it leaves alone (its predecessor belongs to another block).  Whatever this pass leaves behind -- refuted first
+ * lanes, chains across segments -- the single block finds when it verifies every lane again: the pass is an
+ * accelerator, the proof of exactness is still that block's "no lane refuted". */
+#define FIX_SEG 32
+template <class RERUN, class VERIFY>
+__device__ __forceinline__ void fixup_segments(uint32_t lanes, const uint32_t *n_fail, const uint32_t *flags, uint32_t *stat_rerun,
+                                               RERUN rerun, VERIFY verify)
+{
+    if (*(volatile const uint32_t *)n_fail == 0) return;
+    __shared__ uint32_t s_cnt, s_dummy;
+    const uint32_t l1 = min(lanes, (blockIdx.x + 1u) * FIX_SEG);
+    const uint32_t lane = blockIdx.x * FIX_SEG + 1u + threadIdx.x;
+    for (uint32_t round = 0; round < FIX_SEG; round++) {
+        if (threadIdx.x == 0) { s_cnt = 0; s_dummy = 0; }
+        __syncthreads();
+        const bool flagged = lane < l1 && ((volatile const uint32_t *)flags)[lane] != 0;
+        if (flagged) atomicAdd(&s_cnt, 1u);
+        __syncthreads();
+        const uint32_t n = s_cnt;
+        if (n == 0) break;
+        if (threadIdx.x == 0) atomicAdd(stat_rerun, n);
+        if (flagged) rerun(lane);
+        __threadfence();
+        __syncthreads();
+        if (lane < l1) verify(lane, &s_dummy);
+        __threadfence();
+        __syncthreads();
+    }
+}
 template <class RERUN, class VERIFY>
 __device__ __forceinline__ void fixup_loop(uint32_t lanes, uint32_t *n_fail, uint32_t *stat_rerun, uint32_t *errors,
                                            RERUN rerun, VERIFY verify)
 {
     __shared__ uint32_t s_fail;
+    /* the segment pass has changed lanes since the count was taken: count again */
+    __syncthreads();
+    if (threadIdx.x == 0) s_fail = *(volatile uint32_t *)n_fail;
+    __syncthreads();
+    if (s_fail == 0) return;
+    __syncthreads();
+    if (threadIdx.x == 0) *n_fail = 0;
+    __threadfence();
+    __syncthreads();
+    for (uint32_t lane = threadIdx.x; lane < lanes; lane += blockDim.x) verify(lane);
+    __threadfence();
     for (uint32_t round = 0;; round++) {
         __syncthreads();
         if (threadIdx.x == 0) s_fail = *(volatile uint32_t *)n_fail;
@@ -1391,6 +1436,26 @@ __global__ void __launch_bounds__(FIX_THREADS) k2a_fixup_kernel(K2aParams p, uin
     p.mode = 1;
     fixup_loop(p.lanes, n_fail, stat_rerun, errors, [&](uint32_t lane) { k2a_lane<CH>(p, lane); },
                [&](uint32_t lane) { k2a_verify_lane(p, lane, n_fail); });
+}
+template <class CH>
+__global__ void __launch_bounds__(FIX_SEG) k2a_fixseg_kernel(K2aParams p, const uint32_t *n_fail, uint32_t *stat_rerun)
+{
+    p.mode = 1;
+    fixup_segments(p.lanes, n_fail, p.rerun, stat_rerun, [&](uint32_t lane) { k2a_lane<CH>(p, lane); },
+                   [&](uint32_t lane, uint32_t *cnt) { k2a_verify_lane(p, lane, cnt); });
+}
+template <class CH>
+__global__ void __launch_bounds__(FIX_SEG) k2m_fixseg_kernel(K2mParams p, const uint32_t *n_fail, uint32_t *stat_rerun)
+{
+    p.mode = 1;
+    fixup_segments(p.lanes, n_fail, p.rerun, stat_rerun, [&](uint32_t lane) { k2m_lane<CH>(p, lane); },
+                   [&](uint32_t lane, uint32_t *cnt) { k2m_verify_lane(p, lane, cnt); });
+}
+__global__ void __launch_bounds__(FIX_SEG) k2p1_fixseg_kernel(K2p1Params p, const uint32_t *n_fail, uint32_t *stat_rerun)
+{
+    p.mode = 1;
+    fixup_segments(p.lanes, n_fail, p.rerun, stat_rerun, [&](uint32_t lane) { k2p1_lane(p, lane); },
+                   [&](uint32_t lane, uint32_t *cnt) { k2p1_verify_lane(p, lane, cnt); });
 }
 template <class CH>
 __global__ void __launch_bounds__(FIX_THREADS) k2m_fixup_kernel(K2mParams p, uint32_t *n_fail, uint32_t *stat_rerun, uint32_t *errors)

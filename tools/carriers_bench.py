@@ -1,5 +1,5 @@
 """SURVEY 8f N3 on the GPU: a 1.6 MS/s capture with five carriers, device-resident, decoded by the three contexts
-shard.plan_carriers() deals them to.  python tools/carriers_bench.py [mib]   prints lines per carrier and the rate."""
+shard.plan_carriers() deals them to.  python tools/carriers_bench.py [mib] [noise_sigma]   prints lines per carrier and the rate."""
 import importlib, sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import torch
@@ -15,7 +15,7 @@ em = [E("T1", 0x71200023, amp=60.0, offset_hz=325e3 + 6e3, l_field=0x29, period_
       E("S1", 0x19131290, amp=60.0, offset_hz=-325e3 + 2e3, l_field=0x19, period_s=0.17, start_s=0.010, seed=34),
       E("S1", 0x02717473, amp=55.0, offset_hz=100e3 - 3e3, l_field=0x2E, period_s=0.19, start_s=0.060, seed=35)]
 carriers = [(325, "T"), (-150, "T"), (575, "T"), (-325, "S"), (100, "S")]
-cap, plan = synth.synth_capture(n, emitters=em, seed=0xB2000061, noise_sigma=4.0, device="cuda")
+cap, plan = synth.synth_capture(n, emitters=em, seed=0xB2000061, noise_sigma=float(sys.argv[2]) if len(sys.argv) > 2 else 8.0, device="cuda")
 torch.cuda.synchronize()
 ctxs = {}
 def make(flags, **kw):
@@ -33,6 +33,11 @@ for rep in range(4):
     got = shard.decode_carriers(make, run, carriers, "")
     dt = time.perf_counter() - t0
     best = dt if best is None or dt < best else best
+for key, ctx in ctxs.items():
+    st = ctx.stats()
+    print(key, "device pass %.2f ms (demod %.2f, bit sync %.2f)  rl_fallbacks %d  lanes_rerun %d  candidates %s  host gather %.1f decode %.1f batch %.1f ms (cumulative)" % (
+        st.batch_device_ms, st.demod_kernel_ms, st.bitsync_kernel_ms, st.rl_fallbacks, st.lanes_rerun,
+        [list(r) for r in st.candidates], st.host_gather_ms, st.host_decode_ms, st.host_batch_ms))
 print("planted", len(plan), {k: (len(v), sum(1 for l in v if l.split(';')[1] == '1')) for k, v in got.items()})
 print("%d MiB, %d carriers, %d contexts: %.2f ms -> %.1f k Msamples/s of capture, %.1f k carrier-Msamples/s" % (
     mib, len(carriers), len(ctxs), best * 1e3, n / 2 / best / 1e9, len(carriers) * n / 2 / best / 1e9))
