@@ -232,6 +232,29 @@ def check_carriers(pkg, lib, to_device=None):
         assert len(ok) >= 4, (key, len(got[key]), len(ok))
 
 
+def check_cw_interferer(pkg, lib):
+    """A clean carrier next to the channel (here: a CW tone 310 kHz off, through the box filter's side lobe) parks the
+    clock filter near a fixed point between telegrams, where speculative lanes do not re-join the true trajectory: a
+    third of the lanes is refuted and re-run (segment pass + fix-up block).  The lines must not notice."""
+    import importlib
+    synth = importlib.import_module("rtl-wmbus_b200.synth")
+    E = synth.Emitter
+    em = [E("T1", 0x71200023, amp=60.0, offset_hz=6e3, l_field=0x29, period_s=0.11, start_s=0.004, seed=31),
+          E("S1", 0x19131290, amp=50.0, offset_hz=2e3, l_field=0x19, period_s=0.17, start_s=0.050, seed=34)]
+    cap, _ = synth.synth_capture(2 << 20, emitters=em, seed=0xB2000071, noise_sigma=2.0)
+    x = cap.numpy().astype(np.float64).reshape(-1, 2)
+    tone = 30.0 * np.exp(2j * np.pi * 310e3 / 1.6e6 * np.arange(len(x)))
+    x[:, 0] += tone.real; x[:, 1] += tone.imag
+    cu8 = np.ascontiguousarray(np.clip(np.round(x), 0, 255).astype(np.uint8).reshape(-1))
+    want = oracle_lines(cu8, "-v")
+    assert len(want) >= 12
+    for tuning in (dict(chunk_samples=4096), dict(chunk_samples=1024, max_batch_mib=1), dict()):
+        got, st = run_lines(pkg, lib, cu8, "-v", **tuning)
+        assert got == want
+        if tuning:
+            assert st.lanes_rerun > 50, "the capture is meant to refute lanes (%d of %d)" % (st.lanes_rerun, st.lanes_run)
+
+
 def check_sample_index_wrap(pkg, lib):
     """The device keeps 40 bits of the decimated sample index in its bit events (15.9 days of streaming at 800 kS/s).
     A stream positioned just below 2^40 must decode the telegrams that span the wrap exactly like a fresh stream:

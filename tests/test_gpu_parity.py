@@ -155,3 +155,7 @@ def test_table_overflow_costs_lines_not_the_stream(pkg, gpu_lib):
 def test_many_carriers_per_capture(pkg, gpu_lib):
     import torch
     pc.check_carriers(pkg, gpu_lib, to_device=lambda a: torch.from_numpy(a).cuda())
+
+
+def test_cw_interferer_refutes_lanes_not_lines(pkg, gpu_lib):
+    pc.check_cw_interferer(pkg, gpu_lib)

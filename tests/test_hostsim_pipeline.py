@@ -78,3 +78,7 @@ def test_table_overflow_costs_lines_not_the_stream(pkg, hostsim_lib):
 
 def test_many_carriers_per_capture(pkg, hostsim_lib):
     pc.check_carriers(pkg, hostsim_lib)
+
+
+def test_cw_interferer_refutes_lanes_not_lines(pkg, hostsim_lib):
+    pc.check_cw_interferer(pkg, hostsim_lib)
