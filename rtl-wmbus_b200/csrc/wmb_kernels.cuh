@@ -1360,7 +1360,7 @@ __global__ void k2m_carry_kernel(const RlState *end, RlState *carry, const uint3
  * again until no lane is refuted -- what the host used to drive with a stream synchronisation per round. */
 #define FIX_THREADS 128
 /* Before that block: the same thing in parallel over segments of FIX_SEG lanes, one warp per segment (skipped when no
- * lane is refuted).  A clean out-of-channel carrier or a very quiet band leaves the clock filter near a fixed point,
+ * lane is refuted).  A clean carrier next to the channel leaves the clock filter near a fixed point between telegrams,
  * where two trajectories can stay an ulp apart for good: then whole runs of lanes are refuted (measured: every lane of
  * a five-carrier capture at noise sigma 4) and one block of 128 threads takes lanes / 128 lane times per round.  A
  * segment's warp iterates re-run + verify over its lanes until they are consistent with the segment's FIRST lane,
