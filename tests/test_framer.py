@@ -151,7 +151,9 @@ def framer_cases(synth, n_random=1500):
     return cases
 
 
-def check_device_framer(lib, pkg, synth):
+def check_device_framer(lib, pkg, synth, orc_mod=None):
+    """K4 against its host twin, field by field, and -- third column -- against the oracle's per-bit state machines
+    (consumed bits and the formatted line) on the same candidates."""
     cases = framer_cases(synth)
     n = len(cases)
     frames = (pkg.WmbFrame * n)()
@@ -183,15 +185,35 @@ def check_device_framer(lib, pkg, synth):
                    (d.mode, d.crc_ok, d.ok_3of6, d.packet_rssi, d.current_rssi, d.serial, d.len), i
             assert bytes(h.datagram[:h.len]) == bytes(d.datagram[:d.len]), i
     assert seen[0] > 500 and seen[1] > 100 and seen[2] > 10, seen
+    if orc_mod is None:
+        return
+    lib.wmb_format_line.argtypes = [C.POINTER(Decoded), C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+    lib.wmb_format_line.restype = C.c_size_t
+    buf = C.create_string_buffer(2048)
+    n_lines = 0
+    for i, (chain, bits, rssi) in enumerate(cases):
+        d = dev[i]
+        oc, oline = oracle_decode(orc_mod, chain, bits, rssi)
+        if d.status == 2:                               # NEED_MORE: the oracle ran through the whole list
+            assert oline is None and oc == len(bits), i
+            continue
+        assert d.consumed == oc, (i, chain, d.consumed, oc)
+        line = None
+        if d.status == 1:
+            k = lib.wmb_format_line(C.byref(d), b"rla;", b"TS", buf, 2048)
+            line = buf.raw[:k].decode().rstrip("\n")
+            n_lines += 1
+        assert line == oline, (i, chain)
+    assert n_lines > 100
 
 
-def test_device_framer_matches_host_twin_hostsim(hostsim_lib, pkg):
-    check_device_framer(hostsim_lib, pkg, importlib.import_module("rtl-wmbus_b200.synth"))
+def test_device_framer_matches_host_twin_and_oracle_hostsim(hostsim_lib, pkg, orc_mod):
+    check_device_framer(hostsim_lib, pkg, importlib.import_module("rtl-wmbus_b200.synth"), orc_mod)
 
 
 @pytest.mark.gpu
-def test_device_framer_matches_host_twin_gpu(gpu_lib, pkg):
-    check_device_framer(gpu_lib, pkg, importlib.import_module("rtl-wmbus_b200.synth"))
+def test_device_framer_matches_host_twin_and_oracle_gpu(gpu_lib, pkg, orc_mod):
+    check_device_framer(gpu_lib, pkg, importlib.import_module("rtl-wmbus_b200.synth"), orc_mod)
 
 
 def test_time_string_format(hostsim_lib):
