@@ -74,6 +74,11 @@ typedef struct wmb_opts {
      * table, rtl_wmbus.c:974-993), |offset| <= fs / 2.  The reference's -s is {+13, -13}.  A capture with more than two
      * carriers is decoded by several contexts over the same input (shard.decode_carriers in the Python mirror). */
     int32_t  carrier_25khz[2];
+    /* SURVEY 8f N4 -- 1: the reference's dormant 23-tap pre-decimation low-pass (lp_fir_butter_1600kHz_160kHz_200kHz_*,
+     * rtl_wmbus.c:197-239, never called upstream) takes the place of the moving averages in front of the decimation.
+     * 1.6 MS/s only (decimation 2).  Not a switch of the reference: there are no reference lines to compare with; the
+     * stages are checked against those functions themselves (oracle/ref_stages.c). */
+    uint32_t prefilter;
 } wmb_opts;
 
 typedef struct wmb_ctx wmb_ctx;

@@ -11,7 +11,9 @@
  *
  * Built by oracle/Makefile into oracle/_ref/ref_stages (git-ignored).
  *
- *   ref_stages <chain 0|1> <decimation> <accurate 0|1> <remove_dc 0|1> <simultaneous 0|1> < in.cu8 > out.f32
+ *   ref_stages <chain 0|1> <decimation> <accurate 0|1> <remove_dc 0|1> <simultaneous 0|1> [prefilter 0|1] < in.cu8 > out.f32
+ *   prefilter 1: the reference's dormant lp_fir_butter_1600kHz_160kHz_200kHz_* (rtl_wmbus.c:197-239) instead of the
+ *   moving averages in front of the decimation
  *
  * Output: per decimated sample 6 floats: si, sq, dphi_raw, dphi, rssi, clock(0/1).
  */
@@ -27,6 +29,7 @@ int main(int argc, char **argv)
     const int accurate = atoi(argv[3]);
     const int dc = atoi(argv[4]);
     const int simul = atoi(argv[5]);
+    const int pre = argc > 6 ? atoi(argv[6]) : 0;
     const int fs_kHz = (int)(d * 800u);
     uint8_t block[4096];
     unsigned idx = 0;
@@ -38,8 +41,10 @@ int main(int argc, char **argv)
             float it = (float)block[k] - 127.5f, qt = (float)block[k + 1] - 127.5f;
             float is = it, qs = qt;
             if (simul) shift_freq_plus_minus325(&it, &qt, &is, &qs, fs_kHz);
-            const float i_t1 = moving_average_t1_c1(it, 0), q_t1 = moving_average_t1_c1(qt, 1);
-            const float i_s1 = moving_average_s1(is, 0), q_s1 = moving_average_s1(qs, 1);
+            const float i_t1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_t1_c1(it, 0) : moving_average_t1_c1(it, 0);
+            const float q_t1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_t1_c1(qt, 1) : moving_average_t1_c1(qt, 1);
+            const float i_s1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_s1(is, 0) : moving_average_s1(is, 0);
+            const float q_s1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_s1(qs, 1) : moving_average_s1(qs, 1);
             if (++idx < d) continue;
             idx = 0;
             float rec[6];

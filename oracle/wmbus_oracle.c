@@ -181,6 +181,15 @@ void orc_frontend(const uint8_t *cu8, size_t n_iq, const orc_opts *o, int chain,
         }
     }
 
+    /* the dormant pre-decimation low-pass (rtl_wmbus.c:197-239: the same 23 coefficients for both chains), run through
+     * firf() (fir.h:49-72): y = sum_j b[j] x[n-j], accumulated from 0 in that order, zero history at the start */
+    static const float pre_b[23] = {
+        0.000140535927, 1.102280392e-05, 0.0001309279731, 0.001356012537, 0.00551787474, 0.01499414005, 0.03160167988,
+        0.05525973093, 0.08315031015, 0.1099887688, 0.1295143636, 0.1366692652, 0.1295143636, 0.1099887688, 0.08315031015,
+        0.05525973093, 0.03160167988, 0.01499414005, 0.00551787474, 0.001356012537, 0.0001309279731, 1.102280392e-05,
+        0.000140535927 };
+    float pre_i[23] = {0}, pre_q[23] = {0};                 /* [0] = newest */
+
     for (size_t k = 0; k < n_iq; k++) {
         float xi = (float)cu8[2 * k] - 127.5f;              /* :1312 */
         float xq = (float)cu8[2 * k + 1] - 127.5f;          /* :1313 */
@@ -191,6 +200,17 @@ void orc_frontend(const uint8_t *cu8, size_t n_iq, const orc_opts *o, int chain,
             const float ix = xi * c, qx = xq * c, iz = xi * z, qz = xq * z;
             if (!mix_conj) { xi = ix - qz; xq = qx + iz; }  /* :1025-1026 (the T1/C1 chain) */
             else           { xi = ix + qz; xq = qx - iz; }  /* :1029-1030 (the S1 chain)    */
+        }
+        if (o->prefilter) {
+            memmove(pre_i + 1, pre_i, 22 * sizeof(float)); pre_i[0] = xi;
+            memmove(pre_q + 1, pre_q, 22 * sizeof(float)); pre_q[0] = xq;
+            if (++since < d) continue;                      /* the filter runs on every sample; only these outputs are used */
+            since = 0;
+            float yi = 0, yq = 0;
+            for (int j = 0; j < 23; j++) { yi += pre_b[j] * pre_i[j]; yq += pre_b[j] * pre_q[j]; }
+            si[m] = yi; sq[m] = yq;
+            m++;
+            continue;
         }
         const int vi = (int)xi, vq = (int)xq;               /* float -> int param of mavgi() */
         sum_i += vi - ring_i[pos]; ring_i[pos] = vi;

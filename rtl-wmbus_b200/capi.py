@@ -15,7 +15,7 @@ class WmbOpts(C.Structure):
                 ("s1_enabled", C.c_uint8), ("simultaneous", C.c_uint8), ("show_algorithm", C.c_uint8),
                 ("chunk_samples", C.c_uint32), ("warmup_samples", C.c_uint32),
                 ("max_batch_mib", C.c_uint32), ("manual_frames", C.c_uint32), ("reserved", C.c_uint32 * 2),
-                ("carrier_25khz", C.c_int32 * 2)]
+                ("carrier_25khz", C.c_int32 * 2), ("prefilter", C.c_uint32)]
 
 
 class WmbFrame(C.Structure):

@@ -81,6 +81,15 @@ WMB_CONSTANT float c_fir_t1c1[11] = {
     -0.00456638213, -0.002571450348, 0.02689425925, 0.1141330398, 0.2264456422, 0.2793297826,
     0.2264456422, 0.1141330398, 0.02689425925, -0.002571450348, -0.00456638213 };
 
+/* the reference's dormant pre-decimation low-pass, 1.6 MS/s, pass band 160 kHz, stop band 200 kHz (rtl_wmbus.c:197-239:
+ * lp_fir_butter_1600kHz_160kHz_200kHz_t1_c1 and _s1 hold the same 23 coefficients); SURVEY 8f N4 */
+WMB_CONSTANT float c_fir_pre[23] = {
+    0.000140535927, 1.102280392e-05, 0.0001309279731, 0.001356012537, 0.00551787474, 0.01499414005, 0.03160167988,
+    0.05525973093, 0.08315031015, 0.1099887688, 0.1295143636, 0.1366692652, 0.1295143636, 0.1099887688, 0.08315031015,
+    0.05525973093, 0.03160167988, 0.01499414005, 0.00551787474, 0.001356012537, 0.0001309279731, 1.102280392e-05,
+    0.000140535927 };
+#define K1_PRE_TAPS 23
+
 WMB_CONSTANT float c_fir_s1[46] = {
     -0.000649081282, -0.0009491938209, -0.001361601657, -0.001910785234, -0.002570133495,
     -0.003251218426, -0.003801634695, -0.004012672882, -0.003636803575, -0.002413585945,

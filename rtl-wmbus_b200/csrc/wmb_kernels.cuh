@@ -39,6 +39,7 @@ struct K1Params {
     uint32_t chains;            /* bit0: T1/C1, bit1: S1                                     */
     uint32_t accurate;          /* 0 with -a                                                 */
     uint32_t mix;               /* -s (or explicit carriers)                                 */
+    uint32_t prefilter;         /* 1: the dormant 23-tap low-pass instead of the box filters (d = 2 only; own kernel instance) */
     uint32_t lut_n;             /* mixer table length (fs_kHz/25)                            */
     uint32_t mix_k0;            /* (index of batch sample 0 in the stream) mod lut_n          */
     uint32_t mix_step[WMB_N_CHAINS];  /* table entries per sample = |carrier offset| / 25 kHz, mod lut_n (the reference: 13) */
@@ -61,6 +62,7 @@ struct K1Smem {
     uint64_t *bar;          /* two mbarriers                                     */
     int64_t *pass_tile;     /* [2] tile of the pass whose |s| is in mag2[b] (-1: no more passes)       */
     const WmbAtanTab *atab; /* constants of the discriminator's argument reduction (wmb_exact.cuh); first in the block */
+    float   *xq;            /* prefilter mode only: Q as float per input sample (I takes v's place); last in the block */
 };
 #define K1_ATAB_BYTES 256   /* sizeof(WmbAtanTab) rounded up to the alignment of the IQ buffers */
 static_assert(sizeof(WmbAtanTab) <= K1_ATAB_BYTES, "table block");
@@ -82,14 +84,15 @@ static inline
 #ifndef WMB_HOSTSIM
 __host__ __device__
 #endif
-size_t k1_smem_bytes(uint32_t d)
+size_t k1_smem_bytes(uint32_t d, uint32_t prefilter = 0)
 {
     const size_t nb = (size_t)2 * k1_tile_iq(d);
     const size_t n = K1_TILE + K1_HALO;
-    return 2 * nb + 4 * (size_t)k1_tile_iq(d) + 3 * 4 * n + 2 * 4 * (n + n / 32 + 4) + 64 + 16 + 16 + K1_ATAB_BYTES;
+    return 2 * nb + 4 * (size_t)k1_tile_iq(d) + 3 * 4 * n + 2 * 4 * (n + n / 32 + 4) + 64 + 16 + 16 + K1_ATAB_BYTES
+           + (prefilter ? 4 * (size_t)k1_tile_iq(d) + 16 : 0);
 }
 
-WMB_HD void k1_carve(K1Smem &sm, uint8_t *base, uint32_t d)
+WMB_HD void k1_carve(K1Smem &sm, uint8_t *base, uint32_t d, uint32_t prefilter = 0)
 {
     const size_t nb = (size_t)2 * k1_tile_iq(d);
     const size_t n = K1_TILE + K1_HALO;
@@ -106,6 +109,8 @@ WMB_HD void k1_carve(K1Smem &sm, uint8_t *base, uint32_t d)
     sm.mag2[0] = (float *)(base + off); off += 4 * (n + n / 32 + 4);
     sm.mag2[1] = (float *)(base + off); off += 4 * (n + n / 32 + 4);
     sm.mag = sm.mag2[0];
+    off = (off + 15) & ~(size_t)15;
+    sm.xq = prefilter ? (float *)(base + off) : nullptr;
 }
 
 /* first IQ sample (batch-relative, may be negative) held by tile `t` */
@@ -258,6 +263,90 @@ WMB_D void k1_disc_mag(const K1Params &p, K1Smem &sm, int tid)
         sm.draw[r] = dr;
         /* the RSSI one-pole needs 0.6789f * |s| (rtl_wmbus.c:480); the product is formed here, in the
          * wide phase, so that the serial recurrence below is one FMUL + one FADD per step */
+        sm.mag[k1_pad(r)] = wmb_fmul(0.6789f, wmb_fsqrt(wmb_fadd(wmb_fmul(i, i), wmb_fmul(q, q))));
+    }
+}
+
+/* ---- optional front end: the reference's dormant pre-decimation low-pass ----------------------------
+ * rtl_wmbus.c:197-239 keeps a 23-tap FIR for 1.6 MS/s next to the moving averages and never calls it.  With
+ * opts.prefilter = 1 it takes the box filters' place (d = 2): convert (and mix) to float, y = sum_j b[j] x[k-j]
+ * accumulated from 0 in firf()'s order (fir.h:49-72) at the samples the decimation keeps, then the general atan2f and
+ * sqrt -- the filter outputs are not integers, so none of the bounded variants applies.  A kernel instance of its own
+ * (template parameter PRE): the default kernels are the same code as without it. */
+template <int CHAIN>
+WMB_D void k1_convert_float(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile, int tid)
+{
+    const int64_t k0 = k1_tile_k0(p, tile);
+    const int n = (int)k1_tile_iq(p.d);
+    const int64_t first = -p.n_hist_iq - k0;                    /* samples before the start of the stream are zero (the filter's zero history) */
+    const int jmin = first > 0 ? (first < n ? (int)first : n) : 0;
+    const uint16_t *raw16 = (const uint16_t *)raw;
+    float *xi_out = (float *)sm.v, *xq_out = sm.xq;
+    const uint32_t ln = p.lut_n;
+    int64_t km = k0 % (int64_t)ln;
+    if (km < 0) km += ln;
+    const uint32_t st = p.mix_step[CHAIN];
+    const bool cj = p.mix_conj[CHAIN] != 0;
+    uint32_t idx = (uint32_t)(((uint64_t)st * (((uint64_t)p.mix_k0 + (uint64_t)km + (uint64_t)tid) % ln)) % ln);
+    const uint32_t step = (uint32_t)(((uint64_t)st * K1_THREADS) % ln);
+    for (int j = tid; j < n; j += K1_THREADS) {
+        float xi = 0.0f, xq = 0.0f;
+        if (j >= jmin) {
+            const uint32_t w = raw16[j];
+            xi = wmb_fsub((float)(w & 0xFFu), 127.5f);           /* rtl_wmbus.c:1312-1313 */
+            xq = wmb_fsub((float)(w >> 8), 127.5f);
+            if (p.mix) {                                         /* :997-1031, as in k1_convert */
+                const float c = p.lut_cos[idx], z = p.lut_msin[idx];
+                const float ix = wmb_fmul(xi, c), qx = wmb_fmul(xq, c);
+                const float iz = wmb_fmul(xi, z), qz = wmb_fmul(xq, z);
+                if (!cj) { xi = wmb_fsub(ix, qz); xq = wmb_fadd(qx, iz); }
+                else     { xi = wmb_fadd(ix, qz); xq = wmb_fsub(qx, iz); }
+            }
+        }
+        xi_out[j] = xi; xq_out[j] = xq;
+        idx += step;
+        if (idx >= ln) idx -= ln;
+    }
+}
+
+WMB_D void k1_prefir(const K1Params &p, K1Smem &sm, int tid)
+{
+    const float *xi = (const float *)sm.v, *xq = sm.xq;
+    for (int r = tid; r < K1_TILE + K1_HALO; r += K1_THREADS) {
+        const int jend = (int)p.d * r + (int)p.d - 1 + K1_BOX_MAX;     /* newest input sample of row r (as in k1_box) */
+        float yi = 0.0f, yq = 0.0f;
+#pragma unroll
+        for (int j = 0; j < K1_PRE_TAPS; j++) {
+            /* the window of the first three rows of a tile starts left of what the tile holds (22 samples back, the
+             * overhang is 16): those rows are recomputed halo that nothing reads (the FIR, RSSI and discriminator of
+             * the tile's own outputs reach back 46 rows at most) */
+            const int q = jend - j;
+            const float a = q >= 0 ? xi[q] : 0.0f, b = q >= 0 ? xq[q] : 0.0f;
+            yi = wmb_fadd(yi, wmb_fmul(c_fir_pre[j], a));
+            yq = wmb_fadd(yq, wmb_fmul(c_fir_pre[j], b));
+        }
+        sm.si[r] = yi; sm.sq[r] = yq;
+    }
+}
+
+/* discriminator and |s| on arbitrary floats: the general atan2f, IEEE sqrt */
+WMB_D void k1_disc_mag_general(const K1Params &p, K1Smem &sm, int tid)
+{
+    for (int r = tid; r < K1_TILE + K1_HALO; r += K1_THREADS) {
+        const float i = sm.si[r], q = sm.sq[r];
+        float dr = 0.f;
+        if (r > 0) {
+            const float ip = sm.si[r - 1], qp = sm.sq[r - 1];
+            if (p.accurate) {
+                const float dd = -qp;                            /* conjf(s_last), rtl_wmbus.c:517-534 */
+                const float re = wmb_fsub(wmb_fmul(i, ip), wmb_fmul(q, dd));
+                const float im = wmb_fadd(wmb_fmul(i, dd), wmb_fmul(q, ip));
+                dr = wmb_fmul(wmb_atan2f(im, re), wmb_u2f(0x3ea2f983u));
+            } else {
+                dr = wmb_discriminator_fast(i, q, ip, qp);
+            }
+        }
+        sm.draw[r] = dr;
         sm.mag[k1_pad(r)] = wmb_fmul(0.6789f, wmb_fsqrt(wmb_fadd(wmb_fmul(i, i), wmb_fmul(q, q))));
     }
 }
@@ -510,18 +599,24 @@ __device__ __forceinline__ void k1_bar_arrive(int id, int count)
 #define K1_BAR_READY(pass) (2 + (int)((pass) & 1u))
 #define K1_BAR_FREE(pass)  (4 + (int)((pass) & 1u))
 
-template <class CH>
+template <class CH, bool PRE>
 __device__ __forceinline__ void k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile,
                                          int tid, bool need_convert, uint32_t pass)
 {
     const bool fast = (p.d == 2 && !p.mix);
     if (need_convert) {
-        if (fast) k1_convert_fast(p, sm, raw, tile, tid); else k1_convert<CH::ID>(p, sm, raw, tile, tid);
+        if (PRE) k1_convert_float<CH::ID>(p, sm, raw, tile, tid);
+        else if (fast) k1_convert_fast(p, sm, raw, tile, tid); else k1_convert<CH::ID>(p, sm, raw, tile, tid);
         k1_bar_sync(K1_BAR_P, K1_THREADS);
     }
     sm.mag = (pass & 1u) ? sm.mag2[1] : sm.mag2[0];
     if (pass >= 2) k1_bar_sync(K1_BAR_FREE(pass), K1_BLOCK);         /* the RSSI warp has read what pass - 2 left there */
-    if (fast) k1_box_disc<CH, 1, true>(p, sm, tid);
+    if (PRE) {
+        k1_prefir(p, sm, tid);
+        k1_bar_sync(K1_BAR_P, K1_THREADS);
+        k1_disc_mag_general(p, sm, tid);
+    }
+    else if (fast) k1_box_disc<CH, 1, true>(p, sm, tid);
     else if (p.d == 3) k1_box_disc<CH, 3, false>(p, sm, tid);
     else if (p.d == 2) k1_box_disc<CH, 2, false>(p, sm, tid);
     else if (p.d == 1) k1_box_disc<CH, 1, false>(p, sm, tid);
@@ -539,12 +634,12 @@ __device__ __forceinline__ void k1_chain(const K1Params &p, K1Smem &sm, const ui
 
 /* CHAINS (bit 0 T1/C1, bit 1 S1) is a template parameter so that a one-chain run does not carry the other
  * chain's registers: the S1 filter's unrolled taps would cost the T1/C1-only kernel a resident CTA per SM */
-template <uint32_t CHAINS>
+template <uint32_t CHAINS, bool PRE>
 WMB_D void k1_demod_body(const K1Params &p)
 {
     extern __shared__ __align__(128) uint8_t k1_smem_raw[];
     K1Smem sm;
-    k1_carve(sm, k1_smem_raw, p.d);
+    k1_carve(sm, k1_smem_raw, p.d, PRE ? 1u : 0u);
     const int tid = threadIdx.x;
     const int64_t ntiles = (p.M + K1_TILE - 1) / K1_TILE;
     if (tid == 0) {
@@ -595,8 +690,8 @@ WMB_D void k1_demod_body(const K1Params &p)
         mbar_wait(sm.bar + buf, (phase >> buf) & 1u);
         phase ^= 1u << buf;
         const uint8_t *raw = buf ? sm.bytes[1] : sm.bytes[0];
-        if (CHAINS & 1u) k1_chain<ChainT1C1>(p, sm, raw, tile, tid, true, pass++);
-        if (CHAINS & 2u) k1_chain<ChainS1>(p, sm, raw, tile, tid, p.mix || !(CHAINS & 1u), pass++);
+        if (CHAINS & 1u) k1_chain<ChainT1C1, PRE>(p, sm, raw, tile, tid, true, pass++);
+        if (CHAINS & 2u) k1_chain<ChainS1, PRE>(p, sm, raw, tile, tid, p.mix || !(CHAINS & 1u), pass++);
     }
     /* tell the RSSI warp that there is no further pass (its buffer must be free first), then wait until it has read
      * the last two */
@@ -608,7 +703,10 @@ WMB_D void k1_demod_body(const K1Params &p)
 
 /* (resident blocks per SM pinned: the T1/C1-only kernel ran at 40 registers before the RSSI warp moved in) */
 template <uint32_t CHAINS>
-__global__ void __launch_bounds__(K1_BLOCK, CHAINS == 1u ? 5 : 4) k1_demod_kernel(const K1Params p) { k1_demod_body<CHAINS>(p); }
+__global__ void __launch_bounds__(K1_BLOCK, CHAINS == 1u ? 5 : 4) k1_demod_kernel(const K1Params p) { k1_demod_body<CHAINS, false>(p); }
+/* the prefilter front end (opts.prefilter): its own instances, three resident blocks */
+template <uint32_t CHAINS>
+__global__ void __launch_bounds__(K1_BLOCK, 3) k1_demod_pre_kernel(const K1Params p) { k1_demod_body<CHAINS, true>(p); }
 
 #endif /* !WMB_HOSTSIM */
 

@@ -9,8 +9,15 @@ template <class CH>
 static void hostsim_k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile, bool need_convert)
 {
     const bool fast = (p.d == 2 && !p.mix);
-    if (need_convert) for (int t = 0; t < K1_THREADS; t++) { if (fast) k1_convert_fast(p, sm, raw, tile, t); else k1_convert<CH::ID>(p, sm, raw, tile, t); }
-    if (fast) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 1, true>(p, sm, t); }
+    if (need_convert) for (int t = 0; t < K1_THREADS; t++) {
+        if (p.prefilter) k1_convert_float<CH::ID>(p, sm, raw, tile, t);
+        else if (fast) k1_convert_fast(p, sm, raw, tile, t); else k1_convert<CH::ID>(p, sm, raw, tile, t);
+    }
+    if (p.prefilter) {
+        for (int t = 0; t < K1_THREADS; t++) k1_prefir(p, sm, t);
+        for (int t = 0; t < K1_THREADS; t++) k1_disc_mag_general(p, sm, t);
+    }
+    else if (fast) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 1, true>(p, sm, t); }
     else if (p.d == 3) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 3, false>(p, sm, t); }
     else if (p.d == 2) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 2, false>(p, sm, t); }
     else if (p.d == 1) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 1, false>(p, sm, t); }
@@ -25,11 +32,11 @@ static void hostsim_k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, 
 static int launch_k1(wmb_ctx *c, const K1Params &p, cudaStream_t)
 {
     const int64_t ntiles = (p.M + K1_TILE - 1) / K1_TILE;
-    std::vector<uint8_t> smem(k1_smem_bytes(p.d) + 256, 0xA5);   /* garbage-filled like real smem */
+    std::vector<uint8_t> smem(k1_smem_bytes(p.d, p.prefilter) + 256, 0xA5);   /* garbage-filled like real smem */
     K1Smem sm;
     uint8_t *base = smem.data();
     base += (128 - ((uintptr_t)base & 127)) & 127;
-    k1_carve(sm, base, p.d);
+    k1_carve(sm, base, p.d, p.prefilter);
     for (int i = 0; i < WMB_ATAN_TAB_ELEMS; i++) wmb_atan_tab_fill((WmbAtanTab *)base, i);
     for (int64_t tile = 0; tile < ntiles; tile++) {
         const K1Load L = k1_plan_load(p, tile);

@@ -13,7 +13,7 @@ class OrcOpts(C.Structure):
     _fields_ = [("decimation", C.c_uint32), ("accurate_atan", C.c_uint8), ("remove_dc", C.c_uint8),
                 ("rla_enabled", C.c_uint8), ("t2_enabled", C.c_uint8), ("t1c1_enabled", C.c_uint8),
                 ("s1_enabled", C.c_uint8), ("simultaneous", C.c_uint8), ("show_algorithm", C.c_uint8),
-                ("real_timestamp", C.c_uint8), ("carrier_25khz", C.c_int32 * 2)]
+                ("real_timestamp", C.c_uint8), ("carrier_25khz", C.c_int32 * 2), ("prefilter", C.c_uint32)]
 
 
 class OrcEvent(C.Structure):
@@ -177,6 +177,6 @@ def ref_lines(cu8_bytes, flags):
 def ref_stage_dump(cu8_bytes, chain, o):
     exe = os.path.join(REF_DIR, "ref_stages")
     out = subprocess.run([exe, str(chain), str(o.decimation), str(int(o.accurate_atan)),
-                          str(int(o.remove_dc)), str(int(o.simultaneous))],
+                          str(int(o.remove_dc)), str(int(o.simultaneous)), str(int(o.prefilter))],
                          input=bytes(cu8_bytes), capture_output=True, check=True).stdout
     return np.frombuffer(out, np.float32).reshape(-1, 6)

@@ -45,9 +45,11 @@ def check_golden(pkg, lib, golden_lines, only=None, **tuning):
     return total
 
 
-def check_stages(pkg, lib, cu8, flags, **tuning):
+def check_stages(pkg, lib, cu8, flags, orc_extra=None, **tuning):
     """dphi (post-FIR) and (unsigned)rssi of the demod kernel vs the oracle, bit for bit."""
     o = orc.opts_from_flags(flags)
+    for k, v in (orc_extra or {}).items():
+        setattr(o, k, v)
     gran = 4096 * max(1, o.decimation)          # one batch: the stage tap returns the last batch only
     data = np.ascontiguousarray(cu8[:len(cu8) // gran * gran], np.uint8)
     with pkg.WmbusB200(flags, lib=lib, **tuning) as ctx:
@@ -253,6 +255,33 @@ def check_cw_interferer(pkg, lib):
         assert got == want
         if tuning:
             assert st.lanes_rerun > 50, "the capture is meant to refute lanes (%d of %d)" % (st.lanes_rerun, st.lanes_run)
+
+
+def check_prefilter(pkg, lib):
+    """the reference's dormant 23-tap pre-decimation low-pass as the front end (opts.prefilter = 1).  The
+    oracle's version is pinned against the reference's own functions (tests/test_oracle.py); here the product against
+    the oracle: every dphi / rssi sample, and the lines, without and with the mixer, through several batches."""
+    import importlib
+    synth = importlib.import_module("rtl-wmbus_b200.synth")
+    cu8 = load_fixture("synth_mixed_1m6.cu8")
+    for flags in ("", "-a", "-o"):
+        check_stages(pkg, lib, cu8[:1 << 19], flags, orc_extra=dict(prefilter=1), prefilter=1)
+    cap, _ = synth.synth_capture(1 << 21, fs=1.6e6, emitters=synth.default_emitters("mixed"), seed=0xB2000081, center_shift_hz=325e3)
+    shifted = np.ascontiguousarray(cap.numpy())
+    check_stages(pkg, lib, shifted[:1 << 19], "-s", orc_extra=dict(prefilter=1), prefilter=1)
+    for data, flags in ((cu8, "-v"), (shifted, "-v -s")):
+        o = orc.opts_from_flags(flags)
+        o.prefilter = 1
+        want = [orc.blank_ts(l) for l in orc.run_lines(data, o)]
+        assert len(want) >= 8
+        got, _ = run_lines(pkg, lib, data, flags, prefilter=1)
+        assert got == want
+        got, _ = run_lines(pkg, lib, data, flags, prefilter=1, max_batch_mib=1, pushes=[4096 * 2 * 7, 1 << 19, 12345])
+        assert got == want
+    # only defined at 1.6 MS/s
+    o = pkg.opts_from_flags(lib, "-d 3", prefilter=1)
+    ctx = C.c_void_p()
+    assert lib.wmb_create(C.byref(o), 0, C.byref(ctx)) == -1 and b"decimation" in lib.wmb_last_error()
 
 
 def check_sample_index_wrap(pkg, lib):

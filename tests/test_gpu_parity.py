@@ -159,3 +159,7 @@ def test_many_carriers_per_capture(pkg, gpu_lib):
 
 def test_cw_interferer_refutes_lanes_not_lines(pkg, gpu_lib):
     pc.check_cw_interferer(pkg, gpu_lib)
+
+
+def test_dormant_prefilter_front_end(pkg, gpu_lib):
+    pc.check_prefilter(pkg, gpu_lib)

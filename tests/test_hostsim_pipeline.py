@@ -82,3 +82,7 @@ def test_many_carriers_per_capture(pkg, hostsim_lib):
 
 def test_cw_interferer_refutes_lanes_not_lines(pkg, hostsim_lib):
     pc.check_cw_interferer(pkg, hostsim_lib)
+
+
+def test_dormant_prefilter_front_end(pkg, hostsim_lib):
+    pc.check_prefilter(pkg, hostsim_lib)

@@ -91,6 +91,23 @@ def test_oracle_stages_match_reference_leaf_functions(orc_mod):
 
 
 @needs_ref
+def test_oracle_prefilter_matches_the_reference_dormant_functions(orc_mod):
+    """the oracle with the dormant 23-tap pre-decimation low-pass (rtl_wmbus.c:197-239) against the
+    reference's own lp_fir_butter_1600kHz_160kHz_200kHz_* driven by ref_stages.c, every stage, both chains."""
+    for name, flags in [("excerpt_samples2_a.cu8", ""), ("synth_mixed_1m6.cu8", "-o"), ("synth_mixed_1m6.cu8", "-a")]:
+        cu8 = load_fixture(name)
+        o = orc_mod.opts_from_flags(flags)
+        o.prefilter = 1
+        for chain in (0, 1):
+            st = orc_mod.stages(cu8, o, chain)
+            ref = orc_mod.ref_stage_dump(cu8.tobytes(), chain, o)
+            assert len(ref) == st["M"]
+            for j, k in enumerate(["si", "sq", "dphi_raw", "dphi", "rssi"]):
+                assert np.array_equal(ref[:, j].view(np.uint32), st[k].view(np.uint32)), (name, flags, chain, k)
+            assert np.array_equal(ref[:, 5].astype(np.uint8), st["clk"]), (name, flags, chain, "clk")
+
+
+@needs_ref
 def test_synthetic_generator_is_decoded_by_the_reference(orc_mod, pkg):
     """Every telegram type the generator plants (T1, C1-A, C1-B, S1) comes out of the reference with CRC_OK=1."""
     import importlib
