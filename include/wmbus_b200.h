@@ -194,9 +194,9 @@ typedef struct wmb_stats {
     double   host_batch_ms;       /* cumulative wall time in the enqueue+verify part of batches */
     double   host_gather_ms;      /* cumulative wall time gathering candidate frames          */
     double   host_decode_ms;      /* cumulative wall time in the host framers                 */
-    uint64_t overflow_batches;    /* batches whose candidates did not fit a device table (frame words, datagram pool,
-                                     access-code matches, pending candidates) and lost some or all of their lines; the
-                                     stream goes on.  Takes an input no receiver produces: sized for one access-code
+    uint64_t overflow_batches;    /* batches whose bits or candidates did not fit a device table (a run-length lane's
+                                     event buffer, frame words, datagram pool, access-code matches, pending
+                                     candidates) and may have lost lines; the stream goes on.  Takes an input no receiver produces: sized for one access-code
                                      match per 256 decimated samples, sustained over a whole batch                 */
 } wmb_stats;
 

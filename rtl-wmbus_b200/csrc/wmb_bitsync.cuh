@@ -701,6 +701,9 @@ struct K2mParams {
     const RlState *carry;
     uint32_t *rerun;
     uint32_t *errors;           /* bit0 event overflow, bit1 run-length tracker out of range  */
+    uint32_t *lane_err;         /* [lanes] the same bits per lane: a speculative lane that started from the wrong state may
+                                   overflow its buffer or leave the tracker's range without the stream doing so -- only
+                                   what a lane's LAST run (the verified one) reports counts, and K2c collects it        */
     uint32_t mode;
     const uint32_t *run_if;     /* optional: the whole pass happens only if this word is nonzero (T1/C1 fallback
                                    from the two-phase path, decided on the device)                */
@@ -899,7 +902,8 @@ WMB_D void k2m_lane(const K2mParams &p, uint32_t lane)
     p.st_end[lane] = s;
     p.cnt[lane] = o.n < o.cap ? o.n : o.cap;
     if (o.overflow) err |= 1u;
-    if (err) {
+    if (p.lane_err) p.lane_err[lane] = err;
+    else if (err) {
 #ifdef WMB_HOSTSIM
         *p.errors |= err;
 #else

@@ -98,6 +98,7 @@ struct ChainBuf {
     IirState *ia_carry = nullptr;
     RlState *rl_start = nullptr, *rl_end = nullptr, *rl_carry = nullptr;
     uint32_t *rerun = nullptr;
+    uint32_t *lane_err = nullptr;   /* [lanes_max] error bits of the run-length lanes' verified runs */
     /* two-phase run-length path (T1/C1) */
     uint64_t *p1_rec = nullptr; uint32_t *p1_cnt = nullptr; uint64_t *p1_base = nullptr;
     P1State *p1_start = nullptr, *p1_end = nullptr; uint32_t *p1_rerun = nullptr;
@@ -625,6 +626,7 @@ static int ctx_alloc(wmb_ctx *c)
         TRY(dev_alloc(c, &b.rl_end, c->lanes_max));
         TRY(dev_alloc(c, &b.rl_carry, 1));
         TRY(dev_alloc(c, &b.rerun, c->lanes_max, true));
+        TRY(dev_alloc(c, &b.lane_err, c->lanes_max, true));
         if (ch == 0 && c->two_phase && c->o.rla_enabled) {
             TRY(dev_alloc(c, &b.p1_rec, (size_t)c->p1_lanes_max * K2P1_CAP));
             TRY(dev_alloc(c, &b.p1_cnt, c->p1_lanes_max, true));
@@ -1043,7 +1045,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
                 if ((uint64_t)lanes * p.cap > c->cap_words_rl) return set_err(WMB_E_INVAL, "internal: event buffers too small for C=%u", C);
                 p.ev = b.s[WMB_ALGO_RLA].ev; p.cnt = b.s[WMB_ALGO_RLA].cnt;
                 p.st_start = b.rl_start; p.st_end = b.rl_end; p.carry = b.rl_carry; p.rerun = b.rerun;
-                p.errors = c->d_errors;
+                p.errors = c->d_errors; p.lane_err = b.lane_err;
                 p.mode = 0; p.run_if = run_if;
                 if (!run_if) c->st.lanes_run += lanes;
                 return WMB_OK;
@@ -1057,6 +1059,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
                 q.m_base = (int64_t)c->m_consumed;
                 q.ring = s.ring; q.ring_mask = s.ring_cap - 1; q.sd = s.sd; q.cand = s.cand; q.cand_cap = c->cand_cap;
                 q.agg = s.agg; q.rssi = b.set[set].rssi + c->W; q.run_if = run_if;
+                q.lane_err = b.lane_err; q.errors = c->d_errors;
                 return launch_k2c(c, q, st);
             };
             /* S1 (and a forced T1/C1) beside the two-phase path of T1/C1 */
@@ -1214,11 +1217,12 @@ static int consume_oldest(wmb_ctx *c)
     const size_t lb = (size_t)f.slot * c->slot_cap, pb = (size_t)f.slot * c->slot_pool;
     const BatchRec r = c->h_rec[f.slot];
     const uint32_t err = r.errors;
-    if (err & 1u) return set_err(WMB_E_OVERFLOW, "bit event buffer overflow (pathological input)");
     if (err & 2u) return set_err(WMB_E_OVERFLOW, "run-length tracker left its defined range (the reference would spin here)");
     if (err & 32u) return set_err(WMB_E_OVERFLOW, "bit event ring overflow");
-    /* frame words (4), datagram pool (8), access-code matches (16), pending candidates (64): the device dropped what did
-     * not fit and cleared the flags; the reference would have gone on decoding, so does the stream */
+    /* lane event buffer (1: a run-length lane emitted more than one bit per four samples plus one capped edge -- the
+     * tracker's bit length has collapsed to a fraction of a sample), frame words (4), datagram pool (8), access-code
+     * matches (16), pending candidates (64): the device dropped what did not fit and cleared the flags; the reference
+     * would have gone on decoding, so does the stream */
     if (err & K3_SOFT_ERRORS) c->st.overflow_batches++;
     if (err & 256u) return set_err(WMB_E_STATE, "internal: lane verification does not converge");
     bool more = false;

@@ -729,12 +729,21 @@ struct K2cParams {
     uint64_t *agg;                  /* [SCAN_THREADS] scan scratch                         */
     const uint8_t *rssi;            /* (unsigned)rssi, index 0 = batch sample 0            */
     const uint32_t *run_if;         /* optional: only if this word is nonzero              */
+    const uint32_t *lane_err;       /* [lanes] error bits of each lane's verified run (K2mParams.lane_err) */
+    uint32_t *errors;
 };
 
 WMB_D void k2c_compact(const K2cParams &p, uint32_t lane, int tid, int nthr)
 {
     if (lane >= p.lanes) return;
     if (p.run_if && !*p.run_if) return;
+    if (tid == 0 && p.lane_err && p.lane_err[lane]) {
+#ifdef WMB_HOSTSIM
+        *p.errors |= p.lane_err[lane];
+#else
+        atomicOr(p.errors, p.lane_err[lane]);
+#endif
+    }
     const uint32_t n = p.cnt[lane];
     const uint64_t base = p.base[lane];
     const uint32_t *src = p.ev + (size_t)lane * p.cap;
@@ -822,7 +831,7 @@ struct K3Params {
     uint32_t final;                 /* end of input: nothing is carried over                */
 };
 
-#define K3_SOFT_ERRORS (4u | 8u | 16u | 64u)
+#define K3_SOFT_ERRORS (1u | 4u | 8u | 16u | 64u)
 WMB_D void k3_flag(uint32_t *errors, uint32_t bit)
 {
 #ifdef WMB_HOSTSIM
@@ -861,8 +870,8 @@ WMB_D void k3_publish(const K3Params &p)
     const GatherDev &g = *p.gd;
     BatchRec r;
     r.n = g.n; r.n_words = g.n_words; r.pool_n = g.pool_n; r.errors = *p.errors;
-    /* the capacity overflows (frame words 4, datagram pool 8, matches 16, pending candidates 64) cost this batch's
-     * candidates, not the stream: the host counts them, the flags start the next batch clean */
+    /* the capacity overflows (lane event buffer 1, frame words 4, datagram pool 8, matches 16, pending candidates 64)
+     * cost bits or candidates of this batch, not the stream: the host counts them, the flags start the next batch clean */
     *p.errors &= ~K3_SOFT_ERRORS;
     r.lanes_rerun = g.lanes_rerun; r.rl_fallbacks = g.rl_fallbacks;
     for (int k = 0; k < WMB_N_STREAMS; k++) { r.total[k] = g.total_prev[k]; r.n_cand_total[k] = g.n_cand_total[k]; }

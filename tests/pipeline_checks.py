@@ -284,6 +284,26 @@ def check_prefilter(pkg, lib):
     assert lib.wmb_create(C.byref(o), 0, C.byref(ctx)) == -1 and b"decimation" in lib.wmb_last_error()
 
 
+def check_lane_event_overflow(pkg, lib):
+    """Found by tools/fuzz_hostsim.py (seed 22, case 525): 0.8 MS/s, an in-channel CW tone under three emitters.  The
+    T1/C1 run-length tracker's bit length collapses to a fraction of a sample and single edges emit tens of thousands of
+    bits (193 k in one 1024-sample stretch): more than a lane's event buffer holds.  That used to end the stream
+    (WMB_E_OVERFLOW); now the lane keeps what fits, the batch is counted in wmb_stats.overflow_batches and the lines are
+    still the reference's -- there is no telegram in such a stretch."""
+    import fuzz_cases
+    c = fuzz_cases.case(22, 525)
+    assert c["flags"] == "-v -d 1" and c["n"] == 827392
+    cu8 = fuzz_cases.build_capture(c)
+    want = oracle_lines(cu8, c["flags"])
+    assert len(want) == 7
+    seen = 0
+    for tuning, pushes in ((dict(), None), (dict(chunk_samples=8192), None), (c["tuning"], c["pushes"]), (dict(max_batch_mib=1, chunk_samples=4096), None)):
+        got, st = run_lines(pkg, lib, cu8, c["flags"], pushes=pushes, **tuning)
+        assert got == want, tuning
+        seen += st.overflow_batches
+    assert seen >= 2, "the capture is meant to overflow a lane's event buffer"
+
+
 def check_sample_index_wrap(pkg, lib):
     """The device keeps 40 bits of the decimated sample index in its bit events (15.9 days of streaming at 800 kS/s).
     A stream positioned just below 2^40 must decode the telegrams that span the wrap exactly like a fresh stream:

@@ -86,3 +86,7 @@ def test_cw_interferer_refutes_lanes_not_lines(pkg, hostsim_lib):
 
 def test_dormant_prefilter_front_end(pkg, hostsim_lib):
     pc.check_prefilter(pkg, hostsim_lib)
+
+
+def test_lane_event_overflow_costs_bits_not_the_stream(pkg, hostsim_lib):
+    pc.check_lane_event_overflow(pkg, hostsim_lib)
