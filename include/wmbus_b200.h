@@ -195,8 +195,8 @@ typedef struct wmb_stats {
     double   host_gather_ms;      /* cumulative wall time gathering candidate frames          */
     double   host_decode_ms;      /* cumulative wall time in the host framers                 */
     uint64_t overflow_batches;    /* batches whose bits or candidates did not fit a device table (a run-length lane's
-                                     event buffer, frame words, datagram pool, access-code matches, pending
-                                     candidates) and may have lost lines; the stream goes on.  Takes an input no receiver produces: sized for one access-code
+                                     event buffer, a stream's event ring, frame words, datagram pool, access-code
+                                     matches, pending candidates) and may have lost lines; the stream goes on.  Takes an input no receiver produces: sized for one access-code
                                      match per 256 decimated samples, sustained over a whole batch                 */
 } wmb_stats;
 

@@ -1218,7 +1218,6 @@ static int consume_oldest(wmb_ctx *c)
     const BatchRec r = c->h_rec[f.slot];
     const uint32_t err = r.errors;
     if (err & 2u) return set_err(WMB_E_OVERFLOW, "run-length tracker left its defined range (the reference would spin here)");
-    if (err & 32u) return set_err(WMB_E_OVERFLOW, "bit event ring overflow");
     /* lane event buffer (1: a run-length lane emitted more than one bit per four samples plus one capped edge -- the
      * tracker's bit length has collapsed to a fraction of a sample), frame words (4), datagram pool (8), access-code
      * matches (16), pending candidates (64): the device dropped what did not fit and cleared the flags; the reference

@@ -831,7 +831,7 @@ struct K3Params {
     uint32_t final;                 /* end of input: nothing is carried over                */
 };
 
-#define K3_SOFT_ERRORS (1u | 4u | 8u | 16u | 64u)
+#define K3_SOFT_ERRORS (1u | 4u | 8u | 16u | 32u | 64u)
 WMB_D void k3_flag(uint32_t *errors, uint32_t bit)
 {
 #ifdef WMB_HOSTSIM
@@ -846,18 +846,23 @@ WMB_D void k3_plan(const K3Params &p)
 {
     GatherDev &g = *p.gd;
     uint32_t n = 0;
+    bool overrun = false;
     for (int k = 0; k < WMB_N_STREAMS; k++) {
         g.off[k] = n;
         if (!p.sd[k]) continue;
         StreamDev &sd = *p.sd[k];
         if (sd.cand_overflow) { k3_flag(p.errors, 16u); sd.cand_overflow = 0; sd.n_cand = p.cand_cap; }
-        if (sd.total - g.total_prev[k] > p.ring_mask[k] + 1 - WMB_MAXBITS - 64) k3_flag(p.errors, 32u);   /* ring overrun */
+        /* ring overrun: the batch wrote more events into a stream's ring than it holds (a run-length tracker whose bit
+         * length has collapsed, lane after lane): bits of candidates may be overwritten -- no candidate of this batch is
+         * decoded, pending ones included */
+        if (sd.total - g.total_prev[k] > p.ring_mask[k] + 1 - WMB_MAXBITS - 64) { k3_flag(p.errors, 32u); overrun = true; }
         g.total_prev[k] = sd.total;
         g.n_cand_total[k] += sd.n_cand;
         n += g.n_pend[k] + sd.n_cand;
     }
     g.off[WMB_N_STREAMS] = n;
-    if (n > p.cand_cap || n > p.log_cap) { k3_flag(p.errors, 64u); n = 0; for (int k = 0; k <= WMB_N_STREAMS; k++) g.off[k] = 0; }
+    if (n > p.cand_cap || n > p.log_cap) { k3_flag(p.errors, 64u); overrun = true; }
+    if (overrun) { n = 0; for (int k = 0; k <= WMB_N_STREAMS; k++) g.off[k] = 0; }
     g.n = n;
     g.base = p.log_base;
     g.n_words = 0;
@@ -870,7 +875,7 @@ WMB_D void k3_publish(const K3Params &p)
     const GatherDev &g = *p.gd;
     BatchRec r;
     r.n = g.n; r.n_words = g.n_words; r.pool_n = g.pool_n; r.errors = *p.errors;
-    /* the capacity overflows (lane event buffer 1, frame words 4, datagram pool 8, matches 16, pending candidates 64)
+    /* the capacity overflows (lane event buffer 1, frame words 4, datagram pool 8, matches 16, ring 32, pending candidates 64)
      * cost bits or candidates of this batch, not the stream: the host counts them, the flags start the next batch clean */
     *p.errors &= ~K3_SOFT_ERRORS;
     r.lanes_rerun = g.lanes_rerun; r.rl_fallbacks = g.rl_fallbacks;
