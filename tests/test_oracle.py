@@ -120,3 +120,23 @@ def test_synthetic_generator_is_decoded_by_the_reference(orc_mod, pkg):
     want = {em[p.emitter].expected_fields(p.k)[2] for p in plan}
     got = {l.split(";")[8] for l in lines if l.split(";")[2] == "1"}
     assert len(want & got) >= 0.8 * len(want)
+
+
+@needs_ref
+def test_oracle_matches_reference_binary_on_random_captures(orc_mod):
+    """The fuzzer's captures and flag sets (tests/fuzz_cases.py: 1-4 emitters of every mode, noise sigma 1-20, CW
+    interferers, dead air, every flag of the reference's getopt string) through the unmodified reference binary and
+    through the oracle: same lines.  tools/fuzz_oracle_vs_ref.py is the open-ended version of this loop."""
+    import fuzz_cases
+    rng = np.random.default_rng(20260924)
+    cases = lines = 0
+    while cases < 40:
+        c = fuzz_cases.draw_case(rng)
+        if c["prefilter"]:
+            continue
+        cu8 = fuzz_cases.build_capture(c)
+        want = orc_mod.ref_lines(cu8, c["flags"])
+        got = [orc_mod.blank_ts(l) for l in orc_mod.run_lines(cu8, orc_mod.opts_from_flags(c["flags"]))]
+        assert got == want, (cases, c["flags"], len(got), len(want))
+        cases += 1; lines += len(want)
+    assert lines > 100
