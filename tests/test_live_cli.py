@@ -168,3 +168,49 @@ def test_flow_watchdog_cpu_build(hostsim_lib, mode):
 
 def test_flow_watchdog_quiet_cpu_build(hostsim_lib):
     check_watchdog_quiet(_sim_exe(hostsim_lib))
+
+
+# ---- the process contract of SURVEY.md 8(b), argv by argv against the reference binary itself ----
+
+ARGVS = ["-h", "-V", "-x", "-d", "-p", "-p X", "-p s", "-p t", "-r 1", "-r 0", "-t 2", "-t 0", "-d abc", "-d 0", "-d 1", "-d 9 -s",
+         "-r 0 -t 0", "-p S -p T", "-o -a -v -s", "", "-v", "-o", "-a -v", "-v -r 0 -p S", "-f", "-f -v -p S", "stray", "-v stray -o", "-d 3 -V", "-V -x", "-x -V"]
+
+
+def _normalise(text, exe):
+    """program name (getopt's and the usage text's argv[0]) and the version block are the builds' own"""
+    out = []
+    for l in text.decode().replace(exe, "EXE").split("\n"):
+        if l.startswith("rtl_wmbus: ") and "monitoring flow" not in l and "flow stopped" not in l.lower():
+            l = "rtl_wmbus: VERSION"
+        out.append(l)
+    return out
+
+
+def check_argv_matrix(exe, real_stdin):
+    ref = orc.ref_binary()
+    cu8 = bytes(load_fixture("synth_mixed_1m6.cu8")) if real_stdin else b""
+    for args in ARGVS:
+        a = subprocess.run([ref] + args.split(), input=cu8, capture_output=True, timeout=60)
+        b = subprocess.run([exe] + args.split(), input=cu8, capture_output=True, timeout=60)
+        assert a.returncode == b.returncode, (args, a.returncode, b.returncode, b.stderr)
+        assert _normalise(a.stderr, ref) == _normalise(b.stderr, exe), (args, a.stderr, b.stderr)
+        la, lb = _normalise(a.stdout, ref), _normalise(b.stdout, exe)
+        if a.returncode == 0 and la[0] == "rtl_wmbus: VERSION":     # `-V`: name line + the build's commit / ABI line (rtl_wmbus.c:886-890)
+            assert lb[0] == la[0] and len(lb) == len(la)
+            continue
+        blank = lambda ls: [orc.blank_ts(l) if l.count(";") >= 7 else l for l in ls]
+        assert blank(la) == blank(lb), (args, la[:3], lb[:3])
+
+
+@pytest.mark.skipif(orc.ref_binary() is None, reason="compiled reference (oracle/_ref) not present")
+def test_argv_matrix_matches_the_reference_binary_cpu_build(hostsim_lib):
+    """getopt string, usage text, exit codes, `-V`, stray operands, repeated options, and the decoded lines of a short
+    capture for every accepted flag set: the reference binary and the drop-in host program side by side
+    (rtl_wmbus.c:869-967)."""
+    check_argv_matrix(_sim_exe(hostsim_lib), real_stdin=True)
+
+
+@gpu
+@pytest.mark.skipif(orc.ref_binary() is None, reason="compiled reference (oracle/_ref) not present")
+def test_argv_matrix_matches_the_reference_binary(pkg, gpu_lib):
+    check_argv_matrix(_exe(pkg), real_stdin=True)
