@@ -74,8 +74,12 @@ typedef struct wmb_opts {
      * table, rtl_wmbus.c:974-993), |offset| <= fs / 2.  The reference's -s is {+13, -13}.  A capture with more than two
      * carriers is decoded by several contexts over the same input (shard.decode_carriers in the Python mirror). */
     int32_t  carrier_25khz[2];
-    /* SURVEY 8f N4 -- 1: the reference's dormant 23-tap pre-decimation low-pass (lp_fir_butter_1600kHz_160kHz_200kHz_*,
-     * rtl_wmbus.c:197-239, never called upstream) takes the place of the moving averages in front of the decimation.
+    /* SURVEY 8f N4 -- one of the reference's dormant pre-decimation low-passes (rtl_wmbus.c:197-333, never called
+     * upstream) takes the place of the moving averages in front of the decimation:
+     *   1  lp_fir_butter_1600kHz_160kHz_200kHz_{t1_c1,s1}: 23-tap float FIR through firf() (fir.h:49-72)
+     *   2  lp_ppf_butter_1600kHz_160kHz_200kHz: the same taps as a two-phase polyphase filter, ppf() (ppf.h:44-58)
+     *   3  lp_firfp_butter_1600kHz_160kHz_200kHz: 1 in 24.8 fixed point, firfp() (fir.h:106-130, fixedptc.h)
+     *   4  lp_ppffp_butter_1600kHz_160kHz_200kHz: 2 in 24.8 fixed point, ppffp() (ppf.h:69-83)
      * 1.6 MS/s only (decimation 2).  Not a switch of the reference: there are no reference lines to compare with; the
      * stages are checked against those functions themselves (oracle/ref_stages.c). */
     uint32_t prefilter;

@@ -11,9 +11,11 @@
  *
  * Built by oracle/Makefile into oracle/_ref/ref_stages (git-ignored).
  *
- *   ref_stages <chain 0|1> <decimation> <accurate 0|1> <remove_dc 0|1> <simultaneous 0|1> [prefilter 0|1] < in.cu8 > out.f32
- *   prefilter 1: the reference's dormant lp_fir_butter_1600kHz_160kHz_200kHz_* (rtl_wmbus.c:197-239) instead of the
- *   moving averages in front of the decimation
+ *   ref_stages <chain 0|1> <decimation> <accurate 0|1> <remove_dc 0|1> <simultaneous 0|1> [prefilter 0..4] < in.cu8 > out.f32
+ *   prefilter 1..4: one of the reference's dormant pre-decimation low-passes instead of the moving averages in front of
+ *   the decimation -- 1 lp_fir_butter_1600kHz_160kHz_200kHz_* (rtl_wmbus.c:197-233), 2 lp_ppf_butter_... (:258-295,
+ *   ppf.h), 3 lp_firfp_butter_... (:235-256, fixedptc), 4 lp_ppffp_butter_... (:297-333).  2..4 keep ONE filter state
+ *   for both chains, so only the requested chain's samples go through them.
  *
  * Output: per decimated sample 6 floats: si, sq, dphi_raw, dphi, rssi, clock(0/1).
  */
@@ -41,10 +43,22 @@ int main(int argc, char **argv)
             float it = (float)block[k] - 127.5f, qt = (float)block[k + 1] - 127.5f;
             float is = it, qs = qt;
             if (simul) shift_freq_plus_minus325(&it, &qt, &is, &qs, fs_kHz);
-            const float i_t1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_t1_c1(it, 0) : moving_average_t1_c1(it, 0);
-            const float q_t1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_t1_c1(qt, 1) : moving_average_t1_c1(qt, 1);
-            const float i_s1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_s1(is, 0) : moving_average_s1(is, 0);
-            const float q_s1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_s1(qs, 1) : moving_average_s1(qs, 1);
+            float i_t1, q_t1, i_s1, q_s1;
+            if (pre >= 2) {
+                const float xi = chain == 0 ? it : is, xq = chain == 0 ? qt : qs;
+                const float yi = pre == 2 ? lp_ppf_butter_1600kHz_160kHz_200kHz(xi, 0)
+                               : pre == 3 ? lp_firfp_butter_1600kHz_160kHz_200kHz(xi, 0)
+                                          : lp_ppffp_butter_1600kHz_160kHz_200kHz(xi, 0);
+                const float yq = pre == 2 ? lp_ppf_butter_1600kHz_160kHz_200kHz(xq, 1)
+                               : pre == 3 ? lp_firfp_butter_1600kHz_160kHz_200kHz(xq, 1)
+                                          : lp_ppffp_butter_1600kHz_160kHz_200kHz(xq, 1);
+                i_t1 = i_s1 = yi; q_t1 = q_s1 = yq;
+            } else {
+                i_t1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_t1_c1(it, 0) : moving_average_t1_c1(it, 0);
+                q_t1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_t1_c1(qt, 1) : moving_average_t1_c1(qt, 1);
+                i_s1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_s1(is, 0) : moving_average_s1(is, 0);
+                q_s1 = pre ? lp_fir_butter_1600kHz_160kHz_200kHz_s1(qs, 1) : moving_average_s1(qs, 1);
+            }
             if (++idx < d) continue;
             idx = 0;
             float rec[6];

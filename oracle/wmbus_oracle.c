@@ -181,14 +181,31 @@ void orc_frontend(const uint8_t *cu8, size_t n_iq, const orc_opts *o, int chain,
         }
     }
 
-    /* the dormant pre-decimation low-pass (rtl_wmbus.c:197-239: the same 23 coefficients for both chains), run through
-     * firf() (fir.h:49-72): y = sum_j b[j] x[n-j], accumulated from 0 in that order, zero history at the start */
+    /* the dormant pre-decimation low-passes (rtl_wmbus.c:197-333), one 23-tap design in four arithmetics:
+     *   1  lp_fir_butter_1600kHz_160kHz_200kHz_{t1_c1,s1} (:197-233, the same coefficients for both chains) through firf()
+     *      (fir.h:49-72): y = sum_j b[j] x[n-j], accumulated from 0 in that order, zero history at the start
+     *   2  lp_ppf_butter_1600kHz_160kHz_200kHz (:258-295) through ppf() (ppf.h:44-58): two 12-tap firf()s, the even-phase
+     *      samples through the odd coefficients (+ a zero tap), the odd-phase samples through the even ones
+     *      ("!inverted indexing of fir!"); sum = 0 at phase 0, sum += firf() at each phase; read after phase 1
+     *   3  lp_firfp_butter_1600kHz_160kHz_200kHz (:235-256) through firfp() (fir.h:106-130): 24.8 fixed point
+     *      (fixedptc.h: FIXEDPT_BITS 32, FIXEDPT_WBITS 24), sample = fixedpt_fromint(float) = (int64)x << 8 cut to 32 bits,
+     *      taps fixedpt_rconst(b) = (int32)(b * 256 + 0.5), products (int64)b * h >> 8, back through fixedpt_tofloat
+     *   4  lp_ppffp_butter_1600kHz_160kHz_200kHz (:297-333) through ppffp() (ppf.h:69-83): 2 in the arithmetic of 3 */
     static const float pre_b[23] = {
         0.000140535927, 1.102280392e-05, 0.0001309279731, 0.001356012537, 0.00551787474, 0.01499414005, 0.03160167988,
         0.05525973093, 0.08315031015, 0.1099887688, 0.1295143636, 0.1366692652, 0.1295143636, 0.1099887688, 0.08315031015,
         0.05525973093, 0.03160167988, 0.01499414005, 0.00551787474, 0.001356012537, 0.0001309279731, 1.102280392e-05,
         0.000140535927 };
-    float pre_i[23] = {0}, pre_q[23] = {0};                 /* [0] = newest */
+    static const double pre_bd[23] = {                      /* the literals as the fixedpt_rconst() macro sees them: doubles */
+        0.000140535927, 1.102280392e-05, 0.0001309279731, 0.001356012537, 0.00551787474, 0.01499414005, 0.03160167988,
+        0.05525973093, 0.08315031015, 0.1099887688, 0.1295143636, 0.1366692652, 0.1295143636, 0.1099887688, 0.08315031015,
+        0.05525973093, 0.03160167988, 0.01499414005, 0.00551787474, 0.001356012537, 0.0001309279731, 1.102280392e-05,
+        0.000140535927 };
+    int32_t pre_bx[24];
+    for (int j = 0; j < 23; j++) pre_bx[j] = (int32_t)(pre_bd[j] * 256 + (pre_bd[j] >= 0 ? 0.5 : -0.5));
+    pre_bx[23] = (int32_t)(0 * 256 + 0.5);                  /* fixedpt_rconst(0), the polyphase branch's zero tap */
+    float pre_i[24] = {0}, pre_q[24] = {0};                 /* [0] = newest */
+    int32_t prx_i[24] = {0}, prx_q[24] = {0};
 
     for (size_t k = 0; k < n_iq; k++) {
         float xi = (float)cu8[2 * k] - 127.5f;              /* :1312 */
@@ -202,12 +219,51 @@ void orc_frontend(const uint8_t *cu8, size_t n_iq, const orc_opts *o, int chain,
             else           { xi = ix + qz; xq = qx - iz; }  /* :1029-1030 (the S1 chain)    */
         }
         if (o->prefilter) {
-            memmove(pre_i + 1, pre_i, 22 * sizeof(float)); pre_i[0] = xi;
-            memmove(pre_q + 1, pre_q, 22 * sizeof(float)); pre_q[0] = xq;
+            memmove(pre_i + 1, pre_i, 23 * sizeof(float)); pre_i[0] = xi;
+            memmove(pre_q + 1, pre_q, 23 * sizeof(float)); pre_q[0] = xq;
+            memmove(prx_i + 1, prx_i, 23 * sizeof(int32_t)); prx_i[0] = (int32_t)((int64_t)xi * 256);   /* fixedpt_fromint */
+            memmove(prx_q + 1, prx_q, 23 * sizeof(int32_t)); prx_q[0] = (int32_t)((int64_t)xq * 256);
             if (++since < d) continue;                      /* the filter runs on every sample; only these outputs are used */
             since = 0;
+            /* d = 2 (the product's precondition for the 1.6 MS/s designs): the kept sample is the polyphase filter's
+             * phase 1, so [0], [2], .. are the odd-phase samples and [1], [3], .. the even-phase ones */
             float yi = 0, yq = 0;
-            for (int j = 0; j < 23; j++) { yi += pre_b[j] * pre_i[j]; yq += pre_b[j] * pre_q[j]; }
+            if (o->prefilter == 1) {
+                for (int j = 0; j < 23; j++) { yi += pre_b[j] * pre_i[j]; yq += pre_b[j] * pre_q[j]; }
+            } else if (o->prefilter == 2) {
+                float ei = 0, eq = 0, oi = 0, oq = 0;
+                for (int j = 0; j < 12; j++) {              /* phase 0: fir[0] = b[1][] = taps 1, 3, .., 21 and a zero */
+                    const float b = j < 11 ? pre_b[2 * j + 1] : 0.0f;
+                    ei += b * pre_i[2 * j + 1]; eq += b * pre_q[2 * j + 1];
+                }
+                for (int j = 0; j < 12; j++) {              /* phase 1: fir[1] = b[0][] = taps 0, 2, .., 22 */
+                    oi += pre_b[2 * j] * pre_i[2 * j]; oq += pre_b[2 * j] * pre_q[2 * j];
+                }
+                yi = 0; yi += ei; yi += oi;                 /* ppf.h:50, :53 */
+                yq = 0; yq += eq; yq += oq;
+            } else {
+                int32_t ai = 0, aq = 0;
+                if (o->prefilter == 3) {
+                    for (int j = 0; j < 23; j++) {
+                        ai += (int32_t)(((int64_t)pre_bx[j] * (int64_t)prx_i[j]) >> 8);
+                        aq += (int32_t)(((int64_t)pre_bx[j] * (int64_t)prx_q[j]) >> 8);
+                    }
+                } else {
+                    int32_t ei = 0, eq = 0, oi = 0, oq = 0;
+                    for (int j = 0; j < 12; j++) {
+                        const int32_t b = j < 11 ? pre_bx[2 * j + 1] : pre_bx[23];
+                        ei += (int32_t)(((int64_t)b * (int64_t)prx_i[2 * j + 1]) >> 8);
+                        eq += (int32_t)(((int64_t)b * (int64_t)prx_q[2 * j + 1]) >> 8);
+                    }
+                    for (int j = 0; j < 12; j++) {
+                        oi += (int32_t)(((int64_t)pre_bx[2 * j] * (int64_t)prx_i[2 * j]) >> 8);
+                        oq += (int32_t)(((int64_t)pre_bx[2 * j] * (int64_t)prx_q[2 * j]) >> 8);
+                    }
+                    ai = 0 + ei + oi; aq = 0 + eq + oq;
+                }
+                yi = (float)(ai * ((float)(1) / (float)(1 << 8)));   /* fixedpt_tofloat */
+                yq = (float)(aq * ((float)(1) / (float)(1 << 8)));
+            }
             si[m] = yi; sq[m] = yq;
             m++;
             continue;

@@ -45,8 +45,9 @@ typedef struct orc_opts {
      * sample (the reference: 13 = 325 kHz / 25 kHz) and entry vs conjugate (the sign) -- per chain.  Pinned by the
      * reference only at {+13, -13}; other carriers are this restatement's own generalisation. */
     int32_t  carrier_25khz[2];
-    /* 1: the reference's dormant 23-tap low-pass lp_fir_butter_1600kHz_160kHz_200kHz_{t1_c1,s1} (rtl_wmbus.c:197-239,
-     * never called upstream) in place of the moving averages in front of the decimation.  Pinned against
+    /* 1..4: one of the reference's dormant pre-decimation low-passes (rtl_wmbus.c:197-333, never called upstream) in
+     * place of the moving averages in front of the decimation -- 1 lp_fir_ (23-tap float FIR), 2 lp_ppf_
+     * (polyphase, ppf.h), 3 lp_firfp_, 4 lp_ppffp_ (their 24.8 fixed-point twins, fixedptc.h).  Pinned against
      * those functions themselves through ref_stages.c; there is no reference output to compare lines with. */
     uint32_t prefilter;
 } orc_opts;

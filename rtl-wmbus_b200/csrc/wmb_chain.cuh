@@ -89,6 +89,16 @@ WMB_CONSTANT float c_fir_pre[23] = {
     0.05525973093, 0.03160167988, 0.01499414005, 0.00551787474, 0.001356012537, 0.0001309279731, 1.102280392e-05,
     0.000140535927 };
 #define K1_PRE_TAPS 23
+/* the same taps as fixedpt_rconst() makes them for lp_firfp_ / lp_ppffp_butter_1600kHz_160kHz_200kHz (rtl_wmbus.c:235-256,
+ * :297-333; fixedptc.h:104 with FIXEDPT_BITS 32, FIXEDPT_WBITS 24: (int32)(b * 256 + 0.5), the literal read as a double);
+ * entry 23 is fixedpt_rconst(0), the polyphase branch's twelfth tap */
+#define WMB_FXC(R) ((int32_t)((R) * 256 + 0.5))
+WMB_CONSTANT int32_t c_fir_pre_fx[24] = {
+    WMB_FXC(0.000140535927), WMB_FXC(1.102280392e-05), WMB_FXC(0.0001309279731), WMB_FXC(0.001356012537), WMB_FXC(0.00551787474),
+    WMB_FXC(0.01499414005), WMB_FXC(0.03160167988), WMB_FXC(0.05525973093), WMB_FXC(0.08315031015), WMB_FXC(0.1099887688),
+    WMB_FXC(0.1295143636), WMB_FXC(0.1366692652), WMB_FXC(0.1295143636), WMB_FXC(0.1099887688), WMB_FXC(0.08315031015),
+    WMB_FXC(0.05525973093), WMB_FXC(0.03160167988), WMB_FXC(0.01499414005), WMB_FXC(0.00551787474), WMB_FXC(0.001356012537),
+    WMB_FXC(0.0001309279731), WMB_FXC(1.102280392e-05), WMB_FXC(0.000140535927), WMB_FXC(0) };
 
 WMB_CONSTANT float c_fir_s1[46] = {
     -0.000649081282, -0.0009491938209, -0.001361601657, -0.001910785234, -0.002570133495,

@@ -691,8 +691,8 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
     if (o->decimation > 64) return set_err(WMB_E_INVAL, "decimation %u not supported (max 64)", o->decimation);
     if (o->simultaneous && o->decimation == 0) return set_err(WMB_E_INVAL, "-s with -d 0 is undefined in the reference");
     if (o->simultaneous > 2) return set_err(WMB_E_INVAL, "simultaneous: 0, 1 (-s) or 2 (explicit carriers)");
-    if (o->prefilter > 1) return set_err(WMB_E_INVAL, "prefilter: 0 (moving averages) or 1 (the 23-tap low-pass)");
-    if (o->prefilter && o->decimation != 2) return set_err(WMB_E_INVAL, "the 23-tap pre-decimation low-pass is a 1.6 MS/s design: decimation must be 2");
+    if (o->prefilter > 4) return set_err(WMB_E_INVAL, "prefilter: 0 (moving averages), 1 (23-tap FIR), 2 (polyphase), 3 / 4 (their fixed-point twins)");
+    if (o->prefilter && o->decimation != 2) return set_err(WMB_E_INVAL, "the pre-decimation low-passes are 1.6 MS/s designs: decimation must be 2");
     if (o->simultaneous == 2)
         for (int ch = 0; ch < 2; ch++)
             if (o->carrier_25khz[ch] == INT32_MIN || 2 * (o->carrier_25khz[ch] < 0 ? -o->carrier_25khz[ch] : o->carrier_25khz[ch]) > (int32_t)(o->decimation * 32u))
@@ -898,7 +898,7 @@ static int run_batch(wmb_ctx *c, const uint8_t *src, size_t nbytes, cudaEvent_t 
     k1.n_hist_iq = c->hist_iq;
     k1.M = M; k1.d = d; k1.chains = c->chains;
     k1.accurate = c->o.accurate_atan; k1.mix = c->o.simultaneous ? 1u : 0u;
-    k1.prefilter = c->o.prefilter ? 1u : 0u;
+    k1.prefilter = c->o.prefilter;
     k1.lut_n = c->o.simultaneous ? (c->o.decimation * 800u) / 25u : 1u;
     k1.mix_k0 = (uint32_t)(c->iq_consumed % k1.lut_n);
     for (int ch = 0; ch < WMB_N_CHAINS; ch++) {

@@ -39,7 +39,7 @@ struct K1Params {
     uint32_t chains;            /* bit0: T1/C1, bit1: S1                                     */
     uint32_t accurate;          /* 0 with -a                                                 */
     uint32_t mix;               /* -s (or explicit carriers)                                 */
-    uint32_t prefilter;         /* 1: the dormant 23-tap low-pass instead of the box filters (d = 2 only; own kernel instance) */
+    uint32_t prefilter;         /* 1..4: one of the dormant pre-decimation low-passes instead of the box filters (d = 2 only; own kernel instance) */
     uint32_t lut_n;             /* mixer table length (fs_kHz/25)                            */
     uint32_t mix_k0;            /* (index of batch sample 0 in the stream) mod lut_n          */
     uint32_t mix_step[WMB_N_CHAINS];  /* table entries per sample = |carrier offset| / 25 kHz, mod lut_n (the reference: 13) */
@@ -309,21 +309,78 @@ WMB_D void k1_convert_float(const K1Params &p, K1Smem &sm, const uint8_t *raw, i
     }
 }
 
+/* p.prefilter: 1 the 23-tap float FIR through firf(); 2 the float polyphase filter (ppf.h:44-58, rtl_wmbus.c:258-295): the
+ * even-phase samples through taps 1, 3, .., 21 and a zero tap, the odd-phase samples through taps 0, 2, .., 22, each
+ * branch a firf() accumulated from 0, then (0 + even) + odd -- the kept sample of d = 2 is the filter's phase 1;
+ * 3 / 4 the 24.8 fixed-point twins of 1 / 2 (firfp(), ppffp(); fixedptc.h): sample (int64)x << 8, products >> 8, sum / 256 */
 WMB_D void k1_prefir(const K1Params &p, K1Smem &sm, int tid)
 {
     const float *xi = (const float *)sm.v, *xq = sm.xq;
+    const uint32_t mode = p.prefilter;
     for (int r = tid; r < K1_TILE + K1_HALO; r += K1_THREADS) {
         const int jend = (int)p.d * r + (int)p.d - 1 + K1_BOX_MAX;     /* newest input sample of row r (as in k1_box) */
+        /* the window of the first three rows of a tile starts left of what the tile holds (22 or 23 samples back, the
+         * overhang is 16): those rows are recomputed halo that nothing reads (the FIR, RSSI and discriminator of the
+         * tile's own outputs reach back 46 rows at most) */
         float yi = 0.0f, yq = 0.0f;
+        if (mode == 1u) {
 #pragma unroll
-        for (int j = 0; j < K1_PRE_TAPS; j++) {
-            /* the window of the first three rows of a tile starts left of what the tile holds (22 samples back, the
-             * overhang is 16): those rows are recomputed halo that nothing reads (the FIR, RSSI and discriminator of
-             * the tile's own outputs reach back 46 rows at most) */
-            const int q = jend - j;
-            const float a = q >= 0 ? xi[q] : 0.0f, b = q >= 0 ? xq[q] : 0.0f;
-            yi = wmb_fadd(yi, wmb_fmul(c_fir_pre[j], a));
-            yq = wmb_fadd(yq, wmb_fmul(c_fir_pre[j], b));
+            for (int j = 0; j < K1_PRE_TAPS; j++) {
+                const int q = jend - j;
+                const float a = q >= 0 ? xi[q] : 0.0f, b = q >= 0 ? xq[q] : 0.0f;
+                yi = wmb_fadd(yi, wmb_fmul(c_fir_pre[j], a));
+                yq = wmb_fadd(yq, wmb_fmul(c_fir_pre[j], b));
+            }
+        } else if (mode == 2u) {
+            float ei = 0.0f, eq = 0.0f, oi = 0.0f, oq = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                const int q = jend - 1 - 2 * j;
+                const float c = j < 11 ? c_fir_pre[2 * j + 1] : 0.0f;
+                const float a = q >= 0 ? xi[q] : 0.0f, b = q >= 0 ? xq[q] : 0.0f;
+                ei = wmb_fadd(ei, wmb_fmul(c, a));
+                eq = wmb_fadd(eq, wmb_fmul(c, b));
+            }
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                const int q = jend - 2 * j;
+                const float a = q >= 0 ? xi[q] : 0.0f, b = q >= 0 ? xq[q] : 0.0f;
+                oi = wmb_fadd(oi, wmb_fmul(c_fir_pre[2 * j], a));
+                oq = wmb_fadd(oq, wmb_fmul(c_fir_pre[2 * j], b));
+            }
+            yi = wmb_fadd(wmb_fadd(0.0f, ei), oi);
+            yq = wmb_fadd(wmb_fadd(0.0f, eq), oq);
+        } else {
+            int32_t ai = 0, aq = 0;
+            if (mode == 3u) {
+#pragma unroll
+                for (int j = 0; j < K1_PRE_TAPS; j++) {
+                    const int q = jend - j;
+                    const int32_t a = q >= 0 ? (int32_t)xi[q] * 256 : 0, b = q >= 0 ? (int32_t)xq[q] * 256 : 0;
+                    ai += (int32_t)(((int64_t)c_fir_pre_fx[j] * (int64_t)a) >> 8);
+                    aq += (int32_t)(((int64_t)c_fir_pre_fx[j] * (int64_t)b) >> 8);
+                }
+            } else {
+                int32_t ei = 0, eq = 0, oi = 0, oq = 0;
+#pragma unroll
+                for (int j = 0; j < 12; j++) {
+                    const int q = jend - 1 - 2 * j;
+                    const int32_t c = c_fir_pre_fx[j < 11 ? 2 * j + 1 : 23];
+                    const int32_t a = q >= 0 ? (int32_t)xi[q] * 256 : 0, b = q >= 0 ? (int32_t)xq[q] * 256 : 0;
+                    ei += (int32_t)(((int64_t)c * (int64_t)a) >> 8);
+                    eq += (int32_t)(((int64_t)c * (int64_t)b) >> 8);
+                }
+#pragma unroll
+                for (int j = 0; j < 12; j++) {
+                    const int q = jend - 2 * j;
+                    const int32_t a = q >= 0 ? (int32_t)xi[q] * 256 : 0, b = q >= 0 ? (int32_t)xq[q] * 256 : 0;
+                    oi += (int32_t)(((int64_t)c_fir_pre_fx[2 * j] * (int64_t)a) >> 8);
+                    oq += (int32_t)(((int64_t)c_fir_pre_fx[2 * j] * (int64_t)b) >> 8);
+                }
+                ai = ei + oi; aq = eq + oq;
+            }
+            yi = wmb_fmul((float)ai, 0.00390625f);                     /* fixedpt_tofloat: T * (1.0f / 256) */
+            yq = wmb_fmul((float)aq, 0.00390625f);
         }
         sm.si[r] = yi; sm.sq[r] = yq;
     }

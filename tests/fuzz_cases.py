@@ -42,7 +42,9 @@ def draw_case(rng):
     if rng.random() < 0.5: tuning["chunk_samples"] = int(rng.choice([1024, 2048, 4096, 8192]))
     if rng.random() < 0.3: tuning["warmup_samples"] = int(rng.choice([256, 1024, 8192, 32768]))
     pre = 0
-    if d == 2 and rng.random() < 0.15: pre = 1; tuning["prefilter"] = 1
+    if d == 2:                                                # (one draw at d = 2 only, as when there was one dormant filter: the cases keep their numbers)
+        u = rng.random()
+        if u < 0.15: pre = 1 + int(u / 0.15 * 4); tuning["prefilter"] = pre
     pushes = None
     if rng.random() < 0.6:
         pushes, left = [], n

@@ -258,30 +258,35 @@ def check_cw_interferer(pkg, lib):
 
 
 def check_prefilter(pkg, lib):
-    """the reference's dormant 23-tap pre-decimation low-pass as the front end (opts.prefilter = 1).  The
-    oracle's version is pinned against the reference's own functions (tests/test_oracle.py); here the product against
+    """the reference's dormant pre-decimation low-passes as the front end -- opts.prefilter = 1 the 23-tap
+    float FIR, 2 the float polyphase filter of ppf.h, 3 / 4 their 24.8 fixed-point twins (rtl_wmbus.c:197-333).  The
+    oracle's versions are pinned against the reference's own functions (tests/test_oracle.py); here the product against
     the oracle: every dphi / rssi sample, and the lines, without and with the mixer, through several batches."""
     import importlib
     synth = importlib.import_module("rtl-wmbus_b200.synth")
     cu8 = load_fixture("synth_mixed_1m6.cu8")
-    for flags in ("", "-a", "-o"):
-        check_stages(pkg, lib, cu8[:1 << 19], flags, orc_extra=dict(prefilter=1), prefilter=1)
     cap, _ = synth.synth_capture(1 << 21, fs=1.6e6, emitters=synth.default_emitters("mixed"), seed=0xB2000081, center_shift_hz=325e3)
     shifted = np.ascontiguousarray(cap.numpy())
-    check_stages(pkg, lib, shifted[:1 << 19], "-s", orc_extra=dict(prefilter=1), prefilter=1)
-    for data, flags in ((cu8, "-v"), (shifted, "-v -s")):
-        o = orc.opts_from_flags(flags)
-        o.prefilter = 1
-        want = [orc.blank_ts(l) for l in orc.run_lines(data, o)]
-        assert len(want) >= 8
-        got, _ = run_lines(pkg, lib, data, flags, prefilter=1)
-        assert got == want
-        got, _ = run_lines(pkg, lib, data, flags, prefilter=1, max_batch_mib=1, pushes=[4096 * 2 * 7, 1 << 19, 12345])
-        assert got == want
-    # only defined at 1.6 MS/s
-    o = pkg.opts_from_flags(lib, "-d 3", prefilter=1)
+    for mode in (1, 2, 3, 4):
+        for flags in ("", "-a", "-o") if mode == 1 else ("", "-a -p S"):
+            check_stages(pkg, lib, cu8[:1 << 19], flags, orc_extra=dict(prefilter=mode), prefilter=mode)
+        check_stages(pkg, lib, shifted[:1 << 19], "-s", orc_extra=dict(prefilter=mode), prefilter=mode)
+        for data, flags in ((cu8, "-v"), (shifted, "-v -s")):
+            o = orc.opts_from_flags(flags)
+            o.prefilter = mode
+            want = [orc.blank_ts(l) for l in orc.run_lines(data, o)]
+            assert len(want) >= 8
+            if mode == 1 or flags == "-v":
+                got, _ = run_lines(pkg, lib, data, flags, prefilter=mode)
+                assert got == want
+            got, _ = run_lines(pkg, lib, data, flags, prefilter=mode, max_batch_mib=1, pushes=[4096 * 2 * 7, 1 << 19, 12345])
+            assert got == want
+    # only defined at 1.6 MS/s, and there are four of them
     ctx = C.c_void_p()
+    o = pkg.opts_from_flags(lib, "-d 3", prefilter=1)
     assert lib.wmb_create(C.byref(o), 0, C.byref(ctx)) == -1 and b"decimation" in lib.wmb_last_error()
+    o = pkg.opts_from_flags(lib, "", prefilter=5)
+    assert lib.wmb_create(C.byref(o), 0, C.byref(ctx)) == -1 and b"prefilter" in lib.wmb_last_error()
 
 
 def check_lane_event_overflow(pkg, lib):

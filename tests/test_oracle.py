@@ -92,19 +92,35 @@ def test_oracle_stages_match_reference_leaf_functions(orc_mod):
 
 @needs_ref
 def test_oracle_prefilter_matches_the_reference_dormant_functions(orc_mod):
-    """the oracle with the dormant 23-tap pre-decimation low-pass (rtl_wmbus.c:197-239) against the
-    reference's own lp_fir_butter_1600kHz_160kHz_200kHz_* driven by ref_stages.c, every stage, both chains."""
-    for name, flags in [("excerpt_samples2_a.cu8", ""), ("synth_mixed_1m6.cu8", "-o"), ("synth_mixed_1m6.cu8", "-a")]:
-        cu8 = load_fixture(name)
-        o = orc_mod.opts_from_flags(flags)
-        o.prefilter = 1
-        for chain in (0, 1):
-            st = orc_mod.stages(cu8, o, chain)
-            ref = orc_mod.ref_stage_dump(cu8.tobytes(), chain, o)
-            assert len(ref) == st["M"]
-            for j, k in enumerate(["si", "sq", "dphi_raw", "dphi", "rssi"]):
-                assert np.array_equal(ref[:, j].view(np.uint32), st[k].view(np.uint32)), (name, flags, chain, k)
-            assert np.array_equal(ref[:, 5].astype(np.uint8), st["clk"]), (name, flags, chain, "clk")
+    """the oracle with each of the dormant pre-decimation low-passes (rtl_wmbus.c:197-333: 23-tap float FIR,
+    float polyphase filter of ppf.h, and the 24.8 fixed-point twins of both) against the reference's own lp_fir_ /
+    lp_ppf_ / lp_firfp_ / lp_ppffp_butter_1600kHz_160kHz_200kHz* driven by ref_stages.c, every stage, both chains, with
+    and without the -s mixer in front."""
+    shifted = load_fixture("synth_mixed_1m6.cu8")
+    for mode in (1, 2, 3, 4):
+        for name, flags in [("excerpt_samples2_a.cu8", ""), ("synth_mixed_1m6.cu8", "-o"), ("synth_mixed_1m6.cu8", "-a"),
+                            ("synth_mixed_1m6.cu8", "-s")]:
+            cu8 = load_fixture(name) if name != "synth_mixed_1m6.cu8" else shifted
+            if mode > 1 or flags == "-s":
+                cu8 = cu8[:1 << 19]
+            o = orc_mod.opts_from_flags(flags)
+            o.prefilter = mode
+            for chain in (0, 1):
+                st = orc_mod.stages(cu8, o, chain)
+                ref = orc_mod.ref_stage_dump(cu8.tobytes(), chain, o)
+                assert len(ref) == st["M"]
+                for j, k in enumerate(["si", "sq", "dphi_raw", "dphi", "rssi"]):
+                    assert np.array_equal(ref[:, j].view(np.uint32), st[k].view(np.uint32)), (mode, name, flags, chain, k)
+                assert np.array_equal(ref[:, 5].astype(np.uint8), st["clk"]), (mode, name, flags, chain, "clk")
+        if mode >= 3:       # the fixed-point outputs are multiples of 1/256, and the two orders of summation agree
+            assert np.array_equal(st["si"] * 256, np.round(st["si"] * 256))
+            fx = fx_prev if mode == 4 else None
+            fx_prev = st["si"].copy()
+            assert fx is None or np.array_equal(fx, st["si"])
+        else:
+            fl = fl_prev if mode == 2 else None
+            fl_prev = st["si"].copy()
+            assert fl is None or (not np.array_equal(fl, st["si"]) and np.allclose(fl, st["si"], atol=1e-4))
 
 
 @needs_ref
