@@ -159,11 +159,3 @@ def test_many_carriers_per_capture(pkg, gpu_lib):
 
 def test_cw_interferer_refutes_lanes_not_lines(pkg, gpu_lib):
     pc.check_cw_interferer(pkg, gpu_lib)
-
-
-def test_dormant_prefilter_front_end(pkg, gpu_lib):
-    pc.check_prefilter(pkg, gpu_lib)
-
-
-def test_lane_event_overflow_costs_bits_not_the_stream(pkg, gpu_lib):
-    pc.check_lane_event_overflow(pkg, gpu_lib)

@@ -210,11 +210,3 @@ def test_argv_matrix_matches_the_reference_binary_cpu_build(hostsim_lib):
     capture for every accepted flag set: the reference binary and the drop-in host program side by side
     (rtl_wmbus.c:869-967)."""
     check_argv_matrix(_sim_exe(hostsim_lib), real_stdin=True)
-
-
-@gpu
-@pytest.mark.skipif(orc.ref_binary() is None, reason="compiled reference (oracle/_ref) not present")
-def test_argv_matrix_matches_the_reference_binary(pkg, gpu_lib):
-    """the same on the GPU, without the three argvs that decode at a decimation no GPU test has run yet (0, 9): written
-    when the round's GPU minutes were spent, and the decimations the GPU suite covers are 1-4"""
-    check_argv_matrix(_exe(pkg), real_stdin=True, skip=("-d abc", "-d 0", "-d 9 -s"))
