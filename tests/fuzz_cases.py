@@ -1,4 +1,4 @@
-"""Random test cases for the differential fuzzer (tools/fuzz_hostsim.py) and for the regression tests that came out of
+"""Random test cases for the differential fuzzer (tests/tools/fuzz_hostsim.py) and for the regression tests that came out of
 it: draw_case() only draws parameters (cheap, so a test can skip to case k of seed s), build_capture() makes the cu8."""
 import importlib
 

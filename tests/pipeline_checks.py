@@ -290,7 +290,7 @@ def check_prefilter(pkg, lib):
 
 
 def check_lane_event_overflow(pkg, lib):
-    """Found by tools/fuzz_hostsim.py (seed 22, case 525): 0.8 MS/s, an in-channel CW tone under three emitters.  The
+    """Found by tests/tools/fuzz_hostsim.py (seed 22, case 525): 0.8 MS/s, an in-channel CW tone under three emitters.  The
     T1/C1 run-length tracker's bit length collapses to a fraction of a sample and single edges emit tens of thousands of
     bits (193 k in one 1024-sample stretch): more than a lane's event buffer holds.  That used to end the stream
     (WMB_E_OVERFLOW); now the lane keeps what fits, the batch is counted in wmb_stats.overflow_batches and the lines are

@@ -142,7 +142,7 @@ def test_synthetic_generator_is_decoded_by_the_reference(orc_mod, pkg):
 def test_oracle_matches_reference_binary_on_random_captures(orc_mod):
     """The fuzzer's captures and flag sets (tests/fuzz_cases.py: 1-4 emitters of every mode, noise sigma 1-20, CW
     interferers, dead air, every flag of the reference's getopt string) through the unmodified reference binary and
-    through the oracle: same lines.  tools/fuzz_oracle_vs_ref.py is the open-ended version of this loop."""
+    through the oracle: same lines.  tests/tools/fuzz_oracle_vs_ref.py is the open-ended version of this loop."""
     import fuzz_cases
     rng = np.random.default_rng(20260924)
     cases = lines = 0

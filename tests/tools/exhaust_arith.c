@@ -7,7 +7,7 @@
  * reduces -- and compares, bit for bit:
  *     the device function (CPU build)  ==  the oracle's restatement of fdlibm  ==  this machine's libm atan2f
  * plus the zero / axis cases.  1.6 G triples; about a minute per process, split by binade across processes:
- *     gcc -O2 -o /tmp/exhaust_arith tools/exhaust_arith.c -ldl -lm
+ *     gcc -O2 -o /tmp/exhaust_arith tests/tools/exhaust_arith.c -ldl -lm
  *     /tmp/exhaust_arith tests/hostsim/_build/libwmbus_hostsim.so oracle/_ref/liboracle.so [first_binade last_binade]
  * With `div` as third argument it walks the run-length tracker's division instead:
  * wmb_div_small(wmb_div_pow2(x, 5), n) == x / (32 * n) in C's truncating division for every |x| <= 2^29 and n = 1..8

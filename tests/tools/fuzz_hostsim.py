@@ -1,7 +1,7 @@
 """Differential fuzzing of the library's host logic and kernel phase functions on the CPU build (tests/hostsim) against
 the oracle: random captures (noise level, emitters, interferers, dead air), random flags, lane geometry and push sizes
 (tests/fuzz_cases.py draws them).
-    python tools/fuzz_hostsim.py [seconds] [seed]      prints one line per case; exits 1 at the first mismatch"""
+    python tests/tools/fuzz_hostsim.py [seconds] [seed]      prints one line per case; exits 1 at the first mismatch"""
 import importlib, sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np

@@ -1,9 +1,9 @@
 """Differential fuzzing of the ORACLE (oracle/wmbus_oracle.c, the restatement every parity test compares with) against the
 UNMODIFIED reference binary (oracle/_ref/rtl_wmbus, compiled from /root/reference by oracle/Makefile): the same random
-captures and flag sets as tools/fuzz_hostsim.py (tests/fuzz_cases.py draws them), so that the chain
+captures and flag sets as tests/tools/fuzz_hostsim.py (tests/fuzz_cases.py draws them), so that the chain
 reference binary == oracle == product is closed on random input and not only on the fixtures.  Needs the reference
 binary, i.e. the container that holds /root/reference.
-    python tools/fuzz_oracle_vs_ref.py [seconds] [seed]      one line per case; exits 1 at the first mismatch"""
+    python tests/tools/fuzz_oracle_vs_ref.py [seconds] [seed]      one line per case; exits 1 at the first mismatch"""
 import sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np

@@ -1,7 +1,7 @@
 """Time-chunk sharding under random conditions, on the CPU build: random captures and flags
 (tests/fuzz_cases.py), 2-4 chunks, halos of 2^16..2^18 decimated samples; the merged lines must be the oracle's, in
 order; a chunk whose boundary digest differs from its left neighbour's repeats with a 4x longer halo.
-    python tools/fuzz_time_chunks.py [seconds] [seed]"""
+    python tests/tools/fuzz_time_chunks.py [seconds] [seed]"""
 import importlib, sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np

@@ -1,7 +1,7 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck):
-   compute-sanitizer --tool memcheck python tools/sanitize_run.py"""
+   compute-sanitizer --tool memcheck python tests/tools/sanitize_run.py"""
 import importlib, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 pkg = importlib.import_module("rtl-wmbus_b200")
