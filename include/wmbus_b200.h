@@ -47,7 +47,7 @@ extern "C" {
 /* Options == the reference's command-line switches (rtl_wmbus.c:855-866, getopt
  * string "ofad:p:r:vVst:" at :896). */
 typedef struct wmb_opts {
-    uint32_t decimation;      /* -d N : input rate = N x 800 kS/s; default 2 (:857)        */
+    uint32_t decimation;      /* -d N : input rate = N x 800 kS/s; default 2 (:857); N <= 25 (20 MS/s) */
     uint8_t  accurate_atan;   /* 0 with -a (cross-product discriminator, :536-551)         */
     uint8_t  remove_dc;       /* -o  (:497-515)                                            */
     uint8_t  rla_enabled;     /* 0 with -r 0                                               */

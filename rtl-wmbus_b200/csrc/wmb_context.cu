@@ -688,7 +688,10 @@ extern "C" int wmb_create(const wmb_opts *o, int cuda_device, wmb_ctx **out)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return set_err(WMB_E_NODEVICE, "no CUDA device available (libwmbus_b200 has no CPU fallback)");
     if (cuda_device < 0 || cuda_device >= ndev) return set_err(WMB_E_NODEVICE, "CUDA device %d of %d", cuda_device, ndev);
-    if (o->decimation > 64) return set_err(WMB_E_INVAL, "decimation %u not supported (max 64)", o->decimation);
+    /* the demod block stages one tile of raw samples (twice) and its converted words in shared memory: 8 bytes per input
+     * sample of a 1024-row tile.  227 KB per block hold that up to decimation 25 (20 MS/s input; an RTL-SDR delivers 3.2) */
+    if (o->decimation > WMB_MAX_DECIMATION)
+        return set_err(WMB_E_INVAL, "decimation %u not supported (max %u: 20 MS/s input)", o->decimation, (unsigned)WMB_MAX_DECIMATION);
     if (o->simultaneous && o->decimation == 0) return set_err(WMB_E_INVAL, "-s with -d 0 is undefined in the reference");
     if (o->simultaneous > 2) return set_err(WMB_E_INVAL, "simultaneous: 0, 1 (-s) or 2 (explicit carriers)");
     if (o->prefilter > 4) return set_err(WMB_E_INVAL, "prefilter: 0 (moving averages), 1 (23-tap FIR), 2 (polyphase), 3 / 4 (their fixed-point twins)");

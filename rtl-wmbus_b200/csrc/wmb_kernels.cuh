@@ -92,6 +92,12 @@ size_t k1_smem_bytes(uint32_t d, uint32_t prefilter = 0)
            + (prefilter ? 4 * (size_t)k1_tile_iq(d) + 16 : 0);
 }
 
+/* largest decimation whose tile fits the 227 KB a block may have (232448 B, 1152 B of them static) */
+#define WMB_MAX_DECIMATION 25u
+static_assert(2 * 2 * (WMB_MAX_DECIMATION * (K1_TILE + K1_HALO) + K1_BOX_MAX) + 4 * (WMB_MAX_DECIMATION * (K1_TILE + K1_HALO) + K1_BOX_MAX)
+              + 3 * 4 * (K1_TILE + K1_HALO) + 2 * 4 * ((K1_TILE + K1_HALO) + (K1_TILE + K1_HALO) / 32 + 4) + 96 + K1_ATAB_BYTES + 1152 <= 232448,
+              "K1 tile of the largest decimation must fit a block's shared memory");
+
 WMB_HD void k1_carve(K1Smem &sm, uint8_t *base, uint32_t d, uint32_t prefilter = 0)
 {
     const size_t nb = (size_t)2 * k1_tile_iq(d);

@@ -51,6 +51,11 @@ def test_error_paths(pkg, hostsim_lib):
     ctx = C.c_void_p()
     assert hostsim_lib.wmb_create(C.byref(o), 0, C.byref(ctx)) == -1        # WMB_E_INVAL
     assert b"decimation" in hostsim_lib.wmb_last_error()
+    o = pkg.opts_from_flags(hostsim_lib, "-d 26")                           # one more than a block's shared memory holds
+    assert hostsim_lib.wmb_create(C.byref(o), 0, C.byref(ctx)) == -1 and b"max 25" in hostsim_lib.wmb_last_error()
+    o = pkg.opts_from_flags(hostsim_lib, "-d 25")
+    assert hostsim_lib.wmb_create(C.byref(o), 0, C.byref(ctx)) == 0
+    hostsim_lib.wmb_destroy(ctx)
     o = pkg.opts_from_flags(hostsim_lib, "")
     assert hostsim_lib.wmb_create(C.byref(o), 7, C.byref(ctx)) == -2        # WMB_E_NODEVICE
 
