@@ -5,28 +5,59 @@
  * another over all threads, which is what __syncthreads() guarantees on the device.
  */
 
+/* Order in which the simulated threads (or lanes, or blocks) of one barrier-separated phase run.  On the device they run
+ * concurrently, so nothing may depend on it: WMB_HOSTSIM_ORDER=1 runs every phase backwards, 2 in a scrambled order
+ * (i -> (a * i + b) mod n, a coprime to n).  A missing barrier or a lane that reads what another lane of the same launch
+ * writes shows up as a result that changes with the order (tests/test_hostsim_pipeline.py runs the suite's core in all three). */
+static int hs_order()
+{
+    static int o = -1;
+    if (o < 0) { const char *e = getenv("WMB_HOSTSIM_ORDER"); o = e ? atoi(e) : 0; }
+    return o;
+}
+static void hs_for_impl(uint32_t n, void (*fn)(void *, uint32_t), void *ctx)
+{
+    const int o = hs_order();
+    if (o == 1) { for (uint32_t i = n; i--;) fn(ctx, i); return; }
+    if (o == 2 && n > 2) {
+        uint64_t a = (uint64_t)(n * 0.6180339887) | 1u;
+        auto gcd = [](uint64_t x, uint64_t y) { while (y) { const uint64_t t = x % y; x = y; y = t; } return x; };
+        while (gcd(a, n) != 1) a += 2;
+        const uint64_t b = n / 3;
+        for (uint32_t i = 0; i < n; i++) fn(ctx, (uint32_t)((a * i + b) % n));
+        return;
+    }
+    for (uint32_t i = 0; i < n; i++) fn(ctx, i);
+}
+/* (one loop body per call site: the phase functions are large and fully unrolled) */
+template <class F>
+static void hs_for(uint32_t n, F f)
+{
+    hs_for_impl(n, [](void *c, uint32_t i) { (*(F *)c)(i); }, &f);
+}
+
 template <class CH>
 static void hostsim_k1_chain(const K1Params &p, K1Smem &sm, const uint8_t *raw, int64_t tile, bool need_convert)
 {
     const bool fast = (p.d == 2 && !p.mix);
-    if (need_convert) for (int t = 0; t < K1_THREADS; t++) {
+    if (need_convert) hs_for(K1_THREADS, [&](uint32_t t) {
         if (p.prefilter) k1_convert_float<CH::ID>(p, sm, raw, tile, t);
         else if (fast) k1_convert_fast(p, sm, raw, tile, t); else k1_convert<CH::ID>(p, sm, raw, tile, t);
-    }
+    });
     if (p.prefilter) {
-        for (int t = 0; t < K1_THREADS; t++) k1_prefir(p, sm, t);
-        for (int t = 0; t < K1_THREADS; t++) k1_disc_mag_general(p, sm, t);
+        hs_for(K1_THREADS, [&](uint32_t t) { k1_prefir(p, sm, t); });
+        hs_for(K1_THREADS, [&](uint32_t t) { k1_disc_mag_general(p, sm, t); });
     }
-    else if (fast) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 1, true>(p, sm, t); }
-    else if (p.d == 3) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 3, false>(p, sm, t); }
-    else if (p.d == 2) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 2, false>(p, sm, t); }
-    else if (p.d == 1) { for (int t = 0; t < K1_THREADS; t++) k1_box_disc<CH, 1, false>(p, sm, t); }
+    else if (fast) { hs_for(K1_THREADS, [&](uint32_t t) { k1_box_disc<CH, 1, true>(p, sm, t); }); }
+    else if (p.d == 3) { hs_for(K1_THREADS, [&](uint32_t t) { k1_box_disc<CH, 3, false>(p, sm, t); }); }
+    else if (p.d == 2) { hs_for(K1_THREADS, [&](uint32_t t) { k1_box_disc<CH, 2, false>(p, sm, t); }); }
+    else if (p.d == 1) { hs_for(K1_THREADS, [&](uint32_t t) { k1_box_disc<CH, 1, false>(p, sm, t); }); }
     else {
-        for (int t = 0; t < K1_THREADS; t++) k1_box<CH>(p, sm, t);
-        for (int t = 0; t < K1_THREADS; t++) k1_disc_mag(p, sm, t);
+        hs_for(K1_THREADS, [&](uint32_t t) { k1_box<CH>(p, sm, t); });
+        hs_for(K1_THREADS, [&](uint32_t t) { k1_disc_mag(p, sm, t); });
     }
-    for (int t = 0; t < K1_THREADS; t++) k1_fir<CH>(p, sm, tile, t);
-    for (int t = 0; t < 32; t++) k1_rssi<CH>(p, sm.mag, tile, t);            /* the block's RSSI warp */
+    hs_for(K1_THREADS, [&](uint32_t t) { k1_fir<CH>(p, sm, tile, t); });
+    hs_for(32, [&](uint32_t t) { k1_rssi<CH>(p, sm.mag, tile, t); });            /* the block's RSSI warp */
 }
 
 static int launch_k1(wmb_ctx *c, const K1Params &p, cudaStream_t)
@@ -37,18 +68,19 @@ static int launch_k1(wmb_ctx *c, const K1Params &p, cudaStream_t)
     uint8_t *base = smem.data();
     base += (128 - ((uintptr_t)base & 127)) & 127;
     k1_carve(sm, base, p.d, p.prefilter);
-    for (int i = 0; i < WMB_ATAN_TAB_ELEMS; i++) wmb_atan_tab_fill((WmbAtanTab *)base, i);
-    for (int64_t tile = 0; tile < ntiles; tile++) {
+    hs_for(WMB_ATAN_TAB_ELEMS, [&](uint32_t i) { wmb_atan_tab_fill((WmbAtanTab *)base, i); });
+    int rc = WMB_OK;
+    hs_for((uint32_t)ntiles, [&](uint32_t tile) {
         const K1Load L = k1_plan_load(p, tile);
         if (L.n0) memcpy(sm.bytes[0], L.src0, (size_t)L.n0);
         if (L.n1) memcpy(sm.bytes[0] + L.off1, L.src1, (size_t)L.n1);
-        if ((L.n0 | L.n1 | L.off1) & 15) return set_err(WMB_E_STATE, "hostsim: unaligned bulk copy");
+        if ((L.n0 | L.n1 | L.off1) & 15) { rc = set_err(WMB_E_STATE, "hostsim: unaligned bulk copy"); return; }
         const uint8_t *raw = sm.bytes[0];
         if (p.chains & 1u) hostsim_k1_chain<ChainT1C1>(p, sm, raw, tile, true);
         if (p.chains & 2u) hostsim_k1_chain<ChainS1>(p, sm, raw, tile, p.mix || !(p.chains & 1u));
-    }
+    });
     c->st.kernel_launches++;
-    return WMB_OK;
+    return rc;
 }
 
 /* speculative pass, verification, and the fix-up loop of k2*_fixup_kernel (re-run refuted lanes from their
@@ -60,18 +92,18 @@ static int hostsim_fixup(wmb_ctx *c, uint32_t lanes, uint32_t *n_fail, RERUN rer
         if (round > lanes + 2) { *c->d_errors |= 256u; *n_fail = 0; break; }
         c->d_gd->lanes_rerun += *n_fail;
         *n_fail = 0;
-        for (uint32_t lane = 0; lane < lanes; lane++) rerun(lane);
-        for (uint32_t lane = 0; lane < lanes; lane++) verify(lane);
+        hs_for(lanes, [&](uint32_t lane) { rerun(lane); });
+        hs_for(lanes, [&](uint32_t lane) { verify(lane); });
     }
     return WMB_OK;
 }
 
 static int launch_k2a_lanes(wmb_ctx *c, int chain, const K2aParams &p, cudaStream_t)
 {
-    for (uint32_t lane = 0; lane < p.lanes; lane++) {
+    hs_for(p.lanes, [&](uint32_t lane) {
         if (chain == 0) k2a_lane<ChainT1C1>(p, lane);
         else            k2a_lane<ChainS1>(p, lane);
-    }
+    });
     c->st.kernel_launches += 1;
     return WMB_OK;
 }
@@ -80,7 +112,7 @@ static int launch_k2a_verify(wmb_ctx *c, int chain, const K2aParams &p0)
 {
     K2aParams p = p0;
     uint32_t *nf = c->d_nfail + chain;
-    for (uint32_t lane = 0; lane < p.lanes; lane++) k2a_verify_lane(p, lane, nf);
+    hs_for(p.lanes, [&](uint32_t lane) { k2a_verify_lane(p, lane, nf); });
     p.mode = 1;
     c->st.kernel_launches += 2;
     return hostsim_fixup(c, p.lanes, nf,
@@ -92,11 +124,11 @@ static int launch_k2m(wmb_ctx *c, int chain, const K2mParams &p0, cudaStream_t)
 {
     K2mParams p = p0;
     uint32_t *nf = c->d_nfail + 2 + chain;
-    for (uint32_t lane = 0; lane < p.lanes; lane++) {
+    hs_for(p.lanes, [&](uint32_t lane) {
         if (chain == 0) k2m_lane<ChainT1C1>(p, lane);
         else            k2m_lane<ChainS1>(p, lane);
-    }
-    for (uint32_t lane = 0; lane < p.lanes; lane++) k2m_verify_lane(p, lane, nf);
+    });
+    hs_for(p.lanes, [&](uint32_t lane) { k2m_verify_lane(p, lane, nf); });
     p.mode = 1;
     c->st.kernel_launches += 3;
     return hostsim_fixup(c, p.lanes, nf,
@@ -108,8 +140,8 @@ static int launch_k2p1(wmb_ctx *c, const K2p1Params &p0)
 {
     K2p1Params p = p0;
     uint32_t *nf = c->d_nfail + 4;
-    for (uint32_t lane = 0; lane < p.lanes; lane++) k2p1_lane(p, lane);
-    for (uint32_t lane = 0; lane < p.lanes; lane++) k2p1_verify_lane(p, lane, nf);
+    hs_for(p.lanes, [&](uint32_t lane) { k2p1_lane(p, lane); });
+    hs_for(p.lanes, [&](uint32_t lane) { k2p1_verify_lane(p, lane, nf); });
     p.mode = 1;
     c->st.kernel_launches += 3;
     return hostsim_fixup(c, p.lanes, nf, [&](uint32_t lane) { k2p1_lane(p, lane); },
@@ -125,40 +157,41 @@ static void launch_cscan(wmb_ctx *c, const uint32_t *cnt, uint64_t *base, uint32
     s.skip_invert = skip_invert;
     static uint64_t part[SCAN_BLOCK];
     const uint32_t tiles = scan_tiles(n);
-    for (uint32_t b = 0; b < tiles; b++) {
-        for (uint32_t t = 0; t < SCAN_BLOCK; t++) cscan_local(s, b, t, part);
+    hs_for(tiles, [&](uint32_t b) {
+        hs_for(SCAN_BLOCK, [&](uint32_t t) { cscan_local(s, b, t, part); });
         cscan_a_finish(s, b, part);
-    }
+    });
     cscan_b(s);
-    for (uint32_t b = 0; b < tiles; b++) {
-        for (uint32_t t = 0; t < SCAN_BLOCK; t++) cscan_local(s, b, t, part);
+    hs_for(tiles, [&](uint32_t b) {
+        hs_for(SCAN_BLOCK, [&](uint32_t t) { cscan_local(s, b, t, part); });
         cscan_c_block(s, b, part);
-        for (uint32_t t = 0; t < SCAN_BLOCK; t++) cscan_c_write(s, b, t, part);
-    }
+        hs_for(SCAN_BLOCK, [&](uint32_t t) { cscan_c_write(s, b, t, part); });
+    });
     c->st.kernel_launches += 3;
 }
 
 static int launch_k2p_rest(wmb_ctx *c, const K2pcParams &pc, K2p2Params p2)
 {
     launch_cscan(c, pc.cnt, pc.base, pc.lanes, pc.agg, &pc.pd->n_rec, nullptr, &pc.pd->fallback, 1);
-    for (uint32_t lane = 0; lane < pc.lanes; lane++)
-        for (int t = 0; t < 4; t++) k2pc_compact(pc, lane, t, 4);
-    for (uint32_t lane = 0; lane < p2.lanes; lane++) k2p2_count(p2, lane);
+    hs_for(pc.lanes, [&](uint32_t lane) {
+        hs_for(4, [&](uint32_t t) { k2pc_compact(pc, lane, t, 4); });
+    });
+    hs_for(p2.lanes, [&](uint32_t lane) { k2p2_count(p2, lane); });
     {
         static uint32_t part[K2P2W_THREADS];
-        for (uint32_t lane = 0; lane < p2.lanes; lane++) {
-            for (uint32_t t = 0; t < K2P2W_THREADS; t++) k2p2w_a(p2, lane, t, part);
+        hs_for(p2.lanes, [&](uint32_t lane) {
+            hs_for(K2P2W_THREADS, [&](uint32_t t) { k2p2w_a(p2, lane, t, part); });
             k2p2_sum_finish(p2, lane, part);
-        }
+        });
     }
     launch_cscan(c, p2.cnt, p2.base, p2.lanes, p2.agg, &p2.sd->total, &p2.pd->fallback);
     {
         static uint32_t part[K2P2W_THREADS];
-        for (uint32_t lane = 0; lane < p2.lanes; lane++) {
-            for (uint32_t t = 0; t < K2P2W_THREADS; t++) k2p2w_a(p2, lane, t, part);
+        hs_for(p2.lanes, [&](uint32_t lane) {
+            hs_for(K2P2W_THREADS, [&](uint32_t t) { k2p2w_a(p2, lane, t, part); });
             k2p2w_b(part, 0);
-            for (uint32_t t = 0; t < K2P2W_THREADS; t++) k2p2w_c(p2, lane, t, part);
-        }
+            hs_for(K2P2W_THREADS, [&](uint32_t t) { k2p2w_c(p2, lane, t, part); });
+        });
     }
     c->st.kernel_launches += 4;
     return WMB_OK;
@@ -182,20 +215,20 @@ static int launch_k2m_carry(wmb_ctx *c, const RlState *end, RlState *carry, cons
 template <class CH>
 static void hostsim_k2t(const K2tParams &p)
 {
-    for (uint32_t lane = 0; lane < p.lanes; lane++) k2t_count<CH>(p, lane);
+    hs_for(p.lanes, [&](uint32_t lane) { k2t_count<CH>(p, lane); });
     static T2Fold part[SCAN_BLOCK];
     const uint32_t tiles = scan_tiles(p.lanes);
-    for (uint32_t b = 0; b < tiles; b++) {
-        for (uint32_t t = 0; t < SCAN_BLOCK; t++) t2scan_local<CH>(p, b, t, part);
+    hs_for(tiles, [&](uint32_t b) {
+        hs_for(SCAN_BLOCK, [&](uint32_t t) { t2scan_local<CH>(p, b, t, part); });
         t2scan_a_finish<CH>(p, b, part);
-    }
+    });
     t2scan_b<CH>(p);
-    for (uint32_t b = 0; b < tiles; b++) {
-        for (uint32_t t = 0; t < SCAN_BLOCK; t++) t2scan_local<CH>(p, b, t, part);
+    hs_for(tiles, [&](uint32_t b) {
+        hs_for(SCAN_BLOCK, [&](uint32_t t) { t2scan_local<CH>(p, b, t, part); });
         t2scan_c_block<CH>(p, b, part);
-        for (uint32_t t = 0; t < SCAN_BLOCK; t++) t2scan_c_write<CH>(p, b, t, part);
-    }
-    for (uint32_t lane = 0; lane < p.lanes; lane++) k2t_write<CH>(p, lane);
+        hs_for(SCAN_BLOCK, [&](uint32_t t) { t2scan_c_write<CH>(p, b, t, part); });
+    });
+    hs_for(p.lanes, [&](uint32_t lane) { k2t_write<CH>(p, lane); });
 }
 
 static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
@@ -208,8 +241,9 @@ static int launch_k2t(wmb_ctx *c, int chain, const K2tParams &p)
 static int launch_k2c(wmb_ctx *c, const K2cParams &p, cudaStream_t)
 {
     launch_cscan(c, p.cnt, p.base, p.lanes, p.agg, &p.sd->total, p.run_if, nullptr, 0, nullptr, p.run_if ? 1u : 0u);
-    for (uint32_t lane = 0; lane < p.lanes; lane++)
-        for (int t = 0; t < 4; t++) k2c_compact(p, lane, t, 4);
+    hs_for(p.lanes, [&](uint32_t lane) {
+        hs_for(4, [&](uint32_t t) { k2c_compact(p, lane, t, 4); });
+    });
     c->st.kernel_launches += 1;
     return WMB_OK;
 }
@@ -218,20 +252,22 @@ static int launch_k3_k4(wmb_ctx *c, const K3Params &p, const K4Params *q)
 {
     k3_plan(p);
     const uint32_t n = p.gd->n;
-    for (uint32_t i = 0; i < n; i++) k3_fill(p, i, 0, 1);
-    for (uint32_t i = 0; i < n; i++) k3_size(p, i);
-    for (uint32_t i = 0; i < n; i++)
-        for (int t = 0; t < 4; t++) k3_cut(p, i, t, 4);
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) k3_offsets_a(p, t);
+    hs_for(n, [&](uint32_t i) { k3_fill(p, i, 0, 1); });
+    hs_for(n, [&](uint32_t i) { k3_size(p, i); });
+    hs_for(n, [&](uint32_t i) {
+        hs_for(4, [&](uint32_t t) { k3_cut(p, i, t, 4); });
+    });
+    hs_for(SCAN_THREADS, [&](uint32_t t) { k3_offsets_a(p, t); });
     k3_offsets_b(p);
-    for (uint32_t t = 0; t < SCAN_THREADS; t++) k3_offsets_c(p, t);
-    for (uint32_t i = 0; i < n; i++)
-        for (int t = 0; t < 4; t++) k3_copy(p, i, t, 4);
-    for (uint32_t i = 0; i < (n > WMB_N_STREAMS ? n : WMB_N_STREAMS); i++) k3_carry(p, i);
+    hs_for(SCAN_THREADS, [&](uint32_t t) { k3_offsets_c(p, t); });
+    hs_for(n, [&](uint32_t i) {
+        hs_for(4, [&](uint32_t t) { k3_copy(p, i, t, 4); });
+    });
+    hs_for((n > WMB_N_STREAMS ? n : WMB_N_STREAMS), [&](uint32_t i) { k3_carry(p, i); });
     c->st.kernel_launches += 8;
     if (q) {
         static K4Smem sm;                   /* the block's phases need real barriers: one simulated thread */
-        for (uint32_t i = 0; i < n; i++) k4_decode(*q, i, 0, 1, sm);
+        hs_for(n, [&](uint32_t i) { k4_decode(*q, i, 0, 1, sm); });
         c->st.kernel_launches += 1;
     }
     k3_publish(p);
@@ -241,7 +277,7 @@ static int launch_k3_k4(wmb_ctx *c, const K3Params &p, const K4Params *q)
 static int launch_k4(wmb_ctx *c, const K4Params &p)
 {
     static K4Smem sm;                   /* the block's phases need real barriers: one simulated thread */
-    for (uint32_t i = 0; i < p.n; i++) k4_decode(p, i, 0, 1, sm);
+    hs_for(p.n, [&](uint32_t i) { k4_decode(p, i, 0, 1, sm); });
     c->st.kernel_launches += 1;
     return WMB_OK;
 }

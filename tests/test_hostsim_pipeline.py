@@ -95,3 +95,21 @@ def test_dormant_prefilter_front_end(pkg, hostsim_lib):
 
 def test_lane_event_overflow_costs_bits_not_the_stream(pkg, hostsim_lib):
     pc.check_lane_event_overflow(pkg, hostsim_lib)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_results_do_not_depend_on_the_order_of_simulated_threads(hostsim_lib, order):
+    """On the device the threads of a phase, the lanes and the blocks of a launch run concurrently; the CPU build runs
+    them one after another, in index order by default.  WMB_HOSTSIM_ORDER=1 runs every phase backwards, 2 in a scrambled
+    order (tests/hostsim/hostsim_launch.inl: hs_for): a missing barrier between two phases of the demod block, or a lane
+    that reads what another lane of the same launch writes, would change a result.  The core of this file again, in a
+    process of its own per order (the variable is read once)."""
+    import os, subprocess, sys
+    from conftest import ROOT
+    env = dict(os.environ, WMB_HOSTSIM_ORDER=str(order))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "not gpu", "-p", "no:cacheprovider",
+                        os.path.join(ROOT, "tests", "test_hostsim_pipeline.py"), os.path.join(ROOT, "tests", "test_framer.py"),
+                        "-k", "golden or stage or invariance or second_reset or prefilter or lane_event or device_framer or carriers"],
+                       env=env, cwd=ROOT, capture_output=True, timeout=1200)
+    assert r.returncode == 0, r.stdout.decode()[-3000:]
+    assert b"passed" in r.stdout
