@@ -33,10 +33,54 @@ static inline cudaError_t cudaGetDeviceCount(int *n)
     return cudaSuccess;
 }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? cudaSuccess : 2; }
-static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+/* cudaMalloc does not clear what it returns (and a process that creates context after context gets its own stale data
+ * back), so the simulation hands out memory filled with a pattern -- 0xA5 by default, WMB_HOSTSIM_POISON=<byte> for
+ * another -- and a kernel that reads what nothing has written yet changes a result here too.  The buffers are sized for
+ * 1 GiB batches and mostly untouched by a test, so the pattern must not cost a write per page: the allocation is a
+ * private mapping of one pattern-filled 32 MiB memory file, over and over (read faults share its pages, writes copy). */
+#include <sys/mman.h>
+#include <unistd.h>
+#define HS_PAT_BYTES ((size_t)32 << 20)
+struct hs_alloc_rec { void *p; size_t n; };
+static inline struct hs_alloc_rec *hs_alloc_table(void) { static struct hs_alloc_rec t[4096]; return t; }
+static inline int hs_pattern_fd(void)
+{
+    static int fd = -1;
+    if (fd >= 0) return fd;
+    const char *e = getenv("WMB_HOSTSIM_POISON");
+    const int fill = e ? (int)(strtoul(e, NULL, 0) & 0xFF) : 0xA5;
+    fd = memfd_create("wmb_hostsim_pattern", 0);
+    if (fd < 0 || ftruncate(fd, (off_t)HS_PAT_BYTES) != 0) abort();
+    void *m = mmap(NULL, HS_PAT_BYTES, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (m == MAP_FAILED) abort();
+    memset(m, fill, HS_PAT_BYTES);
+    munmap(m, HS_PAT_BYTES);
+    return fd;
+}
+static inline cudaError_t cudaMalloc(void **p, size_t n)
+{
+    const size_t page = 4096, len = ((n ? n : 1) + page - 1) / page * page;
+    const int fd = hs_pattern_fd();
+    uint8_t *base = (uint8_t *)mmap(NULL, len, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (base == MAP_FAILED) return 2;
+    for (size_t off = 0; off < len; off += HS_PAT_BYTES) {
+        const size_t k = len - off < HS_PAT_BYTES ? len - off : HS_PAT_BYTES;
+        if (mmap(base + off, k, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_FIXED | MAP_NORESERVE, fd, 0) == MAP_FAILED) { munmap(base, len); return 2; }
+    }
+    struct hs_alloc_rec *t = hs_alloc_table();
+    for (int i = 0; i < 4096; i++) if (!t[i].p) { t[i].p = base; t[i].n = len; *p = base; return cudaSuccess; }
+    munmap(base, len);
+    return 2;
+}
+static inline cudaError_t cudaFree(void *p)
+{
+    if (!p) return cudaSuccess;
+    struct hs_alloc_rec *t = hs_alloc_table();
+    for (int i = 0; i < 4096; i++) if (t[i].p == p) { munmap(p, t[i].n); t[i].p = NULL; return cudaSuccess; }
+    abort();                                                  /* not ours */
+}
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
-static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeHost(void *p) { return cudaFree(p); }
 static inline cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
