@@ -67,8 +67,10 @@ typedef struct wmb_opts {
                                  wmb_push feeds the context's framers itself.            */
     uint32_t reserved[2];     /* test knobs, 0 in production: [0] = 1 forces the monolithic run-length lanes for
                                  T1/C1; [1] bit 0 keeps the clock-sign words for wmb_debug_copy_bits(.., 2, ..),
-                                 [1] >> 8 (if not 0) is the size of the per-batch candidate tables, to reach the
-                                 overflow path (wmb_stats.overflow_batches) with a small capture                  */
+                                 [1] bit 1 sizes the run-length streams' event rings by the large-batch rule (a
+                                 quarter event per sample) also for small batches, [1] >> 8 (if not 0) is the size of
+                                 the per-batch candidate tables: both to reach the overflow paths
+                                 (wmb_stats.overflow_batches) with a small capture                                 */
     /* simultaneous == 2 (many carriers per capture): offset of the carrier the T1/C1 chain [0] and the
      * S1 chain [1] listen to from the capture's centre frequency, in units of 25 kHz (the grid of the reference's
      * table, rtl_wmbus.c:974-993), |offset| <= fs / 2.  The reference's -s is {+13, -13}.  A capture with more than two

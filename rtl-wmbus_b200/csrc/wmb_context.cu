@@ -161,7 +161,7 @@ struct wmb_ctx {
     bool taps = false;              /* opts.reserved[1] & 1: keep the clock-sign words for wmb_debug_copy_bits */
     K2pDev *h_pd = nullptr;
     uint32_t cap_words_rl = 0;
-    size_t ring_events = 0;
+    size_t ring_events = 0, ring_events_rl = 0;
     std::vector<void *> dev_allocs, host_allocs;
     uint8_t *d_tmp = nullptr;       /* scratch for the history slides                    */
     uint32_t cand_cap = 1u << 20;
@@ -556,6 +556,13 @@ static int ctx_alloc(wmb_ctx *c)
     const size_t words_rl = (size_t)c->M_max / 4 + (size_t)c->lanes_max * (K2_EDGE_EMIT_CAP + 8) + 1024;
     c->cap_words_rl = (uint32_t)std::min<size_t>(words_rl, 0xFFFFFFFFu);
     c->ring_events = next_pow2((size_t)c->M_max / 4 + 65536 + WMB_MAXBITS);
+    /* A run-length stream's ring: in the regime where the tracker's bit length has collapsed (an in-channel carrier) the
+     * lanes emit up to their event buffers' capacity, 1.25 events per sample, and a burst of that is as long in a small
+     * batch as in a large one.  Up to 2^26 events (128 MiB batches; the CLI's live hand-overs and its 64 MiB default) the
+     * ring holds whatever the monolithic lanes of a batch can emit, so it cannot be overrun by them; larger batches keep
+     * the size they were measured with, which is at least that */
+    c->ring_events_rl = std::max<size_t>(c->ring_events, std::min<size_t>(next_pow2(words_rl + 65536 + WMB_MAXBITS), (size_t)1 << 26));
+    if (c->o.reserved[1] & 2u) c->ring_events_rl = c->ring_events;      /* tests: reach the overrun path with a small capture */
     c->p1_lanes_max = (uint32_t)(c->M_max / K2P1_CHUNK + 2);
     c->rec_max = (size_t)c->M_max / 5 + 2 * (size_t)c->p1_lanes_max + 64;
     c->p2_lanes_max = (uint32_t)(c->rec_max / K2P2_RECORDS + 2);
@@ -663,7 +670,7 @@ static int ctx_alloc(wmb_ctx *c)
             if (a == WMB_ALGO_RLA) TRY(dev_alloc(c, &s.ev, c->cap_words_rl));
             TRY(dev_alloc(c, &s.cnt, nl, true));
             TRY(dev_alloc(c, &s.base, nl));
-            s.ring_cap = c->ring_events;
+            s.ring_cap = a == WMB_ALGO_RLA ? c->ring_events_rl : c->ring_events;
             TRY(dev_alloc(c, &s.ring, s.ring_cap));
             TRY(dev_alloc(c, &s.sd, 1, true));
             TRY(dev_alloc(c, &s.cand, c->cand_cap));

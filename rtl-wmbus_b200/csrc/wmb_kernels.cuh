@@ -909,23 +909,22 @@ WMB_D void k3_plan(const K3Params &p)
 {
     GatherDev &g = *p.gd;
     uint32_t n = 0;
-    bool overrun = false;
     for (int k = 0; k < WMB_N_STREAMS; k++) {
         g.off[k] = n;
         if (!p.sd[k]) continue;
         StreamDev &sd = *p.sd[k];
         if (sd.cand_overflow) { k3_flag(p.errors, 16u); sd.cand_overflow = 0; sd.n_cand = p.cand_cap; }
-        /* ring overrun: the batch wrote more events into a stream's ring than it holds (a run-length tracker whose bit
-         * length has collapsed, lane after lane): bits of candidates may be overwritten -- no candidate of this batch is
-         * decoded, pending ones included */
-        if (sd.total - g.total_prev[k] > p.ring_mask[k] + 1 - WMB_MAXBITS - 64) { k3_flag(p.errors, 32u); overrun = true; }
-        g.total_prev[k] = sd.total;
         g.n_cand_total[k] += sd.n_cand;
-        n += g.n_pend[k] + sd.n_cand;
+        uint32_t nk = g.n_pend[k] + sd.n_cand;
+        /* ring overrun: the batch wrote more events into this stream's ring than it holds (a run-length tracker whose bit
+         * length has collapsed, lane after lane): bits of its candidates may be overwritten -- none of THIS stream's
+         * candidates is decoded in this batch, pending ones included; the other streams have their own rings */
+        if (sd.total - g.total_prev[k] > p.ring_mask[k] + 1 - WMB_MAXBITS - 64) { k3_flag(p.errors, 32u); g.n_pend[k] = 0; nk = 0; }
+        g.total_prev[k] = sd.total;
+        n += nk;
     }
     g.off[WMB_N_STREAMS] = n;
-    if (n > p.cand_cap || n > p.log_cap) { k3_flag(p.errors, 64u); overrun = true; }
-    if (overrun) { n = 0; for (int k = 0; k <= WMB_N_STREAMS; k++) g.off[k] = 0; }
+    if (n > p.cand_cap || n > p.log_cap) { k3_flag(p.errors, 64u); n = 0; for (int k = 0; k <= WMB_N_STREAMS; k++) g.off[k] = 0; }
     g.n = n;
     g.base = p.log_base;
     g.n_words = 0;

@@ -77,3 +77,23 @@ def case(seed, k):
     for _ in range(k):
         c = draw_case(rng)
     return c
+
+
+def draw_time_chunk_case(rng):
+    """One case of tests/tools/fuzz_time_chunks.py: a capture long enough for 2-4 chunks with their halos, the number of
+    chunks, the halo.  None where the draw is skipped (the order of the draws is part of the contract here too)."""
+    c = draw_case(rng)
+    if c["prefilter"]:
+        return None
+    c["n"] = int(rng.integers(600, 1500)) * 4096 * c["d"]
+    c["world"] = int(rng.integers(2, 5)); c["halo"] = int(rng.choice([1 << 16, 1 << 17, 1 << 18]))
+    return c
+
+
+def time_chunk_case(seed, k):
+    """parameters of case k (1-based, skipped draws counted) of the time-chunk fuzzer run with this seed"""
+    rng = np.random.default_rng(seed)
+    c = None
+    for _ in range(k):
+        c = draw_time_chunk_case(rng)
+    return c

@@ -307,18 +307,39 @@ def check_lane_event_overflow(pkg, lib):
         assert got == want, tuning
         seen += st.overflow_batches
     assert seen >= 2, "the capture is meant to overflow a lane's event buffer"
-    # seed 33, case 1190 (2.4 MS/s, -d 3, a CW tone 506 kHz off): the same regime for so long that a 2 MiB batch writes
-    # more events than its ring holds.  Nothing of that batch is decoded (a line is lost), the stream goes on; with the
-    # default batch size the ring is large enough and nothing is lost.
+    # seed 33, case 1190 (2.4 MS/s, -d 3, a CW tone 506 kHz off): the same regime for so long that a 2 MiB batch wrote
+    # more events than its ring held.  The rings of the run-length streams are now sized for what the lanes of a batch can
+    # emit (batches up to 128 MiB), so nothing is lost; with the ring sized by the large-batch rule (test knob) the batch
+    # loses that stream's candidates -- and only that stream's: every missing line is a run-length line -- and the
+    # stream goes on.
     c = fuzz_cases.case(33, 1190)
     assert c["flags"] == "-d 3" and c["tuning"] == dict(max_batch_mib=2)
     cu8 = fuzz_cases.build_capture(c)
     want = oracle_lines(cu8, c["flags"])
     got, st = run_lines(pkg, lib, cu8, c["flags"], pushes=c["pushes"], **c["tuning"])
+    assert got == want and st.overflow_batches == 0
+    got, st = run_lines(pkg, lib, cu8, c["flags"], pushes=c["pushes"], reserved=(C.c_uint32 * 2)(0, 2), **c["tuning"])
     it = iter(want)
-    assert st.overflow_batches >= 1 and len(got) >= len(want) - 2 and all(any(l == w for w in it) for l in got)
+    assert st.overflow_batches >= 1 and len(want) - 2 <= len(got) <= len(want) and all(any(l == w for w in it) for l in got)
     got, st = run_lines(pkg, lib, cu8, c["flags"])
     assert got == want and st.overflow_batches == 0
+    # time-chunk fuzzer, seed 777, case 322 (3.2 MS/s, -d 4, noise sigma 1, a CW tone 614 kHz off): 1 / 2 / 4 MiB batches
+    # used to overrun the T1/C1 run-length ring, and the overrun used to cost the batch's time2 candidates as well (15 of
+    # 259 lines).  With the knob: only run-length lines are missing; without: none.
+    c = fuzz_cases.time_chunk_case(777, 322)
+    assert c["flags"] == "-v -d 4" and c["n"] == 23887872
+    cu8 = fuzz_cases.build_capture(c)
+    want = oracle_lines(cu8, c["flags"])
+    assert len(want) == 259
+    for mib in (1, 4):
+        got, st = run_lines(pkg, lib, cu8, c["flags"], max_batch_mib=mib)
+        assert got == want and st.overflow_batches == 0, mib
+        got, st = run_lines(pkg, lib, cu8, c["flags"], max_batch_mib=mib, reserved=(C.c_uint32 * 2)(0, 2))
+        assert st.overflow_batches >= 1, mib
+        missing = list(want)
+        for l in got:
+            missing.remove(l)                                    # (raises if a line was invented)
+        assert all(l.startswith("rla;") for l in missing), (mib, missing[:3])
 
 
 def check_sample_index_wrap(pkg, lib):

@@ -14,14 +14,14 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 4242)
 t0 = time.time(); k = 0; total_retries = 0
 while time.time() - t0 < budget:
     k += 1
-    c = fuzz_cases.draw_case(rng)
-    if c["prefilter"]:
+    c = fuzz_cases.draw_time_chunk_case(rng)
+    if c is None:
         continue
-    c["n"] = int(rng.integers(600, 1500)) * 4096 * c["d"]        # long enough for 2-4 chunks with their halos
     cu8 = fuzz_cases.build_capture(c)
     flags = c["flags"]
     want = pc.oracle_lines(cu8, flags)
-    world = int(rng.integers(2, 5)); halo = int(rng.choice([1 << 16, 1 << 17, 1 << 18]))
+    world, halo = c["world"], c["halo"]
+    overflow = 0
     got, ends, retries, ok = [], [], 0, True
     for rank in range(world):
         h = halo
@@ -29,6 +29,7 @@ while time.time() - t0 < budget:
             with pkg.WmbusB200(flags, lib=lib, max_batch_mib=1) as ctx:
                 lines, ds, de, start = shard.decode_time_chunk(ctx, lambda lo, hi: ctx.push(cu8.ctypes.data + lo, hi - lo),
                                                                len(cu8), c["d"], rank, world, h)
+                overflow += ctx.stats().overflow_batches
             if rank == 0 or start == 0 or ds == ends[rank - 1]:
                 break
             h *= 4; retries += 1
@@ -37,8 +38,12 @@ while time.time() - t0 < budget:
                 break
         ends.append(de); got.append(lines)
     total_retries += retries
-    same = ok and shard.merge_lines(got) == want
-    print("case %d %s flags=%r world=%d halo=%d lines=%d retries=%d" % (k, "ok" if same else "MISMATCH", flags, world, halo, len(want), retries), flush=True)
+    merged = shard.merge_lines(got)
+    same = ok and merged == want
+    if ok and not same and overflow:                          # a device table was full (1 MiB batches): lines may be missing, none may be invented
+        it = iter(want)
+        same = all(any(l == w for w in it) for l in merged)
+    print("case %d %s flags=%r world=%d halo=%d lines=%d retries=%d overflow_batches=%d" % (k, "ok" if same else "MISMATCH", flags, world, halo, len(want), retries, overflow), flush=True)
     if not same:
         sys.exit(1)
 print("done", k, "cases,", total_retries, "halo retries")
