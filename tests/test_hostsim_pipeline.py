@@ -113,3 +113,17 @@ def test_results_do_not_depend_on_the_order_of_simulated_threads(hostsim_lib, or
                        env=env, cwd=ROOT, capture_output=True, timeout=1200)
     assert r.returncode == 0, r.stdout.decode()[-3000:]
     assert b"passed" in r.stdout
+
+
+def test_decimations_up_to_the_limit(pkg, hostsim_lib):
+    """-d beyond what an RTL-SDR delivers (8: 6.4 MS/s, 25: 20 MS/s = WMB_MAX_DECIMATION, where a tile's raw samples still
+    fit a block's shared memory): demod stages sample by sample and the lines, one shot and in ragged pushes."""
+    import importlib
+    synth = importlib.import_module("rtl-wmbus_b200.synth")
+    for d, flags in ((8, "-v -d 8 -s -o"), (25, "-v -d 25")):
+        cap, _ = synth.synth_capture(4096 * d * 96, fs=800e3 * d, emitters=synth.default_emitters("mixed"), seed=1234 + d)
+        cu8 = np.ascontiguousarray(cap.numpy())
+        pc.check_stages(pkg, hostsim_lib, cu8, flags)
+        want = pc.oracle_lines(cu8, flags)
+        got, _ = pc.run_lines(pkg, hostsim_lib, cu8, flags, max_batch_mib=1, pushes=[12345, 1 << 18, 4096 * d * 3])
+        assert got == want and (len(want) >= 10 or "-s" in flags)
