@@ -241,8 +241,9 @@ int wmb_debug_arith(wmb_ctx *c, int mode, const float *y, const float *x, float 
  * neighbour took after pushing up to the same sample -- equal bytes mean that every recurrence, shift
  * register and telegram in flight is bit-identical from there on, so the chunk decodes exactly as in
  * the sequential run; a mismatch means the halo was too short (retry with a longer one; position 0 is
- * exact by definition), (3) pushes its chunk and a right halo of one maximum telegram and keeps only
- * the lines whose access-code match lies in [lo, hi). */
+ * exact by definition), (3) pushes its chunk and a right halo of one maximum telegram -- and goes on pushing
+ * while wmb_pending_before(hi) says that a telegram matched in the chunk is still in flight -- and keeps
+ * only the lines whose access-code match lies in [lo, hi). */
 
 /* wmb_reset() plus: the next byte pushed is IQ sample `first_iq_sample` of the capture (mixer and
  * decimation phases, sample indices).  Must be a multiple of 2048 * decimation. */
@@ -251,6 +252,13 @@ int wmb_seek(wmb_ctx *c, uint64_t first_iq_sample);
 /* Only telegrams whose access-code match falls on a decimated sample in [sync_lo, sync_hi) produce
  * lines (default: all).  The others are still decoded: they keep the decoders busy as in the reference. */
 int wmb_set_line_window(wmb_ctx *c, uint64_t sync_lo, uint64_t sync_hi);
+
+/* Number of telegrams in flight -- access-code matches whose decoder is still waiting for bits -- whose match lies on a
+ * decimated sample below sync_hi.  A worker pushes its right halo until this is 0 for its chunk's end: the halo of "one
+ * maximum telegram" is a statement about samples with edges in them, and a telegram that runs into a gap in the input
+ * (dead air: the run-length tracker emits nothing until the next edge, then all the bits at once) ends arbitrarily
+ * late.  Gathers what is enqueued first, like wmb_boundary_state().  Negative: error. */
+long wmb_pending_before(wmb_ctx *c, uint64_t sync_hi);
 
 /* Everything that couples the samples pushed so far to the output still to come: the carried filter,
  * clock and run-length states, the shift registers, and the bit events of every telegram in flight

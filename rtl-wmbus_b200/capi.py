@@ -78,13 +78,15 @@ def _bind(lib):
     lib.wmb_set_line_window.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     lib.wmb_boundary_state.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.wmb_boundary_state.restype = C.c_long
+    lib.wmb_pending_before.argtypes = [C.c_void_p, C.c_uint64]
+    lib.wmb_pending_before.restype = C.c_long
     return lib
 
 
 EXPORTS = ["wmb_reset", "wmb_host_alloc", "wmb_host_free", "wmb_default_opts", "wmb_abi_version", "wmb_last_error", "wmb_version_string", "wmb_create",
            "wmb_destroy", "wmb_push", "wmb_push_device", "wmb_poll", "wmb_decode_frames", "wmb_take_lines",
            "wmb_process", "wmb_process_device", "wmb_get_stats", "wmb_debug_copy_stage", "wmb_debug_copy_bits", "wmb_debug_copy_events", "wmb_debug_arith",
-           "wmb_seek", "wmb_set_line_window", "wmb_boundary_state"]
+           "wmb_seek", "wmb_set_line_window", "wmb_boundary_state", "wmb_pending_before"]
 
 
 def load_library(path: str | None = None):
@@ -242,6 +244,10 @@ class WmbusB200:
 
     def set_line_window(self, sync_lo: int, sync_hi: int):
         self._check(self.lib.wmb_set_line_window(self._ctx, sync_lo, sync_hi))
+
+    def pending_before(self, sync_hi: int) -> int:
+        """telegrams in flight whose access-code match lies below decimated sample sync_hi"""
+        return self._check(self.lib.wmb_pending_before(self._ctx, sync_hi))
 
     def boundary_state(self) -> bytes:
         if not hasattr(self, "_bbuf"):

@@ -1886,6 +1886,39 @@ extern "C" long wmb_boundary_state(wmb_ctx *c, uint8_t *buf, size_t cap)
     return (long)out.size();
 }
 
+extern "C" long wmb_pending_before(wmb_ctx *c, uint64_t sync_hi)
+{
+    if (!c) return set_err(WMB_E_INVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ctx_alloc(c);
+    if (rc) return rc;
+    rc = consume_all(c);                                /* every enqueued batch is gathered and booked first */
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->cs));
+    GatherDev gd;
+    CUDA_TRY(cudaMemcpy(&gd, c->d_gd, sizeof(gd), cudaMemcpyDeviceToHost));
+    long n_before = 0;
+    std::vector<uint64_t> pend;
+    for (int ch = 0; ch < WMB_N_CHAINS; ch++) {
+        if (!(c->chains & (1u << ch))) continue;
+        for (int a = 0; a < WMB_N_ALGOS; a++) {
+            if ((a == WMB_ALGO_RLA && !c->o.rla_enabled) || (a == WMB_ALGO_T2A && !c->o.t2_enabled)) continue;
+            Stream &s = c->cb[ch].s[a];
+            pend.resize(gd.n_pend[ch * WMB_N_ALGOS + a]);
+            if (pend.empty()) continue;
+            CUDA_TRY(cudaMemcpy(pend.data(), s.pend, pend.size() * 8, cudaMemcpyDeviceToHost));
+            for (uint64_t ord : pend) {
+                if ((int64_t)ord <= s.busy_until) continue;              /* inside a telegram already decoded: will be ignored */
+                uint64_t ev = 0;                                         /* the flagged bit's event: its sample is the match */
+                CUDA_TRY(cudaMemcpy(&ev, s.ring + (ord & (s.ring_cap - 1)), 8, cudaMemcpyDeviceToHost));
+                const uint64_t m = c->m_consumed - ((c->m_consumed - EVG_M(ev)) & EVG_M_MASK);   /* 40 bits -> stream position */
+                if (m < sync_hi) n_before++;
+            }
+        }
+    }
+    return n_before;
+}
+
 extern "C" int wmb_get_stats(wmb_ctx *c, wmb_stats *s)
 {
     if (!c || !s) return set_err(WMB_E_INVAL, "null argument");

@@ -101,8 +101,16 @@ def decode_time_chunk(ctx, push, n_bytes: int, d: int, rank: int, world: int, ha
     lines += ctx.take_lines(2)
     dig_end = hashlib.sha256(ctx.boundary_state()).digest()
     if rank + 1 < world:                              # finish the telegrams that started in the chunk
-        tail = min(k[world], hi + (MAX_TELEGRAM_M * d + gran - 1) // gran * gran)
+        step = (MAX_TELEGRAM_M * d + gran - 1) // gran * gran
+        tail = min(k[world], hi + step)
         push(2 * hi, 2 * tail)
+        # MAX_TELEGRAM_M bounds a telegram whose samples carry edges.  One that runs into a gap in the input (dead air:
+        # the run-length tracker emits nothing until the next edge, then all the missing bits at once) ends arbitrarily
+        # late: go on while a telegram matched in the chunk is still in flight
+        while tail < k[world] and ctx.pending_before(hi // d) > 0:
+            nxt = min(k[world], tail + step)
+            push(2 * tail, 2 * nxt)
+            tail = nxt
         ctx.poll_flush()
     else:
         if n_bytes > 2 * hi:

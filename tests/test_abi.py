@@ -28,7 +28,8 @@ def exported_symbols(path):
 def test_header_declares_expected_surface():
     names = declared_functions()
     for n in ["wmb_create", "wmb_destroy", "wmb_push", "wmb_push_device", "wmb_poll", "wmb_decode_frames",
-              "wmb_take_lines", "wmb_process", "wmb_process_device", "wmb_host_alloc", "wmb_host_free"]:
+              "wmb_take_lines", "wmb_process", "wmb_process_device", "wmb_host_alloc", "wmb_host_free", "wmb_seek",
+              "wmb_set_line_window", "wmb_boundary_state", "wmb_pending_before"]:
         assert n in names
 
 

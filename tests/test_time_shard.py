@@ -66,6 +66,23 @@ def test_short_halo_is_detected_and_repeated(hostsim_lib, pkg):
     assert retries >= 1, "a 1024-sample halo cannot re-join the clock-recovery filters"
 
 
+def test_telegram_that_ends_after_a_gap_in_the_input(hostsim_lib, pkg):
+    """Found by tests/tools/fuzz_time_chunks.py (seed 882, case 126): a T1 telegram starts in chunk 0, the input goes dead
+    (constant samples: no edges, so the run-length tracker delivers no bits) for 456 k decimated samples, and the first
+    edge after the gap delivers the rest of the telegram at once -- 291 k samples after the chunk's end, beyond a right
+    halo of one maximum telegram.  The worker goes on pushing while wmb_pending_before() reports a telegram matched in
+    its chunk in flight; the line (CRC and 3-out-of-6 failed, printed all the same by the reference) comes from chunk 0."""
+    import fuzz_cases
+    c = fuzz_cases.time_chunk_case(882, 126)
+    assert c["flags"] == "-v" and c["world"] == 4 and c["dead"] == 578583
+    cu8 = fuzz_cases.build_capture(c)
+    check_time_chunks(pkg, hostsim_lib, cu8, c["flags"], world=4, halo_m=1 << 18)
+    with pkg.WmbusB200("-v", lib=hostsim_lib, max_batch_mib=1) as ctx:      # the new entry point by itself
+        assert ctx.pending_before(1 << 62) == 0
+        ctx.push(cu8.ctypes.data, 2 * 2 * 454656)                            # up to chunk 0's end: the telegram is in flight
+        assert ctx.pending_before(454656) >= 1 and ctx.pending_before(1000) == 0
+
+
 def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -1,7 +1,9 @@
 """Differential fuzzing of the library's host logic and kernel phase functions on the CPU build (tests/hostsim) against
 the oracle: random captures (noise level, emitters, interferers, dead air), random flags, lane geometry and push sizes
 (tests/fuzz_cases.py draws them).
-    python tests/tools/fuzz_hostsim.py [seconds] [seed]      prints one line per case; exits 1 at the first mismatch"""
+    python tests/tools/fuzz_hostsim.py [seconds] [seed] [tone]     prints one line per case; exits 1 at the first mismatch
+`tone` forces every case into the regime the first campaign found: a CW carrier inside the channel,
+noise sigma <= 3 -- the run-length tracker's bit length collapses, event buffers and rings fill."""
 import importlib, sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np
@@ -12,11 +14,16 @@ lib = pkg.load_library(HOSTSIM_SO)
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 600.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rng = np.random.default_rng(seed)
+tone = len(sys.argv) > 3 and sys.argv[3] == "tone"
+rng_tone = np.random.default_rng(seed + 1000003)             # (its own generator: the cases keep their numbers)
 t_end = time.time() + budget
 k = 0
 while time.time() < t_end:
     k += 1
     c = fuzz_cases.draw_case(rng)
+    if tone:
+        c["cw"] = (float(rng_tone.uniform(-60e3, 60e3)), float(rng_tone.uniform(10, 60)))
+        c["sigma"] = float(rng_tone.choice([1.0, 3.0]))
     print("start %d flags=%r d=%d n=%d sigma=%g tuning=%r pushes=%r" % (k, c["flags"], c["d"], c["n"], c["sigma"], c["tuning"], c["pushes"]), flush=True)
     cu8 = fuzz_cases.build_capture(c)
     o = orc.opts_from_flags(c["flags"]); o.prefilter = c["prefilter"]
