@@ -3,7 +3,7 @@ UNMODIFIED reference binary (oracle/_ref/rtl_wmbus, compiled from /root/referenc
 captures and flag sets as tests/tools/fuzz_hostsim.py (tests/fuzz_cases.py draws them), so that the chain
 reference binary == oracle == product is closed on random input and not only on the fixtures.  Needs the reference
 binary, i.e. the container that holds /root/reference.
-    python tests/tools/fuzz_oracle_vs_ref.py [seconds] [seed]      one line per case; exits 1 at the first mismatch"""
+    python tests/tools/fuzz_oracle_vs_ref.py [seconds] [seed] [tone]     one line per case; exits 1 at the first mismatch"""
 import sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np
@@ -14,6 +14,8 @@ if not orc.ref_binary():
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 600.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rng = np.random.default_rng(seed)
+tone = len(sys.argv) > 3 and sys.argv[3] == "tone"           # every case with a CW carrier inside the channel, noise sigma <= 3 (as fuzz_hostsim.py)
+rng_tone = np.random.default_rng(seed + 1000003)
 t_end = time.time() + budget
 k = lines = 0
 while time.time() < t_end:
@@ -21,6 +23,9 @@ while time.time() < t_end:
     c = fuzz_cases.draw_case(rng)
     if c["prefilter"]:
         continue                                             # the reference cannot be switched into that mode
+    if tone:
+        c["cw"] = (float(rng_tone.uniform(-60e3, 60e3)), float(rng_tone.uniform(10, 60)))
+        c["sigma"] = float(rng_tone.choice([1.0, 3.0]))
     cu8 = fuzz_cases.build_capture(c)
     want = orc.ref_lines(cu8, c["flags"])
     got = [orc.blank_ts(l) for l in orc.run_lines(cu8, orc.opts_from_flags(c["flags"]))]

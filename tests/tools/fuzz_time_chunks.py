@@ -12,6 +12,7 @@ lib = pkg.load_library(HOSTSIM_SO)
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 600.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 4242)
 t0 = time.time(); k = 0; total_retries = 0
+rng_b = np.random.default_rng((int(sys.argv[2]) if len(sys.argv) > 2 else 4242) + 7000003)     # batch size per case (its own generator)
 while time.time() - t0 < budget:
     k += 1
     c = fuzz_cases.draw_time_chunk_case(rng)
@@ -22,11 +23,12 @@ while time.time() - t0 < budget:
     want = pc.oracle_lines(cu8, flags)
     world, halo = c["world"], c["halo"]
     overflow = 0
+    mib = int(rng_b.choice([1, 1, 2, 8, 64]))
     got, ends, retries, ok = [], [], 0, True
     for rank in range(world):
         h = halo
         while True:
-            with pkg.WmbusB200(flags, lib=lib, max_batch_mib=1) as ctx:
+            with pkg.WmbusB200(flags, lib=lib, max_batch_mib=mib) as ctx:
                 lines, ds, de, start = shard.decode_time_chunk(ctx, lambda lo, hi: ctx.push(cu8.ctypes.data + lo, hi - lo),
                                                                len(cu8), c["d"], rank, world, h)
                 overflow += ctx.stats().overflow_batches
@@ -43,7 +45,7 @@ while time.time() - t0 < budget:
     if ok and not same and overflow:                          # a device table was full (1 MiB batches): lines may be missing, none may be invented
         it = iter(want)
         same = all(any(l == w for w in it) for l in merged)
-    print("case %d %s flags=%r world=%d halo=%d lines=%d retries=%d overflow_batches=%d" % (k, "ok" if same else "MISMATCH", flags, world, halo, len(want), retries, overflow), flush=True)
+    print("case %d %s flags=%r world=%d halo=%d mib=%d lines=%d retries=%d overflow_batches=%d" % (k, "ok" if same else "MISMATCH", flags, world, halo, mib, len(want), retries, overflow), flush=True)
     if not same:
         sys.exit(1)
 print("done", k, "cases,", total_retries, "halo retries")
