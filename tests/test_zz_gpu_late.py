@@ -25,3 +25,12 @@ def test_argv_matrix_matches_the_reference_binary(pkg, gpu_lib):
     """SURVEY 8(b), argv by argv against the reference binary on the GPU build of the host program, without the three
     argvs that decode at a decimation no GPU test has run yet (0, 9): the decimations the GPU suite covers are 1-4"""
     check_argv_matrix(_exe(pkg), real_stdin=True, skip=("-d abc", "-d 0", "-d 9 -s"))
+
+
+def test_telegram_that_ends_after_a_gap_in_the_input(pkg, gpu_lib):
+    """time chunks: a telegram that runs into dead air ends 291 k samples after its chunk's end; the worker's right halo
+    goes on while wmb_pending_before() reports it in flight (tests/test_time_shard.py has the CPU-build twin)"""
+    import fuzz_cases
+    from test_time_shard import check_time_chunks
+    c = fuzz_cases.time_chunk_case(882, 126)
+    check_time_chunks(pkg, gpu_lib, fuzz_cases.build_capture(c), c["flags"], world=4, halo_m=1 << 18)
