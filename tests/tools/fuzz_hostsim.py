@@ -30,11 +30,13 @@ while time.time() < t_end:
     want = [orc.blank_ts(l) for l in orc.run_lines(cu8, o)]
     got, st = pc.run_lines(pkg, lib, cu8, c["flags"], pushes=c["pushes"], **c["tuning"])
     ok = got == want
+    lost = 0
     if not ok and st.overflow_batches:                       # a device table was full: lines may be missing, none may be invented
         it = iter(want)
         ok = all(any(l == w for w in it) for l in got)
-    print("case %d (seed %d) %s lines=%d rerun=%d fallbacks=%d overflow_batches=%d" % (
-        k, seed, "ok" if ok else "MISMATCH", len(want), st.lanes_rerun, st.rl_fallbacks, st.overflow_batches), flush=True)
+        lost = len(want) - len(got)
+    print("case %d (seed %d) %s lines=%d rerun=%d fallbacks=%d overflow_batches=%d lost=%d" % (
+        k, seed, "ok" if ok else "MISMATCH", len(want), st.lanes_rerun, st.rl_fallbacks, st.overflow_batches, lost), flush=True)
     if not ok:
         print("got", len(got), "want", len(want)); sys.exit(1)
 print("done", k, "cases")

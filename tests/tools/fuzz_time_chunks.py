@@ -42,10 +42,12 @@ while time.time() - t0 < budget:
     total_retries += retries
     merged = shard.merge_lines(got)
     same = ok and merged == want
-    if ok and not same and overflow:                          # a device table was full (1 MiB batches): lines may be missing, none may be invented
+    lost = 0
+    if ok and not same and overflow:                          # a device table was full: lines may be missing, none may be invented
         it = iter(want)
         same = all(any(l == w for w in it) for l in merged)
-    print("case %d %s flags=%r world=%d halo=%d mib=%d lines=%d retries=%d overflow_batches=%d" % (k, "ok" if same else "MISMATCH", flags, world, halo, mib, len(want), retries, overflow), flush=True)
+        lost = len(want) - len(merged)
+    print("case %d %s flags=%r world=%d halo=%d mib=%d lines=%d retries=%d overflow_batches=%d lost=%d" % (k, "ok" if same else "MISMATCH", flags, world, halo, mib, len(want), retries, overflow, lost), flush=True)
     if not same:
         sys.exit(1)
 print("done", k, "cases,", total_retries, "halo retries")
