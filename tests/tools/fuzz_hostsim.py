@@ -1,7 +1,7 @@
 """Differential fuzzing of the library's host logic and kernel phase functions on the CPU build (tests/hostsim) against
 the oracle: random captures (noise level, emitters, interferers, dead air), random flags, lane geometry and push sizes
 (tests/fuzz_cases.py draws them).
-    python tests/tools/fuzz_hostsim.py [seconds] [seed] [tone]     prints one line per case; exits 1 at the first mismatch
+    python tests/tools/fuzz_hostsim.py [seconds] [seed] [tone|manual]     prints one line per case; exits 1 at the first mismatch
 `tone` forces every case into the regime the first campaign found: a CW carrier inside the channel,
 noise sigma <= 3 -- the run-length tracker's bit length collapses, event buffers and rings fill."""
 import importlib, sys, time
@@ -15,6 +15,25 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 600.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rng = np.random.default_rng(seed)
 tone = len(sys.argv) > 3 and sys.argv[3] == "tone"
+manual = len(sys.argv) > 3 and sys.argv[3] == "manual"       # the caller drives the framers: wmb_push / wmb_poll / wmb_decode_frames
+
+
+def run_manual(cu8, flags, pushes, tuning):
+    data = np.ascontiguousarray(cu8, np.uint8)
+    lines, off = [], 0
+    with pkg.WmbusB200(flags, lib=lib, manual_frames=1, **tuning) as ctx:
+        for n in list(pushes or []) + [1 << 19] * (len(data) // (1 << 19) + 1):
+            n = min(n, len(data) - off)
+            if n <= 0:
+                break
+            ctx.push(data.ctypes.data + off, n); off += n
+            arr, k = ctx.poll(flush=False)
+            ctx.decode_frames(arr, k)
+            lines += ctx.take_lines()
+        arr, k = ctx.poll(flush=True)
+        ctx.decode_frames(arr, k)
+        lines += ctx.take_lines()
+        return lines, ctx.stats()
 rng_tone = np.random.default_rng(seed + 1000003)             # (its own generator: the cases keep their numbers)
 t_end = time.time() + budget
 k = 0
@@ -28,7 +47,10 @@ while time.time() < t_end:
     cu8 = fuzz_cases.build_capture(c)
     o = orc.opts_from_flags(c["flags"]); o.prefilter = c["prefilter"]
     want = [orc.blank_ts(l) for l in orc.run_lines(cu8, o)]
-    got, st = pc.run_lines(pkg, lib, cu8, c["flags"], pushes=c["pushes"], **c["tuning"])
+    if manual:
+        got, st = run_manual(cu8, c["flags"], c["pushes"], c["tuning"])
+    else:
+        got, st = pc.run_lines(pkg, lib, cu8, c["flags"], pushes=c["pushes"], **c["tuning"])
     ok = got == want
     lost = 0
     if not ok and st.overflow_batches:                       # a device table was full: lines may be missing, none may be invented
