@@ -24,11 +24,12 @@ while time.time() - t0 < budget:
     world, halo = c["world"], c["halo"]
     overflow = 0
     mib = int(rng_b.choice([1, 1, 2, 8, 64]))
+    geom = {k_: v for k_, v in c["tuning"].items() if k_ in ("chunk_samples", "warmup_samples")}      # lane geometry of the case
     got, ends, retries, ok = [], [], 0, True
     for rank in range(world):
         h = halo
         while True:
-            with pkg.WmbusB200(flags, lib=lib, max_batch_mib=mib) as ctx:
+            with pkg.WmbusB200(flags, lib=lib, max_batch_mib=mib, **geom) as ctx:
                 lines, ds, de, start = shard.decode_time_chunk(ctx, lambda lo, hi: ctx.push(cu8.ctypes.data + lo, hi - lo),
                                                                len(cu8), c["d"], rank, world, h)
                 overflow += ctx.stats().overflow_batches
@@ -47,7 +48,7 @@ while time.time() - t0 < budget:
         it = iter(want)
         same = all(any(l == w for w in it) for l in merged)
         lost = len(want) - len(merged)
-    print("case %d %s flags=%r world=%d halo=%d mib=%d lines=%d retries=%d overflow_batches=%d lost=%d" % (k, "ok" if same else "MISMATCH", flags, world, halo, mib, len(want), retries, overflow, lost), flush=True)
+    print("case %d %s flags=%r world=%d halo=%d mib=%d geom=%r lines=%d retries=%d overflow_batches=%d lost=%d" % (k, "ok" if same else "MISMATCH", flags, world, halo, mib, geom, len(want), retries, overflow, lost), flush=True)
     if not same:
         sys.exit(1)
 print("done", k, "cases,", total_retries, "halo retries")
